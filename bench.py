@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- Gibbs variable-samples/s of the sweep hot path on N B200s (one process per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A "step" is one inference sweep (GibbsSamplerThread::sample over every variable,
+--sample_evidence) of the synthetic graph BASELINE.json's metric is quoted on that fits one
+GPU: configs[1], the Boolean graph of 10 M variables x (8 unary ISTRUE + 1 IMPLY) with 1 k
+shared weights, after the configured learning epochs.  One replica per GPU, no data-path
+collective in the timed region except the final tally reduction ("scaling": "weak").
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      algorithmic bytes of a sweep / CUDA-event duration vs the
+                measured HBM copy peak in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own CPU path (oracle/_ref/dw, built from the unmodified reference
+                sources) on this host's cores, on a bounded sample of the same workload
+  e2e           the same metric through the C ABI with HOST buffers: dwg_create (H2D upload of
+                the compiled graph) + K sweeps + dwg_get_tallies (D2H), wall-clocked
+  learn         learning-epoch throughput (free-chain draw + evid clamp/draw + SGD per variable)
+
+--impl reference times the reference CPU implementation only (rank 0; other ranks exit 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+REF_DW = os.path.join(ROOT, "oracle", "_ref", "dw")
+WORKLOADS = {
+    # name: (generator kwargs, description)
+    "c2": dict(nvar=10_000_000, desc="configs[1]: Boolean 10M vars x (8 unary ISTRUE + 1 IMPLY_NATURAL), "
+               "1k shared weights, 50% evidence, --sample_evidence"),
+}
+LEARN = dict(n_epoch=20, alpha=0.01, diminish=0.95, reg_param=0.01)  # SURVEY.md 8(d) C2 dw-args
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.lines = []
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen([exe, "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mxc = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: take whatever we saw
+            sm = [float(l.split(",")[1]) for _, l in self.lines if len(l.split(",")) >= 9][-3:] or [0.0]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# the reference's CPU path, on a bounded sample of the workload
+# --------------------------------------------------------------------------------------
+def run_reference_cpu(nvar_sample: int, n_infer: int, n_learn: int, tmpdir: str):
+    """oracle/_ref/dw gibbs (the unmodified reference, -Ofast, all host threads) on a C2 graph of
+    nvar_sample variables.  Returns per-epoch vars/sec lists (inference, learning)."""
+    from sampler_b200 import graphgen, graphio
+    if not os.path.exists(REF_DW):
+        return None
+    raw = graphgen.c2_boolean(nvar_sample)
+    paths = graphio.write_binary(raw, tmpdir)
+    threads = os.cpu_count() or 1
+    cmd = [REF_DW, "gibbs", "-m", paths["meta"], "-v", paths["variables"], "-f", paths["factors"],
+           "-w", paths["weights"], "-o", tmpdir, "-l", str(n_learn), "-i", str(n_infer),
+           "--alpha", str(LEARN["alpha"]), "--diminish", str(LEARN["diminish"]),
+           "--reg_param", str(LEARN["reg_param"]), "--sample_evidence", "-t", str(threads), "-c", "1"]
+    t0 = time.time()
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    wall = time.time() - t0
+    inf = [float(x) for x in re.findall(r"INFERENCE EPOCH.*?sec\.,([0-9.eE+]+) vars/sec", out)]
+    lrn = [float(x) for x in re.findall(r"LEARNING EPOCH.*?sec\.,([0-9.eE+]+) vars/sec", out)]
+    for k in ("variables", "factors", "weights", "domains"):
+        try:
+            os.remove(paths[k])
+        except OSError:
+            pass
+    return dict(infer=inf, learn=lrn, threads=threads, wall=wall, nvar=nvar_sample)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload]
+    nvar_sample = args.ref_nvar
+    tmp = tempfile.mkdtemp(prefix="dwref_")
+    try:
+        r = run_reference_cpu(nvar_sample, args.steps + args.warmup, 0, tmp)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    if r is None or len(r["infer"]) < args.warmup + 1:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/dw missing or produced no epochs"}))
+        return 0
+    timed = r["infer"][args.warmup:]
+    # whole-run throughput over the timed epochs: total samples / total time
+    secs = [nvar_sample / v for v in timed]
+    value = nvar_sample * len(timed) / sum(secs)
+    sample = "C2 graph scaled to %d variables (same per-variable structure), %d inference sweeps" % (nvar_sample, len(timed))
+    line = {
+        "impl": "reference", "metric": "gibbs_variable_samples_per_sec", "value": value, "unit": "variable-samples/s",
+        "n_gpus": args.gpus, "steps": len(timed), "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "reference_sample": sample, "binary": "oracle/_ref/dw (unmodified reference, -Ofast)",
+                   "threads": r["threads"], "n_datacopy": 1},
+        "cpu_baseline": {"value": value, "unit": "variable-samples/s", "cores": r["threads"], "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "variable-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+class _DevArray:
+    """__cuda_array_interface__ view of library-owned device memory (for torch.distributed)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def ours(args):
+    import torch
+    import sampler_b200 as sb
+    from sampler_b200 import graphgen
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            log("bench.py --gpus %d must be launched with torch.distributed.run (one rank per GPU)" % args.gpus)
+            return 2
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    sb.load(build=not os.path.exists(sb.api.lib_path()))
+    L = sb.load()
+    wl = WORKLOADS[args.workload]
+    nvar = args.nvar or wl["nvar"]
+    t0 = time.time()
+    raw = graphgen.c2_boolean(nvar)
+    t_gen = time.time() - t0
+    t0 = time.time()
+    graph = sb.Graph.from_raw(raw, sb.SCHED_AUTO)
+    t_compile = time.time() - t0
+    del raw
+    info = graph.info
+    if rank == 0:
+        log("graph: %d vars, %d edge records, %d colours, %.1f MiB/replica; gen %.1fs compile %.1fs"
+            % (info.num_variables, info.num_index_entries, info.num_colors, info.device_bytes / 2**20, t_gen, t_compile))
+    smp = sb.Sampler(graph, device=local, sample_evidence=True, reg_param=LEARN["reg_param"], seed=1234, replica=rank)
+    stream = torch.cuda.ExternalStream(smp.stream(), device=torch.device("cuda", local))
+    w_t = torch.as_tensor(_DevArray(smp.weights_device_ptr(), info.num_weights, "<f8"), device=torch.device("cuda", local))
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    # ---- learning phase: ceil(l / N) epochs per replica, weights averaged every epoch ----
+    n_learn = -(-LEARN["n_epoch"] // world)
+    step = LEARN["alpha"]
+    smp.learn_epoch(step)  # warm-up epoch (JIT-free, but first touch of everything)
+    smp.sync()
+    barrier()
+    e0, e1 = ev(), ev()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(n_learn):
+            smp.learn_epoch(step)
+            if dist is not None:
+                dist.all_reduce(w_t)
+                smp.finish_weight_average(world, want_norms=False)
+            step *= LEARN["diminish"]
+        e1.record(stream)
+    smp.sync()
+    learn_ms = e0.elapsed_time(e1) / n_learn
+    lt = torch.tensor([learn_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+    learn_ms = float(lt.item())
+
+    # ---- inference: W warm-up sweeps, K timed ----
+    smp.clear_tallies()
+    smp.infer_epochs(args.warmup)
+    smp.clear_tallies()
+    smp.sync()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = L.dwg_launch_count()
+    tall_t = torch.as_tensor(_DevArray(smp.tallies_device_ptr(), info.num_values, "<i4"), device=torch.device("cuda", local))
+    e0, e1, e2 = ev(), ev(), ev()
+    t_wall0 = time.time()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        smp.infer_epochs(args.steps)
+        e1.record(stream)
+        if dist is not None:
+            dist.reduce(tall_t, dst=0)  # sample tallies reduced at the end of inference
+        e2.record(stream)
+    smp.sync()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    barrier()
+    launches = L.dwg_launch_count() - launches0
+    sweep_ms = e0.elapsed_time(e1) / args.steps
+    total_ms = e0.elapsed_time(e2)
+    tt = torch.tensor([total_ms, sweep_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, sweep_ms = float(tt[0].item()), float(tt[1].item())
+    value = nvar * world * args.steps / (total_ms * 1e-3)
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    t, ns = smp.tallies()
+    assert int(ns[0]) == args.steps
+    frac1 = float(t.sum()) / (float(nvar) * args.steps * world)
+
+    # ---- e2e through the C ABI from host buffers: create (H2D) + K sweeps + tallies (D2H) ----
+    smp.close()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    s2 = sb.Sampler(graph, device=local, sample_evidence=True, reg_param=LEARN["reg_param"], seed=99, replica=rank)
+    s2.infer_epochs(args.steps)
+    t2, n2 = s2.tallies()
+    e2e_s = time.time() - t0
+    e2e_value = nvar * args.steps / e2e_s
+    s2.close()
+
+    # ---- the reference's CPU path on this host, bounded sample ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        tmp = tempfile.mkdtemp(prefix="dwref_")
+        try:
+            r = run_reference_cpu(args.ref_nvar, 6, 3, tmp)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        if r and len(r["infer"]) >= 3:
+            cpu = {"value": float(np.median(r["infer"][1:])), "unit": "variable-samples/s", "cores": r["threads"],
+                   "kind": "reference",
+                   "sample": "oracle/_ref/dw (unmodified reference, -Ofast) -t %d -c 1 on the C2 graph scaled to %d variables; "
+                             "median of inference epochs 2..6; learning epochs %s vars/s"
+                             % (r["threads"], r["nvar"], ("%.3g" % np.median(r["learn"][1:])) if len(r["learn"]) > 1 else "n/a")}
+        else:
+            cpu = {"value": None, "unit": "variable-samples/s", "cores": os.cpu_count(), "kind": "reference",
+                   "sample": "oracle/_ref/dw unavailable on this box"}
+
+    peak, peak_src = measured_peak()
+    bytes_sweep = float(info.bytes_per_sweep_infer)
+    achieved = bytes_sweep / (sweep_ms * 1e-3) / 1e9
+    line = {
+        "metric": "gibbs_variable_samples_per_sec", "value": value, "unit": "variable-samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"] if nvar == wl["nvar"] else wl["desc"] + " [nvar overridden: %d]" % nvar,
+                   "nvar_per_replica": nvar, "schedule": "chromatic" if info.schedule == 2 else "hogwild",
+                   "colors": info.num_colors, "replicas": world,
+                   "l2_policy": "inputs larger than L2 (%.0f MiB streamed per sweep vs 126 MB L2); no flush" % (info.device_bytes / 2**20),
+                   "learn_epochs_before": n_learn + 1, "seed": 1234},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_infer<uint8_t>",
+                     "algorithmic_bytes_per_sweep": bytes_sweep, "bytes_per_variable_sample": bytes_sweep / nvar,
+                     "launches_per_sweep": info.num_colors},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "variable-samples/s",
+                "h2d_bytes_per_step": int(info.device_bytes / args.steps), "d2h_bytes_per_step": int(4 * info.num_values / args.steps),
+                "what": "dwg_create (upload of the compiled graph from host memory) + %d sweeps + dwg_get_tallies, wall clock" % args.steps},
+        "learn": {"value": nvar * world / (learn_ms * 1e-3), "unit": "variable-updates/s", "ms_per_epoch": learn_ms,
+                  "epochs": n_learn, "hbm_gbs": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9},
+        "gpu_launches": int(launches), "clocks": clk, "frac_true": frac1,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--nvar", type=int, default=0, help="override variables per replica (debug)")
+    ap.add_argument("--ref-nvar", type=int, default=1_000_000, help="variables of the reference's bounded sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return reference_arm(args)
+    return ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -231,16 +231,30 @@ void orc_sgd_on_variable(const orc_graph *g, const orc_opts *o, orc_state *s,
   }
 }
 
+/* Uniform source: the reference consumes one erand48 stream per thread
+ * (src/gibbs_sampler.h:203,237,177).  For schedule-order parity tests the same code can be fed
+ * explicit per-variable uniforms instead: u[0] for the first draw of the step, u[1] for the
+ * second. */
+typedef struct {
+  unsigned short *seed; /* erand48 state, or NULL */
+  double u[2];
+  int k;
+} usrc;
+static double next_u(usrc *s) {
+  if (s->seed) return erand48(s->seed);
+  return s->u[s->k < 1 ? s->k++ : 1];
+}
+
 static int has_truthiness(const orc_graph *g, uint64_t vid) {
   return !is_linear_zero(g->total_truthiness[vid]); /* variable.h:105 */
 }
 
 /* GibbsSamplerThread::sample_evid, src/gibbs_sampler.h:171-190 */
 static uint64_t sample_evid(const orc_graph *g, const orc_opts *o, orc_state *s,
-                            uint64_t vid, unsigned short seed[3]) {
+                            uint64_t vid, usrc *seed) {
   if (!o->noise_aware && g->is_evid[vid]) return g->assignment_dense[vid];
   if (o->noise_aware && has_truthiness(g, vid)) {
-    double r = erand48(seed);
+    double r = next_u(seed);
     double sum = 0;
     for (uint64_t i = 0; i < g->card[vid]; ++i) {
       sum += g->truthiness[g->var_val_base[vid] + i];
@@ -252,16 +266,16 @@ static uint64_t sample_evid(const orc_graph *g, const orc_opts *o, orc_state *s,
   if (g->dtype[vid] == 0) {
     double pos = orc_potential(g, vid, 1, s->assign_evid, s->weights);
     double neg = orc_potential(g, vid, 0, s->assign_evid, s->weights);
-    return orc_draw_boolean(pos, neg, erand48(seed));
+    return orc_draw_boolean(pos, neg, next_u(seed));
   }
-  return orc_draw_sample_r(g, vid, s->assign_evid, s->weights, erand48(seed));
+  return orc_draw_sample_r(g, vid, s->assign_evid, s->weights, next_u(seed));
 }
 
 /* src/gibbs_sampler.h:151-169 */
-void orc_sample_single_variable(const orc_graph *g, const orc_opts *o, orc_state *s,
-                                uint64_t vid, unsigned short seed[3]) {
+static void sample_single_variable(const orc_graph *g, const orc_opts *o, orc_state *s,
+                                   uint64_t vid, usrc *seed) {
   if (g->is_evid[vid] && !o->sample_evidence) return;
-  uint64_t p = orc_draw_sample_r(g, vid, s->assign_evid, s->weights, erand48(seed));
+  uint64_t p = orc_draw_sample_r(g, vid, s->assign_evid, s->weights, next_u(seed));
   if (p == ORC_INVALID) abort();
   s->assign_evid[vid] = p;
   ++s->nsamples[vid];
@@ -270,10 +284,10 @@ void orc_sample_single_variable(const orc_graph *g, const orc_opts *o, orc_state
 }
 
 /* src/gibbs_sampler.h:127-149 */
-void orc_sample_sgd_single_variable(const orc_graph *g, const orc_opts *o,
-                                    orc_state *s, uint64_t vid, double stepsize,
-                                    unsigned short seed[3]) {
-  uint64_t p = orc_draw_sample_r(g, vid, s->assign_free, s->weights, erand48(seed));
+static void sample_sgd_single_variable(const orc_graph *g, const orc_opts *o,
+                                       orc_state *s, uint64_t vid, double stepsize,
+                                       usrc *seed) {
+  uint64_t p = orc_draw_sample_r(g, vid, s->assign_free, s->weights, next_u(seed));
   if (p == ORC_INVALID) abort();
   s->assign_free[vid] = p;
   uint64_t e = sample_evid(g, o, s, vid, seed);
@@ -283,6 +297,39 @@ void orc_sample_sgd_single_variable(const orc_graph *g, const orc_opts *o,
                                  (o->noise_aware && !has_truthiness(g, vid))))
     return;
   orc_sgd_on_variable(g, o, s, vid, stepsize);
+}
+
+void orc_sample_single_variable(const orc_graph *g, const orc_opts *o, orc_state *s,
+                                uint64_t vid, unsigned short seed[3]) {
+  usrc u = {seed, {0, 0}, 0};
+  sample_single_variable(g, o, s, vid, &u);
+}
+void orc_sample_sgd_single_variable(const orc_graph *g, const orc_opts *o,
+                                    orc_state *s, uint64_t vid, double stepsize,
+                                    unsigned short seed[3]) {
+  usrc u = {seed, {0, 0}, 0};
+  sample_sgd_single_variable(g, o, s, vid, stepsize, &u);
+}
+
+/* The same per-variable steps in an explicit variable order with explicit uniforms
+ * (r0[v]: first draw of v's step, r1[v]: second).  Sequential and in `order`, so it is the
+ * reference algorithm for a different scan order -- what a chromatic / schedule-order
+ * sweep must reproduce exactly. */
+void orc_sweep_infer_seq(const orc_graph *g, const orc_opts *o, orc_state *s,
+                         const uint64_t *order, uint64_t n, const double *r0) {
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t v = order[i];
+    usrc u = {NULL, {r0[v], 0}, 0};
+    sample_single_variable(g, o, s, v, &u);
+  }
+}
+void orc_sweep_learn_seq(const orc_graph *g, const orc_opts *o, orc_state *s, double stepsize,
+                         const uint64_t *order, uint64_t n, const double *r0, const double *r1) {
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t v = order[i];
+    usrc u = {NULL, {r0[v], r1[v]}, 0};
+    sample_sgd_single_variable(g, o, s, v, stepsize, &u);
+  }
 }
 
 /* shard bounds, src/gibbs_sampler.cc:52-54 */
@@ -297,7 +344,8 @@ void orc_sweep_infer(const orc_graph *g, const orc_opts *o, orc_state *s,
                      uint64_t ith, uint64_t n, unsigned short seed[3]) {
   uint64_t a, b;
   shard(g->nvar, ith, n, &a, &b);
-  for (uint64_t v = a; v < b; ++v) orc_sample_single_variable(g, o, s, v, seed);
+  usrc u = {seed, {0, 0}, 0};
+  for (uint64_t v = a; v < b; ++v) sample_single_variable(g, o, s, v, &u);
 }
 
 /* GibbsSamplerThread::sample_sgd, src/gibbs_sampler.cc:71-75 */
@@ -306,8 +354,8 @@ void orc_sweep_learn(const orc_graph *g, const orc_opts *o, orc_state *s,
                      unsigned short seed[3]) {
   uint64_t a, b;
   shard(g->nvar, ith, n, &a, &b);
-  for (uint64_t v = a; v < b; ++v)
-    orc_sample_sgd_single_variable(g, o, s, v, stepsize, seed);
+  usrc u = {seed, {0, 0}, 0};
+  for (uint64_t v = a; v < b; ++v) sample_sgd_single_variable(g, o, s, v, stepsize, &u);
 }
 
 /* DimmWitted::learn + inference with one sampler, one worker:

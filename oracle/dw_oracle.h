@@ -129,6 +129,11 @@ void orc_sweep_infer(const orc_graph *g, const orc_opts *o, orc_state *s,
 void orc_sweep_learn(const orc_graph *g, const orc_opts *o, orc_state *s,
                      double stepsize, uint64_t ith_shard, uint64_t n_shards,
                      unsigned short seed[3]);
+/* explicit scan order + explicit uniforms (r0[v] first draw, r1[v] second draw of v's step) */
+void orc_sweep_infer_seq(const orc_graph *g, const orc_opts *o, orc_state *s,
+                         const uint64_t *order, uint64_t n, const double *r0);
+void orc_sweep_learn_seq(const orc_graph *g, const orc_opts *o, orc_state *s, double stepsize,
+                         const uint64_t *order, uint64_t n, const double *r0, const double *r1);
 /* whole single-replica, single-thread schedule = `dw gibbs -t 1 -c 1` after
  * srand(srand_seed) (src/dimmwitted.cc:121-207); srand_seed<0 => no srand. */
 void orc_run(const orc_graph *g, const orc_opts *o, orc_state *s, uint64_t n_learn,

@@ -1,0 +1,58 @@
+"""Build recipes for the native parts (in-tree, so the .so files travel with the repo).
+
+  libdwg.so   CUDA kernels (sm_100a) + C ABI + C++ host (loader, compiler, CLI)
+  dw          the `dw` command-line front end (thin main over dwg_dw_main)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libdwg.so")
+DW = os.path.join(PKG, "dw")
+
+CU_SOURCES = ["dwg_api.cu"]
+HOST_SOURCES = ["host/compile.cc", "host/loader.cc", "host/cmd_parser.cc", "host/gibbs_app.cc",
+                "host/text2bin.cc"]
+HEADERS = ["dwg_device.cuh", "dwg_kernels.cuh", "graph_image.h", "host/cmd_parser.h",
+           os.path.join(ROOT, "include", "dwg.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES + HOST_SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = srcs + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    if force or _stale(LIB, deps):
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-ldl", "-lpthread"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    main = os.path.join(CSRC, "host", "dw_main.cc")
+    if os.path.exists(main) and (force or _stale(DW, [main, LIB])):
+        cmd = ["g++", "-O2", "-std=c++17", "-o", DW, main, "-L" + PKG, "-ldwg",
+               "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    build(force="--force" in sys.argv, verbose=True)

@@ -1,0 +1,758 @@
+// dwg_api.cu -- the C ABI (include/dwg.h) over the sweep kernels.
+//
+// dwg_graph  = a GraphImage (host) ; dwg_handle = one replica on one GPU.
+// All device work of a handle goes to its own non-blocking stream; sweeps are
+// asynchronous, getters synchronise.  No CPU fallback exists: every compute entry point
+// needs a CUDA device and reports DWG_ERR_CUDA without one.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <atomic>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dwg.h"
+#include "dwg_kernels.cuh"
+#include "graph_image.h"
+
+using namespace dwg;
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(DWG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+  } while (0)
+
+struct dwg_graph {
+  GraphImage img;
+};
+
+namespace {
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t count) {
+    n = count;
+    // 16 B of slack so tile-granular (16 B) bulk copies may overrun the logical end
+    return cudaMalloc((void **)&p, count * sizeof(T) + 16);
+  }
+  template <typename S>
+  cudaError_t upload(const std::vector<S> &v, cudaStream_t s) {
+    static_assert(sizeof(S) == sizeof(T), "");
+    cudaError_t e = alloc(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+}  // namespace
+
+struct dwg_handle {
+  const GraphImage *img = nullptr;
+  dwg_opts_t opts{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  // graph
+  DevBuf<uint8_t> var_flags, e_tag, w_fixed, evid_val8;
+  DevBuf<uint32_t> evid_val32, var_row, row_ptr, row_oth, e_wid, oth;
+  DevBuf<float> e_fv32;
+  DevBuf<double> e_fv64, truthiness;
+  // state
+  DevBuf<uint8_t> assign_free8, assign_evid8;
+  DevBuf<uint32_t> assign_free32, assign_evid32, tallies;
+  DevBuf<double> weights, prev_weights, norms;
+  DevBuf<double> r_free, r_evid;  // parity hook
+  bool explicit_r = false, sequential = false;
+  uint64_t sweep_counter = 0, infer_sweeps = 0;
+  std::vector<uint64_t> extra_nsamples;  // from dwg_add_tallies
+  DevGraph dg{};
+  DevState ds{};
+  // CUDA graph of one full inference sweep (all colour classes), sweep counter read from
+  // device memory is not needed: the counter only seeds Philox, so each replay must differ --
+  // we therefore capture per-launch kernel nodes and update their params on replay.
+  size_t device_bytes = 0;
+  ~dwg_handle() {
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+extern "C" {
+
+const char *dwg_last_error(void) { return g_err.c_str(); }
+const char *dwg_version(void) { return "dwg 0.1 (sm_100a)"; }
+uint64_t dwg_launch_count(void) { return g_launches.load(); }
+
+void dwg_opts_default(dwg_opts_t *o) {
+  std::memset(o, 0, sizeof(*o));
+  o->reg_param = 0.01;  // src/cmd_parser.cc:162
+  o->schedule = DWG_SCHED_AUTO;
+  o->seed = 0x5eed5eedull;
+}
+
+int dwg_graph_from_raw(const dwg_raw_t *raw, int schedule, dwg_graph **out) {
+  if (!raw || !out) return fail(DWG_ERR_INVALID, "null argument");
+  RawView v;
+  v.nvar = raw->nvar; v.ndom = raw->ndom; v.nfac = raw->nfac; v.nweight = raw->nweight;
+  v.var_role = raw->var_role; v.var_init = raw->var_init; v.var_dtype = raw->var_dtype;
+  v.var_card = raw->var_card; v.dom_vid = raw->dom_vid; v.dom_ptr = raw->dom_ptr;
+  v.dom_val = raw->dom_val; v.dom_truth = raw->dom_truth; v.fac_func = raw->fac_func;
+  v.fac_ptr = raw->fac_ptr; v.edge_vid = raw->edge_vid; v.edge_eq = raw->edge_eq;
+  v.fac_wid = raw->fac_wid; v.fac_fv = raw->fac_fv; v.w_init = raw->w_init; v.w_fixed = raw->w_fixed;
+  static const uint64_t zero = 0;
+  if (!v.fac_ptr) v.fac_ptr = &zero;
+  if (!v.dom_ptr) v.dom_ptr = &zero;
+  std::unique_ptr<dwg_graph> g(new dwg_graph);
+  int err = 0;
+  std::string msg;
+  try {
+    msg = compile_graph(v, schedule, &g->img, &err);
+  } catch (const std::exception &e) {
+    return fail(DWG_ERR_INVALID, std::string("compile: ") + e.what());
+  }
+  if (!msg.empty()) return fail(err, msg);
+  *out = g.release();
+  return DWG_OK;
+}
+
+int dwg_graph_from_files(const char *meta, int n_var, const char *const *var_files, int n_dom,
+                         const char *const *dom_files, int n_fac, const char *const *fac_files,
+                         int n_wgt, const char *const *wgt_files, int schedule, dwg_graph **out) {
+  if (!meta || !out) return fail(DWG_ERR_INVALID, "null argument");
+  try {
+    MetaCounts m;
+    std::string msg = read_meta(meta, &m);
+    if (!msg.empty()) return fail(DWG_ERR_IO, msg);
+    auto vec = [](int n, const char *const *p) {
+      std::vector<std::string> v;
+      for (int i = 0; i < n; ++i) v.emplace_back(p[i]);
+      return v;
+    };
+    RawGraph raw;
+    int err = 0;
+    msg = load_raw(m, vec(n_var, var_files), vec(n_dom, dom_files), vec(n_fac, fac_files),
+                   vec(n_wgt, wgt_files), &raw, &err);
+    if (!msg.empty()) return fail(err, msg);
+    std::unique_ptr<dwg_graph> g(new dwg_graph);
+    msg = compile_graph(view_of(raw), schedule, &g->img, &err);
+    if (!msg.empty()) return fail(err, msg);
+    *out = g.release();
+  } catch (const std::exception &e) {
+    return fail(DWG_ERR_INVALID, std::string("load: ") + e.what());
+  }
+  return DWG_OK;
+}
+
+void dwg_graph_free(dwg_graph *g) { delete g; }
+
+static size_t image_device_bytes(const GraphImage &m) {
+  size_t b = 0;
+  b += m.var_flags.size() + m.e_tag.size() + m.w_fixed.size();
+  b += (size_t)m.assign_bytes * m.nvar * 3;  // evid_val + two chains
+  b += 4 * (m.var_row.size() + m.row_ptr.size() + m.row_oth.size() + m.e_wid.size() + m.oth.size());
+  b += 4 * m.e_fv32.size() + 8 * m.e_fv64.size() + 8 * m.truthiness.size();
+  b += 4 * m.nrow;         // tallies
+  b += 8 * 2 * m.nweight;  // weights + prev
+  return b;
+}
+
+int dwg_graph_info(const dwg_graph *g, dwg_graph_info_t *o) {
+  if (!g || !o) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = g->img;
+  std::memset(o, 0, sizeof(*o));
+  o->num_variables = m.nvar; o->num_factors = m.nfac; o->num_weights = m.nweight;
+  o->num_edges = m.nedge; o->num_values = m.nrow;
+  o->num_variables_evidence = m.nvar_evid; o->num_variables_query = m.nvar_query;
+  o->num_index_entries = m.nindex; o->num_other_refs = m.noth;
+  o->num_colors = m.ncolor(); o->schedule = m.schedule;
+  o->has_categorical = m.has_categorical; o->has_multi_arity = m.has_multi;
+  o->fv_mode = m.fv_mode; o->assign_bytes = m.assign_bytes;
+  o->device_bytes = image_device_bytes(m);
+  o->bytes_per_sweep_infer = m.bytes_infer;
+  o->bytes_per_sweep_infer_query = m.bytes_infer_query;
+  o->bytes_per_sweep_learn = m.bytes_learn;
+  return DWG_OK;
+}
+
+int dwg_graph_var_meta(const dwg_graph *g, uint8_t *dtype, uint8_t *is_evid, uint64_t *value_base,
+                       uint64_t *values) {
+  if (!g) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = g->img;
+  if (dtype) std::memcpy(dtype, m.var_dtype.data(), m.nvar);
+  if (is_evid) std::memcpy(is_evid, m.var_is_evid.data(), m.nvar);
+  if (value_base) std::memcpy(value_base, m.value_base.data(), 8 * (m.nvar + 1));
+  if (values) std::memcpy(values, m.values.data(), 8 * m.nrow);
+  return DWG_OK;
+}
+
+int dwg_debug_schedule(const dwg_graph *g, uint64_t *perm, uint64_t *color_start) {
+  if (!g) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = g->img;
+  if (perm) for (uint64_t d = 0; d < m.nvar; ++d) perm[d] = m.perm[d];
+  if (color_start) for (size_t c = 0; c < m.color_start.size(); ++c) color_start[c] = m.color_start[c];
+  return DWG_OK;
+}
+
+int dwg_debug_image(const dwg_graph *g, const char *name, const void **data, uint64_t *count,
+                    uint32_t *elem_size) {
+  if (!g || !name || !data || !count || !elem_size) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = g->img;
+  const std::string n(name);
+#define ARR(field)                                                    \
+  if (n == #field) {                                                  \
+    *data = m.field.data(); *count = m.field.size();                  \
+    *elem_size = (uint32_t)sizeof(m.field[0]);                        \
+    return DWG_OK;                                                    \
+  }
+  ARR(perm) ARR(inv) ARR(color_start) ARR(var_flags) ARR(evid_val) ARR(var_row) ARR(row_ptr)
+  ARR(row_oth) ARR(truthiness) ARR(e_wid) ARR(e_fv32) ARR(e_fv64) ARR(e_tag) ARR(oth) ARR(w_init)
+  ARR(w_fixed) ARR(row_of_value) ARR(values) ARR(value_base)
+#undef ARR
+  if (n == "oth_packed") {
+    static thread_local uint32_t v;
+    v = m.oth_packed; *data = &v; *count = 1; *elem_size = 4;
+    return DWG_OK;
+  }
+  return fail(DWG_ERR_INVALID, "unknown image array " + n);
+}
+
+// ---------------------------------------------------------------------------------
+static int init_state(dwg_handle *h) {
+  // InferenceResult ctor, src/inference_result.cc:24-42: both chains start at the evidence
+  // value (0 for query variables); weights from the Weight records; tallies cleared.
+  const GraphImage &m = *h->img;
+  if (m.assign_bytes == 1) {
+    CU(cudaMemcpyAsync(h->assign_free8.p, h->evid_val8.p, m.nvar, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->assign_evid8.p, h->evid_val8.p, m.nvar, cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    CU(cudaMemcpyAsync(h->assign_free32.p, h->evid_val32.p, 4 * m.nvar, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->assign_evid32.p, h->evid_val32.p, 4 * m.nvar, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  CU(cudaMemsetAsync(h->tallies.p, 0, 4 * m.nrow + 16, h->stream));
+  h->infer_sweeps = 0;
+  return DWG_OK;
+}
+
+int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handle **out) {
+  if (!g || !out) return fail(DWG_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(DWG_ERR_CUDA, "no CUDA device: the Gibbs sweep has no CPU path");
+  if (device < 0 || device >= ndev) return fail(DWG_ERR_CUDA, "bad device index");
+  CU(cudaSetDevice(device));
+  std::unique_ptr<dwg_handle> h(new dwg_handle);
+  h->img = &g->img;
+  if (opts) h->opts = *opts; else dwg_opts_default(&h->opts);
+  h->device = device;
+  CU(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const GraphImage &m = g->img;
+  cudaStream_t s = h->stream;
+  CU(h->var_flags.upload(m.var_flags, s));
+  CU(h->e_tag.upload(m.e_tag, s));
+  CU(h->w_fixed.upload(m.w_fixed, s));
+  CU(h->row_ptr.upload(m.row_ptr, s));
+  CU(h->e_wid.upload(m.e_wid, s));
+  if (m.has_categorical) CU(h->var_row.upload(m.var_row, s));
+  if (m.has_multi) { CU(h->row_oth.upload(m.row_oth, s)); CU(h->oth.upload(m.oth, s)); }
+  if (m.fv_mode == FV_F32) CU(h->e_fv32.upload(m.e_fv32, s));
+  if (m.fv_mode == FV_F64) CU(h->e_fv64.upload(m.e_fv64, s));
+  if (m.has_truthiness) CU(h->truthiness.upload(m.truthiness, s));
+  std::vector<uint8_t> ev8;
+  if (m.assign_bytes == 1) {
+    ev8.assign(m.evid_val.begin(), m.evid_val.end());
+    CU(h->evid_val8.upload(ev8, s));
+    CU(h->assign_free8.alloc(m.nvar));
+    CU(h->assign_evid8.alloc(m.nvar));
+  } else {
+    CU(h->evid_val32.upload(m.evid_val, s));
+    CU(h->assign_free32.alloc(m.nvar));
+    CU(h->assign_evid32.alloc(m.nvar));
+  }
+  CU(h->tallies.alloc(m.nrow));
+  CU(h->weights.upload(m.w_init, s));
+  CU(h->prev_weights.upload(m.w_init, s));
+  CU(h->norms.alloc(2));
+  int rc = init_state(h.get());
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(s));  // ev8 goes out of scope; uploads must have landed
+  h->device_bytes = image_device_bytes(m);
+
+  DevGraph &dg = h->dg;
+  dg.nvar = (uint32_t)m.nvar; dg.nrow = (uint32_t)m.nrow;
+  dg.var_flags = h->var_flags.p;
+  dg.evid_val = m.assign_bytes == 1 ? (const void *)h->evid_val8.p : (const void *)h->evid_val32.p;
+  dg.var_row = m.has_categorical ? h->var_row.p : nullptr;
+  dg.row_ptr = h->row_ptr.p;
+  dg.row_oth = m.has_multi ? h->row_oth.p : nullptr;
+  dg.truthiness = m.has_truthiness ? h->truthiness.p : nullptr;
+  dg.e_wid = h->e_wid.p;
+  dg.e_fv32 = m.fv_mode == FV_F32 ? h->e_fv32.p : nullptr;
+  dg.e_fv64 = m.fv_mode == FV_F64 ? h->e_fv64.p : nullptr;
+  dg.e_tag = h->e_tag.p;
+  dg.oth = h->oth.p;
+  dg.oth_packed = m.oth_packed;
+  dg.w_fixed = h->w_fixed.p;
+  DevState &ds = h->ds;
+  ds.assign_free = m.assign_bytes == 1 ? (void *)h->assign_free8.p : (void *)h->assign_free32.p;
+  ds.assign_evid = m.assign_bytes == 1 ? (void *)h->assign_evid8.p : (void *)h->assign_evid32.p;
+  ds.weights = h->weights.p;
+  ds.tallies = h->tallies.p;
+  *out = h.release();
+  return DWG_OK;
+}
+
+void dwg_destroy(dwg_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  delete h;
+}
+
+static SweepParams make_params(dwg_handle *h, double stepsize) {
+  SweepParams p{};
+  const uint64_t key = h->opts.seed;
+  p.key0 = (uint32_t)key;
+  p.key1 = (uint32_t)(key >> 32) ^ (h->opts.replica * 0x9E3779B9u + h->opts.replica);
+  p.sweep_lo = (uint32_t)h->sweep_counter;
+  p.sweep_hi = (uint32_t)(h->sweep_counter >> 32);
+  p.sample_evidence = h->opts.sample_evidence;
+  p.learn_non_evidence = h->opts.learn_non_evidence;
+  p.noise_aware = h->opts.noise_aware;
+  p.reg_l1 = h->opts.regularization == 1;
+  p.reg_param = h->opts.reg_param;
+  p.stepsize = stepsize;
+  p.sequential = h->sequential;
+  p.r_free = h->explicit_r ? h->r_free.p : nullptr;
+  p.r_evid = h->explicit_r ? h->r_evid.p : nullptr;
+  return p;
+}
+
+static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
+  const GraphImage &m = *h->img;
+  CU(cudaSetDevice(h->device));
+  SweepParams p = make_params(h, stepsize);
+  ++h->sweep_counter;
+  for (uint32_t c = 0; c < m.ncolor(); ++c) {
+    p.d_begin = m.color_start[c];
+    p.d_end = m.color_start[c + 1];
+    const uint32_t n = p.d_end - p.d_begin;
+    if (!n) continue;
+    uint32_t blocks = (n + SWEEP_THREADS - 1) / SWEEP_THREADS;
+    uint32_t threads = SWEEP_THREADS;
+    if (h->sequential) { blocks = 1; threads = 1; }
+    if (m.assign_bytes == 1) {
+      if (learn) k_sweep_learn<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+      else k_sweep_infer<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+    } else {
+      if (learn) k_sweep_learn<uint32_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+      else k_sweep_infer<uint32_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+    }
+    ++g_launches;
+  }
+  CU(cudaGetLastError());
+  return DWG_OK;
+}
+
+int dwg_learn_epoch(dwg_handle *h, double stepsize) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  return launch_sweep(h, true, stepsize);
+}
+
+int dwg_infer_epoch(dwg_handle *h) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  int rc = launch_sweep(h, false, 0.0);
+  if (rc == DWG_OK) ++h->infer_sweeps;
+  return rc;
+}
+
+int dwg_infer_epochs(dwg_handle *h, uint64_t n) {
+  for (uint64_t i = 0; i < n; ++i) {
+    int rc = dwg_infer_epoch(h);
+    if (rc) return rc;
+  }
+  return DWG_OK;
+}
+
+int dwg_sync(dwg_handle *h) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return DWG_OK;
+}
+
+void *dwg_stream(dwg_handle *h) { return h ? (void *)h->stream : nullptr; }
+void *dwg_weights_device_ptr(dwg_handle *h) { return h ? (void *)h->weights.p : nullptr; }
+void *dwg_tallies_device_ptr(dwg_handle *h) { return h ? (void *)h->tallies.p : nullptr; }
+
+int dwg_clear_tallies(dwg_handle *h) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemsetAsync(h->tallies.p, 0, 4 * h->img->nrow, h->stream));
+  h->infer_sweeps = 0;
+  h->extra_nsamples.clear();
+  return DWG_OK;
+}
+
+int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  const GraphImage &m = *h->img;
+  CU(cudaSetDevice(h->device));
+  if (tallies) {
+    std::vector<uint32_t> t(m.nrow);
+    CU(cudaMemcpyAsync(t.data(), h->tallies.p, 4 * m.nrow, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (uint64_t i = 0; i < m.nrow; ++i) tallies[i] = t[m.row_of_value[i]];
+  }
+  if (nsamples) {
+    // ++agg_nsamples for every sampled variable every sweep (src/gibbs_sampler.h:157,163)
+    for (uint64_t v = 0; v < m.nvar; ++v) {
+      bool sampled = !m.var_is_evid[v] || h->opts.sample_evidence;
+      nsamples[v] = (sampled ? h->infer_sweeps : 0) + (h->extra_nsamples.empty() ? 0 : h->extra_nsamples[v]);
+    }
+  }
+  return DWG_OK;
+}
+
+int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsamples) {
+  if (!h || !tallies || !nsamples) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = *h->img;
+  CU(cudaSetDevice(h->device));
+  std::vector<uint32_t> t(m.nrow);
+  for (uint64_t i = 0; i < m.nrow; ++i) t[m.row_of_value[i]] = (uint32_t)tallies[i];
+  DevBuf<uint32_t> tmp;
+  CU(tmp.upload(t, h->stream));
+  if (m.nrow) {
+    k_add_u32<<<(uint32_t)((m.nrow + 255) / 256), 256, 0, h->stream>>>(h->tallies.p, tmp.p, (uint32_t)m.nrow);
+    ++g_launches;
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->extra_nsamples.empty()) h->extra_nsamples.assign(m.nvar, 0);
+  for (uint64_t v = 0; v < m.nvar; ++v) h->extra_nsamples[v] += nsamples[v];
+  return DWG_OK;
+}
+
+int dwg_get_weights(dwg_handle *h, double *out) {
+  if (!h || !out) return fail(DWG_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(out, h->weights.p, 8 * h->img->nweight, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DWG_OK;
+}
+
+int dwg_set_weights(dwg_handle *h, const double *in) {
+  if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->weights.p, in, 8 * h->img->nweight, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->prev_weights.p, in, 8 * h->img->nweight, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DWG_OK;
+}
+
+int dwg_get_assignments(dwg_handle *h, int evid_chain, uint64_t *out) {
+  if (!h || !out) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = *h->img;
+  CU(cudaSetDevice(h->device));
+  const void *src = evid_chain ? h->ds.assign_evid : h->ds.assign_free;
+  if (m.assign_bytes == 1) {
+    std::vector<uint8_t> t(m.nvar);
+    CU(cudaMemcpyAsync(t.data(), src, m.nvar, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (uint64_t d = 0; d < m.nvar; ++d) out[m.perm[d]] = t[d];
+  } else {
+    std::vector<uint32_t> t(m.nvar);
+    CU(cudaMemcpyAsync(t.data(), src, 4 * m.nvar, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (uint64_t d = 0; d < m.nvar; ++d) out[m.perm[d]] = t[d];
+  }
+  return DWG_OK;
+}
+
+int dwg_set_assignments(dwg_handle *h, int evid_chain, const uint64_t *in) {
+  if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = *h->img;
+  CU(cudaSetDevice(h->device));
+  void *dst = evid_chain ? h->ds.assign_evid : h->ds.assign_free;
+  if (m.assign_bytes == 1) {
+    std::vector<uint8_t> t(m.nvar);
+    for (uint64_t d = 0; d < m.nvar; ++d) t[d] = (uint8_t)in[m.perm[d]];
+    CU(cudaMemcpyAsync(dst, t.data(), m.nvar, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  } else {
+    std::vector<uint32_t> t(m.nvar);
+    for (uint64_t d = 0; d < m.nvar; ++d) t[d] = (uint32_t)in[m.perm[d]];
+    CU(cudaMemcpyAsync(dst, t.data(), 4 * m.nvar, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return DWG_OK;
+}
+
+int dwg_finish_weight_average(dwg_handle *h, int n_replicas, double *lmax, double *l2) {
+  if (!h || n_replicas < 1) return fail(DWG_ERR_INVALID, "bad argument");
+  const uint32_t n = (uint32_t)h->img->nweight;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemsetAsync(h->norms.p, 0, 16, h->stream));
+  if (n) {
+    uint32_t blocks = std::min<uint32_t>((n + 255) / 256, (uint32_t)h->num_sms * 4);
+    k_finish_average<<<blocks, 256, 0, h->stream>>>(h->weights.p, h->prev_weights.p, n,
+                                                    1.0 / n_replicas, n_replicas > 1, h->norms.p);
+    ++g_launches;
+    CU(cudaGetLastError());
+  }
+  if (lmax || l2) {
+    double host[2];
+    CU(cudaMemcpyAsync(host, h->norms.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (lmax) *lmax = host[0];
+    if (l2) *l2 = host[1];  // sum of squares; the caller prints sqrt(l2)/stepsize
+  }
+  return DWG_OK;
+}
+
+// ---- NCCL, dlopen'ed so that libdwg.so itself has no NCCL dependency ----------------
+namespace {
+struct NcclApi {
+  int (*CommInitAll)(void **, int, const int *) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  std::string err;
+  bool ok = false;
+};
+constexpr int NCCL_UINT32 = 3, NCCL_FLOAT64 = 8, NCCL_SUM = 0;  // nccl.h enums
+
+NcclApi &nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void *lib = nullptr;
+  if (!dlsym(RTLD_DEFAULT, "ncclAllReduce")) {  // not already in the process (e.g. via torch)
+    const char *env = getenv("DWG_NCCL_LIB");
+    if (env) lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+      api.err = "libnccl.so.2 not loadable (set DWG_NCCL_LIB or LD_LIBRARY_PATH)";
+      return api;
+    }
+  }
+  void *h = lib ? lib : RTLD_DEFAULT;
+#define SYM(name) api.name = (decltype(api.name))dlsym(h, "nccl" #name)
+  SYM(CommInitAll); SYM(CommDestroy); SYM(AllReduce); SYM(Reduce); SYM(GroupStart); SYM(GroupEnd);
+  SYM(GetErrorString);
+#undef SYM
+  api.ok = api.CommInitAll && api.CommDestroy && api.AllReduce && api.Reduce && api.GroupStart && api.GroupEnd;
+  if (!api.ok) api.err = "libnccl is missing expected symbols";
+  return api;
+}
+int nccl_fail(int rc, const char *what) {
+  NcclApi &n = nccl();
+  return fail(DWG_ERR_NCCL, std::string(what) + ": " + (n.GetErrorString ? n.GetErrorString(rc) : "nccl error"));
+}
+}  // namespace
+
+int dwg_comm_init_all(int n, const int *devices, void **comms_out) {
+  if (n < 1 || !devices || !comms_out) return fail(DWG_ERR_INVALID, "bad argument");
+  NcclApi &api = nccl();
+  if (!api.ok) return fail(DWG_ERR_NCCL, api.err);
+  int rc = api.CommInitAll(comms_out, n, devices);
+  if (rc) return nccl_fail(rc, "ncclCommInitAll");
+  return DWG_OK;
+}
+
+int dwg_comm_destroy(void *comm) {
+  if (!comm) return DWG_OK;
+  NcclApi &api = nccl();
+  if (!api.ok) return fail(DWG_ERR_NCCL, api.err);
+  api.CommDestroy(comm);
+  return DWG_OK;
+}
+
+int dwg_average_weights_nccl(dwg_handle *h, void *comm, int n_replicas, double *lmax, double *l2) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  if (n_replicas > 1) {
+    if (!comm) return fail(DWG_ERR_INVALID, "null communicator");
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(DWG_ERR_NCCL, api.err);
+    CU(cudaSetDevice(h->device));
+    int rc = api.AllReduce(h->weights.p, h->weights.p, h->img->nweight, NCCL_FLOAT64, NCCL_SUM, comm, h->stream);
+    if (rc) return nccl_fail(rc, "ncclAllReduce");
+  }
+  return dwg_finish_weight_average(h, n_replicas, lmax, l2);
+}
+
+int dwg_average_weights_multi(dwg_handle *const *hs, void *const *comms, int n, double *lmax, double *l2) {
+  if (!hs || n < 1) return fail(DWG_ERR_INVALID, "bad argument");
+  const size_t nw = hs[0]->img->nweight;
+  if (n > 1 && comms) {
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(DWG_ERR_NCCL, api.err);
+    int rc = api.GroupStart();
+    if (rc) return nccl_fail(rc, "ncclGroupStart");
+    for (int i = 0; i < n; ++i) {
+      rc = api.AllReduce(hs[i]->weights.p, hs[i]->weights.p, nw, NCCL_FLOAT64, NCCL_SUM, comms[i], hs[i]->stream);
+      if (rc) { api.GroupEnd(); return nccl_fail(rc, "ncclAllReduce"); }
+    }
+    rc = api.GroupEnd();
+    if (rc) return nccl_fail(rc, "ncclGroupEnd");
+  } else if (n > 1) {
+    // no NCCL: sum on the host (what the reference's main thread does, dimmwitted.cc:214-215)
+    std::vector<double> sum(nw, 0.0), tmp(nw);
+    for (int i = 0; i < n; ++i) {
+      int rc = dwg_get_weights(hs[i], tmp.data());
+      if (rc) return rc;
+      for (size_t j = 0; j < nw; ++j) sum[j] += tmp[j];
+    }
+    for (int i = 0; i < n; ++i) {
+      CU(cudaSetDevice(hs[i]->device));
+      CU(cudaMemcpyAsync(hs[i]->weights.p, sum.data(), 8 * nw, cudaMemcpyHostToDevice, hs[i]->stream));
+      CU(cudaStreamSynchronize(hs[i]->stream));
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    int rc = dwg_finish_weight_average(hs[i], n, i == 0 ? lmax : nullptr, i == 0 ? l2 : nullptr);
+    if (rc) return rc;
+  }
+  return DWG_OK;
+}
+
+int dwg_reduce_tallies_multi(dwg_handle *const *hs, void *const *comms, int n) {
+  if (!hs || n < 1) return fail(DWG_ERR_INVALID, "bad argument");
+  const GraphImage &m = *hs[0]->img;
+  if (n > 1 && comms) {
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(DWG_ERR_NCCL, api.err);
+    int rc = api.GroupStart();
+    if (rc) return nccl_fail(rc, "ncclGroupStart");
+    for (int i = 0; i < n; ++i) {
+      rc = api.Reduce(hs[i]->tallies.p, hs[i]->tallies.p, m.nrow, NCCL_UINT32, NCCL_SUM, 0, comms[i], hs[i]->stream);
+      if (rc) { api.GroupEnd(); return nccl_fail(rc, "ncclReduce"); }
+    }
+    rc = api.GroupEnd();
+    if (rc) return nccl_fail(rc, "ncclGroupEnd");
+    for (int i = 1; i < n; ++i) hs[0]->infer_sweeps += hs[i]->infer_sweeps;
+  } else if (n > 1) {
+    std::vector<uint64_t> t(m.nrow), ns(m.nvar);
+    for (int i = 1; i < n; ++i) {
+      int rc = dwg_get_tallies(hs[i], t.data(), ns.data());
+      if (rc) return rc;
+      rc = dwg_add_tallies(hs[0], t.data(), ns.data());
+      if (rc) return rc;
+    }
+  }
+  return DWG_OK;
+}
+
+// ---- parity hooks --------------------------------------------------------------------
+int dwg_eval_potentials(dwg_handle *h, uint64_t n, const uint64_t *vids, const uint64_t *proposals,
+                        int evid_chain, double *out) {
+  if (!h || !vids || !proposals || !out) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = *h->img;
+  CU(cudaSetDevice(h->device));
+  std::vector<uint32_t> ds(n), ps(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    if (vids[i] >= m.nvar) return fail(DWG_ERR_INVALID, "variable id out of range");
+    uint64_t k = proposals[i];
+    if (m.var_dtype[vids[i]] && k >= m.value_base[vids[i] + 1] - m.value_base[vids[i]])
+      return fail(DWG_ERR_INVALID, "proposal out of range");
+    ds[i] = m.inv[vids[i]];
+    ps[i] = (uint32_t)std::min<uint64_t>(k, 0xffffffffu);
+  }
+  DevBuf<uint32_t> dd, dp;
+  DevBuf<double> dout;
+  CU(dd.upload(ds, h->stream));
+  CU(dp.upload(ps, h->stream));
+  CU(dout.alloc(n));
+  if (n) {
+    uint32_t blocks = (uint32_t)((n + 127) / 128);
+    if (m.assign_bytes == 1)
+      k_eval_potentials<uint8_t><<<blocks, 128, 0, h->stream>>>(h->dg, h->ds, (uint32_t)n, dd.p, dp.p, evid_chain, dout.p);
+    else
+      k_eval_potentials<uint32_t><<<blocks, 128, 0, h->stream>>>(h->dg, h->ds, (uint32_t)n, dd.p, dp.p, evid_chain, dout.p);
+    ++g_launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return DWG_OK;
+}
+
+int dwg_draw(int device, uint64_t n, const double *pots, uint64_t ld, const uint32_t *card,
+             const double *r, uint32_t *out) {
+  if (!pots || !card || !r || !out) return fail(DWG_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(device));
+  DevBuf<double> dp, dr;
+  DevBuf<uint32_t> dc, dout;
+  CU(dp.alloc(n * ld)); CU(dr.alloc(n)); CU(dc.alloc(n)); CU(dout.alloc(n));
+  CU(cudaMemcpy(dp.p, pots, 8 * n * ld, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dr.p, r, 8 * n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dc.p, card, 4 * n, cudaMemcpyHostToDevice));
+  if (n) {
+    k_draw<<<(uint32_t)((n + 127) / 128), 128>>>((uint32_t)n, dp.p, (uint32_t)ld, dc.p, dr.p, dout.p);
+    ++g_launches;
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpy(out, dout.p, 4 * n, cudaMemcpyDeviceToHost));
+  return DWG_OK;
+}
+
+int dwg_logadd(int device, uint64_t n, const double *a, const double *b, double *out) {
+  if (!a || !b || !out) return fail(DWG_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(device));
+  DevBuf<double> da, db, dout;
+  CU(da.alloc(n)); CU(db.alloc(n)); CU(dout.alloc(n));
+  CU(cudaMemcpy(da.p, a, 8 * n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(db.p, b, 8 * n, cudaMemcpyHostToDevice));
+  if (n) {
+    k_logadd<<<(uint32_t)((n + 127) / 128), 128>>>((uint32_t)n, da.p, db.p, dout.p);
+    ++g_launches;
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpy(out, dout.p, 8 * n, cudaMemcpyDeviceToHost));
+  return DWG_OK;
+}
+
+int dwg_debug_set_uniforms(dwg_handle *h, const double *r_free, const double *r_evid) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  const GraphImage &m = *h->img;
+  CU(cudaSetDevice(h->device));
+  if (!r_free) { h->explicit_r = false; return DWG_OK; }
+  std::vector<double> a(m.nvar), b(m.nvar, 0.0);
+  for (uint64_t d = 0; d < m.nvar; ++d) {
+    a[d] = r_free[m.perm[d]];
+    if (r_evid) b[d] = r_evid[m.perm[d]];
+  }
+  if (!h->r_free.p) { CU(h->r_free.alloc(m.nvar)); CU(h->r_evid.alloc(m.nvar)); }
+  CU(cudaMemcpyAsync(h->r_free.p, a.data(), 8 * m.nvar, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->r_evid.p, b.data(), 8 * m.nvar, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->explicit_r = true;
+  return DWG_OK;
+}
+
+int dwg_debug_set_sequential(dwg_handle *h, int on) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  h->sequential = on != 0;
+  return DWG_OK;
+}
+
+}  // extern "C"

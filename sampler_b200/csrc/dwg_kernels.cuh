@@ -1,0 +1,270 @@
+// dwg_kernels.cuh -- the sweep kernels (sm_100a): thread-per-variable Gibbs sweeps over
+// the schedule-ordered CSR (graph_image.h).
+//
+//   k_sweep_infer  replaces GibbsSamplerThread::sample -> sample_single_variable
+//                  (src/gibbs_sampler.cc:65-69, src/gibbs_sampler.h:151-169)
+//   k_sweep_learn  replaces GibbsSamplerThread::sample_sgd -> sample_sgd_single_variable
+//                  (src/gibbs_sampler.cc:71-75, src/gibbs_sampler.h:127-149) with
+//                  sgd_on_variable / sgd_on_factor (src/factor_graph.cc:243-314) and
+//                  update_weight (src/inference_result.h:66-85) as atomic updates
+// One launch covers one colour class [d_begin, d_end).  HBM-bound: the edge arrays are
+// streamed once per sweep; weights and the u8 chains are L2-resident gathers.
+#ifndef DWG_KERNELS_CUH_
+#define DWG_KERNELS_CUH_
+#include "dwg_device.cuh"
+
+namespace dwg {
+
+constexpr int SWEEP_THREADS = 256;
+
+__device__ __forceinline__ void dev_uniforms(const SweepParams &p, uint32_t d, double &r0, double &r1) {
+  if (p.r_free) {
+    r0 = p.r_free[d];
+    r1 = p.r_evid ? p.r_evid[d] : 0.0;
+    return;
+  }
+  uint32_t o[4];
+  philox4x32_10(d, 0u, p.sweep_lo, p.sweep_hi, p.key0, p.key1, o);
+  r0 = u01(o[0], o[1]);
+  r1 = u01(o[2], o[3]);
+}
+
+template <typename AssignT, bool LIVE>
+__device__ __forceinline__ uint32_t dev_draw_sample(const DevGraph &g, uint32_t d, bool cat,
+                                                    uint32_t row0, uint32_t K, const AssignT *a,
+                                                    const double *w, double r) {
+  if (!cat) {
+    double pos, neg;
+    dev_bool_potentials<AssignT, LIVE>(g, d, row0, a, w, pos, neg);
+    return dev_draw_boolean(pos, neg, r);
+  }
+  return dev_draw_categorical<AssignT, LIVE>(g, d, row0, K, a, w, r);
+}
+
+template <typename AssignT>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+k_sweep_infer(const DevGraph g, const DevState st, const SweepParams p) {
+  AssignT *a = static_cast<AssignT *>(st.assign_evid);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t d = p.d_begin + blockIdx.x * blockDim.x + threadIdx.x; d < p.d_end; d += stride) {
+    const uint8_t fl = __ldg(g.var_flags + d);
+    if ((fl & VF_EVID) && !p.sample_evidence) continue;  // gibbs_sampler.h:157
+    const bool cat = fl & VF_CATEGORICAL;
+    uint32_t row0 = d, K = 1;
+    if (g.var_row) {
+      row0 = __ldg(g.var_row + d);
+      K = __ldg(g.var_row + d + 1) - row0;
+    }
+    double r0, r1;
+    dev_uniforms(p, d, r0, r1);
+    const uint32_t prop = dev_draw_sample<AssignT, false>(g, d, cat, row0, K, a, st.weights, r0);
+    a[d] = (AssignT)prop;  // :160
+    // agg_nsamples is implicit (every sampled variable gains one per sweep, :163);
+    // Boolean: tally only proposal == 1 at the single row; categorical: row of the value (:164-167)
+    if (cat) st.tallies[row0 + prop] += 1u;
+    else if (prop == 1u) st.tallies[row0] += 1u;
+  }
+}
+
+// InferenceResult::update_weight, src/inference_result.h:66-85.  Concurrent mode: the
+// same update expressed as one atomicAdd of  w*(c-1) - diff  (l2, c = 1/(1+reg*step)) or
+// reg*(w<0) - diff  (l1, sic) on a weight read at L2 -- exact when reg == 0, Hogwild otherwise.
+// Sequential mode (parity hook): the reference's read-modify-write, bit for bit.
+__device__ __forceinline__ void dev_update_weight(double *w, uint32_t wid, const SweepParams &p,
+                                                  double step, double grad) {
+  const double diff = __dmul_rn(step, grad);
+  if (p.sequential) {
+    double x = w[wid];
+    if (p.reg_l1) x = __dadd_rn(x, __dmul_rn(p.reg_param, x < 0 ? 1.0 : 0.0));
+    else x = __dmul_rn(x, __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(p.reg_param, step))));
+    w[wid] = __dsub_rn(x, diff);
+    return;
+  }
+  double delta = -diff;
+  if (p.reg_param != 0.0) {
+    const double x = __ldcg(w + wid);
+    if (p.reg_l1) delta += p.reg_param * (x < 0 ? 1.0 : 0.0);
+    else {
+      const double rs = p.reg_param * step;
+      delta += x * (-rs / (1.0 + rs));
+    }
+  }
+  if (delta != 0.0) atomicAdd(w + wid, delta);
+}
+
+// sgd_on_factor over one row, src/factor_graph.cc:243-260: for every non-fixed factor,
+// gradient = potential(free chain) - potential(evid chain with this variable := x_evid)
+template <typename AssignT>
+__device__ __forceinline__ void dev_sgd_row(const DevGraph &g, const DevState &st, const SweepParams &p,
+                                            uint32_t d, uint32_t row, bool cat, uint32_t key,
+                                            uint32_t x_evid, uint32_t x_free, double step) {
+  const AssignT *af = static_cast<const AssignT *>(st.assign_free);
+  const AssignT *ae = static_cast<const AssignT *>(st.assign_evid);
+  const uint32_t e0 = __ldg(g.row_ptr + row), e1 = __ldg(g.row_ptr + row + 1);
+  EdgeCursor<AssignT> cur(g, d, g.row_oth ? __ldg(g.row_oth + row) : 0u);
+  for (uint32_t e = e0; e < e1; ++e) {
+    const uint8_t tag = __ldg(g.e_tag + e);
+    const uint32_t wid = __ldg(g.e_wid + e);
+    if (!__ldg(g.w_fixed + wid)) {  // :247
+      const double fv = dev_fv(g, e);
+      double se, sf, unused;
+      cur.signs(tag, cat, key, ae, x_evid, x_evid, se, unused);
+      cur.signs(tag, cat, key, af, x_free, x_free, sf, unused);
+      const double grad = __dsub_rn(__dmul_rn(sf, fv), __dmul_rn(se, fv));  // :255-258
+      dev_update_weight(st.weights, wid, p, step, grad);
+    }
+    cur.advance(tag);
+  }
+}
+
+template <typename AssignT>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+k_sweep_learn(const DevGraph g, const DevState st, const SweepParams p) {
+  AssignT *af = static_cast<AssignT *>(st.assign_free);
+  AssignT *ae = static_cast<AssignT *>(st.assign_evid);
+  const AssignT *evid_val = static_cast<const AssignT *>(g.evid_val);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t d = p.d_begin + blockIdx.x * blockDim.x + threadIdx.x; d < p.d_end; d += stride) {
+    const uint8_t fl = __ldg(g.var_flags + d);
+    const bool cat = fl & VF_CATEGORICAL, evid = fl & VF_EVID, truthy = fl & VF_TRUTHINESS;
+    uint32_t row0 = d, K = 1;
+    if (g.var_row) {
+      row0 = __ldg(g.var_row + d);
+      K = __ldg(g.var_row + d + 1) - row0;
+    }
+    double r0, r1;
+    dev_uniforms(p, d, r0, r1);
+    // the free chain samples EVERY variable, evidence included (gibbs_sampler.h:137-139)
+    const uint32_t pf = dev_draw_sample<AssignT, true>(g, d, cat, row0, K, af, st.weights, r0);
+    af[d] = (AssignT)pf;
+    // sample_evid, gibbs_sampler.h:171-190
+    const uint32_t ev = (uint32_t)evid_val[d];
+    uint32_t pe;
+    if (!p.noise_aware && evid) {
+      pe = ev;
+    } else if (p.noise_aware && truthy) {
+      double sum = 0;
+      pe = 0;
+      const uint32_t card = cat ? K : 2u;
+      for (uint32_t i = 0; i < card; ++i) {
+        sum = __dadd_rn(sum, g.truthiness[row0 + i]);
+        if (sum >= r1) { pe = i; break; }
+      }
+    } else {
+      pe = dev_draw_sample<AssignT, true>(g, d, cat, row0, K, ae, st.weights, r1);
+    }
+    ae[d] = (AssignT)pe;
+    if (!p.learn_non_evidence && ((!p.noise_aware && !evid) || (p.noise_aware && !truthy)))
+      continue;  // :144-146
+    // sgd_on_variable, src/factor_graph.cc:262-314
+    if (!cat) {
+      // Boolean: evidence_value is Variable::assignment_dense even for a query variable (:272)
+      dev_sgd_row<AssignT>(g, st, p, d, row0, false, 0u, ev, pf, p.stepsize);
+    } else {
+      for (uint32_t val = 0; val < K; ++val) {
+        if (!p.noise_aware && val != ev) continue;  // :280
+        double t = 1.0;
+        if (p.noise_aware) {
+          t = g.truthiness ? g.truthiness[row0 + val] : 0.0;
+          if (t <= 0.000001 && t >= -0.000001) continue;  // is_linear_zero :283
+        }
+        const double step = __dmul_rn(p.stepsize, t);
+        dev_sgd_row<AssignT>(g, st, p, d, row0 + val, true, val, val, pf, step);  // :288-292
+        if (val == pf) continue;  // :304
+        dev_sgd_row<AssignT>(g, st, p, d, row0 + pf, true, pf, val, pf, step);  // :306-311
+      }
+    }
+  }
+}
+
+// ---- parity hooks -----------------------------------------------------------------
+
+// FactorGraph::potential (src/factor_graph.h:127-145) for explicit (d, proposal) queries
+template <typename AssignT>
+__global__ void k_eval_potentials(const DevGraph g, const DevState st, uint32_t n, const uint32_t *ds,
+                                  const uint32_t *props, int evid_chain, double *out) {
+  const AssignT *a = static_cast<const AssignT *>(evid_chain ? st.assign_evid : st.assign_free);
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t d = ds[i], prop = props[i];
+  const bool cat = g.var_flags[d] & VF_CATEGORICAL;
+  const uint32_t row0 = g.var_row ? g.var_row[d] : d;
+  if (!cat) {
+    double pos, neg;
+    // a Boolean row answers proposals 0 and 1; any other proposal satisfies nothing
+    const uint32_t e0 = g.row_ptr[row0], e1 = g.row_ptr[row0 + 1];
+    EdgeCursor<AssignT> cur(g, d, g.row_oth ? g.row_oth[row0] : 0u);
+    double pot = 0.0;
+    for (uint32_t e = e0; e < e1; ++e) {
+      const uint8_t tag = g.e_tag[e];
+      double s0, s1;
+      cur.signs(tag, false, 0u, a, prop, prop, s0, s1);
+      cur.advance(tag);
+      pot = dev_acc(pot, st.weights[g.e_wid[e]], s0, dev_fv(g, e));
+    }
+    (void)pos; (void)neg;
+    out[i] = pot;
+  } else {
+    out[i] = dev_row_potential<AssignT, false>(g, d, row0 + prop, prop, a, st.weights);
+  }
+}
+
+__global__ void k_draw(uint32_t n, const double *pots, uint32_t ld, const uint32_t *card,
+                       const double *r, uint32_t *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *p = pots + (size_t)i * ld;
+  out[i] = card[i] == 0 ? dev_draw_boolean(p[0], p[1], r[i]) : dev_draw_categorical_pots(p, card[i], r[i]);
+}
+
+__global__ void k_logadd(uint32_t n, const double *a, const double *b, double *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = dev_logadd(a[i], b[i]);
+}
+
+// ---- replica averaging epilogue ---------------------------------------------------
+// After the cross-replica SUM: w /= n_replicas (average_weights, src/inference_result.cc:75-79),
+// lmax = max |w - prev|, l2sq = sum (w - prev)^2 (src/dimmwitted.cc:220-227), prev = w.
+__global__ void k_finish_average(double *w, double *prev, uint32_t n, double inv_rep, int scale,
+                                 double *norms /* [0]=lmax, [1]=l2sq */) {
+  __shared__ double s_max[32], s_sum[32];
+  double mx = 0.0, sq = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double x = w[i];
+    if (scale) { x *= inv_rep; w[i] = x; }
+    double diff = fabs(x - prev[i]);
+    prev[i] = x;
+    mx = fmax(mx, diff);
+    sq += diff * diff;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  if (lane == 0) { s_max[wp] = mx; s_sum[wp] = sq; }
+  __syncthreads();
+  if (wp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    mx = lane < nw ? s_max[lane] : 0.0;
+    sq = lane < nw ? s_sum[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+      // non-negative doubles order like their bit patterns
+      atomicMax(reinterpret_cast<unsigned long long *>(norms), (unsigned long long)__double_as_longlong(mx));
+      atomicAdd(norms + 1, sq);
+    }
+  }
+}
+
+// tallies (schedule order, u32) += host-provided counts (aggregate_marginals_from)
+__global__ void k_add_u32(uint32_t *dst, const uint32_t *src, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+}  // namespace dwg
+#endif

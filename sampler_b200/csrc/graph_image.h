@@ -1,0 +1,126 @@
+// graph_image.h -- the factor graph in the layout the sweep kernels stream.
+//
+// Replaces the reference's AoS FactorGraph (src/factor_graph.h:58-70: Variable 64 B,
+// VariableToFactor 32 B, Factor 48 B, FactorToVariable 16 B, size_t everywhere) by a
+// 32-bit SoA CSR in SCHEDULE ORDER: variables are permuted so that each colour class
+// (or the whole graph under hogwild) is one contiguous range, and the
+// variable -> factor_index -> Factor -> vifs pointer chain (src/factor_graph.h:137-142)
+// is flattened into one edge stream per (variable, value) row.
+#ifndef DWG_GRAPH_IMAGE_H_
+#define DWG_GRAPH_IMAGE_H_
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace dwg {
+
+// compact function codes (4 bits of the edge tag); ISTRUE aliases AND (src/factor.h:73)
+enum FuncCode : uint8_t {
+  FC_IMPLY_NATURAL = 0, FC_OR = 1, FC_AND = 2, FC_EQUAL = 3, FC_LINEAR = 4, FC_RATIO = 5,
+  FC_LOGICAL = 6, FC_AND_CATEGORICAL = 7, FC_IMPLY_MLN = 8
+};
+
+// edge tag byte: [3:0] FuncCode | [4] self equal_to == 1 (Boolean rows) | [5] self is the
+// head (last position) | [7:6] form: 0 unary, 1 one other, 2 two others, 3 general
+// (all positions, self included, spelled out in the others stream after a length word)
+constexpr uint8_t TAG_FUNC_MASK = 0x0f;
+constexpr uint8_t TAG_SELF_EQ1 = 0x10;
+constexpr uint8_t TAG_SELF_HEAD = 0x20;
+constexpr int TAG_FORM_SHIFT = 6;
+constexpr uint8_t FORM_GENERAL = 3;
+
+// var_flags
+constexpr uint8_t VF_EVID = 1;
+constexpr uint8_t VF_CATEGORICAL = 2;
+constexpr uint8_t VF_TRUTHINESS = 4;  // has_truthiness(), src/variable.h:105
+
+enum FvMode : int { FV_ONE = 0, FV_F32 = 1, FV_F64 = 2 };
+
+struct GraphImage {
+  // sizes (reference FactorGraphDescriptor, src/factor_graph.h:18-46)
+  uint64_t nvar = 0, nfac = 0, nweight = 0, nedge = 0, nrow = 0;
+  uint64_t nvar_evid = 0, nvar_query = 0;
+  uint64_t nindex = 0;  // edge records after dedupe  (E')
+  uint64_t noth = 0;    // entries in the others stream
+  int schedule = 0;     // resolved DWG_SCHED_*
+  bool has_categorical = false, has_multi = false;
+  bool oth_packed = true;  // others as (d<<1 | eq) words; else (d, eq) pairs
+  int fv_mode = FV_ONE;
+  int assign_bytes = 1;  // 1: u8 chains (max cardinality <= 256), 4: u32
+
+  // schedule order
+  std::vector<uint32_t> perm;         // [nvar]   d -> original vid
+  std::vector<uint32_t> inv;          // [nvar]   original vid -> d
+  std::vector<uint32_t> color_start;  // [ncolor+1] in d space
+
+  // per variable (d order)
+  std::vector<uint8_t> var_flags;   // [nvar]
+  std::vector<uint32_t> evid_val;   // [nvar] Variable::assignment_dense
+  std::vector<uint32_t> var_row;    // [nvar+1] first row of each variable (only if has_categorical)
+
+  // per row = (variable, dense value); Boolean variables own one row
+  std::vector<uint32_t> row_ptr;    // [nrow+1] into the edge arrays
+  std::vector<uint32_t> row_oth;    // [nrow+1] into oth (only if has_multi)
+  std::vector<double> truthiness;   // [nrow]   (only if any is non-zero)
+  bool has_truthiness = false;
+
+  // per edge record, in (row, factor id) order == construct_index order
+  std::vector<uint32_t> e_wid;
+  std::vector<float> e_fv32;
+  std::vector<double> e_fv64;
+  std::vector<uint8_t> e_tag;
+  std::vector<uint32_t> oth;        // others stream (words; pairs take two)
+
+  // weights (original id order)
+  std::vector<double> w_init;
+  std::vector<uint8_t> w_fixed;
+
+  // host-only, original id order, for the ABI getters / writers
+  std::vector<uint8_t> var_dtype, var_is_evid;
+  std::vector<uint64_t> value_base;  // [nvar+1] var_val_base in ORIGINAL order
+  std::vector<uint64_t> values;      // [nrow] sparse domain value of each (vid, k)
+  std::vector<uint32_t> row_of_value;  // [nrow] original value index -> device row
+
+  // ALGORITHMIC bytes per sweep: all variables sampled / query variables only / learning
+  double bytes_infer = 0, bytes_infer_query = 0, bytes_learn = 0;
+  uint32_t ncolor() const { return (uint32_t)color_start.size() - 1; }
+};
+
+// decoded input records (owning)
+struct RawGraph {
+  std::vector<uint8_t> var_role;
+  std::vector<uint64_t> var_init;
+  std::vector<uint16_t> var_dtype;
+  std::vector<uint64_t> var_card;
+  std::vector<uint64_t> dom_vid, dom_ptr{0}, dom_val;
+  std::vector<double> dom_truth;
+  std::vector<int32_t> fac_func;
+  std::vector<uint64_t> fac_ptr{0}, edge_vid, edge_eq, fac_wid;
+  std::vector<double> fac_fv;
+  std::vector<double> w_init;
+  std::vector<uint8_t> w_fixed;
+};
+
+// non-owning view (what dwg_raw_t carries)
+struct RawView {
+  uint64_t nvar, ndom, nfac, nweight;
+  const uint8_t *var_role; const uint64_t *var_init; const uint16_t *var_dtype;
+  const uint64_t *var_card; const uint64_t *dom_vid, *dom_ptr, *dom_val; const double *dom_truth;
+  const int32_t *fac_func; const uint64_t *fac_ptr, *edge_vid, *edge_eq, *fac_wid;
+  const double *fac_fv; const double *w_init; const uint8_t *w_fixed;
+};
+RawView view_of(const RawGraph &r);
+
+// compile.cc: returns "" on success, else the error message (code in *err)
+std::string compile_graph(const RawView &raw, int schedule, GraphImage *out, int *err);
+
+// loader.cc: reads the reference's binary files; returns "" or an error message
+struct MetaCounts { uint64_t nweight = 0, nvar = 0, nfac = 0, nedge = 0; };
+std::string read_meta(const std::string &path, MetaCounts *m);
+std::string load_raw(const MetaCounts &meta, const std::vector<std::string> &var_files,
+                     const std::vector<std::string> &dom_files,
+                     const std::vector<std::string> &fac_files,
+                     const std::vector<std::string> &wgt_files, RawGraph *out, int *err);
+
+}  // namespace dwg
+#endif

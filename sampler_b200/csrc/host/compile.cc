@@ -1,0 +1,402 @@
+// compile.cc -- decoded records -> GraphImage (the device layout).
+//
+// Reproduces, quirks included, what the reference does between reading the files and
+// the first sweep: load_variables / load_domains / load_factors value mapping
+// (src/binary_format.cc:72-226), safety_check (src/factor_graph.cc:201-219) and
+// construct_index (src/factor_graph.cc:90-199: per variable, entries sorted by
+// (dense value, factor id), consecutive duplicates dropped).  On top of that it picks the
+// sweep schedule (greedy colouring), permutes variables into schedule order and flattens
+// factor -> vifs into per-row edge records (graph_image.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../../include/dwg.h"
+#include "../graph_image.h"
+
+namespace dwg {
+
+RawView view_of(const RawGraph &r) {
+  RawView v;
+  v.nvar = r.var_role.size();
+  v.ndom = r.dom_vid.size();
+  v.nfac = r.fac_func.size();
+  v.nweight = r.w_init.size();
+  v.var_role = r.var_role.data(); v.var_init = r.var_init.data();
+  v.var_dtype = r.var_dtype.data(); v.var_card = r.var_card.data();
+  v.dom_vid = r.dom_vid.data(); v.dom_ptr = r.dom_ptr.data(); v.dom_val = r.dom_val.data();
+  v.dom_truth = r.dom_truth.data();
+  v.fac_func = r.fac_func.data(); v.fac_ptr = r.fac_ptr.data(); v.edge_vid = r.edge_vid.data();
+  v.edge_eq = r.edge_eq.data(); v.fac_wid = r.fac_wid.data(); v.fac_fv = r.fac_fv.data();
+  v.w_init = r.w_init.data(); v.w_fixed = r.w_fixed.data();
+  return v;
+}
+
+namespace {
+
+constexpr uint64_t INVALID = ~0ull;
+constexpr uint64_t U32_LIMIT = 0xffffffffull;
+
+int func_code(int32_t f) {
+  switch (f) {
+    case DWG_FUNC_IMPLY_NATURAL: return FC_IMPLY_NATURAL;
+    case DWG_FUNC_OR: return FC_OR;
+    case DWG_FUNC_AND:
+    case DWG_FUNC_ISTRUE: return FC_AND;
+    case DWG_FUNC_EQUAL: return FC_EQUAL;
+    case DWG_FUNC_LINEAR: return FC_LINEAR;
+    case DWG_FUNC_RATIO: return FC_RATIO;
+    case DWG_FUNC_LOGICAL: return FC_LOGICAL;
+    case DWG_FUNC_AND_CATEGORICAL: return FC_AND_CATEGORICAL;
+    case DWG_FUNC_IMPLY_MLN: return FC_IMPLY_MLN;
+    default: return -1;  // src/factor.h:81-84 aborts on these at the first sweep
+  }
+}
+
+struct DomEntry {
+  uint64_t val;
+  uint32_t idx;
+};
+
+// sparse -> dense value maps (Variable::get_domain_index, src/variable.h:118): per domain
+// block a (value, index) table sorted by value.  unordered_map insert-or-assign
+// (src/binary_format.cc:215): a repeated value keeps its LAST index.
+struct Domains {
+  std::vector<int64_t> block_of;  // per var, -1 = identity domain
+  std::vector<uint64_t> tab_ptr;  // per block
+  std::vector<DomEntry> tab;
+  uint64_t lookup(uint64_t v, uint64_t sparse) const {
+    int64_t b = block_of[v];
+    if (b < 0) return sparse;
+    const DomEntry *lo = tab.data() + tab_ptr[b], *hi = tab.data() + tab_ptr[b + 1];
+    const DomEntry *it = std::lower_bound(
+        lo, hi, sparse, [](const DomEntry &e, uint64_t x) { return e.val < x; });
+    if (it == hi || it->val != sparse) return INVALID;
+    return it->idx;
+  }
+};
+
+struct Inc {  // TempValueFactor, src/variable.h:14-29
+  uint32_t key;  // dense value (0 for Boolean, src/binary_format.cc:166-169)
+  uint32_t fid;
+};
+
+}  // namespace
+
+std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *err) {
+  *err = DWG_ERR_INVALID;
+  *g = GraphImage();
+  const uint64_t nvar = raw.nvar, nfac = raw.nfac, nweight = raw.nweight;
+  const uint64_t nedge = nfac ? raw.fac_ptr[nfac] : 0;
+  if (nvar >= U32_LIMIT / 2 || nfac >= U32_LIMIT || nweight >= U32_LIMIT) {
+    *err = DWG_ERR_UNSUPPORTED;
+    return "graph exceeds the 32-bit device layout (variables < 2^31, factors/weights < 2^32)";
+  }
+  g->nvar = nvar; g->nfac = nfac; g->nweight = nweight; g->nedge = nedge;
+  g->w_init.assign(raw.w_init, raw.w_init + nweight);
+  g->w_fixed.assign(raw.w_fixed, raw.w_fixed + nweight);
+
+  // ---- variables (src/binary_format.cc:72-126) ----
+  std::vector<uint64_t> adense(nvar);
+  g->var_dtype.resize(nvar); g->var_is_evid.resize(nvar);
+  uint64_t max_card = 2;
+  for (uint64_t v = 0; v < nvar; ++v) {
+    if (raw.var_dtype[v] > 1)
+      return "variable " + std::to_string(v) + ": only Boolean and categorical variables are supported";
+    bool cat = raw.var_dtype[v] == 1;
+    g->var_dtype[v] = cat;
+    bool ev = raw.var_role[v] >= 1;  // :107
+    g->var_is_evid[v] = ev;
+    adense[v] = ev ? raw.var_init[v] : 0;  // :109
+    if (ev) ++g->nvar_evid; else ++g->nvar_query;
+    if (cat) {
+      g->has_categorical = true;
+      if (raw.var_card[v] >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "cardinality >= 2^32"; }
+      max_card = std::max<uint64_t>(max_card, raw.var_card[v]);
+    }
+  }
+
+  // ---- domains (src/binary_format.cc:192-226) ----
+  Domains dom;
+  dom.block_of.assign(nvar, -1);
+  dom.tab_ptr.assign(raw.ndom + 1, 0);
+  for (uint64_t b = 0; b < raw.ndom; ++b) {
+    uint64_t v = raw.dom_vid[b], n = raw.dom_ptr[b + 1] - raw.dom_ptr[b];
+    if (v >= nvar) return "domain block for unknown variable " + std::to_string(v);
+    if (!g->var_dtype[v]) return "domain given for Boolean variable " + std::to_string(v);  // :206
+    if (raw.var_card[v] != n) return "domain size != cardinality for variable " + std::to_string(v);  // :207
+    dom.block_of[v] = (int64_t)b;
+    dom.tab_ptr[b + 1] = dom.tab_ptr[b] + n;
+  }
+  dom.tab.resize(dom.tab_ptr[raw.ndom]);
+  for (uint64_t b = 0; b < raw.ndom; ++b) {
+    DomEntry *t = dom.tab.data() + dom.tab_ptr[b];
+    uint64_t n = raw.dom_ptr[b + 1] - raw.dom_ptr[b];
+    for (uint64_t i = 0; i < n; ++i) t[i] = {raw.dom_val[raw.dom_ptr[b] + i], (uint32_t)i};
+    std::stable_sort(t, t + n, [](const DomEntry &a, const DomEntry &c) { return a.val < c.val; });
+    // last occurrence of a repeated value wins: keep, for equal values, the largest index first
+    for (uint64_t i = 0; i < n;) {
+      uint64_t j = i;
+      while (j + 1 < n && t[j + 1].val == t[i].val) ++j;
+      if (j > i) std::swap(t[i], t[j]);
+      i = j + 1;
+    }
+  }
+  for (uint64_t v = 0; v < nvar; ++v) {
+    // evidence value remapped only when non-zero (:220-223) -- sparse value 0 stays dense 0
+    if (dom.block_of[v] >= 0 && adense[v]) {
+      adense[v] = dom.lookup(v, adense[v]);
+      if (adense[v] == INVALID)
+        return "initial value of variable " + std::to_string(v) + " is not in its domain";
+    }
+  }
+
+  // ---- factors (src/binary_format.cc:128-190) ----
+  std::vector<uint32_t> edense(nedge);  // FactorToVariable::dense_equal_to
+  std::vector<uint32_t> deg(nvar + 1, 0);
+  bool coupled = false, eq_is_bit = true;
+  for (uint64_t f = 0; f < nfac; ++f) {
+    if (func_code(raw.fac_func[f]) < 0)
+      return "factor " + std::to_string(f) + ": unsupported FACTOR_FUNCTION_TYPE = " +
+             std::to_string(raw.fac_func[f]);
+    uint64_t a = raw.fac_ptr[f], b = raw.fac_ptr[f + 1];
+    // (a zero-arity factor is legal input: it sits in no adjacency list and is never evaluated)
+    if (raw.fac_wid[f] >= nweight) return "factor " + std::to_string(f) + " refers to an unknown weight";
+    if (b - a > 1) g->has_multi = true;
+    for (uint64_t e = a; e < b; ++e) {
+      uint64_t v = raw.edge_vid[e];
+      if (v >= nvar) return "factor " + std::to_string(f) + " refers to an unknown variable";  // :159
+      uint64_t d = dom.lookup(v, raw.edge_eq[e]);
+      if (d == INVALID)
+        return "factor " + std::to_string(f) + ": value " + std::to_string(raw.edge_eq[e]) +
+               " is not in the domain of variable " + std::to_string(v);
+      if (d >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "equal_to value >= 2^32"; }
+      edense[e] = (uint32_t)d;
+      if (d > 1) eq_is_bit = false;
+      if (v != raw.edge_vid[a]) coupled = true;
+      // the reference asserts value_dense < cardinality in construct_index (:186)
+      if (g->var_dtype[v] && d >= raw.var_card[v])
+        return "factor " + std::to_string(f) + ": value index out of range for variable " + std::to_string(v);
+      ++deg[v + 1];
+    }
+  }
+  for (uint64_t v = 0; v < nvar; ++v) deg[v + 1] += deg[v];
+
+  // ---- adjacency + construct_index (src/factor_graph.cc:131-199) ----
+  std::vector<Inc> inc(nedge);
+  {
+    std::vector<uint32_t> fill(deg.begin(), deg.end() - 1);
+    for (uint64_t f = 0; f < nfac; ++f)
+      for (uint64_t e = raw.fac_ptr[f]; e < raw.fac_ptr[f + 1]; ++e) {
+        uint64_t v = raw.edge_vid[e];
+        inc[fill[v]++] = {g->var_dtype[v] ? edense[e] : 0u, (uint32_t)f};
+      }
+  }
+  // factor ids arrive ascending per variable, so only categorical lists need the (value, fid)
+  // sort; then drop consecutive duplicates (same factor under the same value)
+  std::vector<uint32_t> inc_end(nvar);
+  for (uint64_t v = 0; v < nvar; ++v) {
+    Inc *a = inc.data() + deg[v], *b = inc.data() + deg[v + 1];
+    if (g->var_dtype[v])
+      std::stable_sort(a, b, [](const Inc &x, const Inc &y) { return x.key < y.key; });
+    Inc *o = a;
+    for (Inc *p = a; p != b; ++p)
+      if (o == a || o[-1].key != p->key || o[-1].fid != p->fid) *o++ = *p;
+    inc_end[v] = (uint32_t)(o - inc.data());
+  }
+
+  // ---- rows in ORIGINAL order (var_val_base, values, truthiness) ----
+  g->value_base.resize(nvar + 1);
+  uint64_t nrow = 0;
+  for (uint64_t v = 0; v < nvar; ++v) {
+    g->value_base[v] = nrow;
+    nrow += g->var_dtype[v] ? raw.var_card[v] : 1;
+  }
+  g->value_base[nvar] = nrow;
+  if (nrow >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "more than 2^32 (variable, value) rows"; }
+  g->nrow = nrow;
+  g->values.assign(nrow, 0);
+  std::vector<double> truth_orig(nrow, 0.0);
+  std::vector<uint8_t> has_truth(nvar, 0);
+  for (uint64_t v = 0; v < nvar; ++v) {
+    if (!g->var_dtype[v]) continue;
+    uint64_t base = g->value_base[v], K = raw.var_card[v];
+    int64_t b = dom.block_of[v];
+    if (b < 0) {
+      for (uint64_t j = 0; j < K; ++j) g->values[base + j] = j;  // :169-172
+      continue;
+    }
+    // recover the list from the map (:151-164): slots of overwritten duplicates stay INVALID
+    for (uint64_t j = 0; j < K; ++j) g->values[base + j] = INVALID;
+    double total = 0;
+    const DomEntry *t = dom.tab.data() + dom.tab_ptr[b];
+    for (uint64_t i = 0; i < K; ++i) {
+      if (i > 0 && t[i].val == t[i - 1].val) continue;  // not the winning occurrence
+      uint64_t j = t[i].idx;
+      g->values[base + j] = t[i].val;
+      truth_orig[base + j] = raw.dom_truth[raw.dom_ptr[b] + j];
+      total += truth_orig[base + j];
+    }
+    // has_truthiness(): !is_linear_zero(total), src/variable.h:105, src/common.h:111
+    has_truth[v] = !(total <= 0.000001 && total >= -0.000001);
+    if (has_truth[v]) g->has_truthiness = true;
+  }
+
+  // ---- schedule ----
+  if (schedule == DWG_SCHED_AUTO) schedule = coupled ? DWG_SCHED_CHROMATIC : DWG_SCHED_HOGWILD;
+  if (schedule != DWG_SCHED_HOGWILD && schedule != DWG_SCHED_CHROMATIC) return "bad schedule";
+  std::vector<uint32_t> color(nvar, 0);
+  uint32_t ncolor = 1;
+  if (schedule == DWG_SCHED_CHROMATIC && coupled) {
+    // greedy colouring in id order of the conflict graph "share a factor"
+    double cost = 0;
+    for (uint64_t f = 0; f < nfac; ++f) {
+      double n = (double)(raw.fac_ptr[f + 1] - raw.fac_ptr[f]);
+      cost += n * n;
+    }
+    if (cost > 2e10) {
+      *err = DWG_ERR_UNSUPPORTED;
+      return "chromatic schedule: factor arities too large to colour; use the hogwild schedule";
+    }
+    std::vector<uint32_t> stamp;  // stamp[c] == v+1 : colour c is taken by a neighbour of v
+    std::fill(color.begin(), color.end(), 0xffffffffu);
+    for (uint64_t v = 0; v < nvar; ++v) {
+      uint32_t last_f = 0xffffffffu;
+      for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
+        uint32_t f = inc[i].fid;
+        if (f == last_f) continue;
+        last_f = f;
+        for (uint64_t e = raw.fac_ptr[f]; e < raw.fac_ptr[f + 1]; ++e) {
+          uint32_t c = color[raw.edge_vid[e]];
+          if (c == 0xffffffffu) continue;
+          if (c >= stamp.size()) stamp.resize(c + 1, 0);
+          stamp[c] = (uint32_t)v + 1;
+        }
+      }
+      uint32_t c = 0;
+      while (c < stamp.size() && stamp[c] == (uint32_t)v + 1) ++c;
+      color[v] = c;
+      if (c >= stamp.size()) stamp.resize(c + 1, 0);
+      ncolor = std::max(ncolor, c + 1);
+    }
+  } else if (schedule == DWG_SCHED_CHROMATIC) {
+    // nothing couples two variables: one class, i.e. the hogwild launch, and it is exact
+  }
+  g->schedule = schedule;
+  g->color_start.assign(ncolor + 1, 0);
+  for (uint64_t v = 0; v < nvar; ++v) ++g->color_start[color[v] + 1];
+  for (uint32_t c = 0; c < ncolor; ++c) g->color_start[c + 1] += g->color_start[c];
+  g->perm.resize(nvar); g->inv.resize(nvar);
+  {
+    std::vector<uint32_t> fill(g->color_start.begin(), g->color_start.end() - 1);
+    for (uint64_t v = 0; v < nvar; ++v) {
+      uint32_t d = fill[color[v]]++;
+      g->perm[d] = (uint32_t)v;
+      g->inv[v] = d;
+    }
+  }
+
+  // ---- layout knobs ----
+  g->assign_bytes = max_card <= 256 ? 1 : 4;
+  g->oth_packed = !g->has_categorical && eq_is_bit;
+  g->fv_mode = FV_ONE;
+  for (uint64_t f = 0; f < nfac; ++f) {
+    double x = raw.fac_fv[f];
+    if (x == 1.0) continue;
+    if ((double)(float)x == x) g->fv_mode = std::max(g->fv_mode, (int)FV_F32);
+    else g->fv_mode = FV_F64;
+  }
+
+  // ---- emit rows and edge records in schedule order ----
+  g->var_flags.resize(nvar); g->evid_val.resize(nvar);
+  if (g->has_categorical) g->var_row.resize(nvar + 1);
+  g->row_ptr.assign(nrow + 1, 0);
+  if (g->has_multi) g->row_oth.assign(nrow + 1, 0);
+  if (g->has_truthiness) g->truthiness.assign(nrow, 0.0);
+  g->row_of_value.resize(nrow);
+  uint64_t nindex = 0;
+  for (uint64_t v = 0; v < nvar; ++v) nindex += inc_end[v] - deg[v];
+  if (nindex >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "more than 2^32 edge records"; }
+  g->nindex = nindex;
+  g->e_wid.resize(nindex); g->e_tag.resize(nindex);
+  if (g->fv_mode == FV_F32) g->e_fv32.resize(nindex);
+  if (g->fv_mode == FV_F64) g->e_fv64.resize(nindex);
+  g->oth.clear();
+  const int ow = g->oth_packed ? 1 : 2;  // words per others entry
+  auto push_oth = [&](uint32_t d, uint32_t eq) {
+    if (g->oth_packed) g->oth.push_back((d << 1) | eq);
+    else { g->oth.push_back(d); g->oth.push_back(eq); }
+  };
+  uint64_t row = 0, ei = 0;
+  double b_all = 0, b_query = 0, b_learn = 0;
+  for (uint64_t d = 0; d < nvar; ++d) {
+    uint64_t v = g->perm[d];
+    bool cat = g->var_dtype[v];
+    uint64_t K = cat ? raw.var_card[v] : 1;
+    g->var_flags[d] = (g->var_is_evid[v] ? VF_EVID : 0) | (cat ? VF_CATEGORICAL : 0) |
+                      (has_truth[v] ? VF_TRUTHINESS : 0);
+    if (adense[v] >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "initial value >= 2^32"; }
+    g->evid_val[d] = (uint32_t)adense[v];
+    if (g->has_categorical) g->var_row[d] = (uint32_t)row;
+    double vb = 13.0 + (cat ? 4.0 * K : 0.0), vl = 2.0;
+    uint32_t i = deg[v];
+    for (uint64_t k = 0; k < K; ++k, ++row) {
+      g->row_of_value[g->value_base[v] + k] = (uint32_t)row;
+      if (g->has_truthiness) g->truthiness[row] = truth_orig[g->value_base[v] + k];
+      g->row_ptr[row] = (uint32_t)ei;
+      if (g->has_multi) g->row_oth[row] = (uint32_t)(g->oth.size() / ow);
+      for (; i < inc_end[v] && inc[i].key == k; ++i, ++ei) {
+        uint32_t f = inc[i].fid;
+        uint64_t a = raw.fac_ptr[f], b = raw.fac_ptr[f + 1], n = b - a;
+        g->e_wid[ei] = (uint32_t)raw.fac_wid[f];
+        if (g->fv_mode == FV_F32) g->e_fv32[ei] = (float)raw.fac_fv[f];
+        if (g->fv_mode == FV_F64) g->e_fv64[ei] = raw.fac_fv[f];
+        uint8_t tag = (uint8_t)func_code(raw.fac_func[f]);
+        // where does this variable sit in the factor?
+        uint64_t nself = 0, self_pos = 0;
+        for (uint64_t e = a; e < b; ++e)
+          if (raw.edge_vid[e] == v) { ++nself; self_pos = e - a; }
+        uint32_t self_eq = edense[a + self_pos];
+        bool compact = nself == 1 && n <= 3 && (cat ? self_eq == k : self_eq <= 1);
+        if (compact) {
+          if (!cat && self_eq == 1) tag |= TAG_SELF_EQ1;
+          if (self_pos == n - 1) tag |= TAG_SELF_HEAD;
+          tag |= (uint8_t)((n - 1) << TAG_FORM_SHIFT);
+          for (uint64_t e = a; e < b; ++e)
+            if (raw.edge_vid[e] != v) push_oth(g->inv[raw.edge_vid[e]], edense[e]);
+        } else {
+          // general form: length word, then every position (self included) in order
+          tag |= (uint8_t)(FORM_GENERAL << TAG_FORM_SHIFT);
+          if (n >= (g->oth_packed ? (1ull << 31) : U32_LIMIT)) {
+            *err = DWG_ERR_UNSUPPORTED; return "factor arity too large";
+          }
+          if (g->oth_packed) g->oth.push_back((uint32_t)n);
+          else { g->oth.push_back((uint32_t)n); g->oth.push_back(0); }
+          for (uint64_t e = a; e < b; ++e) push_oth(g->inv[raw.edge_vid[e]], edense[e]);
+        }
+        g->e_tag[ei] = tag;
+        vb += 9.0 + 5.0 * (double)(n - 1);
+        vl += 1.0 * (double)(n - 1);
+      }
+      if (g->oth.size() / ow >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "others stream >= 2^32 entries"; }
+    }
+    b_all += vb;
+    if (!g->var_is_evid[v]) b_query += vb;
+    b_learn += vb + vl;
+  }
+  g->row_ptr[nrow] = (uint32_t)ei;
+  if (g->has_multi) g->row_oth[nrow] = (uint32_t)(g->oth.size() / ow);
+  if (g->has_categorical) g->var_row[nvar] = (uint32_t)nrow;
+  g->noth = g->oth.size() / ow;
+  g->bytes_infer = b_all;
+  g->bytes_infer_query = b_query;
+  g->bytes_learn = b_learn;
+  *err = DWG_OK;
+  return "";
+}
+
+}  // namespace dwg

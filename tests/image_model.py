@@ -1,0 +1,95 @@
+"""Pure-Python reading of the compiled device image (graph_image.h): evaluates potentials
+exactly the way the sweep kernels walk the layout.  Test infrastructure: lets the CPU suite
+check compile.cc's layout against the oracle without a GPU."""
+import math
+
+import numpy as np
+
+TAG_FUNC_MASK, TAG_SELF_EQ1, TAG_SELF_HEAD, TAG_FORM_SHIFT, FORM_GENERAL = 0x0F, 0x10, 0x20, 6, 3
+FC_IMPLY_NATURAL, FC_OR, FC_AND, FC_EQUAL, FC_LINEAR, FC_RATIO, FC_LOGICAL, FC_AND_CAT, FC_IMPLY_MLN = range(9)
+VF_EVID, VF_CAT, VF_TRUTH = 1, 2, 4
+
+
+def sign(fc, n, nsb, head):
+    nbody = n - 1
+    body_all = nsb == nbody
+    if fc == FC_AND: return 1.0 if (body_all and head) else -1.0
+    if fc == FC_AND_CAT: return 1.0 if (body_all and head) else 0.0
+    if fc == FC_OR: return 1.0 if (nsb > 0 or head) else -1.0
+    if fc == FC_EQUAL:
+        t = nsb + (1 if head else 0)
+        return 1.0 if t in (0, n) else -1.0
+    if fc == FC_IMPLY_NATURAL: return (1.0 if head else -1.0) if body_all else 0.0
+    if fc == FC_IMPLY_MLN: return (1.0 if head else 0.0) if body_all else 1.0
+    if n == 1: return 1.0 if head else 0.0
+    res = float(nbody) if head else float(nbody - nsb)
+    if fc == FC_LINEAR: return res
+    if fc == FC_RATIO: return math.log2(1.0 + res)
+    return 1.0 if res > 0 else 0.0
+
+
+class ImageModel:
+    def __init__(self, graph):
+        g = graph
+        self.info = g.info
+        for name in ("perm", "inv", "color_start", "var_flags", "evid_val", "var_row", "row_ptr", "row_oth",
+                     "truthiness", "e_wid", "e_fv32", "e_fv64", "e_tag", "oth", "row_of_value", "values",
+                     "value_base"):
+            setattr(self, name, g.image(name))
+        self.packed = bool(g.image("oth_packed")[0])
+        self.nvar = int(g.info.num_variables)
+
+    def row0(self, d):
+        return int(self.var_row[d]) if len(self.var_row) else d
+
+    def nrows(self, d):
+        return int(self.var_row[d + 1] - self.var_row[d]) if len(self.var_row) else 1
+
+    def fv(self, e):
+        if len(self.e_fv32): return float(self.e_fv32[e])
+        if len(self.e_fv64): return float(self.e_fv64[e])
+        return 1.0
+
+    def entry(self, i):
+        if self.packed:
+            w = int(self.oth[i]); return w >> 1, w & 1
+        return int(self.oth[2 * i]), int(self.oth[2 * i + 1])
+
+    def edge_sign(self, tag, oc, d, cat, key, a, x):
+        """-> (sign, span); a = assignments in SCHEDULE order"""
+        fc, form = tag & TAG_FUNC_MASK, tag >> TAG_FORM_SHIFT
+        if form != FORM_GENERAL:
+            self_eq = key if cat else (1 if tag & TAG_SELF_EQ1 else 0)
+            self_head = bool(tag & TAG_SELF_HEAD)
+            nsb, head_oth = 0, False
+            for j in range(form):
+                od, eq = self.entry(oc + j)
+                s = int(a[od]) == eq
+                if (not self_head) and j == form - 1: head_oth = s
+                else: nsb += s
+            m = x == self_eq
+            if self_head: return sign(fc, form + 1, nsb, m), form
+            return sign(fc, form + 1, nsb + m, head_oth), form
+        n = int(self.oth[oc]) if self.packed else int(self.oth[2 * oc])
+        nsb, head = 0, False
+        for i in range(n):
+            od, eq = self.entry(oc + 1 + i)
+            s = (eq == x) if od == d else (int(a[od]) == eq)
+            if i == n - 1: head = s
+            else: nsb += s
+        return sign(fc, n, nsb, head), 1 + n
+
+    def potential(self, vid, proposal, a_orig, weights):
+        """FactorGraph::potential(var, proposal) from the image; a_orig in ORIGINAL id order"""
+        a = np.asarray(a_orig)[self.perm.astype(np.int64)]
+        d = int(self.inv[vid])
+        cat = bool(self.var_flags[d] & VF_CAT)
+        row = self.row0(d) + (proposal if cat else 0)
+        oc = int(self.row_oth[row]) if len(self.row_oth) else 0
+        pot = 0.0
+        for e in range(int(self.row_ptr[row]), int(self.row_ptr[row + 1])):
+            tag = int(self.e_tag[e])
+            s, span = self.edge_sign(tag, oc, d, cat, proposal, a, proposal)
+            oc += span
+            pot += float(weights[self.e_wid[e]]) * (s * self.fv(e))
+        return pot

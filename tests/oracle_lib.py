@@ -94,6 +94,8 @@ def oracle():
     L.orc_sample_sgd_single_variable.argtypes = [GP, OP, SP, C.c_uint64, C.c_double, Seed3]
     L.orc_sweep_infer.argtypes = [GP, OP, SP, C.c_uint64, C.c_uint64, Seed3]
     L.orc_sweep_learn.argtypes = [GP, OP, SP, C.c_double, C.c_uint64, C.c_uint64, Seed3]
+    L.orc_sweep_infer_seq.argtypes = [GP, OP, SP, u64p, C.c_uint64, f64p]
+    L.orc_sweep_learn_seq.argtypes = [GP, OP, SP, C.c_double, u64p, C.c_uint64, f64p, f64p]
     L.orc_run.argtypes = [GP, OP, SP, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_long]
     _oracle = L
     return L
@@ -174,6 +176,16 @@ class Oracle:
 
     def sweep_learn(self, stepsize, seed, ith=0, n=1):
         self.L.orc_sweep_learn(self.g, C.byref(self.opts), self.s, stepsize, ith, n, seed)
+
+    def sweep_infer_seq(self, order, r0):
+        order = np.ascontiguousarray(order, np.uint64)
+        self.L.orc_sweep_infer_seq(self.g, C.byref(self.opts), self.s, order, len(order),
+                                   np.ascontiguousarray(r0, np.float64))
+
+    def sweep_learn_seq(self, stepsize, order, r0, r1):
+        order = np.ascontiguousarray(order, np.uint64)
+        self.L.orc_sweep_learn_seq(self.g, C.byref(self.opts), self.s, stepsize, order, len(order),
+                                   np.ascontiguousarray(r0, np.float64), np.ascontiguousarray(r1, np.float64))
 
     def clear_tallies(self):
         self.L.orc_clear_tallies(self.g, self.s)

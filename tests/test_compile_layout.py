@@ -1,0 +1,169 @@
+"""CPU checks of the host side: loader + compile.cc (the device layout) against the oracle,
+schedule validity, C-ABI error behaviour.  No GPU needed (nothing here launches a kernel)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import sampler_b200 as sb
+from helpers import GRAPHS, graph_paths, load_golden_graph, random_graph
+from image_model import ImageModel, VF_CAT, VF_EVID, VF_TRUTH
+from sampler_b200 import graphio as gio
+
+
+def _check_against_oracle(raw, schedule, rng, nassign=3):
+    g = sb.Graph.from_raw(raw, schedule)
+    m = ImageModel(g)
+    o = ol.Oracle(raw)
+    assert g.info.num_values == o.nval and g.info.num_index_entries == o.nindex
+    perm = m.perm.astype(np.int64)
+    assert sorted(perm.tolist()) == list(range(o.nvar))
+    assert np.array_equal(m.inv[perm], np.arange(o.nvar))
+    # per-variable metadata
+    assert np.array_equal((m.var_flags & VF_EVID) != 0, o.is_evid[perm] != 0)
+    assert np.array_equal((m.var_flags & VF_CAT) != 0, o.dtype[perm] != 0)
+    assert np.array_equal(m.evid_val, o.assignment_dense[perm])
+    dtype, is_evid, base, values = g.var_meta()
+    assert np.array_equal(base[:-1], o.var_val_base) and np.array_equal(values, o.value)
+    if len(m.truthiness):
+        assert np.array_equal(m.truthiness[m.row_of_value.astype(np.int64)], o.truthiness)
+    else:
+        assert not o.truthiness.any()
+    # potentials of every (variable, value) on random chains and weights: bit-exact
+    card = np.where(o.dtype == 0, 2, o.card).astype(np.int64)
+    for _ in range(nassign):
+        a = np.array([rng.integers(0, max(1, c)) for c in card], np.uint64)
+        w = rng.normal(0, 1, o.nweight)
+        o.assign_evid[:] = a
+        o.weights[:] = w
+        for v in range(o.nvar):
+            for p in range(int(card[v])):
+                assert m.potential(v, p, a, w) == o.potential(v, p), (v, p)
+    return g, m, o
+
+
+@pytest.mark.parametrize("name", GRAPHS)
+def test_layout_bundled_graphs(name):
+    rng = np.random.default_rng(1)
+    _check_against_oracle(load_golden_graph(name), sb.SCHED_AUTO, rng)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_layout_random_graphs(seed):
+    rng = np.random.default_rng(500 + seed)
+    raw = random_graph(rng, truthiness=seed % 2 == 0, p_cat=[0.0, 0.4, 1.0][seed % 3])
+    for sched in (sb.SCHED_HOGWILD, sb.SCHED_CHROMATIC):
+        _check_against_oracle(raw, sched, rng, nassign=2)
+
+
+def test_layout_large_cardinality_uses_wide_chains():
+    rng = np.random.default_rng(3)
+    raw = random_graph(rng, nvar=10, nfac=30, p_cat=1.0, with_domains=False)
+    raw.var_card[:] = 300
+    g, m, o = _check_against_oracle(raw, sb.SCHED_AUTO, rng, nassign=1)
+    assert g.info.assign_bytes == 4
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_chromatic_classes_are_independent_sets(seed):
+    rng = np.random.default_rng(40 + seed)
+    raw = random_graph(rng, nvar=60, nfac=150)
+    g = sb.Graph.from_raw(raw, sb.SCHED_CHROMATIC)
+    perm, cs = g.schedule()
+    color = np.zeros(raw.nvar, np.int64)
+    for c in range(len(cs) - 1):
+        color[perm[int(cs[c]):int(cs[c + 1])].astype(np.int64)] = c
+    assert g.info.schedule == sb.SCHED_CHROMATIC and g.info.num_colors == len(cs) - 1
+    for f in range(raw.nfac):
+        vs = set(int(v) for v in raw.edge_vid[int(raw.fac_ptr[f]):int(raw.fac_ptr[f + 1])])
+        cols = [color[v] for v in vs]
+        assert len(set(cols)) == len(cols), "two variables of one factor share a colour"
+
+
+def test_auto_schedule():
+    assert sb.Graph.from_raw(load_golden_graph("biased_coin")).info.schedule == sb.SCHED_HOGWILD
+    g = sb.Graph.from_raw(load_golden_graph("partial_observation"))
+    assert g.info.schedule == sb.SCHED_CHROMATIC and g.info.num_colors == 2
+
+
+@pytest.mark.parametrize("name", GRAPHS)
+def test_loader_matches_raw_records(name):
+    p = graph_paths(name)
+    a = sb.Graph.from_files(p["meta"], [p["variables"]], [p["domains"]], [p["factors"]], [p["weights"]])
+    b = sb.Graph.from_raw(load_golden_graph(name))
+    for arr in ("perm", "row_ptr", "row_oth", "e_wid", "e_tag", "e_fv32", "e_fv64", "oth", "evid_val",
+                "var_flags", "truthiness", "w_init", "w_fixed", "values"):
+        assert np.array_equal(a.image(arr), b.image(arr)), arr
+
+
+def test_loader_multiple_files_and_pipes(tmp_path):
+    """each kind may come in several files (src/cmd_parser.cc:63-70) and from a FIFO
+    (test/run_end_to_end.sh:18-23 feeds `dw` process substitutions)"""
+    raw = load_golden_graph("sparse_domains")
+    d = str(tmp_path)
+    half = raw.nfac // 2
+    ep = int(raw.fac_ptr[half])
+    f1 = gio.encode_factors(raw.fac_func[:half], raw.fac_ptr[:half + 1], raw.edge_vid[:ep], raw.edge_eq[:ep],
+                            raw.fac_wid[:half], raw.fac_fv[:half])
+    f2 = gio.encode_factors(raw.fac_func[half:], raw.fac_ptr[half:] - raw.fac_ptr[half], raw.edge_vid[ep:],
+                            raw.edge_eq[ep:], raw.fac_wid[half:], raw.fac_fv[half:])
+    paths = gio.write_binary(raw, d)
+    open(os.path.join(d, "f1"), "wb").write(f1)
+    fifo = os.path.join(d, "f2.fifo")
+    os.mkfifo(fifo)
+    import threading
+    t = threading.Thread(target=lambda: open(fifo, "wb").write(f2))
+    t.start()
+    v = open(paths["variables"], "rb").read()
+    open(os.path.join(d, "v1"), "wb").write(v[27 * 7:])  # out of order on purpose: placed by id
+    open(os.path.join(d, "v2"), "wb").write(v[:27 * 7])
+    g = sb.Graph.from_files(paths["meta"], [os.path.join(d, "v1"), os.path.join(d, "v2")], [paths["domains"]],
+                            [os.path.join(d, "f1"), fifo], [paths["weights"]])
+    t.join()
+    ref = sb.Graph.from_raw(raw)
+    for arr in ("row_ptr", "e_wid", "e_tag", "oth", "evid_val"):
+        assert np.array_equal(g.image(arr), ref.image(arr)), arr
+
+
+def test_errors_are_codes_not_aborts(tmp_path):
+    raw = load_golden_graph("biased_coin")
+    bad = gio.RawGraph(**{**raw.__dict__})
+    bad.fac_func = raw.fac_func.copy(); bad.fac_func[3] = 5  # src/factor.h:81-84 would abort
+    with pytest.raises(sb.DwgError, match="unsupported FACTOR_FUNCTION_TYPE"):
+        sb.Graph.from_raw(bad)
+    bad = gio.RawGraph(**{**raw.__dict__})
+    bad.edge_vid = raw.edge_vid.copy(); bad.edge_vid[0] = 99
+    with pytest.raises(sb.DwgError, match="unknown variable"):
+        sb.Graph.from_raw(bad)
+    # counts must match the meta file (safety_check, src/factor_graph.cc:203-206)
+    paths = gio.write_binary(raw, str(tmp_path))
+    open(paths["meta"], "w").write("1,18,17,18")
+    with pytest.raises(sb.DwgError, match="number of factors"):
+        sb.Graph.from_files(paths["meta"], [paths["variables"]], [], [paths["factors"]], [paths["weights"]])
+    with pytest.raises(sb.DwgError, match="cannot open"):
+        sb.Graph.from_files(paths["meta"], ["/nonexistent"], [], [paths["factors"]], [paths["weights"]])
+    # meta with trailing junk / no newline parses like atoll on 4 comma fields
+    open(paths["meta"], "w").write("1,18,18,18,out/x,,")
+    sb.Graph.from_files(paths["meta"], [paths["variables"]], [], [paths["factors"]], [paths["weights"]])
+
+
+def test_algorithmic_bytes_formula():
+    """13 B/var + 9 B/unary factor (+5 per other variable); learning +2 B/var"""
+    g = sb.Graph.from_raw(load_golden_graph("biased_coin"))
+    assert g.info.bytes_per_sweep_infer == 18 * (13 + 9)
+    assert g.info.bytes_per_sweep_infer_query == 9 * (13 + 9)
+    assert g.info.bytes_per_sweep_learn == 18 * (13 + 9 + 2)
+    g = sb.Graph.from_raw(load_golden_graph("partial_observation"))  # 12 vars, 8 EQUAL(2): 16 incidences
+    assert g.info.bytes_per_sweep_infer == 12 * 13 + 16 * 14
+    assert g.info.bytes_per_sweep_learn == 12 * 15 + 16 * 15
+
+
+def test_no_device_is_a_loud_error():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    g = sb.Graph.from_raw(load_golden_graph("biased_coin"))
+    with pytest.raises(sb.DwgError, match="no CUDA device"):
+        sb.Sampler(g)

@@ -1,0 +1,422 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the
+reference-generated golden fixtures.  North-star gates:
+  (1) conditional potentials within 1e-6 relative (we require bit-equality where the sums are
+      taken in the reference's order),
+  (2) the Boolean / categorical draw bit-exact given the same uniform,
+  (3) end-to-end marginals within 0.02 absolute and learned weights within 5 % of the
+      reference's results averaged over seeds on the bundled graphs.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import sampler_b200 as sb
+from helpers import (GOLDEN, GRAPHS, dw_args, expected, graph_dir, graph_paths, load_golden_graph,
+                     parse_dw_args, random_graph)
+from sampler_b200 import graphio as gio
+
+pytestmark = pytest.mark.gpu
+
+
+def _all_pairs(o):
+    vids, props = [], []
+    for v in range(o.nvar):
+        for p in range(int(2 if o.dtype[v] == 0 else o.card[v])):
+            vids.append(v); props.append(p)
+    return np.array(vids, np.uint64), np.array(props, np.uint64)
+
+
+def _rand_state(o, rng):
+    card = np.where(o.dtype == 0, 2, o.card).astype(np.int64)
+    a = np.array([rng.integers(0, max(1, c)) for c in card], np.uint64)
+    return a, rng.normal(0, 1, o.nweight)
+
+
+# ---------------------------------------------------------------- (1) potentials
+@pytest.mark.parametrize("name", GRAPHS)
+def test_potentials_bundled(name):
+    rng = np.random.default_rng(5)
+    raw = load_golden_graph(name)
+    o = ol.Oracle(raw)
+    s = sb.Sampler(sb.Graph.from_raw(raw))
+    vids, props = _all_pairs(o)
+    for chain in (0, 1):
+        a, w = _rand_state(o, rng)
+        o.chain_array = o.assign_evid if chain else o.assign_free
+        o.chain_array[:] = a; o.weights[:] = w
+        s.set_assignments(chain, a); s.set_weights(w)
+        got = s.eval_potentials(vids, props, chain)
+        want = np.array([o.potential(int(v), int(p), chain) for v, p in zip(vids, props)])
+        assert np.allclose(got, want, rtol=1e-6, atol=0)
+        assert np.array_equal(got, want)  # same order of fp64 operations => same bits
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_potentials_random_graphs(seed):
+    rng = np.random.default_rng(900 + seed)
+    raw = random_graph(rng, nvar=80, nfac=400, max_arity=5, p_cat=[0.0, 0.4, 1.0][seed % 3])
+    o = ol.Oracle(raw)
+    for sched in (sb.SCHED_HOGWILD, sb.SCHED_CHROMATIC):
+        s = sb.Sampler(sb.Graph.from_raw(raw, sched))
+        vids, props = _all_pairs(o)
+        a, w = _rand_state(o, rng)
+        o.assign_evid[:] = a; o.weights[:] = w
+        s.set_assignments(1, a); s.set_weights(w)
+        got = s.eval_potentials(vids, props, 1)
+        want = np.array([o.potential(int(v), int(p), 1) for v, p in zip(vids, props)])
+        assert np.array_equal(got, want)
+
+
+def test_factor_known_answers_on_device():
+    """the 62 EXPECT_NEARs of the reference's test/factor_test.cc, one single-factor graph each"""
+    kat = json.load(open(os.path.join(GOLDEN, "factor_kat.json")))
+    for c in kat["cases"]:
+        n = len(c["assignments"])
+        raw = gio.RawGraph([0] * n, [0] * n, [0] * n, [2] * n, *gio.empty_domains(), [c["func"]],
+                           [0, len(c["vids"])], c["vids"], c["eqs"], [0], [1.0], [1.0], [1]).normalized()
+        s = sb.Sampler(sb.Graph.from_raw(raw))
+        s.set_assignments(1, np.array(c["assignments"], np.uint64))
+        got = s.eval_potentials([c["vid"]], [c["proposal"]], 1)[0]
+        assert abs(got - c["expected"]) <= kat["tol"], c
+
+
+def test_factor_random_vectors_on_device():
+    """6000 reference-evaluated random factors (all 10 function ids, arity 1..6, repeated
+    variables): every test gets its own 8 variables inside one big graph"""
+    z = np.load(os.path.join(GOLDEN, "factor_random.npz"))
+    N, NV = len(z["func"]), z["assign"].shape[1]
+    card = np.where((z["eqs"].max(axis=1) > 1) | (z["assign"].max(axis=1) > 1) | (z["proposal"] > 1), 4, 2)
+    var_dtype = np.repeat((card == 4).astype(np.uint16), NV)
+    var_card = np.repeat(card.astype(np.uint64), NV)
+    ptr = np.zeros(N + 1, np.uint64); np.cumsum(z["arity"], out=ptr[1:])
+    evid, eeq = [], []
+    for i in range(N):
+        n = int(z["arity"][i])
+        evid.append(z["vids"][i, :n] + np.uint64(i * NV)); eeq.append(z["eqs"][i, :n])
+    raw = gio.RawGraph(np.zeros(N * NV, np.uint8), np.zeros(N * NV, np.uint64), var_dtype, var_card,
+                       *gio.empty_domains(), z["func"], ptr, np.concatenate(evid), np.concatenate(eeq),
+                       np.arange(N, dtype=np.uint64), z["fv"], np.ones(N), np.ones(N, np.uint8)).normalized()
+    s = sb.Sampler(sb.Graph.from_raw(raw, sb.SCHED_HOGWILD))
+    s.set_assignments(1, z["assign"].reshape(-1))
+    vid = z["vid"] + np.arange(N, dtype=np.uint64) * np.uint64(NV)
+    got = s.eval_potentials(vid, z["proposal"], 1)
+    # a categorical row (v, k) only holds the factors bound to v == k (src/factor_graph.h:132-134);
+    # compare where the proposal is one of this variable's bound values (always true for Boolean)
+    checked = 0
+    for i in range(N):
+        n = int(z["arity"][i])
+        mine = z["vids"][i, :n] == z["vid"][i]
+        if card[i] == 2 or (z["eqs"][i, :n][mine] == z["proposal"][i]).any():
+            assert got[i] == z["expected"][i], i
+            checked += 1
+        else:
+            assert got[i] == 0.0
+    assert checked > 4000
+
+
+# ---------------------------------------------------------------- (2) draws
+def test_draw_boolean_bit_exact():
+    z = np.load(os.path.join(GOLDEN, "draw_bool.npz"))
+    pots = np.stack([z["pos"], z["neg"]], axis=1)
+    got = sb.draw(pots, np.zeros(len(z["r"]), np.uint32), z["r"])
+    assert np.array_equal(got.astype(np.uint64), z["expected"])
+
+
+def test_draw_categorical_bit_exact():
+    z = np.load(os.path.join(GOLDEN, "draw_cat.npz"))
+    got = sb.draw(z["pots"], z["card"].astype(np.uint32), z["r"])
+    assert np.array_equal(got.astype(np.uint64), z["expected"])
+
+
+def test_logadd_matches_reference():
+    z = np.load(os.path.join(GOLDEN, "logadd.npz"))
+    got = sb.logadd(z["a"], z["b"])
+    # CUDA exp/log1p are within 1 ulp of glibc's; the branches (swap, a==b, -18.42 cut-off) must agree
+    assert np.allclose(got, z["expected"], rtol=4e-16, atol=0)
+    assert (got == z["expected"]).mean() > 0.95
+
+
+def test_draws_on_random_potentials_vs_oracle():
+    rng = np.random.default_rng(77)
+    L = ol.oracle()
+    n, K = 20000, 12
+    card = rng.integers(0, K + 1, n).astype(np.uint32)
+    card[card == 1] = 0  # 0 = Boolean
+    pots = rng.normal(0, 2.0, (n, K))
+    r = rng.random(n)
+    got = sb.draw(pots, card, r)
+    want = np.array([L.orc_draw_boolean(p[0], p[1], u) if c == 0 else
+                     L.orc_draw_categorical(np.ascontiguousarray(p[:c]), int(c), u)
+                     for p, c, u in zip(pots, card, r)], np.uint64)
+    assert np.array_equal(got.astype(np.uint64), want)
+
+
+# ------------------------------------------------ sweeps: exact against the oracle
+def _mk(raw, sched, **kw):
+    g = sb.Graph.from_raw(raw, sched)
+    okw = dict(sample_evidence=kw.get("sample_evidence", False),
+               learn_non_evidence=kw.get("learn_non_evidence", False),
+               noise_aware=kw.get("noise_aware", False), reg_param=kw.get("reg_param", 0.01),
+               reg_l1=kw.get("regularization", "l2") == "l1")
+    return g, sb.Sampler(g, **kw), ol.Oracle(raw, **okw)
+
+
+def _same_state(s, o):
+    assert np.array_equal(s.assignments(0), o.assign_free)
+    assert np.array_equal(s.assignments(1), o.assign_evid)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_sequential_sweeps_bit_exact(seed):
+    """one-thread launch in schedule order + explicit uniforms == the reference algorithm run
+    in that order: chains, weights (non-atomic reference update) and tallies, bit for bit"""
+    rng = np.random.default_rng(300 + seed)
+    noise = seed % 2 == 1
+    raw = random_graph(rng, nvar=50, nfac=160, truthiness=noise, p_cat=[0.0, 0.5, 1.0][seed % 3])
+    kw = dict(sample_evidence=True, noise_aware=noise, learn_non_evidence=seed % 3 == 0, reg_param=0.05,
+              regularization="l1" if seed == 4 else "l2")
+    for sched in (sb.SCHED_HOGWILD, sb.SCHED_CHROMATIC):
+        g, s, o = _mk(raw, sched, **kw)
+        s.set_sequential(True)
+        perm, _ = g.schedule()
+        for ep in range(3):
+            r0, r1 = rng.random(o.nvar), rng.random(o.nvar)
+            s.set_uniforms(r0, r1)
+            s.learn_epoch(0.05)
+            o.sweep_learn_seq(0.05, perm, r0, r1)
+            _same_state(s, o)
+            assert np.array_equal(s.weights(), o.weights)
+        s.clear_tallies(); o.clear_tallies()
+        for ep in range(3):
+            r0 = rng.random(o.nvar)
+            s.set_uniforms(r0)
+            s.infer_epoch()
+            o.sweep_infer_seq(perm, r0)
+        _same_state(s, o)
+        t, n = s.tallies()
+        assert np.array_equal(t, o.tallies) and np.array_equal(n, o.nsamples)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_parallel_chromatic_inference_is_exact_gibbs(seed):
+    """full-width launches, one per colour class: variables of a class share no factor, so the
+    parallel sweep must equal the sequential one in schedule order exactly"""
+    rng = np.random.default_rng(700 + seed)
+    raw = random_graph(rng, nvar=3000, nfac=6000, nweight=40, p_cat=[0.0, 0.5][seed % 2], max_arity=3)
+    g, s, o = _mk(raw, sb.SCHED_CHROMATIC, sample_evidence=seed % 3 != 0)
+    assert g.info.num_colors > 1
+    perm, _ = g.schedule()
+    w = rng.normal(0, 1, o.nweight)
+    s.set_weights(w); o.weights[:] = w
+    for ep in range(4):
+        r0 = rng.random(o.nvar)
+        s.set_uniforms(r0)
+        s.infer_epoch()
+        o.sweep_infer_seq(perm, r0)
+    assert np.array_equal(s.assignments(1), o.assign_evid)
+    t, n = s.tallies()
+    assert np.array_equal(t, o.tallies) and np.array_equal(n, o.nsamples)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_parallel_learning_with_exact_arithmetic(seed):
+    """parallel learning launches under the chromatic schedule: with fixed weights both chains
+    (free-chain draws of every variable, evid-chain clamps / draws) must equal the sequential
+    reference in schedule order exactly"""
+    rng = np.random.default_rng(800 + seed)
+    raw = random_graph(rng, nvar=2000, nfac=5000, nweight=30, p_cat=[0.0, 0.5][seed % 2], max_arity=3)
+    raw.fac_fv[:] = rng.choice([1.0, 0.5, 2.0, -1.0], raw.nfac)
+    raw.w_fixed[:] = 1  # fixed weights: the launch cannot perturb its own draws
+    g, s, o = _mk(raw, sb.SCHED_CHROMATIC, reg_param=0.0, learn_non_evidence=True)
+    perm, _ = g.schedule()
+    for ep in range(3):
+        r0, r1 = rng.random(o.nvar), rng.random(o.nvar)
+        s.set_uniforms(r0, r1)
+        s.learn_epoch(2.0 ** -6)
+        o.sweep_learn_seq(2.0 ** -6, perm, r0, r1)
+        _same_state(s, o)
+
+
+def test_learning_accumulates_exact_gradient_sum():
+    """unary all-evidence graph, reg 0, step 2^-20 (too small to flip a draw whose margin is
+    >= 1e-3): the parallel sweep's weights equal the sequential reference's up to the order of
+    exactly-representable additions, i.e. exactly"""
+    rng = np.random.default_rng(11)
+    nvar, nw, deg = 20000, 64, 6
+    func = np.full(nvar * deg, gio.FUNC_ISTRUE, np.int32)
+    ptr = np.arange(nvar * deg + 1, dtype=np.uint64)
+    evid = np.repeat(np.arange(nvar, dtype=np.uint64), deg)
+    raw = gio.RawGraph(np.ones(nvar, np.uint8), rng.integers(0, 2, nvar), np.zeros(nvar, np.uint16),
+                       np.full(nvar, 2, np.uint64), *gio.empty_domains(), func, ptr, evid,
+                       rng.integers(0, 2, nvar * deg), rng.integers(0, nw, nvar * deg),
+                       rng.choice([1.0, 0.5, 2.0], nvar * deg), rng.normal(0, 1, nw),
+                       np.zeros(nw, np.uint8)).normalized()
+    g, s, o = _mk(raw, sb.SCHED_AUTO, reg_param=0.0)
+    perm, _ = g.schedule()
+    step = 2.0 ** -20
+    r0 = rng.random(nvar)
+    # keep draws away from the decision boundary so that weight drift (<= nvar*deg*4*step/nw) cannot flip them
+    for v in range(nvar):
+        pos, neg = o.potential(v, 1, 0), o.potential(v, 0, 0)
+        p1 = 1.0 / (1.0 + np.exp(neg - pos))
+        if abs(r0[v] - p1) < 0.05:
+            r0[v] = (p1 + 0.5) % 1.0
+    s.set_uniforms(r0, np.zeros(nvar))
+    s.learn_epoch(step)
+    o.sweep_learn_seq(step, perm, r0, np.zeros(nvar))
+    _same_state(s, o)
+    w = s.weights()
+    assert np.allclose(w, o.weights, rtol=0, atol=1e-12)
+    assert np.abs(w - raw.w_init).max() > 100 * step  # something was learnt
+
+
+# ---------------------------------------------------------------- RNG
+def _philox(c0, c1, c2, c3, k0, k1):
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def test_philox_known_answer_and_device_stream():
+    # Random123 known-answer vectors for philox4x32-10
+    assert _philox(0, 0, 0, 0, 0, 0) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert _philox(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff) == \
+        (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert _philox(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+    # device: factor-less Boolean variables are fair coins: proposal = (r * 2 < 1)
+    n = 5000
+    raw = gio.RawGraph(np.zeros(n, np.uint8), np.zeros(n, np.uint64), np.zeros(n, np.uint16),
+                       np.full(n, 2, np.uint64), *gio.empty_domains(), np.zeros(0, np.int32), [0],
+                       [], [], [], [], [0.0], [1]).normalized()
+    seed, replica = 0x1234567890ABCDEF, 3
+    s = sb.Sampler(sb.Graph.from_raw(raw), seed=seed, replica=replica)
+    k0, k1 = seed & 0xFFFFFFFF, ((seed >> 32) ^ ((replica * 0x9E3779B9 + replica) & 0xFFFFFFFF)) & 0xFFFFFFFF
+    for sweep in range(3):
+        s.infer_epoch()
+        a = s.assignments(1)
+        for d in list(range(0, n, 97)):
+            o = _philox(d, 0, sweep, 0, k0, k1)
+            r = (((o[0] << 32) | o[1]) >> 11) * 2.0 ** -53
+            assert a[d] == (1 if r * 2.0 < 1.0 else 0)
+    t, ns = s.tallies()
+    assert (ns == 3).all() and abs(t.sum() / (3.0 * n) - 0.5) < 0.03
+
+
+# ---------------------------------------------------------------- (3) end to end
+def _run_schedule(raw, a, seed, sched=sb.SCHED_AUTO):
+    """DimmWitted::learn + inference for one replica (src/dimmwitted.cc:121-207)"""
+    s = sb.Sampler(sb.Graph.from_raw(raw, sched), sample_evidence=a["sample_evidence"],
+                   learn_non_evidence=a["learn_non_evidence"], noise_aware=a["noise_aware"],
+                   regularization="l1" if a["reg_l1"] else "l2", reg_param=a["reg_param"], seed=seed)
+    step = a["stepsize"]
+    for _ in range(a["n_learn"]):
+        s.learn_epoch(step)
+        step *= a["decay"]
+    s.clear_tallies()
+    s.infer_epochs(a["n_infer"])
+    return s.weights(), s.marginals()
+
+
+NSEED = 10
+
+
+@pytest.mark.parametrize("name", GRAPHS)
+def test_end_to_end_vs_reference_results(name):
+    a = parse_dw_args(dw_args(name))
+    exp = expected(name)
+    raw = load_golden_graph(name)
+    ws, ms = [], []
+    for seed in range(1, NSEED + 1):
+        w, m = _run_schedule(raw, a, seed)
+        ws.append(w); ms.append(m)
+    w = np.mean(ws, axis=0)
+    wref = np.array(exp["weights_mean"])
+    # weights within 5 % of the reference's seed-averaged result (absolute 0.05 where |ref| < 1:
+    # 5 % of a weight that is 0 by construction is not a tolerance)
+    tol = np.maximum(0.05 * np.abs(wref), 0.05 * (np.abs(wref) < 1.0))
+    assert (np.abs(w - wref) <= tol).all(), (w, wref)
+    keys = exp["marginal_keys"]
+    m = np.array([np.mean([mm[tuple(int(x) for x in k.split())] for mm in ms]) for k in keys])
+    mref = np.array(exp["marginals_mean"])
+    assert len(ms[0]) == len(keys)
+    assert np.abs(m - mref).max() <= 0.02, (np.abs(m - mref).max())
+
+
+@pytest.mark.parametrize("name", ["partial_observation", "sparse_multinomial2", "sparse_domains"])
+def test_hogwild_on_coupled_bundled_graphs_stays_in_tolerance_or_is_documented(name):
+    """the hogwild schedule on graphs with pairwise factors: a synchronous sweep is NOT a Gibbs
+    sampler for coupled variables, which is why AUTO picks the chromatic schedule there; this
+    test documents how far hogwild drifts (it must at least stay a valid distribution)"""
+    a = parse_dw_args(dw_args(name))
+    raw = load_golden_graph(name)
+    w, m = _run_schedule(raw, a, 1, sb.SCHED_HOGWILD)
+    assert np.isfinite(w).all()
+    assert all(0.0 <= p <= 1.0 for p in m.values())
+
+
+def test_reference_check_results_scripts(tmp_path):
+    """the reference's own acceptance criteria (test/*/check_result), restated, on the CLI output"""
+    for name in GRAPHS:
+        out = tmp_path / name
+        out.mkdir()
+        p = graph_paths(name)
+        argv = ["dw", "gibbs", "-m", p["meta"], "-v", p["variables"], "-f", p["factors"], "-w", p["weights"],
+                "--domains", p["domains"], "-o", str(out), "--quiet"] + dw_args(name)
+        assert sb.dw_main(argv) == 0
+        w = gio.read_weights_text(str(out / "inference_result.out.weights.text"))
+        m = gio.read_marginals_text(str(out / "inference_result.out.text"))
+        if name == "biased_coin":
+            assert abs(w[0] - 1.0) <= 0.1 and all(abs(p - 0.89) <= 0.03 for p in m.values()) and len(m) == 18
+        elif name == "biased_coin_continuous":
+            assert abs(w[0]) <= 0.1 and all(abs(p - 0.5) <= 0.03 for p in m.values())
+        elif name == "biased_coin_truthiness":
+            assert abs(w[0] + 0.7) <= 0.1 and abs(w[1] - 0.7) <= 0.1
+            assert all(abs(p - 0.80) <= 0.03 for (v, e), p in m.items() if e == 1)
+        elif name == "biased_coin_with_multinomial":
+            assert abs(w[0] + 1.05) <= 0.1 and abs(w[1] - 1.05) <= 0.1
+            assert all(abs(p - 0.89) <= 0.03 for (v, e), p in m.items() if e == 1)
+        elif name == "partial_observation":
+            assert (w > 0).all() and all(p > 0.9 for p in m.values()) and sorted(v for v, _ in m) == [5, 6, 7]
+        elif name == "sparse_domains":
+            assert all(abs(w[i] - np.log(i + 1)) <= 0.2 for i in range(4))
+            e2, e3 = np.exp(2), np.exp(3)
+            want = {(14, 0): e2 / (e2 + e3 + 1), (14, 1): e3 / (e2 + e3 + 1), (14, 3): 1 / (e2 + e3 + 1),
+                    (15, 1): 1.0, (16, 1): e3 / (e2 + e3), (16, 3): e2 / (e2 + e3), (17, 1): 1.0,
+                    (18, 0): 1 / 7, (18, 1): 2 / 7, (18, 3): 4 / 7, (19, 1): 1 / 3, (19, 3): 2 / 3}
+            for (v, e), p in m.items():
+                assert abs(p - want.get((v, e), (e + 1) / 10.0)) <= 0.04, (v, e, p)
+        elif name == "sparse_multinomial2":
+            want = {(0, 0): 0, (0, 1): 1, (0, 2): 0, (1, 1): 1, (1, 2): 0, (1, 3): 0,
+                    (2, 1): 0.05, (2, 2): 0, (2, 3): 0.95}
+            for k, p in m.items():
+                assert abs(p - want[k]) <= 0.04, (k, p)
+
+
+# ---------------------------------------------------------------- replicas
+def test_two_replicas_one_gpu_average_and_aggregate():
+    """the -c N plumbing with both replicas on one device and no NCCL: weights are averaged
+    (src/dimmwitted.cc:214-216), tallies summed (src/inference_result.cc:116-127)"""
+    import ctypes as C
+    raw = load_golden_graph("biased_coin")
+    g = sb.Graph.from_raw(raw)
+    a = sb.Sampler(g, sample_evidence=True, reg_param=0.0, replica=0)
+    b = sb.Sampler(g, sample_evidence=True, reg_param=0.0, replica=1)
+    a.set_weights([1.0]); b.set_weights([3.0])
+    L = sb.load()
+    hs = (C.c_void_p * 2)(a._h, b._h)
+    lmax, l2 = C.c_double(), C.c_double()
+    assert L.dwg_average_weights_multi(hs, None, 2, C.byref(lmax), C.byref(l2)) == 0
+    assert a.weights()[0] == 2.0 and b.weights()[0] == 2.0
+    assert lmax.value == 1.0 and l2.value == 1.0  # replica 0 moved from 1.0 to 2.0
+    a.infer_epochs(5); b.infer_epochs(7)
+    ta, _ = a.tallies(); tb, _ = b.tallies()
+    assert L.dwg_reduce_tallies_multi(hs, None, 2) == 0
+    t, n = a.tallies()
+    assert np.array_equal(t, ta + tb) and (n == 12).all()
