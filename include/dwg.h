@@ -43,11 +43,17 @@ enum {
 
 /* sweep schedules */
 enum {
-  DWG_SCHED_AUTO = 0,      /* hogwild if every factor touches one variable, else chromatic */
+  DWG_SCHED_AUTO = 0,      /* sequential for tiny graphs (<= DWG_SEQUENTIAL_MAX_EDGES edge records),
+                              else hogwild if every factor touches one variable, else chromatic */
   DWG_SCHED_HOGWILD = 1,   /* one launch per sweep, all variables concurrently (like the
                               reference's Hogwild threads, src/gibbs_sampler.cc:20-33) */
-  DWG_SCHED_CHROMATIC = 2  /* host greedy colouring; one launch per colour class: exact Gibbs */
+  DWG_SCHED_CHROMATIC = 2, /* host greedy colouring; one launch per colour class: exact Gibbs */
+  DWG_SCHED_SEQUENTIAL = 3 /* one chain walking the variables in id order with the reference's
+                              non-atomic per-sample weight update: `dw -t 1 -c 1` semantics exactly.
+                              For graphs too small to parallelise, where per-sample SGD with large
+                              steps and a per-launch mini-batch visibly differ. */
 };
+#define DWG_SEQUENTIAL_MAX_EDGES 256
 
 /* The CmdParser fields the hot path reads (src/cmd_parser.h:41-56) + device knobs. */
 typedef struct dwg_opts {

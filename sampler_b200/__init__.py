@@ -5,5 +5,5 @@ include/dwg.h (libdwg.so, `dw` CLI).  This Python package is only the ctypes stu
 that ABI (api.py), the build recipe (_build.py) and input tooling (graphio.py, graphgen.py).
 """
 from . import graphio  # noqa: F401
-from .api import (DwgError, Graph, Sampler, SCHED_AUTO, SCHED_CHROMATIC, SCHED_HOGWILD,  # noqa: F401
+from .api import (DwgError, Graph, Sampler, SCHED_AUTO, SCHED_CHROMATIC, SCHED_HOGWILD, SCHED_SEQUENTIAL,  # noqa: F401
                   draw, dw_main, load, logadd)

@@ -16,7 +16,7 @@ import numpy as np
 from . import _build
 from .graphio import RawGraph
 
-SCHED_AUTO, SCHED_HOGWILD, SCHED_CHROMATIC = 0, 1, 2
+SCHED_AUTO, SCHED_HOGWILD, SCHED_CHROMATIC, SCHED_SEQUENTIAL = 0, 1, 2, 3
 
 
 class DwgError(RuntimeError):

@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <atomic>
+#include <cmath>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -255,6 +256,11 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     return fail(DWG_ERR_CUDA, "no CUDA device: the Gibbs sweep has no CPU path");
   if (device < 0 || device >= ndev) return fail(DWG_ERR_CUDA, "bad device index");
   CU(cudaSetDevice(device));
+  {
+    double tab[DWG_LOG2_TABLE];
+    for (int k = 0; k < DWG_LOG2_TABLE; ++k) tab[k] = std::log2(1.0 + (double)k);
+    CU(cudaMemcpyToSymbol(c_log2_1p, tab, sizeof(tab)));
+  }
   std::unique_ptr<dwg_handle> h(new dwg_handle);
   h->img = &g->img;
   if (opts) h->opts = *opts; else dwg_opts_default(&h->opts);
@@ -337,7 +343,7 @@ static SweepParams make_params(dwg_handle *h, double stepsize) {
   p.reg_l1 = h->opts.regularization == 1;
   p.reg_param = h->opts.reg_param;
   p.stepsize = stepsize;
-  p.sequential = h->sequential;
+  p.sequential = h->sequential || h->img->schedule == DWG_SCHED_SEQUENTIAL;
   p.r_free = h->explicit_r ? h->r_free.p : nullptr;
   p.r_evid = h->explicit_r ? h->r_evid.p : nullptr;
   return p;
@@ -355,7 +361,7 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
     if (!n) continue;
     uint32_t blocks = (n + SWEEP_THREADS - 1) / SWEEP_THREADS;
     uint32_t threads = SWEEP_THREADS;
-    if (h->sequential) { blocks = 1; threads = 1; }
+    if (p.sequential) { blocks = 1; threads = 1; }
     if (m.assign_bytes == 1) {
       if (learn) k_sweep_learn<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
       else k_sweep_infer<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);

@@ -78,6 +78,12 @@ __host__ __device__ inline double u01(uint32_t hi, uint32_t lo) {
 
 #ifdef __CUDACC__
 
+// log2(1 + k) for k < 64 as the HOST libm rounds it (filled once by dwg_api.cu): FUNC_RATIO
+// (src/factor.h:264-277) takes log2 of a small integer, and CUDA's log2 may differ from
+// glibc's in the last bit.  Larger arguments use the device log2 (<= 1 ulp).
+constexpr int DWG_LOG2_TABLE = 64;
+__constant__ double c_log2_1p[DWG_LOG2_TABLE];
+
 // ---------------------------------------------------------------------------
 // logadd, src/common.h:118-132 (LOG_2 and the -18.42 cut-off as literally spelled there)
 // ---------------------------------------------------------------------------
@@ -120,7 +126,7 @@ __device__ __forceinline__ double dev_sign(uint32_t fc, uint32_t n, uint32_t nsb
   if (n == 1) return head ? 1.0 : 0.0;  // log2(1+1)=1, log2(1+0)=0 exactly
   const double res = head ? (double)nbody : (double)(nbody - nsb);
   if (fc == FC_LINEAR) return res;
-  if (fc == FC_RATIO) return log2(__dadd_rn(1.0, res));
+  if (fc == FC_RATIO) return res < (double)DWG_LOG2_TABLE ? c_log2_1p[(int)res] : log2(__dadd_rn(1.0, res));
   return res > 0.0 ? 1.0 : 0.0;  // FC_LOGICAL
 }
 

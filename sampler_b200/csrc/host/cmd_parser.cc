@@ -167,7 +167,8 @@ CmdParser::CmdParser(int argc, const char *const argv[], int num_gpus) {
     if (sch == "auto") schedule = 0;
     else if (sch == "hogwild") schedule = 1;
     else if (sch == "chromatic") schedule = 2;
-    else error("Argument: --schedule\n             expects auto, hogwild or chromatic");
+    else if (sch == "sequential") schedule = 3;
+    else error("Argument: --schedule\n             expects auto, hogwild, chromatic or sequential");
     seed_given = vals.count("seed") > 0;
     seed = last_u64("seed", seed);
 

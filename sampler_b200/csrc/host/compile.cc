@@ -247,8 +247,14 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   }
 
   // ---- schedule ----
-  if (schedule == DWG_SCHED_AUTO) schedule = coupled ? DWG_SCHED_CHROMATIC : DWG_SCHED_HOGWILD;
-  if (schedule != DWG_SCHED_HOGWILD && schedule != DWG_SCHED_CHROMATIC) return "bad schedule";
+  if (schedule == DWG_SCHED_AUTO) {
+    uint64_t nrec = 0;
+    for (uint64_t v = 0; v < nvar; ++v) nrec += inc_end[v] - deg[v];
+    schedule = nrec <= DWG_SEQUENTIAL_MAX_EDGES ? DWG_SCHED_SEQUENTIAL
+               : coupled ? DWG_SCHED_CHROMATIC : DWG_SCHED_HOGWILD;
+  }
+  if (schedule != DWG_SCHED_HOGWILD && schedule != DWG_SCHED_CHROMATIC && schedule != DWG_SCHED_SEQUENTIAL)
+    return "bad schedule";
   std::vector<uint32_t> color(nvar, 0);
   uint32_t ncolor = 1;
   if (schedule == DWG_SCHED_CHROMATIC && coupled) {

@@ -102,7 +102,8 @@ int gibbs(const CmdParser &args) {
   if (!args.should_be_quiet) {
     std::cout << "Device layout: " << info.num_index_entries << " edge records, "
               << info.num_other_refs << " other-variable refs, schedule="
-              << (info.schedule == DWG_SCHED_CHROMATIC ? "chromatic" : "hogwild") << " ("
+              << (info.schedule == DWG_SCHED_CHROMATIC ? "chromatic"
+                  : info.schedule == DWG_SCHED_SEQUENTIAL ? "sequential" : "hogwild") << " ("
               << info.num_colors << " colour" << (info.num_colors == 1 ? "" : "s") << "), "
               << info.device_bytes / 1048576.0 << " MiB per replica" << std::endl;
   }

@@ -266,6 +266,43 @@ def sampler_kat():
     }, open(os.path.join(HERE, "sampler_kat.json"), "w"), indent=1)
 
 
+SCALE = {
+    # name: (generator, kwargs, dw args)  -- mid-size graphs of the BASELINE.json shapes
+    "c2_small": ("c2_boolean", dict(nvar=20000, nweight=50),
+                 "-l 20 -i 200 --alpha 0.01 --diminish 0.95 --reg_param 0.01 --sample_evidence"),
+    "c3_small": ("c3_categorical", dict(nvar=5000, card=10, nweight=50),
+                 "-l 10 -i 200 --alpha 0.01 --reg_param 0.01 --sample_evidence"),
+    "c4_small": ("unary_boolean", dict(nvar=20000, degree=20, nweight=2000, p_evid=0.9, zipf=1.1, real_features=True),
+                 "-l 10 -i 50 --alpha 0.001 --diminish 0.9 --reg_param 0.01"),
+}
+
+
+def make_scale():
+    """reference results on mid-size synthetic graphs (regenerated in the tests from the same
+    seeded generator, sampler_b200/graphgen.py): learned weights and per-variable marginals,
+    mean over DW_SEED=1..5, -t 1 -c 1"""
+    from sampler_b200 import graphgen
+    for name, (gen, kw, dwargs) in SCALE.items():
+        raw = getattr(graphgen, gen)(**kw)
+        tmp = tempfile.mkdtemp()
+        gio.write_binary(raw, tmp)
+        open(os.path.join(tmp, "dw-args"), "w").write(dwargs)
+        ws, ms, keys = [], [], None
+        for seed in range(1, 6):
+            w, m = run_dw(ol.REF_DW, tmp, seed)
+            ws.append(parse_w(w))
+            mm = parse_m(m)
+            keys = keys or list(mm.keys())
+            ms.append([mm[k] for k in keys])
+        shutil.rmtree(tmp)
+        kv = np.array([[int(x) for x in k.split()] for k in keys], np.int64)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), generator=gen, kwargs=json.dumps(kw),
+                            dw_args=dwargs, weights_mean=np.mean(ws, 0), weights_std=np.std(ws, 0),
+                            marginal_keys=kv, marginals_mean=np.mean(ms, 0).astype(np.float32),
+                            marginals_std=np.std(ms, 0).astype(np.float32), nseeds=5)
+        print(name, "weights", np.mean(ws, 0)[:4], "+-", np.std(ws, 0)[:4], "mean marginal", np.mean(ms))
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF_TEST) and ol.have_ref(), "run `make -C oracle` in the build container first"
     what = sys.argv[1:] or ["graphs", "factor", "logadd", "draw", "sampler"]
@@ -279,3 +316,5 @@ if __name__ == "__main__":
         sampler_kat()
     if "graphs" in what:
         make_graphs()
+    if "scale" in what:
+        make_scale()

@@ -83,9 +83,19 @@ def test_chromatic_classes_are_independent_sets(seed):
 
 
 def test_auto_schedule():
-    assert sb.Graph.from_raw(load_golden_graph("biased_coin")).info.schedule == sb.SCHED_HOGWILD
-    g = sb.Graph.from_raw(load_golden_graph("partial_observation"))
+    # tiny graphs: one sequential chain in id order (the reference's -t 1 semantics)
+    for name in GRAPHS:
+        g = sb.Graph.from_raw(load_golden_graph(name))
+        assert g.info.schedule == sb.SCHED_SEQUENTIAL and g.info.num_colors == 1
+        assert np.array_equal(g.schedule()[0], np.arange(g.info.num_variables))
+    assert sb.Graph.from_raw(load_golden_graph("biased_coin"), sb.SCHED_HOGWILD).info.schedule == sb.SCHED_HOGWILD
+    g = sb.Graph.from_raw(load_golden_graph("partial_observation"), sb.SCHED_CHROMATIC)
     assert g.info.schedule == sb.SCHED_CHROMATIC and g.info.num_colors == 2
+    rng = np.random.default_rng(0)
+    big = random_graph(rng, nvar=200, nfac=600)
+    assert sb.Graph.from_raw(big).info.schedule == sb.SCHED_CHROMATIC
+    unary = random_graph(rng, nvar=200, nfac=600, max_arity=1)
+    assert sb.Graph.from_raw(unary).info.schedule == sb.SCHED_HOGWILD
 
 
 @pytest.mark.parametrize("name", GRAPHS)
