@@ -172,8 +172,9 @@ class Graph:
         _check(load().dwg_graph_var_meta(self._h, _ptr(dtype), _ptr(is_evid), _ptr(base), _ptr(values)))
         return dtype, is_evid, base, values
 
-    _IMG_DTYPES = {"e_fv32": np.float32, "e_fv64": np.float64, "truthiness": np.float64,
-                   "w_init": np.float64}
+    _IMG_DTYPES = {"e_fv32": np.float32, "e_fv64": np.float64, "s_fv32": np.float32, "s_fv64": np.float64,
+                   "truthiness": np.float64, "w_init": np.float64, "cls_N_evid": np.float32,
+                   "cls_Q_evid": np.float32, "cls_N_all": np.float32, "cls_Q_all": np.float32}
 
     def image(self, name: str) -> np.ndarray:
         """copy of one array of the compiled device image (tests)"""

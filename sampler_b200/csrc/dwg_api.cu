@@ -19,6 +19,7 @@
 
 #include "../../include/dwg.h"
 #include "dwg_kernels.cuh"
+#include "dwg_sell.cuh"
 #include "graph_image.h"
 
 using namespace dwg;
@@ -69,29 +70,93 @@ struct dwg_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   int num_sms = 148;
-  // graph
-  DevBuf<uint8_t> var_flags, e_tag, w_fixed, evid_val8;
-  DevBuf<uint32_t> evid_val32, var_row, row_ptr, row_oth, e_wid, oth;
+  // per-variable arrays in schedule order (nvar_pad)
+  DevBuf<uint8_t> var_flags, evid_val8;
+  DevBuf<uint32_t> evid_val32, var_row;
+  // CSR stream: always for categorical graphs; for sliced-ELL graphs only on demand
+  // (parity hooks, sequential debug mode)
+  bool csr_ready = false;
+  DevBuf<uint8_t> e_tag;
+  DevBuf<uint32_t> row_ptr, row_oth, e_wid, oth;
   DevBuf<float> e_fv32;
   DevBuf<double> e_fv64, truthiness;
+  // sliced-ELL stream (Boolean graphs, parallel schedules)
+  DevBuf<uint8_t> s_tag;
+  DevBuf<uint32_t> sl_col, sl_ocol, s_wid, s_oth;
+  DevBuf<float> s_fv32;
+  DevBuf<double> s_fv64;
+  // weights (internal order) and the batch-update statics
+  DevBuf<uint8_t> w_fixed;
+  DevBuf<double> weights, prev_weights, grad_acc, norms;
+  DevBuf<float> cls_N, cls_Q;
+  bool learns = true;  // false: no variable takes an SGD step under these options
   // state
   DevBuf<uint8_t> assign_free8, assign_evid8;
   DevBuf<uint32_t> assign_free32, assign_evid32, tallies;
-  DevBuf<double> weights, prev_weights, norms;
   DevBuf<double> r_free, r_evid;  // parity hook
   bool explicit_r = false, sequential = false;
   uint64_t sweep_counter = 0, infer_sweeps = 0;
   std::vector<uint64_t> extra_nsamples;  // from dwg_add_tallies
   DevGraph dg{};
   DevState ds{};
-  // CUDA graph of one full inference sweep (all colour classes), sweep counter read from
-  // device memory is not needed: the counter only seeds Philox, so each replay must differ --
-  // we therefore capture per-launch kernel nodes and update their params on replay.
+  SellGraph sg{};
+  SellState ss{};
+  int sell_blocks_infer = 0, sell_blocks_learn = 0;
   size_t device_bytes = 0;
   ~dwg_handle() {
     if (stream) cudaStreamDestroy(stream);
   }
 };
+
+// ---- sliced-ELL kernel dispatch over (multi-variable factors?, feature-value mode) ----
+namespace {
+template <typename K>
+int sell_grid(K kernel, size_t smem, int num_sms, int *blocks) {
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SELL_THREADS, smem));
+  if (per_sm < 1) return fail(DWG_ERR_CUDA, "sweep kernel does not fit on an SM");
+  *blocks = per_sm * num_sms;
+  return DWG_OK;
+}
+template <bool MULTI, int FV>
+int sell_setup_t(dwg_handle *h) {
+  const size_t n_hot = h->img->n_hot;
+  int rc = sell_grid(k_sell_infer<MULTI, FV>, 8 * n_hot, h->num_sms, &h->sell_blocks_infer);
+  if (rc) return rc;
+  return sell_grid(k_sell_learn<MULTI, FV>, 16 * n_hot, h->num_sms, &h->sell_blocks_learn);
+}
+template <bool MULTI, int FV>
+void sell_launch_t(dwg_handle *h, bool learn, uint32_t blocks, const SellGraph &sg, const SweepParams &p) {
+  const size_t n_hot = h->img->n_hot;
+  if (learn) k_sell_learn<MULTI, FV><<<blocks, SELL_THREADS, 16 * n_hot, h->stream>>>(sg, h->ss, p);
+  else k_sell_infer<MULTI, FV><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
+}
+#define SELL_SWITCH(CALL)                                                      \
+  if (m.has_multi) {                                                           \
+    if (m.fv_mode == FV_ONE) { CALL(true, FV_ONE); }                           \
+    else if (m.fv_mode == FV_F32) { CALL(true, FV_F32); }                      \
+    else { CALL(true, FV_F64); }                                               \
+  } else {                                                                     \
+    if (m.fv_mode == FV_ONE) { CALL(false, FV_ONE); }                          \
+    else if (m.fv_mode == FV_F32) { CALL(false, FV_F32); }                     \
+    else { CALL(false, FV_F64); }                                              \
+  }
+int sell_setup(dwg_handle *h) {
+  const GraphImage &m = *h->img;
+  int rc = DWG_OK;
+#define CALL(MU, FV) rc = sell_setup_t<MU, FV>(h)
+  SELL_SWITCH(CALL)
+#undef CALL
+  return rc;
+}
+void sell_launch(dwg_handle *h, bool learn, uint32_t blocks, const SellGraph &sg, const SweepParams &p) {
+  const GraphImage &m = *h->img;
+#define CALL(MU, FV) sell_launch_t<MU, FV>(h, learn, blocks, sg, p)
+  SELL_SWITCH(CALL)
+#undef CALL
+}
+}  // namespace
 
 extern "C" {
 
@@ -163,12 +228,18 @@ void dwg_graph_free(dwg_graph *g) { delete g; }
 
 static size_t image_device_bytes(const GraphImage &m) {
   size_t b = 0;
-  b += m.var_flags.size() + m.e_tag.size() + m.w_fixed.size();
-  b += (size_t)m.assign_bytes * m.nvar * 3;  // evid_val + two chains
-  b += 4 * (m.var_row.size() + m.row_ptr.size() + m.row_oth.size() + m.e_wid.size() + m.oth.size());
-  b += 4 * m.e_fv32.size() + 8 * m.e_fv64.size() + 8 * m.truthiness.size();
-  b += 4 * m.nrow;         // tallies
-  b += 8 * 2 * m.nweight;  // weights + prev
+  b += m.var_flags.size() + m.w_fixed.size();
+  b += (size_t)m.assign_bytes * m.nvar_pad * 3;  // evid_val + two chains
+  if (m.sell) {
+    b += m.s_tag.size() + 4 * (m.s_wid.size() + m.s_oth.size() + m.sl_col.size() + m.sl_ocol.size());
+    b += 4 * m.s_fv32.size() + 8 * m.s_fv64.size();
+  } else {
+    b += m.e_tag.size() + 4 * (m.var_row.size() + m.row_ptr.size() + m.row_oth.size() + m.e_wid.size() + m.oth.size());
+    b += 4 * m.e_fv32.size() + 8 * m.e_fv64.size() + 8 * m.truthiness.size();
+  }
+  b += 4 * m.ndrow;        // tallies
+  b += 8 * 3 * m.nweight;  // weights + prev + gradient sums
+  b += 4 * 2 * (m.cls_N_evid.size());
   return b;
 }
 
@@ -204,8 +275,17 @@ int dwg_graph_var_meta(const dwg_graph *g, uint8_t *dtype, uint8_t *is_evid, uin
 int dwg_debug_schedule(const dwg_graph *g, uint64_t *perm, uint64_t *color_start) {
   if (!g) return fail(DWG_ERR_INVALID, "null argument");
   const GraphImage &m = g->img;
-  if (perm) for (uint64_t d = 0; d < m.nvar; ++d) perm[d] = m.perm[d];
-  if (color_start) for (size_t c = 0; c < m.color_start.size(); ++c) color_start[c] = m.color_start[c];
+  // pads (class fillers of sliced-ELL graphs) are not variables: report the compact order
+  uint64_t k = 0;
+  for (uint32_t c = 0; c < m.ncolor(); ++c) {
+    if (color_start) color_start[c] = k;
+    for (uint64_t d = m.color_start[c]; d < m.color_start[c + 1]; ++d)
+      if (m.perm[d] != 0xffffffffu) {
+        if (perm) perm[k] = m.perm[d];
+        ++k;
+      }
+  }
+  if (color_start) color_start[m.ncolor()] = k;
   return DWG_OK;
 }
 
@@ -222,7 +302,9 @@ int dwg_debug_image(const dwg_graph *g, const char *name, const void **data, uin
   }
   ARR(perm) ARR(inv) ARR(color_start) ARR(var_flags) ARR(evid_val) ARR(var_row) ARR(row_ptr)
   ARR(row_oth) ARR(truthiness) ARR(e_wid) ARR(e_fv32) ARR(e_fv64) ARR(e_tag) ARR(oth) ARR(w_init)
-  ARR(w_fixed) ARR(row_of_value) ARR(values) ARR(value_base)
+  ARR(w_fixed) ARR(row_of_value) ARR(values) ARR(value_base) ARR(w_perm) ARR(w_inv)
+  ARR(sl_col) ARR(sl_ocol) ARR(s_tag) ARR(s_wid) ARR(s_fv32) ARR(s_fv64) ARR(s_oth)
+  ARR(cls_N_evid) ARR(cls_Q_evid) ARR(cls_N_all) ARR(cls_Q_all)
 #undef ARR
   if (n == "oth_packed") {
     static thread_local uint32_t v;
@@ -238,14 +320,43 @@ static int init_state(dwg_handle *h) {
   // value (0 for query variables); weights from the Weight records; tallies cleared.
   const GraphImage &m = *h->img;
   if (m.assign_bytes == 1) {
-    CU(cudaMemcpyAsync(h->assign_free8.p, h->evid_val8.p, m.nvar, cudaMemcpyDeviceToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->assign_evid8.p, h->evid_val8.p, m.nvar, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->assign_free8.p, h->evid_val8.p, m.nvar_pad, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->assign_evid8.p, h->evid_val8.p, m.nvar_pad, cudaMemcpyDeviceToDevice, h->stream));
   } else {
-    CU(cudaMemcpyAsync(h->assign_free32.p, h->evid_val32.p, 4 * m.nvar, cudaMemcpyDeviceToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->assign_evid32.p, h->evid_val32.p, 4 * m.nvar, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->assign_free32.p, h->evid_val32.p, 4 * m.nvar_pad, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->assign_evid32.p, h->evid_val32.p, 4 * m.nvar_pad, cudaMemcpyDeviceToDevice, h->stream));
   }
-  CU(cudaMemsetAsync(h->tallies.p, 0, 4 * m.nrow + 16, h->stream));
+  CU(cudaMemsetAsync(h->tallies.p, 0, 4 * m.ndrow + 16, h->stream));
+  CU(cudaMemsetAsync(h->grad_acc.p, 0, 8 * m.nweight + 16, h->stream));
   h->infer_sweeps = 0;
+  return DWG_OK;
+}
+
+// CSR stream on the device (graph_image.h): resident from the start for categorical graphs,
+// uploaded on first use for sliced-ELL graphs
+static int ensure_csr(dwg_handle *h) {
+  if (h->csr_ready) return DWG_OK;
+  const GraphImage &m = *h->img;
+  cudaStream_t s = h->stream;
+  CU(cudaSetDevice(h->device));
+  CU(h->e_tag.upload(m.e_tag, s));
+  CU(h->row_ptr.upload(m.row_ptr, s));
+  CU(h->e_wid.upload(m.e_wid, s));
+  if (m.has_multi) { CU(h->row_oth.upload(m.row_oth, s)); CU(h->oth.upload(m.oth, s)); }
+  if (m.fv_mode == FV_F32) CU(h->e_fv32.upload(m.e_fv32, s));
+  if (m.fv_mode == FV_F64) CU(h->e_fv64.upload(m.e_fv64, s));
+  if (m.has_truthiness) CU(h->truthiness.upload(m.truthiness, s));
+  CU(cudaStreamSynchronize(s));
+  DevGraph &dg = h->dg;
+  dg.row_ptr = h->row_ptr.p;
+  dg.row_oth = m.has_multi ? h->row_oth.p : nullptr;
+  dg.truthiness = m.has_truthiness ? h->truthiness.p : nullptr;
+  dg.e_wid = h->e_wid.p;
+  dg.e_fv32 = m.fv_mode == FV_F32 ? h->e_fv32.p : nullptr;
+  dg.e_fv64 = m.fv_mode == FV_F64 ? h->e_fv64.p : nullptr;
+  dg.e_tag = h->e_tag.p;
+  dg.oth = h->oth.p;
+  h->csr_ready = true;
   return DWG_OK;
 }
 
@@ -270,55 +381,81 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
   const GraphImage &m = g->img;
   cudaStream_t s = h->stream;
   CU(h->var_flags.upload(m.var_flags, s));
-  CU(h->e_tag.upload(m.e_tag, s));
-  CU(h->w_fixed.upload(m.w_fixed, s));
-  CU(h->row_ptr.upload(m.row_ptr, s));
-  CU(h->e_wid.upload(m.e_wid, s));
   if (m.has_categorical) CU(h->var_row.upload(m.var_row, s));
-  if (m.has_multi) { CU(h->row_oth.upload(m.row_oth, s)); CU(h->oth.upload(m.oth, s)); }
-  if (m.fv_mode == FV_F32) CU(h->e_fv32.upload(m.e_fv32, s));
-  if (m.fv_mode == FV_F64) CU(h->e_fv64.upload(m.e_fv64, s));
-  if (m.has_truthiness) CU(h->truthiness.upload(m.truthiness, s));
-  std::vector<uint8_t> ev8;
+  std::vector<uint8_t> ev8, fixed_dev(m.nweight);
+  std::vector<double> w_dev(m.nweight);
+  for (uint64_t i = 0; i < m.nweight; ++i) {
+    w_dev[i] = m.w_init[m.w_perm[i]];
+    fixed_dev[i] = m.w_fixed[m.w_perm[i]];
+  }
   if (m.assign_bytes == 1) {
     ev8.assign(m.evid_val.begin(), m.evid_val.end());
     CU(h->evid_val8.upload(ev8, s));
-    CU(h->assign_free8.alloc(m.nvar));
-    CU(h->assign_evid8.alloc(m.nvar));
+    CU(h->assign_free8.alloc(m.nvar_pad));
+    CU(h->assign_evid8.alloc(m.nvar_pad));
   } else {
     CU(h->evid_val32.upload(m.evid_val, s));
-    CU(h->assign_free32.alloc(m.nvar));
-    CU(h->assign_evid32.alloc(m.nvar));
+    CU(h->assign_free32.alloc(m.nvar_pad));
+    CU(h->assign_evid32.alloc(m.nvar_pad));
   }
-  CU(h->tallies.alloc(m.nrow));
-  CU(h->weights.upload(m.w_init, s));
-  CU(h->prev_weights.upload(m.w_init, s));
+  CU(h->tallies.alloc(m.ndrow));
+  CU(h->w_fixed.upload(fixed_dev, s));
+  CU(h->weights.upload(w_dev, s));
+  CU(h->prev_weights.upload(w_dev, s));
+  CU(h->grad_acc.alloc(m.nweight));
   CU(h->norms.alloc(2));
+  // which variables take SGD steps decides the per-launch update counts (compile.cc)
+  {
+    const bool all = h->opts.learn_non_evidence;
+    CU(h->cls_N.upload(all ? m.cls_N_all : m.cls_N_evid, s));
+    CU(h->cls_Q.upload(all ? m.cls_Q_all : m.cls_Q_evid, s));
+  }
+  if (m.sell) {
+    CU(h->sl_col.upload(m.sl_col, s));
+    CU(h->s_tag.upload(m.s_tag, s));
+    CU(h->s_wid.upload(m.s_wid, s));
+    if (m.has_multi) { CU(h->sl_ocol.upload(m.sl_ocol, s)); CU(h->s_oth.upload(m.s_oth, s)); }
+    if (m.fv_mode == FV_F32) CU(h->s_fv32.upload(m.s_fv32, s));
+    if (m.fv_mode == FV_F64) CU(h->s_fv64.upload(m.s_fv64, s));
+    // Boolean variables have no truthiness: under --noise_aware only --learn_non_evidence learns
+    h->learns = h->opts.learn_non_evidence || !h->opts.noise_aware;
+  }
   int rc = init_state(h.get());
   if (rc) return rc;
-  CU(cudaStreamSynchronize(s));  // ev8 goes out of scope; uploads must have landed
+  CU(cudaStreamSynchronize(s));  // the staging vectors go out of scope
   h->device_bytes = image_device_bytes(m);
 
   DevGraph &dg = h->dg;
-  dg.nvar = (uint32_t)m.nvar; dg.nrow = (uint32_t)m.nrow;
+  dg.nvar = (uint32_t)m.nvar_pad; dg.nrow = (uint32_t)m.ndrow;
   dg.var_flags = h->var_flags.p;
   dg.evid_val = m.assign_bytes == 1 ? (const void *)h->evid_val8.p : (const void *)h->evid_val32.p;
   dg.var_row = m.has_categorical ? h->var_row.p : nullptr;
-  dg.row_ptr = h->row_ptr.p;
-  dg.row_oth = m.has_multi ? h->row_oth.p : nullptr;
-  dg.truthiness = m.has_truthiness ? h->truthiness.p : nullptr;
-  dg.e_wid = h->e_wid.p;
-  dg.e_fv32 = m.fv_mode == FV_F32 ? h->e_fv32.p : nullptr;
-  dg.e_fv64 = m.fv_mode == FV_F64 ? h->e_fv64.p : nullptr;
-  dg.e_tag = h->e_tag.p;
-  dg.oth = h->oth.p;
   dg.oth_packed = m.oth_packed;
   dg.w_fixed = h->w_fixed.p;
   DevState &ds = h->ds;
   ds.assign_free = m.assign_bytes == 1 ? (void *)h->assign_free8.p : (void *)h->assign_free32.p;
   ds.assign_evid = m.assign_bytes == 1 ? (void *)h->assign_evid8.p : (void *)h->assign_evid32.p;
   ds.weights = h->weights.p;
+  ds.grad_acc = h->grad_acc.p;
   ds.tallies = h->tallies.p;
+  if (!m.sell) {
+    rc = ensure_csr(h.get());
+    if (rc) return rc;
+  } else {
+    SellGraph &sg = h->sg;
+    sg.sl_col = h->sl_col.p; sg.sl_ocol = m.has_multi ? h->sl_ocol.p : nullptr;
+    sg.tag = h->s_tag.p; sg.wid = h->s_wid.p;
+    sg.fv32 = m.fv_mode == FV_F32 ? h->s_fv32.p : nullptr;
+    sg.fv64 = m.fv_mode == FV_F64 ? h->s_fv64.p : nullptr;
+    sg.oth = h->s_oth.p;
+    sg.var_flags = h->var_flags.p; sg.evid_val = h->evid_val8.p; sg.w_fixed = h->w_fixed.p;
+    sg.nweight = (uint32_t)m.nweight; sg.n_hot = m.n_hot;
+    SellState &ss = h->ss;
+    ss.assign_free = h->assign_free8.p; ss.assign_evid = h->assign_evid8.p;
+    ss.weights = h->weights.p; ss.grad_acc = h->grad_acc.p; ss.tallies = h->tallies.p;
+    rc = sell_setup(h.get());
+    if (rc) return rc;
+  }
   *out = h.release();
   return DWG_OK;
 }
@@ -354,22 +491,45 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
   CU(cudaSetDevice(h->device));
   SweepParams p = make_params(h, stepsize);
   ++h->sweep_counter;
+  const bool use_sell = m.sell && !p.sequential;
+  if (!use_sell) {
+    int rc = ensure_csr(h);
+    if (rc) return rc;
+  }
   for (uint32_t c = 0; c < m.ncolor(); ++c) {
     p.d_begin = m.color_start[c];
     p.d_end = m.color_start[c + 1];
     const uint32_t n = p.d_end - p.d_begin;
     if (!n) continue;
-    uint32_t blocks = (n + SWEEP_THREADS - 1) / SWEEP_THREADS;
-    uint32_t threads = SWEEP_THREADS;
-    if (p.sequential) { blocks = 1; threads = 1; }
-    if (m.assign_bytes == 1) {
-      if (learn) k_sweep_learn<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
-      else k_sweep_infer<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+    if (use_sell) {
+      SellGraph sg = h->sg;
+      sg.slice_begin = p.d_begin / 32;
+      sg.slice_end = p.d_end / 32;
+      const uint32_t need = (sg.slice_end - sg.slice_begin + SELL_THREADS / 32 - 1) / (SELL_THREADS / 32);
+      const uint32_t cap = (uint32_t)(learn ? h->sell_blocks_learn : h->sell_blocks_infer);
+      sell_launch(h, learn, std::min<uint32_t>(need, cap), sg, p);
     } else {
-      if (learn) k_sweep_learn<uint32_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
-      else k_sweep_infer<uint32_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+      uint32_t blocks = (n + SWEEP_THREADS - 1) / SWEEP_THREADS;
+      uint32_t threads = SWEEP_THREADS;
+      if (p.sequential) { blocks = 1; threads = 1; }
+      if (m.assign_bytes == 1) {
+        if (learn) k_sweep_learn<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+        else k_sweep_infer<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+      } else {
+        if (learn) k_sweep_learn<uint32_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+        else k_sweep_infer<uint32_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+      }
     }
     ++g_launches;
+    if (learn && !p.sequential && m.nweight && (!use_sell || h->learns)) {
+      // integrate this launch's SGD steps (k_apply_weights): the sliced-ELL kernel sums bare
+      // gradients (decay from the static update counts), the CSR kernel sums gradient + decay
+      const size_t row = m.cls_shared ? 0 : (size_t)c * m.nweight;
+      k_apply_weights<<<(uint32_t)((m.nweight + 255) / 256), 256, 0, h->stream>>>(
+          h->weights.p, h->grad_acc.p, h->cls_N.p + row, h->cls_Q.p + row, h->w_fixed.p,
+          (uint32_t)m.nweight, stepsize, h->opts.reg_param, p.reg_l1, use_sell ? 0 : 1);
+      ++g_launches;
+    }
   }
   CU(cudaGetLastError());
   return DWG_OK;
@@ -409,7 +569,7 @@ void *dwg_tallies_device_ptr(dwg_handle *h) { return h ? (void *)h->tallies.p : 
 int dwg_clear_tallies(dwg_handle *h) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemsetAsync(h->tallies.p, 0, 4 * h->img->nrow, h->stream));
+  CU(cudaMemsetAsync(h->tallies.p, 0, 4 * h->img->ndrow, h->stream));
   h->infer_sweeps = 0;
   h->extra_nsamples.clear();
   return DWG_OK;
@@ -420,8 +580,8 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   if (tallies) {
-    std::vector<uint32_t> t(m.nrow);
-    CU(cudaMemcpyAsync(t.data(), h->tallies.p, 4 * m.nrow, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<uint32_t> t(m.ndrow);
+    CU(cudaMemcpyAsync(t.data(), h->tallies.p, 4 * m.ndrow, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     for (uint64_t i = 0; i < m.nrow; ++i) tallies[i] = t[m.row_of_value[i]];
   }
@@ -439,12 +599,12 @@ int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsam
   if (!h || !tallies || !nsamples) return fail(DWG_ERR_INVALID, "null argument");
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
-  std::vector<uint32_t> t(m.nrow);
+  std::vector<uint32_t> t(m.ndrow, 0);
   for (uint64_t i = 0; i < m.nrow; ++i) t[m.row_of_value[i]] = (uint32_t)tallies[i];
   DevBuf<uint32_t> tmp;
   CU(tmp.upload(t, h->stream));
-  if (m.nrow) {
-    k_add_u32<<<(uint32_t)((m.nrow + 255) / 256), 256, 0, h->stream>>>(h->tallies.p, tmp.p, (uint32_t)m.nrow);
+  if (m.ndrow) {
+    k_add_u32<<<(uint32_t)((m.ndrow + 255) / 256), 256, 0, h->stream>>>(h->tallies.p, tmp.p, (uint32_t)m.ndrow);
     ++g_launches;
   }
   CU(cudaStreamSynchronize(h->stream));
@@ -455,17 +615,23 @@ int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsam
 
 int dwg_get_weights(dwg_handle *h, double *out) {
   if (!h || !out) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(out, h->weights.p, 8 * h->img->nweight, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<double> t(m.nweight);
+  CU(cudaMemcpyAsync(t.data(), h->weights.p, 8 * m.nweight, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  for (uint64_t i = 0; i < m.nweight; ++i) out[m.w_perm[i]] = t[i];
   return DWG_OK;
 }
 
 int dwg_set_weights(dwg_handle *h, const double *in) {
   if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(h->weights.p, in, 8 * h->img->nweight, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->prev_weights.p, in, 8 * h->img->nweight, cudaMemcpyHostToDevice, h->stream));
+  std::vector<double> t(m.nweight);
+  for (uint64_t i = 0; i < m.nweight; ++i) t[i] = in[m.w_perm[i]];
+  CU(cudaMemcpyAsync(h->weights.p, t.data(), 8 * m.nweight, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->prev_weights.p, t.data(), 8 * m.nweight, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return DWG_OK;
 }
@@ -476,15 +642,15 @@ int dwg_get_assignments(dwg_handle *h, int evid_chain, uint64_t *out) {
   CU(cudaSetDevice(h->device));
   const void *src = evid_chain ? h->ds.assign_evid : h->ds.assign_free;
   if (m.assign_bytes == 1) {
-    std::vector<uint8_t> t(m.nvar);
-    CU(cudaMemcpyAsync(t.data(), src, m.nvar, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<uint8_t> t(m.nvar_pad);
+    CU(cudaMemcpyAsync(t.data(), src, m.nvar_pad, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    for (uint64_t d = 0; d < m.nvar; ++d) out[m.perm[d]] = t[d];
+    for (uint64_t v = 0; v < m.nvar; ++v) out[v] = t[m.inv[v]];
   } else {
-    std::vector<uint32_t> t(m.nvar);
-    CU(cudaMemcpyAsync(t.data(), src, 4 * m.nvar, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<uint32_t> t(m.nvar_pad);
+    CU(cudaMemcpyAsync(t.data(), src, 4 * m.nvar_pad, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    for (uint64_t d = 0; d < m.nvar; ++d) out[m.perm[d]] = t[d];
+    for (uint64_t v = 0; v < m.nvar; ++v) out[v] = t[m.inv[v]];
   }
   return DWG_OK;
 }
@@ -495,14 +661,14 @@ int dwg_set_assignments(dwg_handle *h, int evid_chain, const uint64_t *in) {
   CU(cudaSetDevice(h->device));
   void *dst = evid_chain ? h->ds.assign_evid : h->ds.assign_free;
   if (m.assign_bytes == 1) {
-    std::vector<uint8_t> t(m.nvar);
-    for (uint64_t d = 0; d < m.nvar; ++d) t[d] = (uint8_t)in[m.perm[d]];
-    CU(cudaMemcpyAsync(dst, t.data(), m.nvar, cudaMemcpyHostToDevice, h->stream));
+    std::vector<uint8_t> t(m.nvar_pad, 0);
+    for (uint64_t v = 0; v < m.nvar; ++v) t[m.inv[v]] = (uint8_t)in[v];
+    CU(cudaMemcpyAsync(dst, t.data(), m.nvar_pad, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   } else {
-    std::vector<uint32_t> t(m.nvar);
-    for (uint64_t d = 0; d < m.nvar; ++d) t[d] = (uint32_t)in[m.perm[d]];
-    CU(cudaMemcpyAsync(dst, t.data(), 4 * m.nvar, cudaMemcpyHostToDevice, h->stream));
+    std::vector<uint32_t> t(m.nvar_pad, 0);
+    for (uint64_t v = 0; v < m.nvar; ++v) t[m.inv[v]] = (uint32_t)in[v];
+    CU(cudaMemcpyAsync(dst, t.data(), 4 * m.nvar_pad, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   }
   return DWG_OK;
@@ -650,7 +816,7 @@ int dwg_reduce_tallies_multi(dwg_handle *const *hs, void *const *comms, int n) {
     int rc = api.GroupStart();
     if (rc) return nccl_fail(rc, "ncclGroupStart");
     for (int i = 0; i < n; ++i) {
-      rc = api.Reduce(hs[i]->tallies.p, hs[i]->tallies.p, m.nrow, NCCL_UINT32, NCCL_SUM, 0, comms[i], hs[i]->stream);
+      rc = api.Reduce(hs[i]->tallies.p, hs[i]->tallies.p, m.ndrow, NCCL_UINT32, NCCL_SUM, 0, comms[i], hs[i]->stream);
       if (rc) { api.GroupEnd(); return nccl_fail(rc, "ncclReduce"); }
     }
     rc = api.GroupEnd();
@@ -674,6 +840,10 @@ int dwg_eval_potentials(dwg_handle *h, uint64_t n, const uint64_t *vids, const u
   if (!h || !vids || !proposals || !out) return fail(DWG_ERR_INVALID, "null argument");
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
+  {
+    int rc = ensure_csr(h);
+    if (rc) return rc;
+  }
   std::vector<uint32_t> ds(n), ps(n);
   for (uint64_t i = 0; i < n; ++i) {
     if (vids[i] >= m.nvar) return fail(DWG_ERR_INVALID, "variable id out of range");
@@ -742,14 +912,14 @@ int dwg_debug_set_uniforms(dwg_handle *h, const double *r_free, const double *r_
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   if (!r_free) { h->explicit_r = false; return DWG_OK; }
-  std::vector<double> a(m.nvar), b(m.nvar, 0.0);
-  for (uint64_t d = 0; d < m.nvar; ++d) {
-    a[d] = r_free[m.perm[d]];
-    if (r_evid) b[d] = r_evid[m.perm[d]];
+  std::vector<double> a(m.nvar_pad, 0.0), b(m.nvar_pad, 0.0);
+  for (uint64_t v = 0; v < m.nvar; ++v) {
+    a[m.inv[v]] = r_free[v];
+    if (r_evid) b[m.inv[v]] = r_evid[v];
   }
-  if (!h->r_free.p) { CU(h->r_free.alloc(m.nvar)); CU(h->r_evid.alloc(m.nvar)); }
-  CU(cudaMemcpyAsync(h->r_free.p, a.data(), 8 * m.nvar, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->r_evid.p, b.data(), 8 * m.nvar, cudaMemcpyHostToDevice, h->stream));
+  if (!h->r_free.p) { CU(h->r_free.alloc(m.nvar_pad)); CU(h->r_evid.alloc(m.nvar_pad)); }
+  CU(cudaMemcpyAsync(h->r_free.p, a.data(), 8 * m.nvar_pad, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->r_evid.p, b.data(), 8 * m.nvar_pad, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   h->explicit_r = true;
   return DWG_OK;

@@ -36,8 +36,9 @@ struct DevGraph {
 
 struct DevState {
   void *assign_free, *assign_evid;  // AssignT[nvar]
-  double *weights;                  // f64[nweight]
-  uint32_t *tallies;                // u32[nrow]
+  double *weights;                  // f64[nweight], internal weight order
+  double *grad_acc;                 // f64[nweight] gradient sums of the current learning launch
+  uint32_t *tallies;                // u32[ndrow]
 };
 
 struct SweepParams {
@@ -77,6 +78,18 @@ __host__ __device__ inline double u01(uint32_t hi, uint32_t lo) {
 }
 
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void dev_uniforms(const SweepParams &p, uint32_t d, double &r0, double &r1) {
+  if (p.r_free) {
+    r0 = p.r_free[d];
+    r1 = p.r_evid ? p.r_evid[d] : 0.0;
+    return;
+  }
+  uint32_t o[4];
+  philox4x32_10(d, 0u, p.sweep_lo, p.sweep_hi, p.key0, p.key1, o);
+  r0 = u01(o[0], o[1]);
+  r1 = u01(o[2], o[3]);
+}
 
 // log2(1 + k) for k < 64 as the HOST libm rounds it (filled once by dwg_api.cu): FUNC_RATIO
 // (src/factor.h:264-277) takes log2 of a small integer, and CUDA's log2 may differ from
@@ -216,12 +229,12 @@ __device__ __forceinline__ double dev_acc(double pot, double w, double sign, dou
 
 // FactorGraph::potential for a Boolean variable, both proposals in one pass over its row
 // (src/factor_graph.h:127-145; draw_sample evaluates proposal 1 then 0, gibbs_sampler.h:201-202)
-// LIVE: weights are being updated by concurrent atomics (learning): read them at L2
-// (ld.global.cg) so a sweep sees other blocks' updates, Hogwild-style; otherwise they are
-// constant for the launch and go through the read-only path.
+// LIVE: the launch itself rewrites weights (the sequential schedule's per-step update), so they
+// are read with ordinary coherent loads; otherwise they are constant for the launch and go
+// through the read-only path.
 template <bool LIVE>
 __device__ __forceinline__ double dev_weight(const double *w, uint32_t wid) {
-  return LIVE ? __ldcg(w + wid) : __ldg(w + wid);
+  return LIVE ? w[wid] : __ldg(w + wid);
 }
 
 template <typename AssignT, bool LIVE>

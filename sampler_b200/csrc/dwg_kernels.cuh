@@ -17,18 +17,6 @@ namespace dwg {
 
 constexpr int SWEEP_THREADS = 256;
 
-__device__ __forceinline__ void dev_uniforms(const SweepParams &p, uint32_t d, double &r0, double &r1) {
-  if (p.r_free) {
-    r0 = p.r_free[d];
-    r1 = p.r_evid ? p.r_evid[d] : 0.0;
-    return;
-  }
-  uint32_t o[4];
-  philox4x32_10(d, 0u, p.sweep_lo, p.sweep_hi, p.key0, p.key1, o);
-  r0 = u01(o[0], o[1]);
-  r1 = u01(o[2], o[3]);
-}
-
 template <typename AssignT, bool LIVE>
 __device__ __forceinline__ uint32_t dev_draw_sample(const DevGraph &g, uint32_t d, bool cat,
                                                     uint32_t row0, uint32_t K, const AssignT *a,
@@ -48,6 +36,7 @@ k_sweep_infer(const DevGraph g, const DevState st, const SweepParams p) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t d = p.d_begin + blockIdx.x * blockDim.x + threadIdx.x; d < p.d_end; d += stride) {
     const uint8_t fl = __ldg(g.var_flags + d);
+    if (fl & VF_PAD) continue;
     if ((fl & VF_EVID) && !p.sample_evidence) continue;  // gibbs_sampler.h:157
     const bool cat = fl & VF_CATEGORICAL;
     uint32_t row0 = d, K = 1;
@@ -66,30 +55,31 @@ k_sweep_infer(const DevGraph g, const DevState st, const SweepParams p) {
   }
 }
 
-// InferenceResult::update_weight, src/inference_result.h:66-85.  Concurrent mode: the
-// same update expressed as one atomicAdd of  w*(c-1) - diff  (l2, c = 1/(1+reg*step)) or
-// reg*(w<0) - diff  (l1, sic) on a weight read at L2 -- exact when reg == 0, Hogwild otherwise.
-// Sequential mode (parity hook): the reference's read-modify-write, bit for bit.
-__device__ __forceinline__ void dev_update_weight(double *w, uint32_t wid, const SweepParams &p,
-                                                  double step, double grad) {
-  const double diff = __dmul_rn(step, grad);
+// InferenceResult::update_weight, src/inference_result.h:66-85, for one SGD step with
+// stepsize step*t (t = truthiness under --noise_aware, else 1).
+// Sequential schedule: the reference's read-modify-write, bit for bit.
+// Parallel schedules: weights are frozen for the launch; the step's gradient AND its decay,
+//   t*g + t*reg/(1+reg*step*t) * w      (l2)      t*g - reg*(w<0)/step      (l1, sic)
+// are summed into grad_acc[wid]; k_apply_weights (dwg_sell.cuh) integrates the launch.
+__device__ __forceinline__ void dev_update_weight(const DevState &st, uint32_t wid, const SweepParams &p,
+                                                  double t, double grad) {
+  double *w = st.weights;
   if (p.sequential) {
+    const double step = __dmul_rn(p.stepsize, t);
+    const double diff = __dmul_rn(step, grad);
     double x = w[wid];
     if (p.reg_l1) x = __dadd_rn(x, __dmul_rn(p.reg_param, x < 0 ? 1.0 : 0.0));
     else x = __dmul_rn(x, __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(p.reg_param, step))));
     w[wid] = __dsub_rn(x, diff);
     return;
   }
-  double delta = -diff;
+  double sum = t * grad;
   if (p.reg_param != 0.0) {
-    const double x = __ldcg(w + wid);
-    if (p.reg_l1) delta += p.reg_param * (x < 0 ? 1.0 : 0.0);
-    else {
-      const double rs = p.reg_param * step;
-      delta += x * (-rs / (1.0 + rs));
-    }
+    const double x = w[wid];
+    if (p.reg_l1) sum -= p.reg_param * (x < 0 ? 1.0 : 0.0) / p.stepsize;
+    else sum += t * p.reg_param / (1.0 + p.reg_param * p.stepsize * t) * x;
   }
-  if (delta != 0.0) atomicAdd(w + wid, delta);
+  if (sum != 0.0) atomicAdd(st.grad_acc + wid, sum);
 }
 
 // sgd_on_factor over one row, src/factor_graph.cc:243-260: for every non-fixed factor,
@@ -97,7 +87,7 @@ __device__ __forceinline__ void dev_update_weight(double *w, uint32_t wid, const
 template <typename AssignT>
 __device__ __forceinline__ void dev_sgd_row(const DevGraph &g, const DevState &st, const SweepParams &p,
                                             uint32_t d, uint32_t row, bool cat, uint32_t key,
-                                            uint32_t x_evid, uint32_t x_free, double step) {
+                                            uint32_t x_evid, uint32_t x_free, double t) {
   const AssignT *af = static_cast<const AssignT *>(st.assign_free);
   const AssignT *ae = static_cast<const AssignT *>(st.assign_evid);
   const uint32_t e0 = __ldg(g.row_ptr + row), e1 = __ldg(g.row_ptr + row + 1);
@@ -111,7 +101,7 @@ __device__ __forceinline__ void dev_sgd_row(const DevGraph &g, const DevState &s
       cur.signs(tag, cat, key, ae, x_evid, x_evid, se, unused);
       cur.signs(tag, cat, key, af, x_free, x_free, sf, unused);
       const double grad = __dsub_rn(__dmul_rn(sf, fv), __dmul_rn(se, fv));  // :255-258
-      dev_update_weight(st.weights, wid, p, step, grad);
+      dev_update_weight(st, wid, p, t, grad);
     }
     cur.advance(tag);
   }
@@ -126,6 +116,7 @@ k_sweep_learn(const DevGraph g, const DevState st, const SweepParams p) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t d = p.d_begin + blockIdx.x * blockDim.x + threadIdx.x; d < p.d_end; d += stride) {
     const uint8_t fl = __ldg(g.var_flags + d);
+    if (fl & VF_PAD) continue;
     const bool cat = fl & VF_CATEGORICAL, evid = fl & VF_EVID, truthy = fl & VF_TRUTHINESS;
     uint32_t row0 = d, K = 1;
     if (g.var_row) {
@@ -159,7 +150,7 @@ k_sweep_learn(const DevGraph g, const DevState st, const SweepParams p) {
     // sgd_on_variable, src/factor_graph.cc:262-314
     if (!cat) {
       // Boolean: evidence_value is Variable::assignment_dense even for a query variable (:272)
-      dev_sgd_row<AssignT>(g, st, p, d, row0, false, 0u, ev, pf, p.stepsize);
+      dev_sgd_row<AssignT>(g, st, p, d, row0, false, 0u, ev, pf, 1.0);
     } else {
       for (uint32_t val = 0; val < K; ++val) {
         if (!p.noise_aware && val != ev) continue;  // :280
@@ -168,10 +159,9 @@ k_sweep_learn(const DevGraph g, const DevState st, const SweepParams p) {
           t = g.truthiness ? g.truthiness[row0 + val] : 0.0;
           if (t <= 0.000001 && t >= -0.000001) continue;  // is_linear_zero :283
         }
-        const double step = __dmul_rn(p.stepsize, t);
-        dev_sgd_row<AssignT>(g, st, p, d, row0 + val, true, val, val, pf, step);  // :288-292
+        dev_sgd_row<AssignT>(g, st, p, d, row0 + val, true, val, val, pf, t);  // :288-292
         if (val == pf) continue;  // :304
-        dev_sgd_row<AssignT>(g, st, p, d, row0 + pf, true, pf, val, pf, step);  // :306-311
+        dev_sgd_row<AssignT>(g, st, p, d, row0 + pf, true, pf, val, pf, t);  // :306-311
       }
     }
   }

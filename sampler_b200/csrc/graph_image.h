@@ -33,6 +33,15 @@ constexpr uint8_t FORM_GENERAL = 3;
 constexpr uint8_t VF_EVID = 1;
 constexpr uint8_t VF_CATEGORICAL = 2;
 constexpr uint8_t VF_TRUTHINESS = 4;  // has_truthiness(), src/variable.h:105
+constexpr uint8_t VF_PAD = 0x80;      // filler slot that rounds a colour class up to 32 variables
+
+// sliced-ELL tag byte (Boolean-only graphs): [7:6] form as above.  Unary records carry the
+// two signs themselves: [1:0] sign when the variable is 1, [3:2] when it is 0, coded
+// 0 -> -1, 1 -> 0, 2 -> +1; multi-variable records keep the CSR tag; SELL_NOP pads a slice.
+constexpr uint8_t SELL_NOP = 0xff;
+
+// weights with internal id < n_hot are staged in shared memory by the sweep kernels
+#define DWG_HOT_WEIGHTS 4096
 
 enum FvMode : int { FV_ONE = 0, FV_F32 = 1, FV_F64 = 2 };
 
@@ -47,6 +56,9 @@ struct GraphImage {
   bool oth_packed = true;  // others as (d<<1 | eq) words; else (d, eq) pairs
   int fv_mode = FV_ONE;
   int assign_bytes = 1;  // 1: u8 chains (max cardinality <= 256), 4: u32
+  uint64_t nvar_pad = 0;  // variables in schedule order incl. class padding (== nvar unless sell)
+  uint64_t ndrow = 0;     // device rows: nrow, or nvar_pad for sell graphs
+  bool sell = false;      // Boolean-only + parallel schedule: sliced-ELL arrays below are built
 
   // schedule order
   std::vector<uint32_t> perm;         // [nvar]   d -> original vid
@@ -71,9 +83,25 @@ struct GraphImage {
   std::vector<uint8_t> e_tag;
   std::vector<uint32_t> oth;        // others stream (words; pairs take two)
 
-  // weights (original id order)
-  std::vector<double> w_init;
-  std::vector<uint8_t> w_fixed;
+  // sliced ELL, C = 32 (only if sell)
+  std::vector<uint32_t> sl_col;    // [nslice+1] first edge column of each slice
+  std::vector<uint32_t> sl_ocol;   // [nslice+1] first others column (only if has_multi)
+  std::vector<uint8_t> s_tag;      // [ncol*32]
+  std::vector<uint32_t> s_wid;
+  std::vector<float> s_fv32;
+  std::vector<double> s_fv64;
+  std::vector<uint32_t> s_oth;     // [nocol*32] packed (d<<1|eq) words
+
+  // weights: ABI order is the original id; the device uses internal ids, hottest first
+  std::vector<double> w_init;      // original order
+  std::vector<uint8_t> w_fixed;    // original order
+  std::vector<uint32_t> w_perm;    // internal -> original
+  std::vector<uint32_t> w_inv;     // original -> internal
+  uint32_t n_hot = 0;              // internal ids below this are staged in shared memory
+  // per (colour class, internal weight): SGD updates per learning launch and their curvature
+  // bound; *_evid = evidence variables learn (default), *_all = --learn_non_evidence
+  bool cls_shared = false;         // one class-averaged row instead of ncolor rows
+  std::vector<float> cls_N_evid, cls_Q_evid, cls_N_all, cls_Q_all;
 
   // host-only, original id order, for the ABI getters / writers
   std::vector<uint8_t> var_dtype, var_is_evid;

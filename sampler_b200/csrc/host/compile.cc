@@ -293,18 +293,6 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     // nothing couples two variables: one class, i.e. the hogwild launch, and it is exact
   }
   g->schedule = schedule;
-  g->color_start.assign(ncolor + 1, 0);
-  for (uint64_t v = 0; v < nvar; ++v) ++g->color_start[color[v] + 1];
-  for (uint32_t c = 0; c < ncolor; ++c) g->color_start[c + 1] += g->color_start[c];
-  g->perm.resize(nvar); g->inv.resize(nvar);
-  {
-    std::vector<uint32_t> fill(g->color_start.begin(), g->color_start.end() - 1);
-    for (uint64_t v = 0; v < nvar; ++v) {
-      uint32_t d = fill[color[v]]++;
-      g->perm[d] = (uint32_t)v;
-      g->inv[v] = d;
-    }
-  }
 
   // ---- layout knobs ----
   g->assign_bytes = max_card <= 256 ? 1 : 4;
@@ -316,13 +304,80 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     if ((double)(float)x == x) g->fv_mode = std::max(g->fv_mode, (int)FV_F32);
     else g->fv_mode = FV_F64;
   }
+  // Boolean-only graphs under a parallel schedule get the sliced-ELL stream (graph_image.h)
+  g->sell = !g->has_categorical && schedule != DWG_SCHED_SEQUENTIAL;
 
-  // ---- emit rows and edge records in schedule order ----
-  g->var_flags.resize(nvar); g->evid_val.resize(nvar);
-  if (g->has_categorical) g->var_row.resize(nvar + 1);
-  g->row_ptr.assign(nrow + 1, 0);
-  if (g->has_multi) g->row_oth.assign(nrow + 1, 0);
-  if (g->has_truthiness) g->truthiness.assign(nrow, 0.0);
+  // how one edge record of variable v for factor f is encoded (shared by the sort key, the CSR
+  // emission and the byte accounting): compact forms need v exactly once among <= 3 positions
+  auto edge_form = [&](uint64_t v, uint32_t f, uint64_t k, bool cat, uint64_t *self_pos_out) -> int {
+    uint64_t a = raw.fac_ptr[f], b = raw.fac_ptr[f + 1], n = b - a;
+    uint64_t nself = 0, self_pos = 0;
+    for (uint64_t e = a; e < b; ++e)
+      if (raw.edge_vid[e] == v) { ++nself; self_pos = e - a; }
+    uint32_t self_eq = edense[a + self_pos];
+    if (self_pos_out) *self_pos_out = self_pos;
+    bool compact = nself == 1 && n <= 3 && (cat ? self_eq == k : self_eq <= 1);
+    return compact ? (int)(n - 1) : (int)FORM_GENERAL;
+  };
+
+  // ---- schedule order: colour-major; SELL graphs additionally sort each class by
+  // (is_evidence, degree, others words) so that a 32-variable slice is uniform, and pad every
+  // class to a multiple of 32 ----
+  std::vector<uint32_t> class_count(ncolor, 0);
+  for (uint64_t v = 0; v < nvar; ++v) ++class_count[color[v]];
+  g->color_start.assign(ncolor + 1, 0);
+  for (uint32_t c = 0; c < ncolor; ++c) {
+    uint32_t n = class_count[c];
+    if (g->sell) n = (n + 31u) & ~31u;
+    g->color_start[c + 1] = g->color_start[c] + n;
+  }
+  const uint64_t nvar_pad = g->color_start[ncolor];
+  g->nvar_pad = nvar_pad;
+  g->perm.assign(nvar_pad, 0xffffffffu);
+  g->inv.resize(nvar);
+  if (g->sell) {
+    struct Key { uint64_t k; uint32_t v; };
+    std::vector<Key> keys(nvar);
+    for (uint64_t v = 0; v < nvar; ++v) {
+      uint64_t dg = inc_end[v] - deg[v], ow = 0;
+      for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
+        uint32_t f = inc[i].fid;
+        uint64_t n = raw.fac_ptr[f + 1] - raw.fac_ptr[f];
+        if (n > 1) {
+          int form = edge_form(v, f, 0, false, nullptr);
+          ow += form == (int)FORM_GENERAL ? 1 + n : (uint64_t)form;
+        }
+      }
+      dg = std::min<uint64_t>(dg, (1u << 24) - 1);
+      ow = std::min<uint64_t>(ow, (1u << 24) - 1);
+      keys[v] = {((uint64_t)color[v] << 49) | ((uint64_t)g->var_is_evid[v] << 48) | (dg << 24) | ow, (uint32_t)v};
+    }
+    std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
+      return a.k != b.k ? a.k < b.k : a.v < b.v;
+    });
+    std::vector<uint32_t> fill(g->color_start.begin(), g->color_start.end() - 1);
+    for (auto &kv : keys) {
+      uint32_t d = fill[color[kv.v]]++;
+      g->perm[d] = kv.v;
+      g->inv[kv.v] = d;
+    }
+  } else {
+    std::vector<uint32_t> fill(g->color_start.begin(), g->color_start.end() - 1);
+    for (uint64_t v = 0; v < nvar; ++v) {
+      uint32_t d = fill[color[v]]++;
+      g->perm[d] = (uint32_t)v;
+      g->inv[v] = d;
+    }
+  }
+
+  // ---- emit rows and edge records (CSR) in schedule order ----
+  const uint64_t ndrow = g->sell ? nvar_pad : nrow;  // device rows (pads own an empty row)
+  g->ndrow = ndrow;
+  g->var_flags.assign(nvar_pad, VF_PAD); g->evid_val.assign(nvar_pad, 0);
+  if (g->has_categorical) g->var_row.resize(nvar_pad + 1);
+  g->row_ptr.assign(ndrow + 1, 0);
+  if (g->has_multi) g->row_oth.assign(ndrow + 1, 0);
+  if (g->has_truthiness) g->truthiness.assign(ndrow, 0.0);
   g->row_of_value.resize(nrow);
   uint64_t nindex = 0;
   for (uint64_t v = 0; v < nvar; ++v) nindex += inc_end[v] - deg[v];
@@ -339,8 +394,14 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   };
   uint64_t row = 0, ei = 0;
   double b_all = 0, b_query = 0, b_learn = 0;
-  for (uint64_t d = 0; d < nvar; ++d) {
+  for (uint64_t d = 0; d < nvar_pad; ++d) {
     uint64_t v = g->perm[d];
+    if (v == 0xffffffffu) {  // pad: an empty row
+      g->row_ptr[row] = (uint32_t)ei;
+      if (g->has_multi) g->row_oth[row] = (uint32_t)(g->oth.size() / ow);
+      ++row;
+      continue;
+    }
     bool cat = g->var_dtype[v];
     uint64_t K = cat ? raw.var_card[v] : 1;
     g->var_flags[d] = (g->var_is_evid[v] ? VF_EVID : 0) | (cat ? VF_CATEGORICAL : 0) |
@@ -362,16 +423,12 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         if (g->fv_mode == FV_F32) g->e_fv32[ei] = (float)raw.fac_fv[f];
         if (g->fv_mode == FV_F64) g->e_fv64[ei] = raw.fac_fv[f];
         uint8_t tag = (uint8_t)func_code(raw.fac_func[f]);
-        // where does this variable sit in the factor?
-        uint64_t nself = 0, self_pos = 0;
-        for (uint64_t e = a; e < b; ++e)
-          if (raw.edge_vid[e] == v) { ++nself; self_pos = e - a; }
-        uint32_t self_eq = edense[a + self_pos];
-        bool compact = nself == 1 && n <= 3 && (cat ? self_eq == k : self_eq <= 1);
-        if (compact) {
-          if (!cat && self_eq == 1) tag |= TAG_SELF_EQ1;
+        uint64_t self_pos = 0;
+        int form = edge_form(v, f, k, cat, &self_pos);
+        if (form != (int)FORM_GENERAL) {
+          if (!cat && edense[a + self_pos] == 1) tag |= TAG_SELF_EQ1;
           if (self_pos == n - 1) tag |= TAG_SELF_HEAD;
-          tag |= (uint8_t)((n - 1) << TAG_FORM_SHIFT);
+          tag |= (uint8_t)(form << TAG_FORM_SHIFT);
           for (uint64_t e = a; e < b; ++e)
             if (raw.edge_vid[e] != v) push_oth(g->inv[raw.edge_vid[e]], edense[e]);
         } else {
@@ -394,13 +451,137 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     if (!g->var_is_evid[v]) b_query += vb;
     b_learn += vb + vl;
   }
-  g->row_ptr[nrow] = (uint32_t)ei;
-  if (g->has_multi) g->row_oth[nrow] = (uint32_t)(g->oth.size() / ow);
-  if (g->has_categorical) g->var_row[nvar] = (uint32_t)nrow;
+  g->row_ptr[ndrow] = (uint32_t)ei;
+  if (g->has_multi) g->row_oth[ndrow] = (uint32_t)(g->oth.size() / ow);
+  if (g->has_categorical) g->var_row[nvar_pad] = (uint32_t)ndrow;
   g->noth = g->oth.size() / ow;
   g->bytes_infer = b_all;
   g->bytes_infer_query = b_query;
   g->bytes_learn = b_learn;
+
+  // ---- internal weight ids: hottest first, so that ids < n_hot can live in shared memory ----
+  g->w_perm.resize(nweight); g->w_inv.resize(nweight);
+  {
+    std::vector<uint64_t> cnt(nweight, 0);
+    for (uint64_t e = 0; e < nindex; ++e) ++cnt[g->e_wid[e]];
+    std::iota(g->w_perm.begin(), g->w_perm.end(), 0u);
+    if (nweight > DWG_HOT_WEIGHTS)
+      std::stable_sort(g->w_perm.begin(), g->w_perm.end(),
+                       [&](uint32_t a, uint32_t b) { return cnt[a] > cnt[b]; });
+    for (uint64_t i = 0; i < nweight; ++i) g->w_inv[g->w_perm[i]] = (uint32_t)i;
+    for (uint64_t e = 0; e < nindex; ++e) g->e_wid[e] = g->w_inv[g->e_wid[e]];
+    g->n_hot = (uint32_t)std::min<uint64_t>(nweight, DWG_HOT_WEIGHTS);
+  }
+
+  // ---- per colour class, per weight: how many SGD updates one learning launch makes (N) and
+  // their summed curvature bound (Q), for the semi-implicit batch update (dwg_kernels.cuh).
+  // q = (fv * sign range)^2 / 4 >= Var(f | rest): the conditional is a Bernoulli. ----
+  {
+    uint64_t cells = (uint64_t)ncolor * nweight;
+    g->cls_shared = cells > (64ull << 20);  // too many cells: one class-averaged row
+    uint64_t rows_n = g->cls_shared ? 1 : ncolor;
+    g->cls_N_evid.assign(rows_n * nweight, 0.f); g->cls_Q_evid.assign(rows_n * nweight, 0.f);
+    g->cls_N_all.assign(rows_n * nweight, 0.f); g->cls_Q_all.assign(rows_n * nweight, 0.f);
+    auto srange = [](uint32_t fc, uint64_t n) -> double {
+      switch (fc) {
+        case FC_AND: case FC_OR: case FC_EQUAL: case FC_IMPLY_NATURAL: return 2.0;
+        case FC_LINEAR: return n > 1 ? (double)(n - 1) : 1.0;
+        case FC_RATIO: return n > 1 ? std::log2((double)n) : 1.0;
+        default: return 1.0;
+      }
+    };
+    for (uint32_t c = 0; c < ncolor; ++c) {
+      uint64_t base = g->cls_shared ? 0 : (uint64_t)c * nweight;
+      for (uint64_t d = g->color_start[c]; d < g->color_start[c + 1]; ++d) {
+        uint64_t v = g->perm[d];
+        if (v == 0xffffffffu) continue;
+        bool cat = g->var_dtype[v], ev = g->var_is_evid[v];
+        uint64_t r0 = g->has_categorical ? g->var_row[d] : d;
+        uint64_t r = cat ? r0 + std::min<uint64_t>(g->evid_val[d], raw.var_card[v] ? raw.var_card[v] - 1 : 0) : r0;
+        if (cat && raw.var_card[v] == 0) continue;
+        uint64_t oc = g->has_multi ? g->row_oth[r] : 0;
+        for (uint64_t e = g->row_ptr[r]; e < g->row_ptr[r + 1]; ++e) {
+          uint8_t tag = g->e_tag[e];
+          uint32_t form = tag >> TAG_FORM_SHIFT;
+          uint64_t n = form != FORM_GENERAL ? form + 1 : g->oth[oc * ow];
+          oc += form != FORM_GENERAL ? form : 1 + n;
+          uint32_t w = g->e_wid[e];
+          if (raw.w_fixed[g->w_perm[w]]) continue;
+          double fv = g->fv_mode == FV_F32 ? g->e_fv32[e] : g->fv_mode == FV_F64 ? g->e_fv64[e] : 1.0;
+          double sr = srange(tag & TAG_FUNC_MASK, n);
+          float q = (float)(fv * fv * sr * sr * 0.25), one = cat ? 2.f : 1.f;
+          g->cls_N_all[base + w] += one; g->cls_Q_all[base + w] += q * one;
+          if (ev) { g->cls_N_evid[base + w] += one; g->cls_Q_evid[base + w] += q * one; }
+        }
+      }
+    }
+    if (g->cls_shared)
+      for (uint64_t w = 0; w < nweight; ++w) {
+        g->cls_N_evid[w] /= ncolor; g->cls_Q_evid[w] /= ncolor;
+        g->cls_N_all[w] /= ncolor; g->cls_Q_all[w] /= ncolor;
+      }
+  }
+
+  // ---- sliced ELL (C = 32): slice s owns variables 32s .. 32s+31; its edge records are stored
+  // column-major (record j of lane l at (col0 + j) * 32 + l), padded with NOP tags to the
+  // longest row of the slice; the others stream likewise.  One warp streams one slice with
+  // fully coalesced 32 B / 128 B requests and no shared-memory staging. ----
+  if (g->sell) {
+    const uint64_t nslice = nvar_pad / 32;
+    g->sl_col.assign(nslice + 1, 0);
+    if (g->has_multi) g->sl_ocol.assign(nslice + 1, 0);
+    uint64_t col = 0, ocol = 0;
+    for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
+      uint32_t we = 0, wo = 0;
+      for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
+        we = std::max(we, g->row_ptr[d + 1] - g->row_ptr[d]);
+        if (g->has_multi) wo = std::max(wo, g->row_oth[d + 1] - g->row_oth[d]);
+      }
+      g->sl_col[sidx] = (uint32_t)col;
+      if (g->has_multi) g->sl_ocol[sidx] = (uint32_t)ocol;
+      col += we; ocol += wo;
+      if (col >= U32_LIMIT || ocol >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "more than 2^32 slice columns"; }
+    }
+    g->sl_col[nslice] = (uint32_t)col;
+    if (g->has_multi) g->sl_ocol[nslice] = (uint32_t)ocol;
+    g->s_tag.assign(col * 32, SELL_NOP);
+    g->s_wid.assign(col * 32, 0);
+    if (g->fv_mode == FV_F32) g->s_fv32.assign(col * 32, 0.f);
+    if (g->fv_mode == FV_F64) g->s_fv64.assign(col * 32, 0.0);
+    if (g->has_multi) g->s_oth.assign(ocol * 32, 0);
+    // unary sign when the variable does NOT satisfy the factor (it is +1 when it does)
+    auto code_mismatch = [](uint32_t fc) -> uint8_t {
+      switch (fc) {
+        case FC_AND: case FC_OR: case FC_IMPLY_NATURAL: return 0;  // -1
+        case FC_EQUAL: return 2;                                   // +1
+        default: return 1;                                         //  0
+      }
+    };
+    for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
+      for (uint32_t l = 0; l < 32; ++l) {
+        uint64_t d = sidx * 32 + l;
+        uint64_t e0 = g->row_ptr[d], e1 = g->row_ptr[d + 1];
+        for (uint64_t e = e0; e < e1; ++e) {
+          uint64_t pos = ((uint64_t)g->sl_col[sidx] + (e - e0)) * 32 + l;
+          uint8_t tag = g->e_tag[e];
+          if ((tag >> TAG_FORM_SHIFT) == 0) {
+            uint8_t mm = code_mismatch(tag & TAG_FUNC_MASK);
+            uint8_t s1 = (tag & TAG_SELF_EQ1) ? 2 : mm, s0 = (tag & TAG_SELF_EQ1) ? mm : 2;
+            tag = (uint8_t)((s0 << 2) | s1);
+          }
+          g->s_tag[pos] = tag;
+          g->s_wid[pos] = g->e_wid[e];
+          if (g->fv_mode == FV_F32) g->s_fv32[pos] = g->e_fv32[e];
+          if (g->fv_mode == FV_F64) g->s_fv64[pos] = g->e_fv64[e];
+        }
+        if (g->has_multi) {
+          uint64_t o0 = g->row_oth[d], o1 = g->row_oth[d + 1];
+          for (uint64_t o = o0; o < o1; ++o)
+            g->s_oth[((uint64_t)g->sl_ocol[sidx] + (o - o0)) * 32 + l] = g->oth[o];
+        }
+      }
+    }
+  }
   *err = DWG_OK;
   return "";
 }

@@ -44,7 +44,7 @@ REF_TEST = "/root/reference/test"
 GRAPHS = ["biased_coin", "biased_coin_continuous", "biased_coin_truthiness",
           "biased_coin_with_multinomial", "partial_observation", "sparse_domains",
           "sparse_multinomial2"]
-NSEEDS = 20
+NSEEDS = 200
 KIND = {"variable": "variables", "domain": "domains", "factor": "factors", "weight": "weights"}
 
 

@@ -34,10 +34,18 @@ class ImageModel:
         self.info = g.info
         for name in ("perm", "inv", "color_start", "var_flags", "evid_val", "var_row", "row_ptr", "row_oth",
                      "truthiness", "e_wid", "e_fv32", "e_fv64", "e_tag", "oth", "row_of_value", "values",
-                     "value_base"):
+                     "value_base", "w_perm", "w_inv", "sl_col", "sl_ocol", "s_tag", "s_wid", "s_fv32",
+                     "s_fv64", "s_oth"):
             setattr(self, name, g.image(name))
         self.packed = bool(g.image("oth_packed")[0])
         self.nvar = int(g.info.num_variables)
+        self.nvar_pad = len(self.perm)
+        self.valid = self.perm != 0xFFFFFFFF
+
+    def to_schedule_order(self, a_orig):
+        a = np.zeros(self.nvar_pad, np.uint64)
+        a[self.inv.astype(np.int64)] = np.asarray(a_orig, np.uint64)
+        return a
 
     def row0(self, d):
         return int(self.var_row[d]) if len(self.var_row) else d
@@ -81,7 +89,8 @@ class ImageModel:
 
     def potential(self, vid, proposal, a_orig, weights):
         """FactorGraph::potential(var, proposal) from the image; a_orig in ORIGINAL id order"""
-        a = np.asarray(a_orig)[self.perm.astype(np.int64)]
+        a = self.to_schedule_order(a_orig)
+        weights = np.asarray(weights)[self.w_perm.astype(np.int64)]  # device weight ids are internal
         d = int(self.inv[vid])
         cat = bool(self.var_flags[d] & VF_CAT)
         row = self.row0(d) + (proposal if cat else 0)
@@ -93,3 +102,58 @@ class ImageModel:
             oc += span
             pot += float(weights[self.e_wid[e]]) * (s * self.fv(e))
         return pot
+
+
+    # ---- the sliced-ELL stream (Boolean graphs): same potentials, read the way k_sell_* do ----
+    def sell_potentials(self, vid, a_orig, weights):
+        """(pos, neg) of a Boolean variable from the slice-interleaved arrays"""
+        a = self.to_schedule_order(a_orig)
+        weights = np.asarray(weights)[self.w_perm.astype(np.int64)]
+        d = int(self.inv[vid])
+        s, lane = d // 32, d % 32
+        col0, ncol = int(self.sl_col[s]), int(self.sl_col[s + 1] - self.sl_col[s])
+        obase = int(self.sl_ocol[s]) * 32 + lane if len(self.sl_ocol) else 0
+        oc, pos, neg = 0, 0.0, 0.0
+        code = lambda c: float(c - 1)
+        for j in range(ncol):
+            idx = (col0 + j) * 32 + lane
+            tag = int(self.s_tag[idx])
+            if tag == 0xFF:
+                continue
+            w = float(weights[self.s_wid[idx]])
+            fv = float(self.s_fv32[idx]) if len(self.s_fv32) else float(self.s_fv64[idx]) if len(self.s_fv64) else 1.0
+            form = tag >> TAG_FORM_SHIFT
+            if form == 0:
+                s1, s0 = code(tag & 3), code((tag >> 2) & 3)
+            else:
+                words = lambda c: int(self.s_oth[obase + c * 32])
+                fc = tag & TAG_FUNC_MASK
+                if form != FORM_GENERAL:
+                    self_eq = 1 if tag & TAG_SELF_EQ1 else 0
+                    self_head = bool(tag & TAG_SELF_HEAD)
+                    nsb, head_oth = 0, False
+                    for k in range(form):
+                        wd = words(oc + k)
+                        sat = int(a[wd >> 1]) == (wd & 1)
+                        if (not self_head) and k == form - 1: head_oth = sat
+                        else: nsb += sat
+                    oc += form
+                    if self_head:
+                        s0, s1 = sign(fc, form + 1, nsb, self_eq == 0), sign(fc, form + 1, nsb, self_eq == 1)
+                    else:
+                        s0, s1 = sign(fc, form + 1, nsb + (self_eq == 0), head_oth), sign(fc, form + 1, nsb + (self_eq == 1), head_oth)
+                else:
+                    n = words(oc)
+                    nsb0 = nsb1 = 0; h0 = h1 = False
+                    for k in range(n):
+                        wd = words(oc + 1 + k)
+                        od, eq = wd >> 1, wd & 1
+                        if od == d: t0, t1 = eq == 0, eq == 1
+                        else: t0 = t1 = int(a[od]) == eq
+                        if k == n - 1: h0, h1 = t0, t1
+                        else: nsb0 += t0; nsb1 += t1
+                    oc += 1 + n
+                    s0, s1 = sign(fc, n, nsb0, h0), sign(fc, n, nsb1, h1)
+            pos += w * (s1 * fv)
+            neg += w * (s0 * fv)
+        return pos, neg

@@ -18,13 +18,18 @@ def _check_against_oracle(raw, schedule, rng, nassign=3):
     m = ImageModel(g)
     o = ol.Oracle(raw)
     assert g.info.num_values == o.nval and g.info.num_index_entries == o.nindex
-    perm = m.perm.astype(np.int64)
+    perm = m.perm[m.valid].astype(np.int64)
+    inv = m.inv.astype(np.int64)
     assert sorted(perm.tolist()) == list(range(o.nvar))
-    assert np.array_equal(m.inv[perm], np.arange(o.nvar))
+    assert np.array_equal(m.perm[inv], np.arange(o.nvar))
+    assert ((m.var_flags[~m.valid] & 0x80) != 0).all() and ((m.var_flags[m.valid] & 0x80) == 0).all()
     # per-variable metadata
-    assert np.array_equal((m.var_flags & VF_EVID) != 0, o.is_evid[perm] != 0)
-    assert np.array_equal((m.var_flags & VF_CAT) != 0, o.dtype[perm] != 0)
-    assert np.array_equal(m.evid_val, o.assignment_dense[perm])
+    assert np.array_equal((m.var_flags[inv] & VF_EVID) != 0, o.is_evid != 0)
+    assert np.array_equal((m.var_flags[inv] & VF_CAT) != 0, o.dtype != 0)
+    assert np.array_equal(m.evid_val[inv], o.assignment_dense)
+    # internal weight ids are a permutation, hottest first
+    assert sorted(m.w_perm.tolist()) == list(range(o.nweight))
+    assert np.array_equal(m.w_perm[m.w_inv.astype(np.int64)], np.arange(o.nweight))
     dtype, is_evid, base, values = g.var_meta()
     assert np.array_equal(base[:-1], o.var_val_base) and np.array_equal(values, o.value)
     if len(m.truthiness):
@@ -41,6 +46,9 @@ def _check_against_oracle(raw, schedule, rng, nassign=3):
         for v in range(o.nvar):
             for p in range(int(card[v])):
                 assert m.potential(v, p, a, w) == o.potential(v, p), (v, p)
+            if len(m.sl_col):  # sliced-ELL stream of Boolean graphs: same numbers
+                assert m.sell_potentials(v, a, w) == (o.potential(v, 1), o.potential(v, 0)), v
+    assert (len(m.sl_col) > 0) == (not o.dtype.any() and g.info.schedule != sb.SCHED_SEQUENTIAL)
     return g, m, o
 
 
@@ -104,7 +112,7 @@ def test_loader_matches_raw_records(name):
     a = sb.Graph.from_files(p["meta"], [p["variables"]], [p["domains"]], [p["factors"]], [p["weights"]])
     b = sb.Graph.from_raw(load_golden_graph(name))
     for arr in ("perm", "row_ptr", "row_oth", "e_wid", "e_tag", "e_fv32", "e_fv64", "oth", "evid_val",
-                "var_flags", "truthiness", "w_init", "w_fixed", "values"):
+                "var_flags", "truthiness", "w_init", "w_fixed", "values", "s_tag", "s_wid", "s_oth", "sl_col"):
         assert np.array_equal(a.image(arr), b.image(arr)), arr
 
 
