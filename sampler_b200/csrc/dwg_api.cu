@@ -81,10 +81,7 @@ struct dwg_handle {
   DevBuf<float> e_fv32;
   DevBuf<double> e_fv64, truthiness;
   // sliced-ELL stream (Boolean graphs, parallel schedules)
-  DevBuf<uint8_t> s_tag;
-  DevBuf<uint32_t> sl_col, sl_ocol, s_wid, s_oth;
-  DevBuf<float> s_fv32;
-  DevBuf<double> s_fv64;
+  DevBuf<uint32_t> sl_off, blob;
   // weights (internal order) and the batch-update statics
   DevBuf<uint8_t> w_fixed;
   DevBuf<double> weights, prev_weights, grad_acc, norms;
@@ -231,8 +228,7 @@ static size_t image_device_bytes(const GraphImage &m) {
   b += m.var_flags.size() + m.w_fixed.size();
   b += (size_t)m.assign_bytes * m.nvar_pad * 3;  // evid_val + two chains
   if (m.sell) {
-    b += m.s_tag.size() + 4 * (m.s_wid.size() + m.s_oth.size() + m.sl_col.size() + m.sl_ocol.size());
-    b += 4 * m.s_fv32.size() + 8 * m.s_fv64.size();
+    b += 4 * (m.sl_off.size() + m.blob.size());
   } else {
     b += m.e_tag.size() + 4 * (m.var_row.size() + m.row_ptr.size() + m.row_oth.size() + m.e_wid.size() + m.oth.size());
     b += 4 * m.e_fv32.size() + 8 * m.e_fv64.size() + 8 * m.truthiness.size();
@@ -303,7 +299,7 @@ int dwg_debug_image(const dwg_graph *g, const char *name, const void **data, uin
   ARR(perm) ARR(inv) ARR(color_start) ARR(var_flags) ARR(evid_val) ARR(var_row) ARR(row_ptr)
   ARR(row_oth) ARR(truthiness) ARR(e_wid) ARR(e_fv32) ARR(e_fv64) ARR(e_tag) ARR(oth) ARR(w_init)
   ARR(w_fixed) ARR(row_of_value) ARR(values) ARR(value_base) ARR(w_perm) ARR(w_inv)
-  ARR(sl_col) ARR(sl_ocol) ARR(s_tag) ARR(s_wid) ARR(s_fv32) ARR(s_fv64) ARR(s_oth)
+  ARR(sl_off) ARR(blob)
   ARR(cls_N_evid) ARR(cls_Q_evid) ARR(cls_N_all) ARR(cls_Q_all)
 #undef ARR
   if (n == "oth_packed") {
@@ -411,12 +407,8 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     CU(h->cls_Q.upload(all ? m.cls_Q_all : m.cls_Q_evid, s));
   }
   if (m.sell) {
-    CU(h->sl_col.upload(m.sl_col, s));
-    CU(h->s_tag.upload(m.s_tag, s));
-    CU(h->s_wid.upload(m.s_wid, s));
-    if (m.has_multi) { CU(h->sl_ocol.upload(m.sl_ocol, s)); CU(h->s_oth.upload(m.s_oth, s)); }
-    if (m.fv_mode == FV_F32) CU(h->s_fv32.upload(m.s_fv32, s));
-    if (m.fv_mode == FV_F64) CU(h->s_fv64.upload(m.s_fv64, s));
+    CU(h->sl_off.upload(m.sl_off, s));
+    CU(h->blob.upload(m.blob, s));
     // Boolean variables have no truthiness: under --noise_aware only --learn_non_evidence learns
     h->learns = h->opts.learn_non_evidence || !h->opts.noise_aware;
   }
@@ -443,12 +435,7 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     if (rc) return rc;
   } else {
     SellGraph &sg = h->sg;
-    sg.sl_col = h->sl_col.p; sg.sl_ocol = m.has_multi ? h->sl_ocol.p : nullptr;
-    sg.tag = h->s_tag.p; sg.wid = h->s_wid.p;
-    sg.fv32 = m.fv_mode == FV_F32 ? h->s_fv32.p : nullptr;
-    sg.fv64 = m.fv_mode == FV_F64 ? h->s_fv64.p : nullptr;
-    sg.oth = h->s_oth.p;
-    sg.var_flags = h->var_flags.p; sg.evid_val = h->evid_val8.p; sg.w_fixed = h->w_fixed.p;
+    sg.sl_off = h->sl_off.p; sg.blob = h->blob.p;
     sg.nweight = (uint32_t)m.nweight; sg.n_hot = m.n_hot;
     SellState &ss = h->ss;
     ss.assign_free = h->assign_free8.p; ss.assign_evid = h->assign_evid8.p;

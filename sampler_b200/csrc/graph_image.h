@@ -35,10 +35,38 @@ constexpr uint8_t VF_CATEGORICAL = 2;
 constexpr uint8_t VF_TRUTHINESS = 4;  // has_truthiness(), src/variable.h:105
 constexpr uint8_t VF_PAD = 0x80;      // filler slot that rounds a colour class up to 32 variables
 
-// sliced-ELL tag byte (Boolean-only graphs): [7:6] form as above.  Unary records carry the
-// two signs themselves: [1:0] sign when the variable is 1, [3:2] when it is 0, coded
-// 0 -> -1, 1 -> 0, 2 -> +1; multi-variable records keep the CSR tag; SELL_NOP pads a slice.
-constexpr uint8_t SELL_NOP = 0xff;
+// ---- sliced-ELL blob (Boolean graphs, parallel schedules) ---------------------------------
+// Slice s = the 32 variables d = 32s .. 32s+31 (lane = d & 31).  All data of a slice is ONE
+// contiguous run of 32-bit words starting at word 8 * sl_off[s] of `blob`:
+//   header  8 words (SH_*)
+//   unary   n_un columns x 32 words      record of lane l in column j at  8 + 32 j + l
+//   (fv)    n_un columns x 32 f32 | f64  feature values of the unary records (FV_F32 | FV_F64)
+//   multi   n_mu columns x 32 words
+//   (fv)    n_mu columns x 32 f32 | f64
+//   others  n_oc columns x 32 words      (d << 1 | equal_to) references, or a length word
+// so a warp streams its slice with fully coalesced 128 B requests.  Within a row the unary
+// records come first, then the multi-variable ones, each group in ascending factor id (the
+// CSR stream keeps construct_index's pure factor-id order; the two sums agree to fp64
+// reassociation).  A record word is  wid[22:0] | weight_is_fixed << 23 | tag << 24.
+//   unary tag : [1:0] sign code when the variable is 1, [3:2] when it is 0 (0 -> -1, 1 -> 0,
+//               2 -> +1).  Padding records are SELL_UNARY_NOP with weight id 0 (adds +0.0).
+//   multi tag : slices flagged SF_BINARY (every multi record has exactly one other variable,
+//               record j owns others column j): the factor's whole sign table,
+//               code(x, sat) at bits 2 * (2 x + sat), x = this variable's value, sat = the
+//               other variable satisfies its equal_to; padding = SELL_BINARY_NOP.
+//               other slices: the CSR tag byte above (FuncCode | SELF_EQ1 | SELF_HEAD | form),
+//               records consume others words through a per-lane cursor; form 0 = padding.
+constexpr int SH_N_UNARY = 0, SH_N_MULTI = 1, SH_N_OTH = 2;
+constexpr int SH_EVID_MASK = 3;   // bit l: variable of lane l is evidence
+constexpr int SH_PAD_MASK = 4;    // bit l: lane l is a filler slot
+constexpr int SH_EVVAL_MASK = 5;  // bit l: Variable::assignment_dense of lane l is 1
+constexpr int SH_FLAGS = 6;       // SF_*
+constexpr int SH_WORDS = 8;
+constexpr uint32_t SF_ANTISYM = 1;  // every unary record has sign(1) == -sign(0): neg == -pos
+constexpr uint32_t SF_BINARY = 2;   // every multi record has exactly one other variable
+constexpr uint32_t SELL_WID_MASK = 0x7fffffu, SELL_FIXED_BIT = 0x800000u;
+constexpr uint32_t SELL_UNARY_NOP = 0x05u, SELL_BINARY_NOP = 0x55u;
+constexpr uint64_t SELL_MAX_WEIGHTS = 1ull << 23;
 
 // weights with internal id < n_hot are staged in shared memory by the sweep kernels
 #define DWG_HOT_WEIGHTS 4096
@@ -83,14 +111,10 @@ struct GraphImage {
   std::vector<uint8_t> e_tag;
   std::vector<uint32_t> oth;        // others stream (words; pairs take two)
 
-  // sliced ELL, C = 32 (only if sell)
-  std::vector<uint32_t> sl_col;    // [nslice+1] first edge column of each slice
-  std::vector<uint32_t> sl_ocol;   // [nslice+1] first others column (only if has_multi)
-  std::vector<uint8_t> s_tag;      // [ncol*32]
-  std::vector<uint32_t> s_wid;
-  std::vector<float> s_fv32;
-  std::vector<double> s_fv64;
-  std::vector<uint32_t> s_oth;     // [nocol*32] packed (d<<1|eq) words
+  // sliced-ELL blob (only if sell): see the layout comment above
+  std::vector<uint32_t> sl_off;    // [nslice+1] first word of each slice / 8
+  std::vector<uint32_t> blob;
+  uint32_t sell_max_words = 0;     // longest slice, in words
 
   // weights: ABI order is the original id; the device uses internal ids, hottest first
   std::vector<double> w_init;      // original order

@@ -268,26 +268,46 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       *err = DWG_ERR_UNSUPPORTED;
       return "chromatic schedule: factor arities too large to colour; use the hogwild schedule";
     }
+    // Pass 1, first fit, finds how many colours K the graph needs; pass 2 recolours with the
+    // least-loaded admissible colour among those K, so that every class is large enough to
+    // fill the GPU (first fit alone leaves a tail of tiny classes = latency-bound launches).
     std::vector<uint32_t> stamp;  // stamp[c] == v+1 : colour c is taken by a neighbour of v
-    std::fill(color.begin(), color.end(), 0xffffffffu);
-    for (uint64_t v = 0; v < nvar; ++v) {
-      uint32_t last_f = 0xffffffffu;
-      for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
-        uint32_t f = inc[i].fid;
-        if (f == last_f) continue;
-        last_f = f;
-        for (uint64_t e = raw.fac_ptr[f]; e < raw.fac_ptr[f + 1]; ++e) {
-          uint32_t c = color[raw.edge_vid[e]];
-          if (c == 0xffffffffu) continue;
-          if (c >= stamp.size()) stamp.resize(c + 1, 0);
-          stamp[c] = (uint32_t)v + 1;
+    std::vector<uint64_t> load;
+    for (int pass = 0; pass < 2; ++pass) {
+      const uint32_t K = ncolor;
+      std::fill(color.begin(), color.end(), 0xffffffffu);
+      stamp.assign(K + 1, 0);
+      load.assign(K + 1, 0);
+      ncolor = 1;
+      for (uint64_t v = 0; v < nvar; ++v) {
+        uint32_t last_f = 0xffffffffu;
+        for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
+          uint32_t f = inc[i].fid;
+          if (f == last_f) continue;
+          last_f = f;
+          for (uint64_t e = raw.fac_ptr[f]; e < raw.fac_ptr[f + 1]; ++e) {
+            uint32_t c = color[raw.edge_vid[e]];
+            if (c == 0xffffffffu) continue;
+            stamp[c] = (uint32_t)v + 1;
+          }
         }
+        uint32_t c = 0xffffffffu;
+        if (pass == 0) {
+          c = 0;
+          while (c < stamp.size() && stamp[c] == (uint32_t)v + 1) ++c;
+        } else {
+          for (uint32_t k = 0; k < K; ++k)
+            if (stamp[k] != (uint32_t)v + 1 && (c == 0xffffffffu || load[k] < load[c])) c = k;
+          if (c == 0xffffffffu) {  // every planned colour is taken around v: open a new one
+            c = K;
+            while (c < stamp.size() && stamp[c] == (uint32_t)v + 1) ++c;
+          }
+        }
+        if (c + 1 >= stamp.size()) { stamp.resize(c + 2, 0); load.resize(c + 2, 0); }
+        color[v] = c;
+        ++load[c];
+        ncolor = std::max(ncolor, c + 1);
       }
-      uint32_t c = 0;
-      while (c < stamp.size() && stamp[c] == (uint32_t)v + 1) ++c;
-      color[v] = c;
-      if (c >= stamp.size()) stamp.resize(c + 1, 0);
-      ncolor = std::max(ncolor, c + 1);
     }
   } else if (schedule == DWG_SCHED_CHROMATIC) {
     // nothing couples two variables: one class, i.e. the hogwild launch, and it is exact
@@ -305,7 +325,9 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     else g->fv_mode = FV_F64;
   }
   // Boolean-only graphs under a parallel schedule get the sliced-ELL stream (graph_image.h)
-  g->sell = !g->has_categorical && schedule != DWG_SCHED_SEQUENTIAL;
+  g->sell = !g->has_categorical && schedule != DWG_SCHED_SEQUENTIAL && nweight <= SELL_MAX_WEIGHTS;
+  for (uint64_t v = 0; v < nvar && g->sell; ++v)
+    if (adense[v] > 1) g->sell = false;  // a Boolean evidence value outside {0,1}: CSR kernels only
 
   // how one edge record of variable v for factor f is encoded (shared by the sort key, the CSR
   // emission and the byte accounting): compact forms need v exactly once among <= 3 positions
@@ -339,18 +361,20 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     struct Key { uint64_t k; uint32_t v; };
     std::vector<Key> keys(nvar);
     for (uint64_t v = 0; v < nvar; ++v) {
-      uint64_t dg = inc_end[v] - deg[v], ow = 0;
+      uint64_t n_un = 0, n_mu = 0, ow = 0;
       for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
         uint32_t f = inc[i].fid;
         uint64_t n = raw.fac_ptr[f + 1] - raw.fac_ptr[f];
-        if (n > 1) {
-          int form = edge_form(v, f, 0, false, nullptr);
-          ow += form == (int)FORM_GENERAL ? 1 + n : (uint64_t)form;
-        }
+        int form = edge_form(v, f, 0, false, nullptr);
+        if (form == 0) { ++n_un; continue; }
+        ++n_mu;
+        ow += form == (int)FORM_GENERAL ? 1 + n : (uint64_t)form;
       }
-      dg = std::min<uint64_t>(dg, (1u << 24) - 1);
-      ow = std::min<uint64_t>(ow, (1u << 24) - 1);
-      keys[v] = {((uint64_t)color[v] << 49) | ((uint64_t)g->var_is_evid[v] << 48) | (dg << 24) | ow, (uint32_t)v};
+      n_un = std::min<uint64_t>(n_un, (1u << 16) - 1);
+      n_mu = std::min<uint64_t>(n_mu, (1u << 12) - 1);
+      ow = std::min<uint64_t>(ow, (1u << 20) - 1);
+      keys[v] = {((uint64_t)color[v] << 49) | ((uint64_t)g->var_is_evid[v] << 48) | (n_un << 32) | (n_mu << 20) | ow,
+                 (uint32_t)v};
     }
     std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
       return a.k != b.k ? a.k < b.k : a.v < b.v;
@@ -490,6 +514,25 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         default: return 1.0;
       }
     };
+    // delta(e) = |fv| * (sign range) of record e.  One SGD step of variable v moves weight k
+    // by a gradient whose covariance over the draw is p(1-p) * delta delta^T <= 1/4 delta delta^T;
+    // diag(|delta_k| * sum_j |delta_j|) dominates delta delta^T, so
+    //   q(e) = 1/4 * delta(e) * sum_{e' learnable in the row} delta(e')
+    // summed over a launch bounds the curvature of ALL weights moving together (the features
+    // of one variable are perfectly correlated: a per-weight diagonal alone would overshoot).
+    auto walk_row = [&](uint64_t r, auto &&fn) {
+      uint64_t oc = g->has_multi ? g->row_oth[r] : 0;
+      for (uint64_t e = g->row_ptr[r]; e < g->row_ptr[r + 1]; ++e) {
+        uint8_t tag = g->e_tag[e];
+        uint32_t form = tag >> TAG_FORM_SHIFT;
+        uint64_t n = form != FORM_GENERAL ? form + 1 : g->oth[oc * ow];
+        oc += form != FORM_GENERAL ? form : 1 + n;
+        uint32_t w = g->e_wid[e];
+        if (raw.w_fixed[g->w_perm[w]]) continue;
+        double fv = g->fv_mode == FV_F32 ? g->e_fv32[e] : g->fv_mode == FV_F64 ? g->e_fv64[e] : 1.0;
+        fn(w, std::fabs(fv) * srange(tag & TAG_FUNC_MASK, n));
+      }
+    };
     for (uint32_t c = 0; c < ncolor; ++c) {
       uint64_t base = g->cls_shared ? 0 : (uint64_t)c * nweight;
       for (uint64_t d = g->color_start[c]; d < g->color_start[c + 1]; ++d) {
@@ -499,20 +542,14 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         uint64_t r0 = g->has_categorical ? g->var_row[d] : d;
         uint64_t r = cat ? r0 + std::min<uint64_t>(g->evid_val[d], raw.var_card[v] ? raw.var_card[v] - 1 : 0) : r0;
         if (cat && raw.var_card[v] == 0) continue;
-        uint64_t oc = g->has_multi ? g->row_oth[r] : 0;
-        for (uint64_t e = g->row_ptr[r]; e < g->row_ptr[r + 1]; ++e) {
-          uint8_t tag = g->e_tag[e];
-          uint32_t form = tag >> TAG_FORM_SHIFT;
-          uint64_t n = form != FORM_GENERAL ? form + 1 : g->oth[oc * ow];
-          oc += form != FORM_GENERAL ? form : 1 + n;
-          uint32_t w = g->e_wid[e];
-          if (raw.w_fixed[g->w_perm[w]]) continue;
-          double fv = g->fv_mode == FV_F32 ? g->e_fv32[e] : g->fv_mode == FV_F64 ? g->e_fv64[e] : 1.0;
-          double sr = srange(tag & TAG_FUNC_MASK, n);
-          float q = (float)(fv * fv * sr * sr * 0.25), one = cat ? 2.f : 1.f;
-          g->cls_N_all[base + w] += one; g->cls_Q_all[base + w] += q * one;
-          if (ev) { g->cls_N_evid[base + w] += one; g->cls_Q_evid[base + w] += q * one; }
-        }
+        double rowsum = 0;
+        walk_row(r, [&](uint32_t, double delta) { rowsum += delta; });
+        const float one = cat ? 2.f : 1.f;  // a categorical step also visits the row of the free value
+        walk_row(r, [&](uint32_t w, double delta) {
+          float q = (float)(0.25 * delta * rowsum) * one;
+          g->cls_N_all[base + w] += one; g->cls_Q_all[base + w] += q;
+          if (ev) { g->cls_N_evid[base + w] += one; g->cls_Q_evid[base + w] += q; }
+        });
       }
     }
     if (g->cls_shared)
@@ -522,64 +559,118 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       }
   }
 
-  // ---- sliced ELL (C = 32): slice s owns variables 32s .. 32s+31; its edge records are stored
-  // column-major (record j of lane l at (col0 + j) * 32 + l), padded with NOP tags to the
-  // longest row of the slice; the others stream likewise.  One warp streams one slice with
-  // fully coalesced 32 B / 128 B requests and no shared-memory staging. ----
+  // ---- sliced-ELL blob (graph_image.h): per 32-variable slice one contiguous run of words:
+  // header, unary records (+ feature values), multi records (+ feature values), others.
+  // A warp streams its slice with coalesced 128 B requests, every record exactly once. ----
   if (g->sell) {
     const uint64_t nslice = nvar_pad / 32;
-    g->sl_col.assign(nslice + 1, 0);
-    if (g->has_multi) g->sl_ocol.assign(nslice + 1, 0);
-    uint64_t col = 0, ocol = 0;
+    const uint64_t fvw = g->fv_mode == FV_F32 ? 1 : g->fv_mode == FV_F64 ? 2 : 0;  // words per value
+    g->sl_off.assign(nslice + 1, 0);
+    auto is_unary = [&](uint64_t e) { return (g->e_tag[e] >> TAG_FORM_SHIFT) == 0; };
+    // slice shapes
+    std::vector<uint32_t> s_un(nslice), s_mu(nslice), s_oc(nslice);
+    uint64_t words = 0;
     for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
-      uint32_t we = 0, wo = 0;
+      uint32_t un = 0, mu = 0, oc = 0;
       for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
-        we = std::max(we, g->row_ptr[d + 1] - g->row_ptr[d]);
-        if (g->has_multi) wo = std::max(wo, g->row_oth[d + 1] - g->row_oth[d]);
+        uint32_t u = 0;
+        for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) u += is_unary(e);
+        un = std::max(un, u);
+        mu = std::max<uint32_t>(mu, g->row_ptr[d + 1] - g->row_ptr[d] - u);
+        if (g->has_multi) oc = std::max(oc, g->row_oth[d + 1] - g->row_oth[d]);
       }
-      g->sl_col[sidx] = (uint32_t)col;
-      if (g->has_multi) g->sl_ocol[sidx] = (uint32_t)ocol;
-      col += we; ocol += wo;
-      if (col >= U32_LIMIT || ocol >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "more than 2^32 slice columns"; }
+      s_un[sidx] = un; s_mu[sidx] = mu; s_oc[sidx] = oc;
+      g->sl_off[sidx] = (uint32_t)(words / 8);
+      uint64_t w = SH_WORDS + 32ull * ((uint64_t)(un + mu) * (1 + fvw) + oc);
+      g->sell_max_words = (uint32_t)std::max<uint64_t>(g->sell_max_words, std::min<uint64_t>(w, U32_LIMIT));
+      words += w;
+      if (words / 8 >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "sliced-ELL stream exceeds 2^32 x 32 B"; }
     }
-    g->sl_col[nslice] = (uint32_t)col;
-    if (g->has_multi) g->sl_ocol[nslice] = (uint32_t)ocol;
-    g->s_tag.assign(col * 32, SELL_NOP);
-    g->s_wid.assign(col * 32, 0);
-    if (g->fv_mode == FV_F32) g->s_fv32.assign(col * 32, 0.f);
-    if (g->fv_mode == FV_F64) g->s_fv64.assign(col * 32, 0.0);
-    if (g->has_multi) g->s_oth.assign(ocol * 32, 0);
-    // unary sign when the variable does NOT satisfy the factor (it is +1 when it does)
-    auto code_mismatch = [](uint32_t fc) -> uint8_t {
+    g->sl_off[nslice] = (uint32_t)(words / 8);
+    g->blob.assign(words, 0);
+    // sign tables (host mirror of dev_sign, dwg_device.cuh): codes 0 -> -1, 1 -> 0, 2 -> +1
+    auto sign2 = [](uint32_t fc, uint32_t nsb, bool head) -> int {  // arity 2
+      const bool body_all = nsb == 1;
+      switch (fc) {
+        case FC_AND: return (body_all && head) ? 1 : -1;
+        case FC_AND_CATEGORICAL: return (body_all && head) ? 1 : 0;
+        case FC_OR: return (nsb > 0 || head) ? 1 : -1;
+        case FC_EQUAL: return (nsb + (head ? 1u : 0u)) != 1 ? 1 : -1;
+        case FC_IMPLY_NATURAL: return body_all ? (head ? 1 : -1) : 0;
+        case FC_IMPLY_MLN: return body_all ? (head ? 1 : 0) : 1;
+        default: return (head || nsb == 0) ? 1 : 0;  // LINEAR / RATIO (log2(1+1) = 1) / LOGICAL
+      }
+    };
+    auto code_mismatch = [](uint32_t fc) -> uint32_t {  // arity 1, variable does not satisfy
       switch (fc) {
         case FC_AND: case FC_OR: case FC_IMPLY_NATURAL: return 0;  // -1
         case FC_EQUAL: return 2;                                   // +1
         default: return 1;                                         //  0
       }
     };
+    auto put_fv = [&](uint32_t *slot, uint64_t e) {
+      if (g->fv_mode == FV_F32) std::memcpy(slot, &g->e_fv32[e], 4);
+      else if (g->fv_mode == FV_F64) std::memcpy(slot, &g->e_fv64[e], 8);
+    };
     for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
-      for (uint32_t l = 0; l < 32; ++l) {
-        uint64_t d = sidx * 32 + l;
-        uint64_t e0 = g->row_ptr[d], e1 = g->row_ptr[d + 1];
-        for (uint64_t e = e0; e < e1; ++e) {
-          uint64_t pos = ((uint64_t)g->sl_col[sidx] + (e - e0)) * 32 + l;
-          uint8_t tag = g->e_tag[e];
-          if ((tag >> TAG_FORM_SHIFT) == 0) {
-            uint8_t mm = code_mismatch(tag & TAG_FUNC_MASK);
-            uint8_t s1 = (tag & TAG_SELF_EQ1) ? 2 : mm, s0 = (tag & TAG_SELF_EQ1) ? mm : 2;
-            tag = (uint8_t)((s0 << 2) | s1);
-          }
-          g->s_tag[pos] = tag;
-          g->s_wid[pos] = g->e_wid[e];
-          if (g->fv_mode == FV_F32) g->s_fv32[pos] = g->e_fv32[e];
-          if (g->fv_mode == FV_F64) g->s_fv64[pos] = g->e_fv64[e];
-        }
-        if (g->has_multi) {
-          uint64_t o0 = g->row_oth[d], o1 = g->row_oth[d + 1];
-          for (uint64_t o = o0; o < o1; ++o)
-            g->s_oth[((uint64_t)g->sl_ocol[sidx] + (o - o0)) * 32 + l] = g->oth[o];
-        }
+      uint32_t *h = g->blob.data() + (uint64_t)g->sl_off[sidx] * 8;
+      const uint32_t un = s_un[sidx], mu = s_mu[sidx], oc = s_oc[sidx];
+      const uint64_t o_un = SH_WORDS, o_unfv = o_un + 32ull * un, o_mu = o_unfv + 32ull * un * fvw,
+                     o_mufv = o_mu + 32ull * mu, o_oth = o_mufv + 32ull * mu * fvw;
+      // is every multi record of the slice a one-other-variable record?
+      bool binary = mu > 0, antisym = true;
+      for (uint64_t d = sidx * 32; d < sidx * 32 + 32 && binary; ++d) {
+        for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e)
+          if (!is_unary(e) && (g->e_tag[e] >> TAG_FORM_SHIFT) != 1) binary = false;
       }
+      h[SH_N_UNARY] = un; h[SH_N_MULTI] = mu; h[SH_N_OTH] = oc;
+      for (uint32_t l = 0; l < 32; ++l) {
+        const uint64_t d = sidx * 32 + l;
+        if (g->var_flags[d] & VF_PAD) h[SH_PAD_MASK] |= 1u << l;
+        if (g->var_flags[d] & VF_EVID) h[SH_EVID_MASK] |= 1u << l;
+        if (g->evid_val[d] == 1) h[SH_EVVAL_MASK] |= 1u << l;
+        uint32_t ju = 0, jm = 0;
+        uint64_t o = g->has_multi ? g->row_oth[d] : 0;
+        for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) {
+          const uint8_t tag = g->e_tag[e];
+          const uint32_t fc = tag & TAG_FUNC_MASK, form = tag >> TAG_FORM_SHIFT;
+          const uint32_t wid = g->e_wid[e];
+          const uint32_t base = wid | (raw.w_fixed[g->w_perm[wid]] ? SELL_FIXED_BIT : 0u);
+          if (form == 0) {
+            const uint32_t mm = code_mismatch(fc);
+            const uint32_t s1 = (tag & TAG_SELF_EQ1) ? 2 : mm, s0 = (tag & TAG_SELF_EQ1) ? mm : 2;
+            if (s1 + s0 != 2) antisym = false;
+            h[o_un + 32ull * ju + l] = base | ((s1 | (s0 << 2)) << 24);
+            put_fv(h + o_unfv + (32ull * ju + l) * fvw, e);
+            ++ju;
+            continue;
+          }
+          uint32_t t = tag;
+          uint64_t span = form != FORM_GENERAL ? form : 1 + g->oth[o];
+          if (binary) {
+            // sign table over (this variable's value x, other variable satisfied)
+            const uint32_t self_eq = (tag & TAG_SELF_EQ1) ? 1 : 0;
+            const bool self_head = tag & TAG_SELF_HEAD;
+            t = 0;
+            for (uint32_t x = 0; x < 2; ++x)
+              for (uint32_t sat = 0; sat < 2; ++sat) {
+                const bool m = x == self_eq;
+                const int sgn = self_head ? sign2(fc, sat, m) : sign2(fc, m ? 1u : 0u, sat != 0);
+                t |= (uint32_t)(sgn + 1) << (2 * (2 * x + sat));
+              }
+            h[o_oth + 32ull * jm + l] = g->oth[o];  // record j owns others column j
+          } else {
+            for (uint64_t k = 0; k < span; ++k) h[o_oth + 32ull * (o - g->row_oth[d] + k) + l] = g->oth[o + k];
+          }
+          o += span;
+          h[o_mu + 32ull * jm + l] = base | (t << 24);
+          put_fv(h + o_mufv + (32ull * jm + l) * fvw, e);
+          ++jm;
+        }
+        for (; ju < un; ++ju) h[o_un + 32ull * ju + l] = SELL_UNARY_NOP << 24;
+        for (; jm < mu; ++jm) h[o_mu + 32ull * jm + l] = binary ? SELL_BINARY_NOP << 24 : 0u;  // form 0
+      }
+      h[SH_FLAGS] = (antisym ? SF_ANTISYM : 0u) | (binary ? SF_BINARY : 0u);
     }
   }
   *err = DWG_OK;

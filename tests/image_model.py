@@ -34,8 +34,7 @@ class ImageModel:
         self.info = g.info
         for name in ("perm", "inv", "color_start", "var_flags", "evid_val", "var_row", "row_ptr", "row_oth",
                      "truthiness", "e_wid", "e_fv32", "e_fv64", "e_tag", "oth", "row_of_value", "values",
-                     "value_base", "w_perm", "w_inv", "sl_col", "sl_ocol", "s_tag", "s_wid", "s_fv32",
-                     "s_fv64", "s_oth"):
+                     "value_base", "w_perm", "w_inv", "sl_off", "blob"):
             setattr(self, name, g.image(name))
         self.packed = bool(g.image("oth_packed")[0])
         self.nvar = int(g.info.num_variables)
@@ -104,29 +103,70 @@ class ImageModel:
         return pot
 
 
-    # ---- the sliced-ELL stream (Boolean graphs): same potentials, read the way k_sell_* do ----
+    # ---- the sliced-ELL blob (Boolean graphs): same potentials, read the way k_sell_* do ----
+    def slice_header(self, s):
+        b = int(self.sl_off[s]) * 8
+        h = self.blob[b:b + 8]
+        fvw = 1 if self.info.fv_mode == 1 else 2 if self.info.fv_mode == 2 else 0
+        n_un, n_mu, n_oc = int(h[0]), int(h[1]), int(h[2])
+        un = b + 8
+        mu = un + 32 * n_un * (1 + fvw)
+        oth = mu + 32 * n_mu * (1 + fvw)
+        assert oth + 32 * n_oc == int(self.sl_off[s + 1]) * 8
+        return dict(n_un=n_un, n_mu=n_mu, n_oc=n_oc, evid=int(h[3]), pad=int(h[4]), evval=int(h[5]),
+                    flags=int(h[6]), un=un, mu=mu, oth=oth, fvw=fvw)
+
+    def _sell_fv(self, sec, ncol, j, lane, fvw):
+        if fvw == 0:
+            return 1.0
+        at = sec + 32 * ncol
+        if fvw == 1:
+            return float(self.blob[at + 32 * j + lane:at + 32 * j + lane + 1].view(np.float32)[0])
+        k = at + 2 * (32 * j + lane)
+        return float(self.blob[k:k + 2].view(np.float64)[0])
+
     def sell_potentials(self, vid, a_orig, weights):
-        """(pos, neg) of a Boolean variable from the slice-interleaved arrays"""
+        """(pos, neg) of a Boolean variable from the slice blob: unary records first, then the
+        multi-variable ones (sign tables in binary slices, CSR tags + cursor otherwise)"""
         a = self.to_schedule_order(a_orig)
         weights = np.asarray(weights)[self.w_perm.astype(np.int64)]
         d = int(self.inv[vid])
         s, lane = d // 32, d % 32
-        col0, ncol = int(self.sl_col[s]), int(self.sl_col[s + 1] - self.sl_col[s])
-        obase = int(self.sl_ocol[s]) * 32 + lane if len(self.sl_ocol) else 0
-        oc, pos, neg = 0, 0.0, 0.0
+        h = self.slice_header(s)
+        assert not (h["pad"] >> lane) & 1
+        assert ((h["evid"] >> lane) & 1) == (1 if self.var_flags[d] & VF_EVID else 0)
+        assert ((h["evval"] >> lane) & 1) == int(self.evid_val[d] == 1)
+        pos, neg = 0.0, 0.0
         code = lambda c: float(c - 1)
-        for j in range(ncol):
-            idx = (col0 + j) * 32 + lane
-            tag = int(self.s_tag[idx])
-            if tag == 0xFF:
-                continue
-            w = float(weights[self.s_wid[idx]])
-            fv = float(self.s_fv32[idx]) if len(self.s_fv32) else float(self.s_fv64[idx]) if len(self.s_fv64) else 1.0
-            form = tag >> TAG_FORM_SHIFT
-            if form == 0:
-                s1, s0 = code(tag & 3), code((tag >> 2) & 3)
+        antisym = True
+        for j in range(h["n_un"]):
+            rec = int(self.blob[h["un"] + 32 * j + lane])
+            tag, wid = rec >> 24, rec & 0x7FFFFF
+            w = float(weights[wid])
+            fv = self._sell_fv(h["un"], h["n_un"], j, lane, h["fvw"])
+            s1, s0 = code(tag & 3), code((tag >> 2) & 3)
+            antisym &= (s1 == -s0)
+            pos += w * (s1 * fv)
+            neg += w * (s0 * fv)
+        if h["flags"] & 1:
+            assert antisym
+        binary = bool(h["flags"] & 2)
+        oc = 0
+        words = lambda c: int(self.blob[h["oth"] + 32 * c + lane])
+        for j in range(h["n_mu"]):
+            rec = int(self.blob[h["mu"] + 32 * j + lane])
+            tag, wid = rec >> 24, rec & 0x7FFFFF
+            w = float(weights[wid])
+            fv = self._sell_fv(h["mu"], h["n_mu"], j, lane, h["fvw"])
+            if binary:
+                wd = words(j)
+                sat = int(a[wd >> 1]) == (wd & 1)
+                s0 = code((tag >> (2 * sat)) & 3)
+                s1 = code((tag >> (4 + 2 * sat)) & 3)
             else:
-                words = lambda c: int(self.s_oth[obase + c * 32])
+                form = tag >> TAG_FORM_SHIFT
+                if form == 0:
+                    continue
                 fc = tag & TAG_FUNC_MASK
                 if form != FORM_GENERAL:
                     self_eq = 1 if tag & TAG_SELF_EQ1 else 0
@@ -157,3 +197,18 @@ class ImageModel:
             pos += w * (s1 * fv)
             neg += w * (s0 * fv)
         return pos, neg
+
+    def sell_fixed_bits_ok(self, w_fixed_orig):
+        """every real record's fixed bit == isfixed of its weight (padding: weight id 0, bit clear)"""
+        fixed = np.asarray(w_fixed_orig)[self.w_perm.astype(np.int64)].astype(np.uint32)
+        for s in range(len(self.sl_off) - 1):
+            h = self.slice_header(s)
+            for sec, n, nop in ((h["un"], h["n_un"], 0x05), (h["mu"], h["n_mu"], 0x55 if h["flags"] & 2 else 0)):
+                recs = self.blob[sec:sec + 32 * n]
+                real = (recs >> 24) != nop if nop else ((recs >> 30) != 0)
+                bits = (recs >> 23) & 1
+                if not np.array_equal(bits[real], fixed[(recs & 0x7FFFFF).astype(np.int64)][real]):
+                    return False
+                if bits[~real].any():
+                    return False
+        return True

@@ -46,9 +46,13 @@ def _check_against_oracle(raw, schedule, rng, nassign=3):
         for v in range(o.nvar):
             for p in range(int(card[v])):
                 assert m.potential(v, p, a, w) == o.potential(v, p), (v, p)
-            if len(m.sl_col):  # sliced-ELL stream of Boolean graphs: same numbers
-                assert m.sell_potentials(v, a, w) == (o.potential(v, 1), o.potential(v, 0)), v
-    assert (len(m.sl_col) > 0) == (not o.dtype.any() and g.info.schedule != sb.SCHED_SEQUENTIAL)
+            if len(m.sl_off):  # sliced-ELL blob of Boolean graphs: unary records first, so the
+                # same terms in another order -- equal to fp64 reassociation
+                assert np.allclose(m.sell_potentials(v, a, w), (o.potential(v, 1), o.potential(v, 0)),
+                                   rtol=1e-12, atol=1e-12), v
+    if len(m.sl_off):
+        assert m.sell_fixed_bits_ok(raw.normalized().w_fixed)
+    assert (len(m.sl_off) > 0) == (not o.dtype.any() and g.info.schedule != sb.SCHED_SEQUENTIAL)
     return g, m, o
 
 
@@ -112,7 +116,7 @@ def test_loader_matches_raw_records(name):
     a = sb.Graph.from_files(p["meta"], [p["variables"]], [p["domains"]], [p["factors"]], [p["weights"]])
     b = sb.Graph.from_raw(load_golden_graph(name))
     for arr in ("perm", "row_ptr", "row_oth", "e_wid", "e_tag", "e_fv32", "e_fv64", "oth", "evid_val",
-                "var_flags", "truthiness", "w_init", "w_fixed", "values", "s_tag", "s_wid", "s_oth", "sl_col"):
+                "var_flags", "truthiness", "w_init", "w_fixed", "values", "blob", "sl_off"):
         assert np.array_equal(a.image(arr), b.image(arr)), arr
 
 
