@@ -176,17 +176,11 @@ def reference_arm(args):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
-class _DevArray:
-    """__cuda_array_interface__ view of library-owned device memory (for torch.distributed)."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
-
-
 def ours(args):
     import torch
     import sampler_b200 as sb
     from sampler_b200 import graphgen
+    from sampler_b200.replicas import ReplicaGroup, compute_n_epochs
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,13 +216,14 @@ def ours(args):
             % (info.num_variables, info.num_index_entries, info.num_colors, info.device_bytes / 2**20, t_gen, t_compile))
     smp = sb.Sampler(graph, device=local, sample_evidence=True, reg_param=LEARN["reg_param"], seed=1234, replica=rank)
     stream = torch.cuda.ExternalStream(smp.stream(), device=torch.device("cuda", local))
-    w_t = torch.as_tensor(_DevArray(smp.weights_device_ptr(), info.num_weights, "<f8"), device=torch.device("cuda", local))
+    # one replica per rank: DimmWitted's learn / inference schedule over torch.distributed (NCCL)
+    group = ReplicaGroup(smp, dist, device=local)
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
     # ---- learning phase: ceil(l / N) epochs per replica, weights averaged every epoch ----
-    n_learn = -(-LEARN["n_epoch"] // world)
+    n_learn = compute_n_epochs(LEARN["n_epoch"], world)
     step = LEARN["alpha"]
     smp.learn_epoch(step)  # warm-up epoch (JIT-free, but first touch of everything)
     smp.sync()
@@ -236,12 +231,7 @@ def ours(args):
     e0, e1 = ev(), ev()
     with torch.cuda.stream(stream):
         e0.record(stream)
-        for _ in range(n_learn):
-            smp.learn_epoch(step)
-            if dist is not None:
-                dist.all_reduce(w_t)
-                smp.finish_weight_average(world, want_norms=False)
-            step *= LEARN["diminish"]
+        group.learn(LEARN["n_epoch"], step, LEARN["diminish"])
         e1.record(stream)
     smp.sync()
     learn_ms = e0.elapsed_time(e1) / n_learn
@@ -259,7 +249,6 @@ def ours(args):
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     launches0 = L.dwg_launch_count()
-    tall_t = torch.as_tensor(_DevArray(smp.tallies_device_ptr(), info.num_values, "<i4"), device=torch.device("cuda", local))
     e0, e1, e2 = ev(), ev(), ev()
     t_wall0 = time.time()
     with torch.cuda.stream(stream):
@@ -267,7 +256,7 @@ def ours(args):
         smp.infer_epochs(args.steps)
         e1.record(stream)
         if dist is not None:
-            dist.reduce(tall_t, dst=0)  # sample tallies reduced at the end of inference
+            group.reduce_tallies_device()  # sample tallies reduced at the end of inference
         e2.record(stream)
     smp.sync()
     torch.cuda.synchronize()
@@ -324,6 +313,14 @@ def ours(args):
     peak, peak_src = measured_peak()
     bytes_sweep = float(info.bytes_per_sweep_infer)
     achieved = bytes_sweep / (sweep_ms * 1e-3) / 1e9
+    big_launches = max(1, sum(1 for c in range(info.num_colors)))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath) and nvar == wl["nvar"]:
+        try:  # dram bytes of ONE launch of the sweep kernel from the committed `ncu --set full` capture
+            traffic = json.load(open(tpath))["k_sell_infer"]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
     line = {
         "metric": "gibbs_variable_samples_per_sec", "value": value, "unit": "variable-samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -334,8 +331,11 @@ def ours(args):
                    "l2_policy": "inputs larger than L2 (%.0f MiB streamed per sweep vs 126 MB L2); no flush" % (info.device_bytes / 2**20),
                    "learn_epochs_before": n_learn + 1, "seed": 1234},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_infer<uint8_t>",
+                     "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "k_sell_infer<MULTI=1,FV=0> (one launch per colour class; achieved = bytes of a whole "
+                               "sweep / CUDA-event time of the sweep, i.e. the launch-weighted average)",
                      "algorithmic_bytes_per_sweep": bytes_sweep, "bytes_per_variable_sample": bytes_sweep / nvar,
+                     "algorithmic_bytes_per_launch": bytes_sweep / big_launches,
                      "launches_per_sweep": info.num_colors},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "variable-samples/s",

@@ -65,6 +65,9 @@ typedef struct dwg_opts {
   int schedule;            /* DWG_SCHED_*          */
   uint64_t seed;           /* counter-based RNG key (the reference: rand(), gibbs_sampler.cc:49) */
   uint32_t replica;        /* RNG stream of this replica (== nodeid, gibbs_sampler.h:34) */
+  int learn_chunks;        /* parallel schedules: weight updates per colour class and learning sweep
+                              (the class is swept in that many strided parts, the weights move after
+                              each); 0 = auto (about 32 updates per sweep) */
 } dwg_opts_t;
 void dwg_opts_default(dwg_opts_t *o);
 
@@ -118,6 +121,7 @@ typedef struct dwg_graph_info {
   /* ALGORITHMIC bytes of one sweep: inference over all variables
    * (--sample_evidence), over query variables only, and one learning sweep */
   double bytes_per_sweep_infer, bytes_per_sweep_infer_query, bytes_per_sweep_learn;
+  uint64_t num_device_rows;     /* length of the device tally array (dwg_tallies_device_ptr) */
 } dwg_graph_info_t;
 int dwg_graph_info(const dwg_graph *g, dwg_graph_info_t *info);
 /* per-variable metadata in original id order, for writers (src/inference_result.cc:211-243):
@@ -160,6 +164,10 @@ void *dwg_weights_device_ptr(dwg_handle *h);
  * (fixed ones are restored), compute lmax / l2 of the change since the previous call
  * (dimmwitted.cc:220-227) in one epilogue kernel.  lmax/l2 may be NULL. */
 int dwg_finish_weight_average(dwg_handle *h, int n_replicas, double *lmax, double *l2);
+/* The same exchange through HOST memory (no NCCL: e.g. replicas in different processes talking
+ * gloo/MPI): store the cross-replica SUM of dwg_get_weights() vectors (original weight order),
+ * then call dwg_finish_weight_average.  merge_weights_from, src/inference_result.cc:68-73. */
+int dwg_set_weight_sum(dwg_handle *h, const double *sum);
 /* Same, with the allreduce done here over an ncclComm_t (libnccl is dlopen'ed). */
 int dwg_average_weights_nccl(dwg_handle *h, void *nccl_comm, int n_replicas, double *lmax, double *l2);
 /* In-process replicas (the CLI's -c N: one host thread driving N GPUs, like the reference's

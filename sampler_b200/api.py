@@ -27,7 +27,7 @@ class Opts(C.Structure):
     _fields_ = [("sample_evidence", C.c_int), ("learn_non_evidence", C.c_int),
                 ("noise_aware", C.c_int), ("regularization", C.c_int),
                 ("reg_param", C.c_double), ("schedule", C.c_int), ("seed", C.c_uint64),
-                ("replica", C.c_uint32)]
+                ("replica", C.c_uint32), ("learn_chunks", C.c_int)]
 
 
 class Raw(C.Structure):
@@ -48,7 +48,8 @@ class GraphInfo(C.Structure):
         ("num_colors", C.c_uint32), ("schedule", C.c_int), ("has_categorical", C.c_int),
         ("has_multi_arity", C.c_int), ("fv_mode", C.c_int), ("assign_bytes", C.c_int),
         ("device_bytes", C.c_uint64), ("bytes_per_sweep_infer", C.c_double),
-        ("bytes_per_sweep_infer_query", C.c_double), ("bytes_per_sweep_learn", C.c_double)]
+        ("bytes_per_sweep_infer_query", C.c_double), ("bytes_per_sweep_learn", C.c_double),
+        ("num_device_rows", C.c_uint64)]
 
 
 _lib = None
@@ -94,6 +95,7 @@ def load(build: bool = False):
     L.dwg_add_tallies.argtypes = [vp, vp, vp]
     L.dwg_get_weights.argtypes = [vp, vp]
     L.dwg_set_weights.argtypes = [vp, vp]
+    L.dwg_set_weight_sum.argtypes = [vp, vp]
     L.dwg_get_assignments.argtypes = [vp, i32, vp]
     L.dwg_set_assignments.argtypes = [vp, i32, vp]
     L.dwg_weights_device_ptr.restype = vp
@@ -174,7 +176,8 @@ class Graph:
 
     _IMG_DTYPES = {"e_fv32": np.float32, "e_fv64": np.float64, "s_fv32": np.float32, "s_fv64": np.float64,
                    "truthiness": np.float64, "w_init": np.float64, "cls_N_evid": np.float32,
-                   "cls_Q_evid": np.float32, "cls_N_all": np.float32, "cls_Q_all": np.float32}
+                   "cls_Q_evid": np.float32, "cls_N_all": np.float32, "cls_Q_all": np.float32,
+                   "cls_H_evid": np.float32, "cls_H_all": np.float32}
 
     def image(self, name: str) -> np.ndarray:
         """copy of one array of the compiled device image (tests)"""
@@ -198,17 +201,18 @@ class Sampler:
     src/gibbs_sampler.h:18-57, src/inference_result.h:27-43)."""
 
     def __init__(self, graph: Graph, device: int = 0, sample_evidence=False, learn_non_evidence=False,
-                 noise_aware=False, regularization="l2", reg_param=0.01, seed=0x5eed5eed, replica=0):
+                 noise_aware=False, regularization="l2", reg_param=0.01, seed=0x5eed5eed, replica=0, learn_chunks=0):
         L = load()
         self.graph = graph
         self.opts = Opts(int(sample_evidence), int(learn_non_evidence), int(noise_aware),
-                         1 if regularization == "l1" else 0, float(reg_param), 0, int(seed), int(replica))
+                         1 if regularization == "l1" else 0, float(reg_param), 0, int(seed), int(replica), int(learn_chunks))
         self._h = C.c_void_p()
         _check(L.dwg_create(graph._h, C.byref(self.opts), device, C.byref(self._h)))
         self.device = device
         self.nvar = graph.info.num_variables
         self.nval = graph.info.num_values
         self.nweight = graph.info.num_weights
+        self.ndrow = graph.info.num_device_rows
 
     def close(self):
         if self._h:
@@ -258,6 +262,12 @@ class Sampler:
         w = np.ascontiguousarray(w, np.float64)
         assert w.shape[0] == self.nweight
         _check(load().dwg_set_weights(self._h, _ptr(w)))
+
+    def set_weights_sum(self, w_sum):
+        """store the cross-replica SUM (host exchange); follow with finish_weight_average(n)"""
+        w = np.ascontiguousarray(w_sum, np.float64)
+        assert w.shape[0] == self.nweight
+        _check(load().dwg_set_weight_sum(self._h, _ptr(w)))
 
     def assignments(self, evid_chain: int):
         a = np.zeros(self.nvar, np.uint64)

@@ -85,7 +85,7 @@ struct dwg_handle {
   // weights (internal order) and the batch-update statics
   DevBuf<uint8_t> w_fixed;
   DevBuf<double> weights, prev_weights, grad_acc, norms;
-  DevBuf<float> cls_N, cls_Q;
+  DevBuf<float> cls_N, cls_Q, cls_H;
   bool learns = true;  // false: no variable takes an SGD step under these options
   // state
   DevBuf<uint8_t> assign_free8, assign_evid8;
@@ -235,7 +235,7 @@ static size_t image_device_bytes(const GraphImage &m) {
   }
   b += 4 * m.ndrow;        // tallies
   b += 8 * 3 * m.nweight;  // weights + prev + gradient sums
-  b += 4 * 2 * (m.cls_N_evid.size());
+  b += 4 * 3 * (m.cls_N_evid.size());
   return b;
 }
 
@@ -254,6 +254,7 @@ int dwg_graph_info(const dwg_graph *g, dwg_graph_info_t *o) {
   o->bytes_per_sweep_infer = m.bytes_infer;
   o->bytes_per_sweep_infer_query = m.bytes_infer_query;
   o->bytes_per_sweep_learn = m.bytes_learn;
+  o->num_device_rows = m.ndrow;
   return DWG_OK;
 }
 
@@ -300,7 +301,7 @@ int dwg_debug_image(const dwg_graph *g, const char *name, const void **data, uin
   ARR(row_oth) ARR(truthiness) ARR(e_wid) ARR(e_fv32) ARR(e_fv64) ARR(e_tag) ARR(oth) ARR(w_init)
   ARR(w_fixed) ARR(row_of_value) ARR(values) ARR(value_base) ARR(w_perm) ARR(w_inv)
   ARR(sl_off) ARR(blob)
-  ARR(cls_N_evid) ARR(cls_Q_evid) ARR(cls_N_all) ARR(cls_Q_all)
+  ARR(cls_N_evid) ARR(cls_Q_evid) ARR(cls_N_all) ARR(cls_Q_all) ARR(cls_H_evid) ARR(cls_H_all)
 #undef ARR
   if (n == "oth_packed") {
     static thread_local uint32_t v;
@@ -405,6 +406,7 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     const bool all = h->opts.learn_non_evidence;
     CU(h->cls_N.upload(all ? m.cls_N_all : m.cls_N_evid, s));
     CU(h->cls_Q.upload(all ? m.cls_Q_all : m.cls_Q_evid, s));
+    CU(h->cls_H.upload(all ? m.cls_H_all : m.cls_H_evid, s));
   }
   if (m.sell) {
     CU(h->sl_off.upload(m.sl_off, s));
@@ -470,6 +472,8 @@ static SweepParams make_params(dwg_handle *h, double stepsize) {
   p.sequential = h->sequential || h->img->schedule == DWG_SCHED_SEQUENTIAL;
   p.r_free = h->explicit_r ? h->r_free.p : nullptr;
   p.r_evid = h->explicit_r ? h->r_evid.p : nullptr;
+  p.unit_stride = 1;
+  p.unit_phase = 0;
   return p;
 }
 
@@ -488,34 +492,48 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
     p.d_end = m.color_start[c + 1];
     const uint32_t n = p.d_end - p.d_begin;
     if (!n) continue;
-    if (use_sell) {
-      SellGraph sg = h->sg;
-      sg.slice_begin = p.d_begin / 32;
-      sg.slice_end = p.d_end / 32;
-      const uint32_t need = (sg.slice_end - sg.slice_begin + SELL_THREADS / 32 - 1) / (SELL_THREADS / 32);
-      const uint32_t cap = (uint32_t)(learn ? h->sell_blocks_learn : h->sell_blocks_infer);
-      sell_launch(h, learn, std::min<uint32_t>(need, cap), sg, p);
-    } else {
-      uint32_t blocks = (n + SWEEP_THREADS - 1) / SWEEP_THREADS;
-      uint32_t threads = SWEEP_THREADS;
-      if (p.sequential) { blocks = 1; threads = 1; }
-      if (m.assign_bytes == 1) {
-        if (learn) k_sweep_learn<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
-        else k_sweep_infer<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
-      } else {
-        if (learn) k_sweep_learn<uint32_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
-        else k_sweep_infer<uint32_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
-      }
+    const uint32_t units = (n + 31) / 32;  // 32-variable units (= slices of the sliced-ELL stream)
+    // a learning sweep of a class runs as `chunks` strided parts with a weight update after each
+    uint32_t chunks = 1;
+    if (learn && !p.sequential) {
+      chunks = h->opts.learn_chunks > 0 ? (uint32_t)h->opts.learn_chunks : (32 + m.ncolor() - 1) / m.ncolor();
+      chunks = std::max(1u, std::min(chunks, units));
     }
-    ++g_launches;
-    if (learn && !p.sequential && m.nweight && (!use_sell || h->learns)) {
-      // integrate this launch's SGD steps (k_apply_weights): the sliced-ELL kernel sums bare
-      // gradients (decay from the static update counts), the CSR kernel sums gradient + decay
-      const size_t row = m.cls_shared ? 0 : (size_t)c * m.nweight;
-      k_apply_weights<<<(uint32_t)((m.nweight + 255) / 256), 256, 0, h->stream>>>(
-          h->weights.p, h->grad_acc.p, h->cls_N.p + row, h->cls_Q.p + row, h->w_fixed.p,
-          (uint32_t)m.nweight, stepsize, h->opts.reg_param, p.reg_l1, use_sell ? 0 : 1);
+    for (uint32_t b = 0; b < chunks; ++b) {
+      const uint32_t my_units = (units - b + chunks - 1) / chunks;
+      p.unit_stride = chunks;
+      p.unit_phase = b;
+      if (use_sell) {
+        SellGraph sg = h->sg;
+        sg.slice_begin = p.d_begin / 32 + b;
+        sg.slice_end = p.d_end / 32;
+        sg.slice_stride = chunks;
+        const uint32_t need = (my_units + SELL_THREADS / 32 - 1) / (SELL_THREADS / 32);
+        const uint32_t cap = (uint32_t)(learn ? h->sell_blocks_learn : h->sell_blocks_infer);
+        sell_launch(h, learn, std::min<uint32_t>(need, cap), sg, p);
+      } else {
+        uint32_t blocks = (my_units * 32 + SWEEP_THREADS - 1) / SWEEP_THREADS;
+        uint32_t threads = SWEEP_THREADS;
+        if (p.sequential) { blocks = 1; threads = 1; }
+        if (m.assign_bytes == 1) {
+          if (learn) k_sweep_learn<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+          else k_sweep_infer<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+        } else {
+          if (learn) k_sweep_learn<uint32_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+          else k_sweep_infer<uint32_t><<<blocks, threads, 0, h->stream>>>(h->dg, h->ds, p);
+        }
+      }
       ++g_launches;
+      if (learn && !p.sequential && m.nweight && (!use_sell || h->learns)) {
+        // integrate this launch's SGD steps (k_apply_weights): the sliced-ELL kernel sums bare
+        // gradients (decay from the static update counts), the CSR kernel sums gradient + decay
+        const size_t row = m.cls_shared ? 0 : (size_t)c * m.nweight;
+        k_apply_weights<<<(uint32_t)((m.nweight + 255) / 256), 256, 0, h->stream>>>(
+            h->weights.p, h->grad_acc.p, h->cls_N.p + row, h->cls_Q.p + row, h->cls_H.p + row, h->w_fixed.p,
+            (uint32_t)m.nweight, stepsize, h->opts.reg_param, p.reg_l1, use_sell ? 0 : 1,
+            (double)my_units / (double)units);
+        ++g_launches;
+      }
     }
   }
   CU(cudaGetLastError());
@@ -619,6 +637,17 @@ int dwg_set_weights(dwg_handle *h, const double *in) {
   for (uint64_t i = 0; i < m.nweight; ++i) t[i] = in[m.w_perm[i]];
   CU(cudaMemcpyAsync(h->weights.p, t.data(), 8 * m.nweight, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->prev_weights.p, t.data(), 8 * m.nweight, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DWG_OK;
+}
+
+int dwg_set_weight_sum(dwg_handle *h, const double *in) {
+  if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = *h->img;
+  CU(cudaSetDevice(h->device));
+  std::vector<double> t(m.nweight);
+  for (uint64_t i = 0; i < m.nweight; ++i) t[i] = in[m.w_perm[i]];
+  CU(cudaMemcpyAsync(h->weights.p, t.data(), 8 * m.nweight, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return DWG_OK;
 }

@@ -48,7 +48,14 @@ struct SweepParams {
   int sample_evidence, learn_non_evidence, noise_aware, reg_l1, sequential;
   double reg_param, stepsize;
   const double *r_free, *r_evid;  // explicit uniforms in schedule order (parity hooks) or null
+  // learning chunks: this launch sweeps the 32-variable units  phase, phase + stride, ... of the class
+  uint32_t unit_stride, unit_phase;
 };
+
+// variable handled by global thread `tid` in round `k` of a (possibly strided) class sweep
+__host__ __device__ inline uint64_t sweep_unit_var(const SweepParams &p, uint64_t tid) {
+  return (uint64_t)p.d_begin + (((tid >> 5) * p.unit_stride + p.unit_phase) << 5) + (tid & 31u);
+}
 
 // ---------------------------------------------------------------------------
 // counter-based RNG: Philox4x32-10 (Salmon et al., SC'11).  One call per variable

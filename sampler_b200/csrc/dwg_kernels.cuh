@@ -33,8 +33,14 @@ template <typename AssignT>
 __global__ void __launch_bounds__(SWEEP_THREADS)
 k_sweep_infer(const DevGraph g, const DevState st, const SweepParams p) {
   AssignT *a = static_cast<AssignT *>(st.assign_evid);
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t d = p.d_begin + blockIdx.x * blockDim.x + threadIdx.x; d < p.d_end; d += stride) {
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;; tid += nthreads) {
+    const uint64_t d64 = sweep_unit_var(p, tid);
+    if (d64 >= p.d_end) {  // past the class: done once the whole 32-variable unit is
+      if (d64 - (tid & 31u) >= p.d_end) break;
+      continue;
+    }
+    const uint32_t d = (uint32_t)d64;
     const uint8_t fl = __ldg(g.var_flags + d);
     if (fl & VF_PAD) continue;
     if ((fl & VF_EVID) && !p.sample_evidence) continue;  // gibbs_sampler.h:157
@@ -113,8 +119,14 @@ k_sweep_learn(const DevGraph g, const DevState st, const SweepParams p) {
   AssignT *af = static_cast<AssignT *>(st.assign_free);
   AssignT *ae = static_cast<AssignT *>(st.assign_evid);
   const AssignT *evid_val = static_cast<const AssignT *>(g.evid_val);
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t d = p.d_begin + blockIdx.x * blockDim.x + threadIdx.x; d < p.d_end; d += stride) {
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;; tid += nthreads) {
+    const uint64_t d64 = sweep_unit_var(p, tid);
+    if (d64 >= p.d_end) {  // past the class: done once the whole 32-variable unit is
+      if (d64 - (tid & 31u) >= p.d_end) break;
+      continue;
+    }
+    const uint32_t d = (uint32_t)d64;
     const uint8_t fl = __ldg(g.var_flags + d);
     if (fl & VF_PAD) continue;
     const bool cat = fl & VF_CATEGORICAL, evid = fl & VF_EVID, truthy = fl & VF_TRUTHINESS;

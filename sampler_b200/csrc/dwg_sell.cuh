@@ -32,6 +32,7 @@ constexpr int SELL_MCHUNK = 4;     // multi records / others words loaded togeth
 
 struct SellGraph {
   uint32_t slice_begin, slice_end;  // slices of this launch (one colour class)
+  uint32_t slice_stride;            // 1, or the number of learning chunks (begin carries the phase)
   const uint32_t *sl_off;           // [nslice+1] first word of a slice / 8
   const uint32_t *blob;
   uint32_t nweight, n_hot;
@@ -283,7 +284,9 @@ k_sell_infer(const SellGraph g, const SellState st, const SweepParams p) {
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t s = g.slice_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); s < g.slice_end; s += warps) {
+  for (uint64_t s64 = g.slice_begin + (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * g.slice_stride;
+       s64 < g.slice_end; s64 += (uint64_t)warps * g.slice_stride) {
+    const uint32_t s = (uint32_t)s64;
     const SliceHeader h = sell_header<FV>(g, s);
     // gibbs_sampler.h:157 -- slices are sorted by evidence: one with nothing to sample is skipped
     const uint32_t active = ~h.pad & (p.sample_evidence ? 0xffffffffu : ~h.evid);
@@ -323,7 +326,9 @@ k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t s = g.slice_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); s < g.slice_end; s += warps) {
+  for (uint64_t s64 = g.slice_begin + (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * g.slice_stride;
+       s64 < g.slice_end; s64 += (uint64_t)warps * g.slice_stride) {
+    const uint32_t s = (uint32_t)s64;
     const SliceHeader h = sell_header<FV>(g, s);
     const uint32_t d = s * 32u + lane;
     const bool pad = (h.pad >> lane) & 1u, evid = (h.evid >> lane) & 1u;
@@ -399,19 +404,19 @@ k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
 // w (src/inference_result.h:66-85):   w <- w / (1 + reg*a) - a * g_i      (l2, a = stepsize)
 // A launch makes N such steps with the weights frozen, so it integrates them at once:
 //     S  = sum g_i  +  N * reg/(1+reg*a) * w          (gradient + decay of the N steps)
-//     z  = a * Q  +  N * reg*a/(1+reg*a)               (Q >= curvature of the N steps, compile.cc)
+//     z  = a * D  +  N * reg*a/(1+reg*a)               (D >= curvature of the N steps, see below)
 //     w <- w - a * S * (1 - exp(-z)) / z
 // For z -> 0 this is exactly the sum of the reference's N steps; for large z (a weight shared
 // by thousands of concurrent updates, where N plain steps from a stale weight would overshoot)
 // it tends to the damped Newton step -S/(Q + N*reg), i.e. the same fixed point
 // E[g] + reg*w = 0 the sequential recursion relaxes to, reached without oscillation.
 // l1 (sic, `w += reg * (w < 0)` per step): the decay term is  -N * reg * (w < 0) / a.
-__global__ void k_apply_weights(double *w, double *grad_acc, const float *N, const float *Q,
+__global__ void k_apply_weights(double *w, double *grad_acc, const float *N, const float *Q, const float *H,
                                 const uint8_t *fixed, uint32_t n, double step, double reg, int reg_l1,
-                                int decay_in_acc) {
+                                int decay_in_acc, double share) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || fixed[i]) return;
-  const double nn = (double)N[i];
+  const double nn = (double)N[i] * share;  // this launch swept `share` of the class
   const double acc = grad_acc[i];
   if (nn == 0.0 && acc == 0.0) return;
   grad_acc[i] = 0.0;
@@ -419,7 +424,16 @@ __global__ void k_apply_weights(double *w, double *grad_acc, const float *N, con
   const double r = reg_l1 ? 0.0 : reg * step / (1.0 + reg * step);
   double S = acc;
   if (!decay_in_acc) S += reg_l1 ? -nn * reg * (x < 0 ? 1.0 : 0.0) / step : nn * (r / step) * x;
-  const double z = step * (double)Q[i] + nn * r;
+  // curvature D: the weight's own (diagonal) bound H where the joint step is provably
+  // non-expansive with it, i.e. step * phi(step * D) * R <= 1 with R the row-sum majorizer;
+  // otherwise the smallest D that is (fixed point of D = R (1 - exp(-step D)), approached from above)
+  const double Rk = (double)Q[i] * share, Hk = (double)H[i] * share;
+  double D = Hk;
+  if (Rk * -expm1(-step * D) > D) {
+    D = Rk;
+    for (int it = 0; it < 12; ++it) D = Rk * -expm1(-step * D);
+  }
+  const double z = step * D + nn * r;
   const double phi = z > 1e-8 ? -expm1(-z) / z : 1.0 - 0.5 * z;
   w[i] = x - step * S * phi;
 }

@@ -125,7 +125,9 @@ struct GraphImage {
   // per (colour class, internal weight): SGD updates per learning launch and their curvature
   // bound; *_evid = evidence variables learn (default), *_all = --learn_non_evidence
   bool cls_shared = false;         // one class-averaged row instead of ncolor rows
-  std::vector<float> cls_N_evid, cls_Q_evid, cls_N_all, cls_Q_all;
+  // N = number of SGD steps, H = their own curvature bound (diagonal), Q = the row-sum
+  // majorizer of the joint curvature (compile.cc)
+  std::vector<float> cls_N_evid, cls_Q_evid, cls_H_evid, cls_N_all, cls_Q_all, cls_H_all;
 
   // host-only, original id order, for the ABI getters / writers
   std::vector<uint8_t> var_dtype, var_is_evid;

@@ -24,7 +24,7 @@ const Spec GIBBS_SPECS[] = {
     {"t", "n_threads", 1}, {"a", "alpha", 1}, {"p", "stepsize", 1}, {"d", "diminish", 1},
     {"b", "reg_param", 1}, {"", "regularization", 1}, {"q", "quiet", 0},
     {"", "sample_evidence", 0}, {"", "learn_non_evidence", 0}, {"", "noise_aware", 0},
-    {"", "schedule", 1}, {"", "seed", 1},
+    {"", "schedule", 1}, {"", "seed", 1}, {"", "learn_chunks", 1},
 };
 const Spec BIN2TEXT_SPECS[] = {
     {"m", "fg_meta", 1}, {"v", "variables", 1}, {"", "domains", 1}, {"f", "factors", 1},
@@ -171,6 +171,7 @@ CmdParser::CmdParser(int argc, const char *const argv[], int num_gpus) {
     else error("Argument: --schedule\n             expects auto, hogwild, chromatic or sequential");
     seed_given = vals.count("seed") > 0;
     seed = last_u64("seed", seed);
+    learn_chunks = (int)last_u64("learn_chunks", 0);
 
   } else if (app_name == "text2bin") {
     // dw text2bin MODE INPUT OUTPUT COUNT_OUTPUT [FUNC_ID ARITY VAR_IS_POSITIVE...]  (:173-219)

@@ -25,6 +25,7 @@ struct CmdParser {
   int schedule = 0;          // --schedule auto|hogwild|chromatic
   uint64_t seed = 0x5eed5eedull;  // --seed
   bool seed_given = false;
+  int learn_chunks = 0;      // --learn_chunks N: weight updates per colour class and learning sweep (0 = auto)
 
   // text2bin
   std::string text2bin_mode, text2bin_input, text2bin_output, text2bin_count_output;

@@ -506,6 +506,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     uint64_t rows_n = g->cls_shared ? 1 : ncolor;
     g->cls_N_evid.assign(rows_n * nweight, 0.f); g->cls_Q_evid.assign(rows_n * nweight, 0.f);
     g->cls_N_all.assign(rows_n * nweight, 0.f); g->cls_Q_all.assign(rows_n * nweight, 0.f);
+    g->cls_H_evid.assign(rows_n * nweight, 0.f); g->cls_H_all.assign(rows_n * nweight, 0.f);
     auto srange = [](uint32_t fc, uint64_t n) -> double {
       switch (fc) {
         case FC_AND: case FC_OR: case FC_EQUAL: case FC_IMPLY_NATURAL: return 2.0;
@@ -546,16 +547,16 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         walk_row(r, [&](uint32_t, double delta) { rowsum += delta; });
         const float one = cat ? 2.f : 1.f;  // a categorical step also visits the row of the free value
         walk_row(r, [&](uint32_t w, double delta) {
-          float q = (float)(0.25 * delta * rowsum) * one;
-          g->cls_N_all[base + w] += one; g->cls_Q_all[base + w] += q;
-          if (ev) { g->cls_N_evid[base + w] += one; g->cls_Q_evid[base + w] += q; }
+          float q = (float)(0.25 * delta * rowsum) * one, hd = (float)(0.25 * delta * delta) * one;
+          g->cls_N_all[base + w] += one; g->cls_Q_all[base + w] += q; g->cls_H_all[base + w] += hd;
+          if (ev) { g->cls_N_evid[base + w] += one; g->cls_Q_evid[base + w] += q; g->cls_H_evid[base + w] += hd; }
         });
       }
     }
     if (g->cls_shared)
       for (uint64_t w = 0; w < nweight; ++w) {
-        g->cls_N_evid[w] /= ncolor; g->cls_Q_evid[w] /= ncolor;
-        g->cls_N_all[w] /= ncolor; g->cls_Q_all[w] /= ncolor;
+        g->cls_N_evid[w] /= ncolor; g->cls_Q_evid[w] /= ncolor; g->cls_H_evid[w] /= ncolor;
+        g->cls_N_all[w] /= ncolor; g->cls_Q_all[w] /= ncolor; g->cls_H_all[w] /= ncolor;
       }
   }
 

@@ -120,6 +120,7 @@ int gibbs(const CmdParser &args) {
   opts.schedule = args.schedule;
   // the reference seeds from un-seeded rand() (gibbs_sampler.cc:49): a fixed default; --seed varies it
   opts.seed = args.seed;
+  opts.learn_chunks = args.learn_chunks;
   for (size_t i = 0; i < n_samplers; ++i) {
     std::cout << "CREATE CFG ON GPU ... " << i << std::endl;
     opts.replica = (uint32_t)i;

@@ -74,13 +74,13 @@ def text2bin_dir(src, dst):
     shutil.rmtree(tmp)
 
 
-def run_dw(binary, gdir, seed, extra=()):
+def run_dw(binary, gdir, seed, extra=(), threads=1):
     out = tempfile.mkdtemp()
     args = open(os.path.join(gdir, "dw-args")).read().split()
     cmd = [binary, "gibbs", "-m", os.path.join(gdir, "graph.meta"),
            "-v", os.path.join(gdir, "graph.variables"), "-f", os.path.join(gdir, "graph.factors"),
            "-w", os.path.join(gdir, "graph.weights"), "--domains", os.path.join(gdir, "graph.domains"),
-           "-o", out, "--quiet", "-t", "1", "-c", "1"] + args + list(extra)
+           "-o", out, "--quiet", "-t", str(threads), "-c", "1"] + args + list(extra)
     env = dict(os.environ, DW_SEED=str(seed))
     subprocess.check_call(cmd, env=env, stdout=subprocess.DEVNULL)
     w = open(os.path.join(out, "inference_result.out.weights.text")).read()
@@ -277,10 +277,18 @@ SCALE = {
 }
 
 
+SCALE_SEEDS = 16
+
+
 def make_scale():
     """reference results on mid-size synthetic graphs (regenerated in the tests from the same
-    seeded generator, sampler_b200/graphgen.py): learned weights and per-variable marginals,
-    mean over DW_SEED=1..5, -t 1 -c 1"""
+    seeded generator, sampler_b200/graphgen.py), all from the UNMODIFIED reference -t 1 -c 1:
+      weights_mean/std, marginals_mean/std   learn + infer with the graph's dw-args, DW_SEED=1..16
+      weights_mean_t8, marginals_mean_t8     the same with -t 8 (8 Hogwild threads): how far the reference
+                                             moves from its own -t 1 results when run in parallel
+      marginals_fixed                        inference only (-l 0) under FIXED weights = weights_mean,
+                                             4 seeds x 500 sweeps: the target of the inference sweep
+                                             alone, free of learning noise"""
     from sampler_b200 import graphgen
     for name, (gen, kw, dwargs) in SCALE.items():
         raw = getattr(graphgen, gen)(**kw)
@@ -288,19 +296,46 @@ def make_scale():
         gio.write_binary(raw, tmp)
         open(os.path.join(tmp, "dw-args"), "w").write(dwargs)
         ws, ms, keys = [], [], None
-        for seed in range(1, 6):
+        for seed in range(1, SCALE_SEEDS + 1):
             w, m = run_dw(ol.REF_DW, tmp, seed)
             ws.append(parse_w(w))
             mm = parse_m(m)
             keys = keys or list(mm.keys())
             ms.append([mm[k] for k in keys])
+        # the reference's own spread between thread counts: the same runs with -t 8 (Hogwild)
+        ws8, ms8 = [], []
+        for seed in range(1, SCALE_SEEDS + 1):
+            w, m = run_dw(ol.REF_DW, tmp, seed, threads=8)
+            ws8.append(parse_w(w))
+            mm = parse_m(m)
+            ms8.append([mm[k] for k in keys])
+        # inference under fixed weights
+        wmean = np.mean(ws, 0)
+        raw2 = getattr(graphgen, gen)(**kw)
+        raw2.w_init = wmean.copy()
+        gio.write_binary(raw2, tmp)
+        fixed_args = [a for a in dwargs.split()]
+        for flag in ("-l", "-i"):
+            i = fixed_args.index(flag)
+            fixed_args[i + 1] = "0" if flag == "-l" else "500"
+        open(os.path.join(tmp, "dw-args"), "w").write(" ".join(fixed_args))
+        mf = []
+        for seed in range(1, 5):
+            _, m = run_dw(ol.REF_DW, tmp, seed)
+            mm = parse_m(m)
+            mf.append([mm[k] for k in keys])
         shutil.rmtree(tmp)
         kv = np.array([[int(x) for x in k.split()] for k in keys], np.int64)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), generator=gen, kwargs=json.dumps(kw),
-                            dw_args=dwargs, weights_mean=np.mean(ws, 0), weights_std=np.std(ws, 0),
+                            dw_args=dwargs, weights_mean=wmean, weights_std=np.std(ws, 0),
                             marginal_keys=kv, marginals_mean=np.mean(ms, 0).astype(np.float32),
-                            marginals_std=np.std(ms, 0).astype(np.float32), nseeds=5)
-        print(name, "weights", np.mean(ws, 0)[:4], "+-", np.std(ws, 0)[:4], "mean marginal", np.mean(ms))
+                            marginals_std=np.std(ms, 0).astype(np.float32), nseeds=SCALE_SEEDS,
+                            marginals_fixed=np.mean(mf, 0).astype(np.float32), fixed_nsamples=4 * 500,
+                            weights_mean_t8=np.mean(ws8, 0), weights_std_t8=np.std(ws8, 0),
+                            marginals_mean_t8=np.mean(ms8, 0).astype(np.float32))
+        print("   -t 8 vs -t 1: weights mean|diff|", np.abs(np.mean(ws8, 0) - wmean).mean(), "marginals",
+              np.abs(np.mean(ms8, 0) - np.mean(ms, 0)).mean())
+        print(name, "weights", wmean[:4], "+-", np.std(ws, 0)[:4], "mean marginal", np.mean(ms), np.mean(mf))
 
 
 if __name__ == "__main__":

@@ -165,7 +165,7 @@ def _mk(raw, sched, **kw):
                learn_non_evidence=kw.get("learn_non_evidence", False),
                noise_aware=kw.get("noise_aware", False), reg_param=kw.get("reg_param", 0.01),
                reg_l1=kw.get("regularization", "l2") == "l1")
-    return g, sb.Sampler(g, **kw), ol.Oracle(raw, **okw)
+    return g, sb.Sampler(g, **kw), ol.Oracle(raw, **{k: v for k, v in okw.items()})
 
 
 def _same_state(s, o):
@@ -247,7 +247,8 @@ def test_parallel_learning_with_exact_arithmetic(seed):
 def test_learning_launch_integrates_the_gradient_sum():
     """A parallel learning launch freezes the weights, sums the gradients of its SGD steps per
     weight (shared-memory pre-aggregation + atomics) and applies them in k_apply_weights as
-        w <- w - step * S * (1 - exp(-z)) / z,   z = step * Q     (reg = 0)
+        w <- w - step * S * (1 - exp(-z)) / z,   z = step * H     (reg = 0, one chunk per sweep,
+                                                 H = the weight's own curvature bound)
     On a unary all-evidence graph with dyadic step / feature values the sum S is exact and equals
     what the sequential reference accumulates (its draws use the same potentials as long as no
     draw sits within the weight drift of a decision boundary)."""
@@ -261,7 +262,8 @@ def test_learning_launch_integrates_the_gradient_sum():
                        rng.integers(0, 2, nvar * deg), rng.integers(0, nw, nvar * deg),
                        rng.choice([1.0, 0.5, 2.0], nvar * deg), rng.normal(0, 1, nw),
                        np.zeros(nw, np.uint8)).normalized()
-    g, s, o = _mk(raw, sb.SCHED_AUTO, reg_param=0.0)
+    g = sb.Graph.from_raw(raw, sb.SCHED_AUTO)
+    s, o = sb.Sampler(g, reg_param=0.0, learn_chunks=1), ol.Oracle(raw, reg_param=0.0)
     assert g.info.schedule == sb.SCHED_HOGWILD
     perm, _ = g.schedule()
     step = 2.0 ** -20
@@ -276,12 +278,44 @@ def test_learning_launch_integrates_the_gradient_sum():
     o.sweep_learn_seq(step, perm, r0, np.zeros(nvar))
     _same_state(s, o)
     S = (raw.w_init - o.weights) / step          # the reference's gradient sums (exact: dyadic)
-    Q = g.image("cls_Q_evid").astype(np.float64)[g.image("w_inv").astype(np.int64)]
-    z = step * Q
+    H = g.image("cls_H_evid").astype(np.float64)[g.image("w_inv").astype(np.int64)]
+    z = step * H
     want = raw.w_init - step * S * (-np.expm1(-z) / z)
     w = s.weights()
     assert np.allclose(w, want, rtol=0, atol=1e-13)
     assert np.abs(w - raw.w_init).max() > 100 * step  # something was learnt
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_parallel_learning_gradient_sums_on_coupled_graphs(seed):
+    """The gradient a parallel learning launch accumulates per weight (sliced-ELL sign codes and
+    2x2 sign tables, general records, CSR records for categorical graphs) must be the sum of the
+    reference's SGD gradients.  With a vanishing dyadic step the weights do not move the draws,
+    phi(z) = 1 to 1e-5, and  w0 - w  =  step * sum of gradients  on both sides."""
+    rng = np.random.default_rng(900 + seed)
+    raw = random_graph(rng, nvar=1500, nfac=4000, nweight=24, p_cat=[0.0, 0.0, 0.5][seed % 3],
+                       max_arity=[2, 3, 3][seed % 3])
+    raw.fac_fv[:] = rng.choice([1.0, 0.5, 2.0, -1.0], raw.nfac)
+    raw.w_fixed[:] = rng.random(raw.nweight) < 0.2
+    kw = dict(reg_param=0.0, learn_non_evidence=seed % 2 == 1)
+    for sched in (sb.SCHED_CHROMATIC,):
+        g = sb.Graph.from_raw(raw, sched)
+        s = sb.Sampler(g, learn_chunks=[1, 3][seed % 2], **kw)
+        o = ol.Oracle(raw, **kw)
+        perm, _ = g.schedule()
+        step = 2.0 ** -30
+        for ep in range(2):
+            r0, r1 = rng.random(o.nvar), rng.random(o.nvar)
+            w0 = s.weights()
+            assert np.array_equal(w0, o.weights) or ep > 0
+            o.weights[:] = w0
+            s.set_uniforms(r0, r1)
+            s.learn_epoch(step)
+            o.sweep_learn_seq(step, perm, r0, r1)
+            _same_state(s, o)
+            got, want = (w0 - s.weights()) / step, (w0 - o.weights) / step
+            assert np.abs(want).max() > 10  # gradients were summed
+            assert np.allclose(got, want, rtol=1e-4, atol=1e-6), (got, want)
 
 
 # ---------------------------------------------------------------- RNG
