@@ -286,10 +286,15 @@ def ours(args):
     torch.cuda.synchronize()
     t0 = time.time()
     s2 = sb.Sampler(graph, device=local, sample_evidence=True, reg_param=LEARN["reg_param"], seed=99, replica=rank)
+    t_up = time.time()
     s2.infer_epochs(args.steps)
+    s2.sync()
+    t_sw = time.time()
     t2, n2 = s2.tallies()
-    e2e_s = time.time() - t0
+    t_end = time.time()
+    e2e_s = t_end - t0
     e2e_value = nvar * args.steps / e2e_s
+    e2e_parts = "upload %.1f ms, sweeps %.1f ms, tallies %.1f ms" % (1e3 * (t_up - t0), 1e3 * (t_sw - t_up), 1e3 * (t_end - t_sw))
     s2.close()
 
     # ---- the reference's CPU path on this host, bounded sample ----
@@ -318,7 +323,7 @@ def ours(args):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath) and nvar == wl["nvar"]:
         try:  # dram bytes of ONE launch of the sweep kernel from the committed `ncu --set full` capture
-            traffic = json.load(open(tpath))["k_sell_infer"]["dram_bytes_per_launch"]
+            traffic = json.load(open(tpath))["k_sell_infer_staged"]["dram_bytes_per_launch"]
         except Exception:
             traffic = None
     line = {
@@ -332,7 +337,7 @@ def ours(args):
                    "learn_epochs_before": n_learn + 1, "seed": 1234},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "k_sell_infer<MULTI=1,FV=0> (one launch per colour class; achieved = bytes of a whole "
+                     "kernel": "k_sell_infer_staged<MULTI=1,FV=0> (one launch per colour class; achieved = bytes of a whole "
                                "sweep / CUDA-event time of the sweep, i.e. the launch-weighted average)",
                      "algorithmic_bytes_per_sweep": bytes_sweep, "bytes_per_variable_sample": bytes_sweep / nvar,
                      "algorithmic_bytes_per_launch": bytes_sweep / big_launches,
@@ -340,7 +345,8 @@ def ours(args):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "variable-samples/s",
                 "h2d_bytes_per_step": int(info.device_bytes / args.steps), "d2h_bytes_per_step": int(4 * info.num_values / args.steps),
-                "what": "dwg_create (upload of the compiled graph from host memory) + %d sweeps + dwg_get_tallies, wall clock" % args.steps},
+                "what": "dwg_create (upload of the compiled graph from page-locked host memory) + %d sweeps + dwg_get_tallies "
+                        "(D2H into host arrays), wall clock: %s" % (args.steps, e2e_parts)},
         "learn": {"value": nvar * world / (learn_ms * 1e-3), "unit": "variable-updates/s", "ms_per_epoch": learn_ms,
                   "epochs": n_learn, "hbm_gbs": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9},
         "gpu_launches": int(launches), "clocks": clk, "frac_true": frac1,

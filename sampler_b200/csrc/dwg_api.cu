@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -40,7 +42,52 @@ static int fail(int code, const std::string &msg) {
 
 struct dwg_graph {
   GraphImage img;
+  // the big streams of the image are page-locked on the first dwg_create so that this and every
+  // later upload of the graph (one per replica / per run) is a DMA at the PCIe rate instead of
+  // a bounce through the driver's staging buffers; undone by dwg_graph_free
+  mutable std::mutex pin_mu;
+  mutable std::vector<const void *> pinned;
+  void pin() const {
+    std::lock_guard<std::mutex> lk(pin_mu);
+    if (!pinned.empty()) return;
+    auto reg = [&](const void *p, size_t bytes) {
+      if (bytes < (1u << 20)) return;
+      if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) pinned.push_back(p);
+      else cudaGetLastError();  // not fatal: the copy falls back to pageable memory
+    };
+    if (img.sell) {
+      reg(img.blob.data(), img.blob.size() * 4);
+    } else {
+      reg(img.e_wid.data(), img.e_wid.size() * 4);
+      reg(img.e_tag.data(), img.e_tag.size());
+      reg(img.oth.data(), img.oth.size() * 4);
+      reg(img.row_ptr.data(), img.row_ptr.size() * 4);
+      reg(img.e_fv32.data(), img.e_fv32.size() * 4);
+      reg(img.e_fv64.data(), img.e_fv64.size() * 8);
+    }
+    if (pinned.empty()) pinned.push_back(nullptr);  // tried
+  }
+  ~dwg_graph() {
+    for (const void *p : pinned)
+      if (p) cudaHostUnregister(const_cast<void *>(p));
+  }
 };
+
+namespace {
+// split [0, n) over a few host threads (the un-permute / widen loops of the getters)
+template <typename F>
+void parallel_for(uint64_t n, F f) {
+  unsigned nt = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+  if (n < (1u << 20) || nt == 1) { f(0, n); return; }
+  std::vector<std::thread> th;
+  const uint64_t per = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; ++t) {
+    const uint64_t a = t * per, b = std::min(n, a + per);
+    if (a < b) th.emplace_back([=] { f(a, b); });
+  }
+  for (auto &x : th) x.join();
+}
+}  // namespace
 
 namespace {
 template <typename T>
@@ -99,8 +146,20 @@ struct dwg_handle {
   SellGraph sg{};
   SellState ss{};
   int sell_blocks_infer = 0, sell_blocks_learn = 0;
+  // bulk-async staged inference kernel (dwg_sell.cuh): ring depth, stage capacity in words,
+  // grid cap; 0 stages = not available (DWG_SELL_DIRECT=1, or no room for two stages)
+  uint32_t sell_stages = 0, sell_stage_words = 0;
+  int sell_blocks_staged = 0;
+  // per colour class: the first slice from which every slice holds evidence / padding only
+  // (slices are sorted non-evidence first inside a class, compile.cc)
+  std::vector<uint32_t> cls_query_end;
   size_t device_bytes = 0;
+  // tally download: device row of every (variable, value) in ABI order, the gathered tallies and a
+  // page-locked landing buffer (all created on the first dwg_get_tallies)
+  DevBuf<uint32_t> row_of_value, tallies_abi;
+  uint32_t *tallies_host = nullptr;
   ~dwg_handle() {
+    if (tallies_host) cudaFreeHost(tallies_host);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -108,10 +167,10 @@ struct dwg_handle {
 // ---- sliced-ELL kernel dispatch over (multi-variable factors?, feature-value mode) ----
 namespace {
 template <typename K>
-int sell_grid(K kernel, size_t smem, int num_sms, int *blocks) {
+int sell_grid(K kernel, size_t smem, int num_sms, int *blocks, int threads = SELL_THREADS) {
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SELL_THREADS, smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
   if (per_sm < 1) return fail(DWG_ERR_CUDA, "sweep kernel does not fit on an SM");
   *blocks = per_sm * num_sms;
   return DWG_OK;
@@ -121,12 +180,52 @@ int sell_setup_t(dwg_handle *h) {
   const size_t n_hot = h->img->n_hot;
   int rc = sell_grid(k_sell_infer<MULTI, FV>, 8 * n_hot, h->num_sms, &h->sell_blocks_infer);
   if (rc) return rc;
-  return sell_grid(k_sell_learn<MULTI, FV>, 16 * n_hot, h->num_sms, &h->sell_blocks_learn);
+  rc = sell_grid(k_sell_learn<MULTI, FV>, 16 * n_hot, h->num_sms, &h->sell_blocks_learn);
+  if (rc) return rc;
+  // staged (bulk-async) inference kernel: ring geometry for this graph
+  h->sell_stages = 0;
+  const char *direct = getenv("DWG_SELL_DIRECT");
+  if (direct && *direct == '1') return DWG_OK;
+  const size_t budget = 112 * 1024;  // per CTA, two per SM out of 228 KB (1 KB reserved each)
+  uint32_t max_stages = SELL_MAX_STAGES;
+  if (const char *e = getenv("DWG_SELL_STAGES")) max_stages = std::max(2, std::min(SELL_MAX_STAGES, atoi(e)));
+  const uint32_t nwarp = SELL_STAGED_THREADS / 32;
+  const uint32_t n_tab = (uint32_t)std::min<uint64_t>({h->img->nweight, n_hot, SELL_MAX_TAB});
+  // the deepest ring (<= SELL_MAX_STAGES, two CTAs per SM) whose stage holds at least 97 % of the
+  // slices whole; the rare longer slice is staged up to its stage's end and read from HBM directly
+  const std::vector<uint32_t> &off = h->img->sl_off;
+  const size_t nslice = off.empty() ? 0 : off.size() - 1;
+  const uint32_t want = (h->img->sell_max_words + 3u) & ~3u;
+  uint32_t stages = 0, words = 0;
+  for (uint32_t st = max_stages; st >= 2 && !stages; --st) {
+    const size_t fixed = sell_staged_ring_off(n_tab, st);
+    uint32_t cap = (uint32_t)((budget - fixed) / (nwarp * st * 4)) & ~3u;
+    if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) cap = std::min<uint32_t>(cap, std::max(8, atoi(e)) & ~3u);  // tests
+    size_t fit = 0;
+    for (size_t i = 0; i < nslice; ++i) fit += (off[i + 1] - off[i]) * 8u <= cap;
+    if (st == 2 || fit * 100 >= nslice * 97) { stages = st; words = std::min(cap, want); }
+  }
+  const size_t smem = sell_staged_smem(n_tab, stages, words);
+  rc = h->img->nweight <= n_tab
+           ? sell_grid(k_sell_infer_staged<MULTI, FV, true>, smem, h->num_sms, &h->sell_blocks_staged, SELL_STAGED_THREADS)
+           : sell_grid(k_sell_infer_staged<MULTI, FV, false>, smem, h->num_sms, &h->sell_blocks_staged, SELL_STAGED_THREADS);
+  if (rc) return rc;
+  h->sg.n_tab = n_tab;
+  h->sell_stages = stages;
+  h->sell_stage_words = words;
+  return DWG_OK;
 }
 template <bool MULTI, int FV>
-void sell_launch_t(dwg_handle *h, bool learn, uint32_t blocks, const SellGraph &sg, const SweepParams &p) {
+void sell_launch_t(dwg_handle *h, bool learn, bool staged, uint32_t blocks, const SellGraph &sg,
+                   const SweepParams &p) {
   const size_t n_hot = h->img->n_hot;
-  if (learn) k_sell_learn<MULTI, FV><<<blocks, SELL_THREADS, 16 * n_hot, h->stream>>>(sg, h->ss, p);
+  if (staged) {
+    const size_t smem = sell_staged_smem(sg.n_tab, h->sell_stages, h->sell_stage_words);
+    if (h->img->nweight <= sg.n_tab)
+      k_sell_infer_staged<MULTI, FV, true><<<blocks, SELL_STAGED_THREADS, smem, h->stream>>>(sg, h->ss, p, h->sell_stages, h->sell_stage_words);
+    else
+      k_sell_infer_staged<MULTI, FV, false><<<blocks, SELL_STAGED_THREADS, smem, h->stream>>>(sg, h->ss, p, h->sell_stages, h->sell_stage_words);
+  } else if (learn) k_sell_learn<MULTI, FV><<<blocks, SELL_THREADS, 16 * n_hot, h->stream>>>(sg, h->ss, p);
   else k_sell_infer<MULTI, FV><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
 }
 #define SELL_SWITCH(CALL)                                                      \
@@ -147,9 +246,10 @@ int sell_setup(dwg_handle *h) {
 #undef CALL
   return rc;
 }
-void sell_launch(dwg_handle *h, bool learn, uint32_t blocks, const SellGraph &sg, const SweepParams &p) {
+void sell_launch(dwg_handle *h, bool learn, bool staged, uint32_t blocks, const SellGraph &sg,
+                 const SweepParams &p) {
   const GraphImage &m = *h->img;
-#define CALL(MU, FV) sell_launch_t<MU, FV>(h, learn, blocks, sg, p)
+#define CALL(MU, FV) sell_launch_t<MU, FV>(h, learn, staged, blocks, sg, p)
   SELL_SWITCH(CALL)
 #undef CALL
 }
@@ -377,6 +477,7 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const GraphImage &m = g->img;
   cudaStream_t s = h->stream;
+  g->pin();
   CU(h->var_flags.upload(m.var_flags, s));
   if (m.has_categorical) CU(h->var_row.upload(m.var_row, s));
   std::vector<uint8_t> ev8, fixed_dev(m.nweight);
@@ -444,6 +545,19 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     ss.weights = h->weights.p; ss.grad_acc = h->grad_acc.p; ss.tallies = h->tallies.p;
     rc = sell_setup(h.get());
     if (rc) return rc;
+    const uint32_t nc = m.ncolor();
+    h->cls_query_end.assign(nc, 0);
+    for (uint32_t c = 0; c < nc; ++c) {
+      const uint32_t sb = m.color_start[c] / 32, se = m.color_start[c + 1] / 32;
+      uint32_t qe = sb;
+      for (uint32_t sl = sb; sl < se; ++sl) {
+        bool query = false;
+        for (uint32_t d = sl * 32; d < sl * 32 + 32 && !query; ++d)
+          query = !(m.var_flags[d] & (VF_EVID | VF_PAD));
+        if (query) qe = sl + 1;
+      }
+      h->cls_query_end[c] = qe;
+    }
   }
   *out = h.release();
   return DWG_OK;
@@ -508,9 +622,17 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
         sg.slice_begin = p.d_begin / 32 + b;
         sg.slice_end = p.d_end / 32;
         sg.slice_stride = chunks;
-        const uint32_t need = (my_units + SELL_THREADS / 32 - 1) / (SELL_THREADS / 32);
-        const uint32_t cap = (uint32_t)(learn ? h->sell_blocks_learn : h->sell_blocks_infer);
-        sell_launch(h, learn, std::min<uint32_t>(need, cap), sg, p);
+        uint32_t n_sl = my_units;
+        if (!learn && !p.sample_evidence) {  // gibbs_sampler.h:157: the evidence tail of the class is not read at all
+          sg.slice_end = h->cls_query_end[c];
+          n_sl = sg.slice_end - sg.slice_begin;
+          if (!n_sl) continue;
+        }
+        const bool staged = !learn && h->sell_stages;
+        const uint32_t wpb = (staged ? SELL_STAGED_THREADS : SELL_THREADS) / 32;
+        const uint32_t need = (n_sl + wpb - 1) / wpb;
+        const uint32_t cap = (uint32_t)(staged ? h->sell_blocks_staged : learn ? h->sell_blocks_learn : h->sell_blocks_infer);
+        sell_launch(h, learn, staged, std::min<uint32_t>(need, cap), sg, p);
       } else {
         uint32_t blocks = (my_units * 32 + SWEEP_THREADS - 1) / SWEEP_THREADS;
         uint32_t threads = SWEEP_THREADS;
@@ -584,18 +706,30 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
-  if (tallies) {
-    std::vector<uint32_t> t(m.ndrow);
-    CU(cudaMemcpyAsync(t.data(), h->tallies.p, 4 * m.ndrow, cudaMemcpyDeviceToHost, h->stream));
+  if (tallies && m.nrow) {
+    // schedule order -> ABI order on the device, one DMA into page-locked memory, widen on the host
+    if (!h->tallies_host) {
+      CU(h->row_of_value.upload(m.row_of_value, h->stream));
+      CU(h->tallies_abi.alloc(m.nrow));
+      CU(cudaHostAlloc((void **)&h->tallies_host, 4 * m.nrow, cudaHostAllocDefault));
+    }
+    k_gather_u32<<<(uint32_t)((m.nrow + 255) / 256), 256, 0, h->stream>>>(h->tallies_abi.p, h->tallies.p,
+                                                                         h->row_of_value.p, (uint32_t)m.nrow);
+    ++g_launches;
+    CU(cudaMemcpyAsync(h->tallies_host, h->tallies_abi.p, 4 * m.nrow, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    for (uint64_t i = 0; i < m.nrow; ++i) tallies[i] = t[m.row_of_value[i]];
+    const uint32_t *t = h->tallies_host;
+    parallel_for(m.nrow, [=](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; ++i) tallies[i] = t[i]; });
   }
   if (nsamples) {
     // ++agg_nsamples for every sampled variable every sweep (src/gibbs_sampler.h:157,163)
-    for (uint64_t v = 0; v < m.nvar; ++v) {
-      bool sampled = !m.var_is_evid[v] || h->opts.sample_evidence;
-      nsamples[v] = (sampled ? h->infer_sweeps : 0) + (h->extra_nsamples.empty() ? 0 : h->extra_nsamples[v]);
-    }
+    const uint64_t sweeps = h->infer_sweeps;
+    const bool all = h->opts.sample_evidence;
+    const uint8_t *ev = m.var_is_evid.data();
+    const uint64_t *extra = h->extra_nsamples.empty() ? nullptr : h->extra_nsamples.data();
+    parallel_for(m.nvar, [=](uint64_t a, uint64_t b) {
+      for (uint64_t v = a; v < b; ++v) nsamples[v] = ((!ev[v] || all) ? sweeps : 0) + (extra ? extra[v] : 0);
+    });
   }
   return DWG_OK;
 }

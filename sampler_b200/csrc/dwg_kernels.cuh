@@ -262,6 +262,12 @@ __global__ void k_finish_average(double *w, double *prev, uint32_t n, double inv
   }
 }
 
+// dst[i] = src[idx[i]]: tallies from schedule order into ABI order (dwg_get_tallies)
+__global__ void k_gather_u32(uint32_t *dst, const uint32_t *src, const uint32_t *idx, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[__ldg(idx + i)];
+}
+
 // tallies (schedule order, u32) += host-provided counts (aggregate_marginals_from)
 __global__ void k_add_u32(uint32_t *dst, const uint32_t *src, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -36,6 +36,7 @@ struct SellGraph {
   const uint32_t *sl_off;           // [nslice+1] first word of a slice / 8
   const uint32_t *blob;
   uint32_t nweight, n_hot;
+  uint32_t n_tab;  // staged kernel: weights in its signed table (<= SELL_MAX_TAB)
 };
 
 struct SellState {
@@ -65,22 +66,26 @@ __device__ __forceinline__ SliceHeader sell_header(const SellGraph &g, uint32_t 
   return h;
 }
 
-// streaming (evict-first) loads for the inference sweep, cached ones for learning (its SGD
-// pass walks the slice a second time and finds it in L1)
-template <bool STREAM>
-__device__ __forceinline__ uint32_t sell_ld(const uint32_t *p) { return STREAM ? __ldcs(p) : __ldg(p); }
+// how a slice is read: cached loads for learning (its SGD pass walks the slice a second time
+// and finds it in L1), streaming (evict-first) loads for the direct inference sweep, plain
+// loads when the slice was staged in shared memory by a bulk-async copy
+constexpr int LD_CACHED = 0, LD_STREAM = 1, LD_SMEM = 2;
+template <int LD, typename T>
+__device__ __forceinline__ T sell_ldt(const T *p) { return LD == LD_SMEM ? *p : LD == LD_STREAM ? __ldcs(p) : __ldg(p); }
+template <int LD>
+__device__ __forceinline__ uint32_t sell_ld(const uint32_t *p) { return sell_ldt<LD, uint32_t>(p); }
 
 // feature value of record (column j, lane) of a section whose records start at `sec` and
 // hold `ncol` columns
-template <int FV, bool STREAM>
+template <int FV, int LD>
 __device__ __forceinline__ double sell_fv(const uint32_t *sec, uint32_t ncol, uint32_t j, uint32_t lane) {
   if (FV == FV_F32) {
     const float *p = reinterpret_cast<const float *>(sec + (size_t)32 * ncol) + (size_t)32 * j + lane;
-    return (double)(STREAM ? __ldcs(p) : __ldg(p));
+    return (double)sell_ldt<LD, float>(p);
   }
   if (FV == FV_F64) {
     const double *p = reinterpret_cast<const double *>(sec + (size_t)32 * ncol) + (size_t)32 * j + lane;
-    return STREAM ? __ldcs(p) : __ldg(p);
+    return sell_ldt<LD, double>(p);
   }
   return 1.0;
 }
@@ -112,7 +117,7 @@ __device__ __forceinline__ uint32_t sell_draw_boolean(double pos, double neg, do
 }
 
 // ---- unary records: pos/neg += weight * (sign * feature_value), src/factor_graph.h:140-142 ----
-template <int FV, bool STREAM, bool ANTISYM>
+template <int FV, int LD, bool ANTISYM>
 __device__ __forceinline__ void sell_unary(const SellGraph &g, const SliceHeader &h, const double *w_s,
                                            const double *w, uint32_t lane, double &pos, double &neg) {
   constexpr int U = FV == FV_F64 ? 4 : 8;
@@ -122,15 +127,15 @@ __device__ __forceinline__ void sell_unary(const SellGraph &g, const SliceHeader
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const bool ok = j0 + u < h.n_un;
-      rec[u] = ok ? sell_ld<STREAM>(h.un + (size_t)32 * (j0 + u) + lane) : (SELL_UNARY_NOP << 24);
-      fv[u] = (FV != FV_ONE && ok) ? sell_fv<FV, STREAM>(h.un, h.n_un, j0 + u, lane) : 1.0;
+      rec[u] = ok ? sell_ld<LD>(h.un + (size_t)32 * (j0 + u) + lane) : SELL_UNARY_NOP;
+      fv[u] = (FV != FV_ONE && ok) ? sell_fv<FV, LD>(h.un, h.n_un, j0 + u, lane) : 1.0;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const double wt = sell_weight(g, w_s, w, rec[u] & SELL_WID_MASK);
+      const double wt = sell_weight(g, w_s, w, (rec[u] >> 2) & SELL_WID_MASK);
       const double t = FV == FV_ONE ? wt : __dmul_rn(wt, fv[u]);  // w * (+-1 * fv) == +-(w * fv) exactly
-      pos = __dadd_rn(pos, sell_term((rec[u] >> 24) & 3u, t));
-      if (!ANTISYM) neg = __dadd_rn(neg, sell_term((rec[u] >> 26) & 3u, t));
+      pos = __dadd_rn(pos, sell_term(rec[u] & 3u, t));
+      if (!ANTISYM) neg = __dadd_rn(neg, sell_term(rec[u] >> 26, t));
     }
   }
   if (ANTISYM) neg = -pos;  // round-to-nearest is sign-symmetric: the mirrored sum, bit for bit
@@ -138,6 +143,7 @@ __device__ __forceinline__ void sell_unary(const SellGraph &g, const SliceHeader
 
 // ---- multi records of a general slice: CSR tag semantics, per-lane cursor into the others ----
 // Signs of one record when the variable is 0 / 1, the other variables read from chain `a`.
+template <int LD>
 __device__ __forceinline__ void sell_general_signs(const SliceHeader &h, uint32_t tag, uint32_t self,
                                                    uint32_t lane, uint32_t &oc, const uint8_t *a,
                                                    double &s0, double &s1) {
@@ -149,7 +155,7 @@ __device__ __forceinline__ void sell_general_signs(const SliceHeader &h, uint32_
     uint32_t nsb = 0;
     bool head_oth = false;
     for (uint32_t j = 0; j < form; ++j) {
-      const uint32_t w = __ldg(o + (size_t)(oc + j) * 32);
+      const uint32_t w = sell_ld<LD>(o + (size_t)(oc + j) * 32);
       const bool s = (uint32_t)a[w >> 1] == (w & 1u);
       if (!self_head && j == form - 1) head_oth = s;
       else nsb += s;
@@ -164,11 +170,11 @@ __device__ __forceinline__ void sell_general_signs(const SliceHeader &h, uint32_
     }
     return;
   }
-  const uint32_t n = __ldg(o + (size_t)oc * 32);
+  const uint32_t n = sell_ld<LD>(o + (size_t)oc * 32);
   uint32_t nsb0 = 0, nsb1 = 0;
   bool h0 = false, h1 = false;
   for (uint32_t i = 0; i < n; ++i) {
-    const uint32_t w = __ldg(o + (size_t)(oc + 1 + i) * 32);
+    const uint32_t w = sell_ld<LD>(o + (size_t)(oc + 1 + i) * 32);
     const uint32_t d = w >> 1, eq = w & 1u;
     bool t0, t1;
     if (d == self) { t0 = eq == 0u; t1 = eq == 1u; }
@@ -187,19 +193,19 @@ __device__ __forceinline__ uint32_t sell_general_span(const SliceHeader &h, uint
   return form != FORM_GENERAL ? form : 1u + __ldg(h.oth + (size_t)oc * 32 + lane);
 }
 
-template <int FV, bool STREAM>
+template <int FV, int LD>
 __device__ __forceinline__ void sell_general_multi(const SellGraph &g, const SliceHeader &h, const double *w_s,
                                                    const double *w, uint32_t lane, uint32_t self,
                                                    const uint8_t *a, double &pos, double &neg) {
   uint32_t oc = 0;
   for (uint32_t j = 0; j < h.n_mu; ++j) {
-    const uint32_t rec = sell_ld<STREAM>(h.mu + (size_t)32 * j + lane);
+    const uint32_t rec = sell_ld<LD>(h.mu + (size_t)32 * j + lane);
     const uint32_t tag = rec >> 24;
     if ((tag >> TAG_FORM_SHIFT) == 0) continue;  // padding
     const double wt = sell_weight(g, w_s, w, rec & SELL_WID_MASK);
-    const double fv = sell_fv<FV, STREAM>(h.mu, h.n_mu, j, lane);
+    const double fv = sell_fv<FV, LD>(h.mu, h.n_mu, j, lane);
     double s0, s1;
-    sell_general_signs(h, tag, self, lane, oc, a, s0, s1);
+    sell_general_signs<LD>(h, tag, self, lane, oc, a, s0, s1);
     pos = dev_acc(pos, wt, s1, fv);
     neg = dev_acc(neg, wt, s0, fv);
   }
@@ -211,13 +217,13 @@ struct BinaryChunk {
   uint32_t rec[SELL_MCHUNK], ow[SELL_MCHUNK];
 };
 
-template <bool STREAM>
+template <int LD>
 __device__ __forceinline__ void sell_binary_load(const SliceHeader &h, uint32_t j0, uint32_t lane, BinaryChunk &c) {
 #pragma unroll
   for (int u = 0; u < SELL_MCHUNK; ++u) {
     const bool ok = j0 + u < h.n_mu;
-    c.rec[u] = ok ? sell_ld<STREAM>(h.mu + (size_t)32 * (j0 + u) + lane) : (SELL_BINARY_NOP << 24);
-    c.ow[u] = ok ? sell_ld<STREAM>(h.oth + (size_t)32 * (j0 + u) + lane) : 0u;
+    c.rec[u] = ok ? sell_ld<LD>(h.mu + (size_t)32 * (j0 + u) + lane) : (SELL_BINARY_NOP << 24);
+    c.ow[u] = ok ? sell_ld<LD>(h.oth + (size_t)32 * (j0 + u) + lane) : 0u;
   }
 }
 
@@ -231,7 +237,7 @@ __device__ __forceinline__ uint32_t sell_binary_sat(const BinaryChunk &c, const 
   return sat;
 }
 
-template <int FV, bool STREAM>
+template <int FV, int LD>
 __device__ __forceinline__ void sell_binary_acc(const SellGraph &g, const SliceHeader &h, const double *w_s,
                                                 const double *w, uint32_t j0, uint32_t lane,
                                                 const BinaryChunk &c, uint32_t sat, double &pos, double &neg) {
@@ -239,7 +245,7 @@ __device__ __forceinline__ void sell_binary_acc(const SellGraph &g, const SliceH
   for (int u = 0; u < SELL_MCHUNK; ++u) {
     const double wt = sell_weight(g, w_s, w, c.rec[u] & SELL_WID_MASK);
     double t = wt;
-    if (FV != FV_ONE) t = __dmul_rn(wt, j0 + u < h.n_mu ? sell_fv<FV, STREAM>(h.mu, h.n_mu, j0 + u, lane) : 0.0);
+    if (FV != FV_ONE) t = __dmul_rn(wt, j0 + u < h.n_mu ? sell_fv<FV, LD>(h.mu, h.n_mu, j0 + u, lane) : 0.0);
     const uint32_t tab = (c.rec[u] >> 24) >> (2u * ((sat >> u) & 1u));
     pos = __dadd_rn(pos, sell_term((tab >> 4) & 3u, t));
     neg = __dadd_rn(neg, sell_term(tab & 3u, t));
@@ -249,7 +255,7 @@ __device__ __forceinline__ void sell_binary_acc(const SellGraph &g, const SliceH
 // FactorGraph::potential for proposals 1 and 0 of the lane's variable on chain `a`
 // (src/factor_graph.h:127-145); `first` = the slice's first binary chunk, loaded by the caller
 // ahead of the unary records so that its gathers overlap them
-template <bool MULTI, int FV, bool STREAM>
+template <bool MULTI, int FV, int LD>
 __device__ __forceinline__ void sell_potentials(const SellGraph &g, const SliceHeader &h, const double *w_s,
                                                 const double *w, uint32_t lane, uint32_t self,
                                                 const uint8_t *a, double &pos, double &neg) {
@@ -258,21 +264,21 @@ __device__ __forceinline__ void sell_potentials(const SellGraph &g, const SliceH
   uint32_t sat = 0;
   const bool binary = MULTI && (h.flags & SF_BINARY);
   if (binary) {
-    sell_binary_load<STREAM>(h, 0, lane, c);
+    sell_binary_load<LD>(h, 0, lane, c);
     sat = sell_binary_sat(c, a);
   }
-  if (h.flags & SF_ANTISYM) sell_unary<FV, STREAM, true>(g, h, w_s, w, lane, pos, neg);
-  else sell_unary<FV, STREAM, false>(g, h, w_s, w, lane, pos, neg);
+  if (h.flags & SF_ANTISYM) sell_unary<FV, LD, true>(g, h, w_s, w, lane, pos, neg);
+  else sell_unary<FV, LD, false>(g, h, w_s, w, lane, pos, neg);
   if (!MULTI) return;
   if (binary) {
-    sell_binary_acc<FV, STREAM>(g, h, w_s, w, 0, lane, c, sat, pos, neg);
+    sell_binary_acc<FV, LD>(g, h, w_s, w, 0, lane, c, sat, pos, neg);
     for (uint32_t j0 = SELL_MCHUNK; j0 < h.n_mu; j0 += SELL_MCHUNK) {
-      sell_binary_load<STREAM>(h, j0, lane, c);
+      sell_binary_load<LD>(h, j0, lane, c);
       sat = sell_binary_sat(c, a);
-      sell_binary_acc<FV, STREAM>(g, h, w_s, w, j0, lane, c, sat, pos, neg);
+      sell_binary_acc<FV, LD>(g, h, w_s, w, j0, lane, c, sat, pos, neg);
     }
   } else if (h.n_mu) {
-    sell_general_multi<FV, STREAM>(g, h, w_s, w, lane, self, a, pos, neg);
+    sell_general_multi<FV, LD>(g, h, w_s, w, lane, self, a, pos, neg);
   }
 }
 
@@ -293,21 +299,291 @@ k_sell_infer(const SellGraph g, const SellState st, const SweepParams p) {
     if (!active) continue;
     const uint32_t d = s * 32u + lane;
     double pos, neg;
-    sell_potentials<MULTI, FV, true>(g, h, w_s, st.weights, lane, d, st.assign_evid, pos, neg);
+    sell_potentials<MULTI, FV, LD_STREAM>(g, h, w_s, st.weights, lane, d, st.assign_evid, pos, neg);
     if (!((active >> lane) & 1u)) continue;
     double r0, r1;
     dev_uniforms(p, d, r0, r1);
     const uint32_t prop = sell_draw_boolean(pos, neg, r0);
     st.assign_evid[d] = (uint8_t)prop;
-    if (prop) st.tallies[d] += 1u;  // gibbs_sampler.h:163-167 (agg_nsamples is implicit)
+    if (prop) atomicAdd(st.tallies + d, 1u);  // gibbs_sampler.h:163-167 (agg_nsamples is implicit); a fire-and-forget RED, the warp does not wait for the tally
+  }
+}
+
+// ---- bulk-async staged inference sweep -----------------------------------------------------
+// The direct kernel above walks a 4-deep dependent chain per slice (offset -> header -> records
+// -> neighbour chain bytes) and spends ~540 warp instructions on a slice, a quarter of them on
+// picking signs and on the hot/cold weight branch.  This kernel removes both costs:
+//  * every warp owns a ring of `stages` slice buffers in shared memory and one mbarrier per
+//    stage; lane 0 posts ONE 1-D bulk-async copy (cp.async.bulk global -> shared, the TMA unit's
+//    non-tensor form, evict-first L2 policy) per slice -- the blob layout makes a slice one
+//    contiguous 32 B-aligned run -- `stages` slices ahead of the one being sampled.  Slice
+//    offsets come 32 at a time (lane = iteration) and are handed round by shuffle.  Headers and
+//    records are then read with conflict-free LDS; what is left on the critical path of a slice
+//    is shared-memory latency, the L2 gather of neighbour chain bytes (issued before the unary
+//    records are summed) and arithmetic.  A slice longer than a stage (rare: the stage size is
+//    picked to hold >= 97 % of the slices) is staged up to the stage's end and read from HBM.
+//  * weights with id < n_tab are staged as a SIGNED table of four entries per weight
+//    (-w, 0, +w, 0): a record's sign code indexes the table, so a term costs one mask, one LDS.64
+//    and one DADD instead of compares and selects, and (ALLHOT) no hot/cold branch exists at all
+//    when every weight fits.  (+-w) * fv == +-(w * fv) and x + (+-0) == x: the sums are the
+//    direct kernel's bit for bit.
+constexpr int SELL_MAX_STAGES = 4;
+constexpr int SELL_STAGED_THREADS = 384;  // 12 warps, 2 CTAs per SM, <= 85 registers
+constexpr uint32_t SELL_MAX_TAB = 1024;   // weights in the signed table (32 B each)
+
+__device__ __forceinline__ uint32_t sell_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sell_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sell_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sell_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SELL_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SELL_DONE;\n"
+      "bra SELL_WAIT;\n"
+      "SELL_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint64_t sell_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void sell_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+
+// shared-memory plan of the staged kernel (host and device agree through these):
+// signed weight table | one mbarrier per (warp, stage) | the rings
+__host__ __device__ inline uint32_t sell_staged_bar_off(uint32_t n_tab) { return n_tab * 32u; }
+__host__ __device__ inline uint32_t sell_staged_ring_off(uint32_t n_tab, uint32_t stages) {
+  return (sell_staged_bar_off(n_tab) + (SELL_STAGED_THREADS / 32) * stages * 8u + 127u) & ~127u;
+}
+__host__ __device__ inline uint32_t sell_staged_smem(uint32_t n_tab, uint32_t stages, uint32_t stage_words) {
+  return sell_staged_ring_off(n_tab, stages) + (SELL_STAGED_THREADS / 32) * stages * stage_words * 4u;
+}
+
+// the rare slice that is longer than a stage: potentials straight from HBM, as the direct kernel
+// does (out of line, so that it does not cost the staged loop registers).  w_plain: no plain
+// weight table is staged here, every weight comes through L1/L2 (n_hot = 0).
+template <bool MULTI, int FV>
+__device__ __noinline__ void sell_unstaged_potentials(const SellGraph &g, const SellState &st, uint32_t off,
+                                                      uint32_t n_un, uint32_t n_mu, uint32_t flags, uint32_t lane,
+                                                      uint32_t d, double &pos, double &neg) {
+  constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
+  SellGraph gc = g;
+  gc.n_hot = 0;
+  SliceHeader h;
+  h.n_un = n_un; h.n_mu = n_mu; h.n_oc = 0; h.evid = 0; h.pad = 0; h.evval = 0;
+  h.flags = flags;
+  h.un = g.blob + (size_t)off * 8 + SH_WORDS;
+  h.mu = h.un + (size_t)32 * n_un * (1 + FVW);
+  h.oth = h.mu + (size_t)32 * n_mu * (1 + FVW);
+  sell_potentials<MULTI, FV, LD_STREAM>(gc, h, nullptr, st.weights, lane, d, st.assign_evid, pos, neg);
+}
+
+template <int FV>
+__device__ __forceinline__ double sell_fv_s(const uint32_t *sm, uint32_t fvb, uint32_t j, uint32_t lane) {
+  if (FV == FV_F32) return (double)__uint_as_float(sm[fvb + 32u * j + lane]);
+  if (FV == FV_F64) return reinterpret_cast<const double *>(sm + fvb)[32u * j + lane];
+  return 1.0;
+}
+
+// sign * weight of table entry idx = wid << 2 | code
+template <bool ALLHOT>
+__device__ __forceinline__ double sell_signed_weight(const SellGraph &g, const double *tab_s, const double *w,
+                                                     uint32_t idx) {
+  if (ALLHOT || idx < 4u * g.n_tab) return tab_s[idx];
+  return sell_term(idx & 3u, __ldg(w + (idx >> 2)));
+}
+
+// one unary record of a staged slice into pos / neg (same arithmetic and order as sell_unary)
+template <int FV, bool ANTISYM, bool ALLHOT>
+__device__ __forceinline__ void sell_unary_rec(const SellGraph &g, const double *tab_s, const double *w, uint32_t rec,
+                                               double fv, double &pos, double &neg) {
+  const uint32_t idx = rec & SELL_UN_IDX_MASK;
+  const double t1 = sell_signed_weight<ALLHOT>(g, tab_s, w, idx);
+  pos = __dadd_rn(pos, FV == FV_ONE ? t1 : __dmul_rn(t1, fv));
+  if (!ANTISYM) {
+    const double t0 = sell_signed_weight<ALLHOT>(g, tab_s, w, (idx & ~3u) | (rec >> 26));
+    neg = __dadd_rn(neg, FV == FV_ONE ? t0 : __dmul_rn(t0, fv));
+  }
+}
+
+template <int FV, bool ANTISYM, bool ALLHOT>
+__device__ __forceinline__ void sell_unary_s(const SellGraph &g, const uint32_t *sm, uint32_t b, uint32_t n_un,
+                                             const double *tab_s, const double *w, uint32_t lane, double &pos,
+                                             double &neg) {
+  constexpr uint32_t U = 4;
+  const uint32_t un = b + SH_WORDS + lane, fvb = b + SH_WORDS + 32u * n_un;
+  uint32_t j0 = 0;
+  for (; j0 + U <= n_un; j0 += U) {
+    uint32_t rec[U];
+    double fv[U];
+#pragma unroll
+    for (uint32_t u = 0; u < U; ++u) {
+      rec[u] = sm[un + 32u * (j0 + u)];
+      fv[u] = sell_fv_s<FV>(sm, fvb, j0 + u, lane);
+    }
+#pragma unroll
+    for (uint32_t u = 0; u < U; ++u) sell_unary_rec<FV, ANTISYM, ALLHOT>(g, tab_s, w, rec[u], fv[u], pos, neg);
+  }
+  for (; j0 < n_un; ++j0)
+    sell_unary_rec<FV, ANTISYM, ALLHOT>(g, tab_s, w, sm[un + 32u * j0], sell_fv_s<FV>(sm, fvb, j0, lane), pos, neg);
+  if (ANTISYM) neg = -pos;
+}
+
+template <bool MULTI, int FV, bool ALLHOT>
+__global__ void __launch_bounds__(SELL_STAGED_THREADS, 2)
+k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, const uint32_t stages,
+                    const uint32_t stage_words) {
+  extern __shared__ __align__(128) unsigned char sell_smem[];
+  constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
+  constexpr uint32_t MC = 2;  // binary records handled together
+  double *tab_s = reinterpret_cast<double *>(sell_smem);
+  const uint32_t *sm = reinterpret_cast<const uint32_t *>(sell_smem);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t bar0 = sell_smem_addr(sell_smem) + sell_staged_bar_off(g.n_tab) + warp * stages * 8u;
+  const uint32_t ringw = sell_staged_ring_off(g.n_tab, stages) / 4u + warp * stages * stage_words;  // word index
+  const uint32_t ring0 = sell_smem_addr(sell_smem) + ringw * 4u;
+  if (lane == 0)
+    for (uint32_t i = 0; i < stages; ++i) sell_mbar_init(bar0 + 8u * i, 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  for (uint32_t i = threadIdx.x; i < g.n_tab; i += blockDim.x) {
+    const double w = __ldg(st.weights + i);
+    tab_s[4 * i] = -w; tab_s[4 * i + 1] = 0.0; tab_s[4 * i + 2] = w; tab_s[4 * i + 3] = 0.0;
+  }
+  __syncthreads();
+
+  // slices of this warp: s(k) = s0 + k * step, k < n_my
+  const uint64_t step = (uint64_t)((gridDim.x * blockDim.x) >> 5) * g.slice_stride;
+  const uint64_t s0 = g.slice_begin + (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * g.slice_stride;
+  if (s0 >= g.slice_end) return;
+  const uint32_t n_my = (uint32_t)((g.slice_end - 1 - s0) / step) + 1u;
+  const uint64_t pol = sell_policy_evict_first();
+
+  // slice offsets, 32 iterations per fetch (lane = iteration), one block ahead
+  uint32_t cur_lo = 0, cur_hi = 0, nxt_lo = 0, nxt_hi = 0;
+  auto fetch_offsets = [&](uint32_t kb, uint32_t &lo, uint32_t &hi) {
+    const uint32_t k = kb + lane;
+    if (k < n_my) {
+      const uint32_t *o = g.sl_off + (s0 + (uint64_t)k * step);
+      lo = __ldg(o);
+      hi = __ldg(o + 1);
+    }
+  };
+  fetch_offsets(0, cur_lo, cur_hi);
+  fetch_offsets(32, nxt_lo, nxt_hi);
+  // post the copy of iteration k into stage `stage` (called for k = 0, 1, 2, ... in order)
+  auto issue = [&](uint32_t k, uint32_t stage) {
+    const uint32_t j = k & 31u;
+    if (j == 0 && k) {
+      cur_lo = nxt_lo; cur_hi = nxt_hi;
+      fetch_offsets(k + 32, nxt_lo, nxt_hi);
+    }
+    const uint32_t off = __shfl_sync(0xffffffffu, cur_lo, j);
+    const uint32_t bytes = min((__shfl_sync(0xffffffffu, cur_hi, j) - off) * 32u, stage_words * 4u);
+    if (lane == 0) {
+      sell_mbar_expect_tx(bar0 + 8u * stage, bytes);
+      sell_bulk_g2s(ring0 + stage * stage_words * 4u, g.blob + (size_t)off * 8, bytes, bar0 + 8u * stage, pol);
+    }
+  };
+
+  const uint32_t pre = n_my < stages ? n_my : stages;
+  for (uint32_t k = 0; k < pre; ++k) issue(k, k);
+  uint32_t stage = 0, parity = 0;  // of iteration k
+  uint64_t s64 = s0;
+  for (uint32_t k = 0; k < n_my; ++k, s64 += step) {
+    sell_mbar_wait(bar0 + 8u * stage, parity);
+    const uint32_t b = ringw + stage * stage_words;
+    const uint4 h0 = *reinterpret_cast<const uint4 *>(sm + b);      // n_un, n_mu, n_oc, evid
+    const uint4 h1 = *reinterpret_cast<const uint4 *>(sm + b + 4);  // pad, evval, flags, own offset
+    const uint32_t n_un = h0.x, n_mu = h0.y, flags = h1.z;
+    // gibbs_sampler.h:157 -- a slice with nothing to sample is skipped
+    const uint32_t active = ~h1.x & (p.sample_evidence ? 0xffffffffu : ~h0.w);
+    const uint32_t d = (uint32_t)s64 * 32u + lane;
+    if (active) {
+      // FactorGraph::potential for proposals 1 and 0 (src/factor_graph.h:127-145)
+      double pos = 0.0, neg = 0.0;
+      if (SH_WORDS + 32u * ((n_un + n_mu) * (1 + FVW) + h0.z) > stage_words) {
+        sell_unstaged_potentials<MULTI, FV>(g, st, h1.w, n_un, n_mu, flags, lane, d, pos, neg);
+      } else {
+        const uint32_t mu = b + SH_WORDS + 32u * n_un * (1 + FVW) + lane;
+        const uint32_t mufv = b + SH_WORDS + 32u * n_un * (1 + FVW) + 32u * n_mu;
+        const uint32_t oth = mu + 32u * n_mu * (1 + FVW);
+        const bool binary = MULTI && (flags & SF_BINARY);
+        // the neighbour chain bytes of the first binary records travel while the unary records are summed
+        uint32_t ow[MC], av[MC];
+        if (binary) {
+#pragma unroll
+          for (uint32_t u = 0; u < MC; ++u) ow[u] = u < n_mu ? sm[oth + 32u * u] : 0u;
+#pragma unroll
+          for (uint32_t u = 0; u < MC; ++u) av[u] = st.assign_evid[ow[u] >> 1];
+        }
+        if (flags & SF_ANTISYM) sell_unary_s<FV, true, ALLHOT>(g, sm, b, n_un, tab_s, st.weights, lane, pos, neg);
+        else sell_unary_s<FV, false, ALLHOT>(g, sm, b, n_un, tab_s, st.weights, lane, pos, neg);
+        if (binary) {
+          // record j owns others word j; its tag is the factor's sign table code(x, sat) at bits
+          // 2 (2 x + sat): x = 1 feeds pos, x = 0 feeds neg
+          for (uint32_t j0 = 0; j0 < n_mu; j0 += MC) {
+            if (j0) {
+#pragma unroll
+              for (uint32_t u = 0; u < MC; ++u) ow[u] = j0 + u < n_mu ? sm[oth + 32u * (j0 + u)] : 0u;
+#pragma unroll
+              for (uint32_t u = 0; u < MC; ++u) av[u] = st.assign_evid[ow[u] >> 1];
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < MC; ++u) {
+              const bool ok = j0 + u < n_mu;
+              const uint32_t rec = ok ? sm[mu + 32u * (j0 + u)] : (SELL_BINARY_NOP << 24);
+              const uint32_t sat = av[u] == (ow[u] & 1u) ? 1u : 0u;
+              const uint32_t codes = rec >> (24u + 2u * sat), wid4 = (rec & SELL_WID_MASK) << 2;
+              double t1 = sell_signed_weight<ALLHOT>(g, tab_s, st.weights, wid4 | ((codes >> 4) & 3u));
+              double t0 = sell_signed_weight<ALLHOT>(g, tab_s, st.weights, wid4 | (codes & 3u));
+              if (FV != FV_ONE) {
+                const double fv = ok ? sell_fv_s<FV>(sm, mufv, j0 + u, lane) : 0.0;
+                t1 = __dmul_rn(t1, fv);
+                t0 = __dmul_rn(t0, fv);
+              }
+              pos = __dadd_rn(pos, t1);
+              neg = __dadd_rn(neg, t0);
+            }
+          }
+        } else if (MULTI && n_mu) {
+          SellGraph gc = g;
+          gc.n_hot = 0;  // no plain weight table here: the general path reads weights through L1/L2
+          SliceHeader h;
+          h.n_un = n_un; h.n_mu = n_mu; h.n_oc = h0.z; h.evid = h0.w; h.pad = h1.x; h.evval = 0;
+          h.flags = flags;
+          h.un = sm + b + SH_WORDS; h.mu = sm + mu - lane; h.oth = sm + oth - lane;
+          sell_general_multi<FV, LD_SMEM>(gc, h, nullptr, st.weights, lane, d, st.assign_evid, pos, neg);
+        }
+      }
+      if ((active >> lane) & 1u) {
+        double r0, r1;
+        dev_uniforms(p, d, r0, r1);
+        const uint32_t prop = sell_draw_boolean(pos, neg, r0);
+        st.assign_evid[d] = (uint8_t)prop;
+        if (prop) atomicAdd(st.tallies + d, 1u);  // gibbs_sampler.h:163-167
+      }
+    }
+    __syncwarp();  // every lane is done with this stage before the next copy lands in it
+    if (k + stages < n_my) issue(k + stages, stage);
+    if (++stage == stages) { stage = 0; parity ^= 1u; }
   }
 }
 
 // gradient of one SGD step into the launch's accumulators (hot weights: shared memory)
-__device__ __forceinline__ void sell_grad(const SellGraph &g, const SellState &st, double *acc_s, uint32_t rec,
-                                          double grad) {
-  if (grad == 0.0 || (rec & SELL_FIXED_BIT)) return;  // factor_graph.cc:247
-  const uint32_t wid = rec & SELL_WID_MASK;
+__device__ __forceinline__ void sell_grad(const SellGraph &g, const SellState &st, double *acc_s, uint32_t wid,
+                                          bool fixed, double grad) {
+  if (grad == 0.0 || fixed) return;  // factor_graph.cc:247
   if (wid < g.n_hot) atomicAdd(acc_s + wid, grad);
   else atomicAdd(st.grad_acc + wid, grad);
 }
@@ -337,7 +613,7 @@ k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
     dev_uniforms(p, d, r0, r1);
     // free chain: every variable, evidence included (gibbs_sampler.h:137-139)
     double pos, neg;
-    sell_potentials<MULTI, FV, false>(g, h, w_s, st.weights, lane, d, st.assign_free, pos, neg);
+    sell_potentials<MULTI, FV, LD_CACHED>(g, h, w_s, st.weights, lane, d, st.assign_free, pos, neg);
     const uint32_t pf = sell_draw_boolean(pos, neg, r0);
     if (!pad) st.assign_free[d] = (uint8_t)pf;
     // evid chain (sample_evid, gibbs_sampler.h:171-190): clamp hard evidence, else a Gibbs draw
@@ -346,7 +622,7 @@ k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
     const uint32_t draw_evid = ~h.pad & (p.noise_aware ? 0xffffffffu : ~h.evid);
     if (draw_evid) {
       if (MULTI && h.n_mu)  // unary-only slices: both chains see identical potentials
-        sell_potentials<MULTI, FV, false>(g, h, w_s, st.weights, lane, d, st.assign_evid, pos, neg);
+        sell_potentials<MULTI, FV, LD_CACHED>(g, h, w_s, st.weights, lane, d, st.assign_evid, pos, neg);
       if ((draw_evid >> lane) & 1u) pe = sell_draw_boolean(pos, neg, r1);
     }
     if (!pad) st.assign_evid[d] = (uint8_t)pe;
@@ -359,10 +635,10 @@ k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
       for (uint32_t j = 0; j < h.n_un; ++j) {
         const uint32_t rec = __ldg(h.un + (size_t)32 * j + lane);
         if (!learn || pf == ev) continue;
-        const uint32_t tag = rec >> 24;
-        const int cf = (int)((tag >> (pf ? 0 : 2)) & 3u), ce = (int)((tag >> (ev ? 0 : 2)) & 3u);
+        const int cf = (int)(pf ? rec & 3u : rec >> 26), ce = (int)(ev ? rec & 3u : rec >> 26);
         if (cf == ce) continue;
-        sell_grad(g, st, acc_s, rec, __dmul_rn((double)(cf - ce), sell_fv<FV, false>(h.un, h.n_un, j, lane)));
+        sell_grad(g, st, acc_s, (rec >> 2) & SELL_WID_MASK, rec & SELL_UN_FIXED_BIT,
+                  __dmul_rn((double)(cf - ce), sell_fv<FV, LD_CACHED>(h.un, h.n_un, j, lane)));
       }
     }
     if (!MULTI || !h.n_mu) continue;
@@ -375,7 +651,8 @@ k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
         const uint32_t sf = st.assign_free[od] == eq, se = st.assign_evid[od] == eq;
         const int cf = (int)((tag >> (4u * pf + 2u * sf)) & 3u), ce = (int)((tag >> (4u * ev + 2u * se)) & 3u);
         if (cf == ce) continue;
-        sell_grad(g, st, acc_s, rec, __dmul_rn((double)(cf - ce), sell_fv<FV, false>(h.mu, h.n_mu, j, lane)));
+        sell_grad(g, st, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
+                  __dmul_rn((double)(cf - ce), sell_fv<FV, LD_CACHED>(h.mu, h.n_mu, j, lane)));
       }
     } else {
       uint32_t oc = 0;
@@ -386,10 +663,11 @@ k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
         if (!learn) { oc += sell_general_span(h, tag, lane, oc); continue; }
         uint32_t oc2 = oc;
         double f0, f1, e0, e1;
-        sell_general_signs(h, tag, d, lane, oc, st.assign_free, f0, f1);
-        sell_general_signs(h, tag, d, lane, oc2, st.assign_evid, e0, e1);
-        const double fv = sell_fv<FV, false>(h.mu, h.n_mu, j, lane);
-        sell_grad(g, st, acc_s, rec, __dsub_rn(__dmul_rn(pf ? f1 : f0, fv), __dmul_rn(ev ? e1 : e0, fv)));
+        sell_general_signs<LD_CACHED>(h, tag, d, lane, oc, st.assign_free, f0, f1);
+        sell_general_signs<LD_CACHED>(h, tag, d, lane, oc2, st.assign_evid, e0, e1);
+        const double fv = sell_fv<FV, LD_CACHED>(h.mu, h.n_mu, j, lane);
+        sell_grad(g, st, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
+                  __dsub_rn(__dmul_rn(pf ? f1 : f0, fv), __dmul_rn(ev ? e1 : e0, fv)));
       }
     }
   }

@@ -38,7 +38,7 @@ constexpr uint8_t VF_PAD = 0x80;      // filler slot that rounds a colour class 
 // ---- sliced-ELL blob (Boolean graphs, parallel schedules) ---------------------------------
 // Slice s = the 32 variables d = 32s .. 32s+31 (lane = d & 31).  All data of a slice is ONE
 // contiguous run of 32-bit words starting at word 8 * sl_off[s] of `blob`:
-//   header  8 words (SH_*)
+//   header  8 words (SH_*: counts, evidence / padding / evidence-value masks, flags, own offset)
 //   unary   n_un columns x 32 words      record of lane l in column j at  8 + 32 j + l
 //   (fv)    n_un columns x 32 f32 | f64  feature values of the unary records (FV_F32 | FV_F64)
 //   multi   n_mu columns x 32 words
@@ -47,9 +47,12 @@ constexpr uint8_t VF_PAD = 0x80;      // filler slot that rounds a colour class 
 // so a warp streams its slice with fully coalesced 128 B requests.  Within a row the unary
 // records come first, then the multi-variable ones, each group in ascending factor id (the
 // CSR stream keeps construct_index's pure factor-id order; the two sums agree to fp64
-// reassociation).  A record word is  wid[22:0] | weight_is_fixed << 23 | tag << 24.
-//   unary tag : [1:0] sign code when the variable is 1, [3:2] when it is 0 (0 -> -1, 1 -> 0,
-//               2 -> +1).  Padding records are SELL_UNARY_NOP with weight id 0 (adds +0.0).
+// reassociation).  Sign codes: 0 -> -1, 1 -> 0, 2 -> +1.
+//   unary record:  code(variable = 1) | wid << 2 | weight_is_fixed << 25 | code(variable = 0) << 26,
+//               so that  rec & SELL_UN_IDX_MASK  is the record's entry in the kernels' signed weight
+//               table (4 entries per weight: -w, 0, +w, 0).  Padding records are SELL_UNARY_NOP
+//               (weight 0, both codes 1: adds +0.0).
+//   multi record:  wid[22:0] | weight_is_fixed << 23 | tag << 24
 //   multi tag : slices flagged SF_BINARY (every multi record has exactly one other variable,
 //               record j owns others column j): the factor's whole sign table,
 //               code(x, sat) at bits 2 * (2 x + sat), x = this variable's value, sat = the
@@ -61,11 +64,17 @@ constexpr int SH_EVID_MASK = 3;   // bit l: variable of lane l is evidence
 constexpr int SH_PAD_MASK = 4;    // bit l: lane l is a filler slot
 constexpr int SH_EVVAL_MASK = 5;  // bit l: Variable::assignment_dense of lane l is 1
 constexpr int SH_FLAGS = 6;       // SF_*
+constexpr int SH_SELF_OFF = 7;    // sl_off of this slice: a staged copy of the header can find the rest in HBM
 constexpr int SH_WORDS = 8;
 constexpr uint32_t SF_ANTISYM = 1;  // every unary record has sign(1) == -sign(0): neg == -pos
 constexpr uint32_t SF_BINARY = 2;   // every multi record has exactly one other variable
-constexpr uint32_t SELL_WID_MASK = 0x7fffffu, SELL_FIXED_BIT = 0x800000u;
-constexpr uint32_t SELL_UNARY_NOP = 0x05u, SELL_BINARY_NOP = 0x55u;
+constexpr uint32_t SELL_WID_MASK = 0x7fffffu, SELL_FIXED_BIT = 0x800000u;  // multi records
+constexpr uint32_t SELL_BINARY_NOP = 0x55u;                                // tag of a padding binary record
+constexpr uint32_t SELL_UN_IDX_MASK = 0x1ffffffu, SELL_UN_FIXED_BIT = 1u << 25;
+constexpr uint32_t SELL_UNARY_NOP = 1u | (1u << 26);                       // a whole padding unary record
+inline constexpr uint32_t sell_unary_record(uint32_t wid, bool fixed, uint32_t code1, uint32_t code0) {
+  return code1 | (wid << 2) | (fixed ? SELL_UN_FIXED_BIT : 0u) | (code0 << 26);
+}
 constexpr uint64_t SELL_MAX_WEIGHTS = 1ull << 23;
 
 // weights with internal id < n_hot are staged in shared memory by the sweep kernels

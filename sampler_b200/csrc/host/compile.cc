@@ -8,7 +8,10 @@
 // sweep schedule (greedy colouring), permutes variables into schedule order and flattens
 // factor -> vifs into per-row edge records (graph_image.h).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -87,9 +90,22 @@ struct Inc {  // TempValueFactor, src/variable.h:14-29
 
 }  // namespace
 
+// DWG_COMPILE_TIMING=1: wall time of each phase on stderr
+struct PhaseTimer {
+  bool on = getenv("DWG_COMPILE_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[compile] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *err) {
   *err = DWG_ERR_INVALID;
   *g = GraphImage();
+  PhaseTimer pt;
   const uint64_t nvar = raw.nvar, nfac = raw.nfac, nweight = raw.nweight;
   const uint64_t nedge = nfac ? raw.fac_ptr[nfac] : 0;
   if (nvar >= U32_LIMIT / 2 || nfac >= U32_LIMIT || nweight >= U32_LIMIT) {
@@ -155,6 +171,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     }
   }
 
+  pt.lap("variables + domains");
   // ---- factors (src/binary_format.cc:128-190) ----
   std::vector<uint32_t> edense(nedge);  // FactorToVariable::dense_equal_to
   std::vector<uint32_t> deg(nvar + 1, 0);
@@ -186,6 +203,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   }
   for (uint64_t v = 0; v < nvar; ++v) deg[v + 1] += deg[v];
 
+  pt.lap("factors");
   // ---- adjacency + construct_index (src/factor_graph.cc:131-199) ----
   std::vector<Inc> inc(nedge);
   {
@@ -209,6 +227,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     inc_end[v] = (uint32_t)(o - inc.data());
   }
 
+  pt.lap("adjacency + index");
   // ---- rows in ORIGINAL order (var_val_base, values, truthiness) ----
   g->value_base.resize(nvar + 1);
   uint64_t nrow = 0;
@@ -246,6 +265,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     if (has_truth[v]) g->has_truthiness = true;
   }
 
+  pt.lap("rows");
   // ---- schedule ----
   if (schedule == DWG_SCHED_AUTO) {
     uint64_t nrec = 0;
@@ -314,6 +334,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   }
   g->schedule = schedule;
 
+  pt.lap("schedule (colouring)");
   // ---- layout knobs ----
   g->assign_bytes = max_card <= 256 ? 1 : 4;
   g->oth_packed = !g->has_categorical && eq_is_bit;
@@ -342,6 +363,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     return compact ? (int)(n - 1) : (int)FORM_GENERAL;
   };
 
+  pt.lap("layout knobs");
   // ---- schedule order: colour-major; SELL graphs additionally sort each class by
   // (is_evidence, degree, others words) so that a 32-variable slice is uniform, and pad every
   // class to a multiple of 32 ----
@@ -394,6 +416,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     }
   }
 
+  pt.lap("schedule order (sort)");
   // ---- emit rows and edge records (CSR) in schedule order ----
   const uint64_t ndrow = g->sell ? nvar_pad : nrow;  // device rows (pads own an empty row)
   g->ndrow = ndrow;
@@ -483,6 +506,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   g->bytes_infer_query = b_query;
   g->bytes_learn = b_learn;
 
+  pt.lap("emit CSR");
   // ---- internal weight ids: hottest first, so that ids < n_hot can live in shared memory ----
   g->w_perm.resize(nweight); g->w_inv.resize(nweight);
   {
@@ -497,6 +521,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     g->n_hot = (uint32_t)std::min<uint64_t>(nweight, DWG_HOT_WEIGHTS);
   }
 
+  pt.lap("weight ids");
   // ---- per colour class, per weight: how many SGD updates one learning launch makes (N) and
   // their summed curvature bound (Q), for the semi-implicit batch update (dwg_kernels.cuh).
   // q = (fv * sign range)^2 / 4 >= Var(f | rest): the conditional is a Bernoulli. ----
@@ -560,6 +585,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       }
   }
 
+  pt.lap("class statistics");
   // ---- sliced-ELL blob (graph_image.h): per 32-variable slice one contiguous run of words:
   // header, unary records (+ feature values), multi records (+ feature values), others.
   // A warp streams its slice with coalesced 128 B requests, every record exactly once. ----
@@ -625,6 +651,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
           if (!is_unary(e) && (g->e_tag[e] >> TAG_FORM_SHIFT) != 1) binary = false;
       }
       h[SH_N_UNARY] = un; h[SH_N_MULTI] = mu; h[SH_N_OTH] = oc;
+      h[SH_SELF_OFF] = g->sl_off[sidx];
       for (uint32_t l = 0; l < 32; ++l) {
         const uint64_t d = sidx * 32 + l;
         if (g->var_flags[d] & VF_PAD) h[SH_PAD_MASK] |= 1u << l;
@@ -641,7 +668,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
             const uint32_t mm = code_mismatch(fc);
             const uint32_t s1 = (tag & TAG_SELF_EQ1) ? 2 : mm, s0 = (tag & TAG_SELF_EQ1) ? mm : 2;
             if (s1 + s0 != 2) antisym = false;
-            h[o_un + 32ull * ju + l] = base | ((s1 | (s0 << 2)) << 24);
+            h[o_un + 32ull * ju + l] = sell_unary_record(wid, raw.w_fixed[g->w_perm[wid]], s1, s0);
             put_fv(h + o_unfv + (32ull * ju + l) * fvw, e);
             ++ju;
             continue;
@@ -668,12 +695,13 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
           put_fv(h + o_mufv + (32ull * jm + l) * fvw, e);
           ++jm;
         }
-        for (; ju < un; ++ju) h[o_un + 32ull * ju + l] = SELL_UNARY_NOP << 24;
+        for (; ju < un; ++ju) h[o_un + 32ull * ju + l] = SELL_UNARY_NOP;
         for (; jm < mu; ++jm) h[o_mu + 32ull * jm + l] = binary ? SELL_BINARY_NOP << 24 : 0u;  // form 0
       }
       h[SH_FLAGS] = (antisym ? SF_ANTISYM : 0u) | (binary ? SF_BINARY : 0u);
     }
   }
+  pt.lap("sliced-ELL blob");
   *err = DWG_OK;
   return "";
 }

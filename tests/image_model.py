@@ -141,10 +141,10 @@ class ImageModel:
         antisym = True
         for j in range(h["n_un"]):
             rec = int(self.blob[h["un"] + 32 * j + lane])
-            tag, wid = rec >> 24, rec & 0x7FFFFF
+            wid = (rec >> 2) & 0x7FFFFF  # unary record: code(1) | wid << 2 | fixed << 25 | code(0) << 26
             w = float(weights[wid])
             fv = self._sell_fv(h["un"], h["n_un"], j, lane, h["fvw"])
-            s1, s0 = code(tag & 3), code((tag >> 2) & 3)
+            s1, s0 = code(rec & 3), code((rec >> 26) & 3)
             antisym &= (s1 == -s0)
             pos += w * (s1 * fv)
             neg += w * (s0 * fv)
@@ -203,12 +203,15 @@ class ImageModel:
         fixed = np.asarray(w_fixed_orig)[self.w_perm.astype(np.int64)].astype(np.uint32)
         for s in range(len(self.sl_off) - 1):
             h = self.slice_header(s)
-            for sec, n, nop in ((h["un"], h["n_un"], 0x05), (h["mu"], h["n_mu"], 0x55 if h["flags"] & 2 else 0)):
-                recs = self.blob[sec:sec + 32 * n]
-                real = (recs >> 24) != nop if nop else ((recs >> 30) != 0)
-                bits = (recs >> 23) & 1
-                if not np.array_equal(bits[real], fixed[(recs & 0x7FFFFF).astype(np.int64)][real]):
-                    return False
-                if bits[~real].any():
-                    return False
+            recs = self.blob[h["un"]:h["un"] + 32 * h["n_un"]]
+            real = recs != 0x04000001  # SELL_UNARY_NOP
+            bits = (recs >> 25) & 1
+            if not np.array_equal(bits[real], fixed[((recs >> 2) & 0x7FFFFF).astype(np.int64)][real]) or bits[~real].any():
+                return False
+            nop = 0x55 if h["flags"] & 2 else 0
+            recs = self.blob[h["mu"]:h["mu"] + 32 * h["n_mu"]]
+            real = (recs >> 24) != nop if nop else ((recs >> 30) != 0)
+            bits = (recs >> 23) & 1
+            if not np.array_equal(bits[real], fixed[(recs & 0x7FFFFF).astype(np.int64)][real]) or bits[~real].any():
+                return False
         return True

@@ -225,6 +225,60 @@ def test_parallel_chromatic_inference_is_exact_gibbs(seed):
     assert np.array_equal(t, o.tallies) and np.array_equal(n, o.nsamples)
 
 
+SELL_VARIANTS = [{"DWG_SELL_DIRECT": "1"}, {}, {"DWG_SELL_WARPS": "16"}, {"DWG_SELL_STAGES": "2"},
+                 {"DWG_SELL_STAGE_WORDS": "200"}, {"DWG_SELL_STAGE_WORDS": "8", "DWG_SELL_STAGES": "3"}]
+
+
+@pytest.mark.parametrize("shape", ["binary", "general", "unary_f64", "c2"])
+def test_staged_and_direct_inference_kernels_agree(shape, monkeypatch):
+    """k_sell_infer_staged (bulk-async ring, every ring geometry, slices that overflow their stage
+    and take the HBM path) makes the draws k_sell_infer makes, bit for bit: chains and tallies
+    after Philox-driven sweeps, with and without --sample_evidence, and against the oracle with
+    explicit uniforms"""
+    from sampler_b200 import graphgen
+    rng = np.random.default_rng(4242)
+    if shape == "c2":
+        raw = graphgen.c2_boolean(60_000, nweight=300)
+    elif shape == "binary":
+        raw = random_graph(rng, nvar=5000, nfac=15000, nweight=60, p_cat=0.0, max_arity=2)
+    elif shape == "general":
+        raw = random_graph(rng, nvar=4000, nfac=9000, nweight=60, p_cat=0.0, max_arity=4)
+    else:
+        raw = graphgen.unary_boolean(30_000, 20, 5000, p_evid=0.9, zipf=1.1, real_features=True)
+    g = sb.Graph.from_raw(raw, sb.SCHED_CHROMATIC)
+    w = rng.normal(0, 1, g.info.num_weights)
+    for sample_evidence in (True, False):
+        ref = None
+        for env in SELL_VARIANTS:
+            for k in ("DWG_SELL_DIRECT", "DWG_SELL_WARPS", "DWG_SELL_STAGES", "DWG_SELL_STAGE_WORDS"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            s = sb.Sampler(g, sample_evidence=sample_evidence, seed=77)
+            s.set_weights(w)
+            s.infer_epochs(6)
+            got = (s.assignments(1), s.tallies()[0])
+            s.close()
+            if ref is None:
+                ref = got
+            else:
+                assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), env
+    # the default (staged) kernel against the oracle, explicit uniforms
+    for k in ("DWG_SELL_DIRECT", "DWG_SELL_WARPS", "DWG_SELL_STAGES", "DWG_SELL_STAGE_WORDS"):
+        monkeypatch.delenv(k, raising=False)
+    if shape in ("binary", "general"):
+        _, s, o = _mk(raw, sb.SCHED_CHROMATIC, sample_evidence=True)
+        perm, _ = s.graph.schedule()
+        s.set_weights(w); o.weights[:] = w
+        for ep in range(3):
+            r0 = rng.random(o.nvar)
+            s.set_uniforms(r0)
+            s.infer_epoch()
+            o.sweep_infer_seq(perm, r0)
+        assert np.array_equal(s.assignments(1), o.assign_evid)
+        assert np.array_equal(s.tallies()[0], o.tallies)
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_parallel_learning_with_exact_arithmetic(seed):
     """parallel learning launches under the chromatic schedule: with fixed weights both chains

@@ -121,7 +121,12 @@ def test_mid_size_graph_vs_reference(name):
     d = np.abs(m - mref)
     dm_ref = float(np.abs(z["marginals_mean_t8"].astype(np.float64) - mref).mean())
     assert d.mean() <= max(0.02 + noise.mean(), 2.0 * dm_ref), (d.mean(), noise.mean(), dm_ref)
-    assert abs(m.mean() - mref.mean()) <= 0.005
-    assert np.quantile(d, 0.99) <= 0.15
+    # the mean marginal: on the coupled graph the reference's own -t 8 run moves it by 0.031 from
+    # its -t 1 run (same order-dependent offsets, all of one sign); same 2 x yardstick as above
+    shift_ref = abs(float(z["marginals_mean_t8"].astype(np.float64).mean()) - float(mref.mean()))
+    assert abs(m.mean() - mref.mean()) <= max(0.005, 2.0 * shift_ref), (m.mean(), mref.mean(), shift_ref)
+    # tail: the reference's -t 8 run is itself 0.165 from its -t 1 run at the 99th percentile on c2_small
+    q_ref = float(np.quantile(np.abs(z["marginals_mean_t8"].astype(np.float64) - mref), 0.99))
+    assert np.quantile(d, 0.99) <= max(0.15, 1.5 * q_ref), (np.quantile(d, 0.99), q_ref)
     print("%s: weights mean|d| %.4f (ref -t8 %.4f, noise %.4f) slope %.3f; marginals mean|d| %.4f (ref -t8 %.4f, noise %.4f)"
           % (name, d_ours, d_ref, noise_w, slope, d.mean(), dm_ref, noise.mean()))
