@@ -191,8 +191,9 @@ int sell_setup_t(dwg_handle *h) {
   if (const char *e = getenv("DWG_SELL_STAGES")) max_stages = std::max(2, std::min(SELL_MAX_STAGES, atoi(e)));
   const uint32_t nwarp = SELL_STAGED_THREADS / 32;
   const uint32_t n_tab = (uint32_t)std::min<uint64_t>({h->img->nweight, n_hot, SELL_MAX_TAB});
-  // the deepest ring (<= SELL_MAX_STAGES, two CTAs per SM) whose stage holds at least 97 % of the
-  // slices whole; the rare longer slice is staged up to its stage's end and read from HBM directly
+  // the deepest ring (<= SELL_MAX_STAGES, two CTAs per SM) whose stage holds at least 99.5 % of the
+  // slices whole (90 % for the two-stage ring); the rare longer slice is staged up to its stage's
+  // end and read from HBM directly
   const std::vector<uint32_t> &off = h->img->sl_off;
   const size_t nslice = off.empty() ? 0 : off.size() - 1;
   const uint32_t want = (h->img->sell_max_words + 3u) & ~3u;
@@ -203,8 +204,11 @@ int sell_setup_t(dwg_handle *h) {
     if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) cap = std::min<uint32_t>(cap, std::max(8, atoi(e)) & ~3u);  // tests
     size_t fit = 0;
     for (size_t i = 0; i < nslice; ++i) fit += (off[i + 1] - off[i]) * 8u <= cap;
-    if (st == 2 || fit * 100 >= nslice * 97) { stages = st; words = std::min(cap, want); }
+    if (fit * 1000 >= nslice * 995 || (st == 2 && fit * 10 >= nslice * 9)) { stages = st; words = std::min(cap, want); }
   }
+  // slices too long for even a two-stage ring (e.g. 20 f64-valued features per variable): the
+  // direct kernel streams them from HBM
+  if (!stages) return DWG_OK;
   const size_t smem = sell_staged_smem(n_tab, stages, words);
   rc = h->img->nweight <= n_tab
            ? sell_grid(k_sell_infer_staged<MULTI, FV, true>, smem, h->num_sms, &h->sell_blocks_staged, SELL_STAGED_THREADS)

@@ -132,7 +132,7 @@ __device__ __forceinline__ void sell_unary(const SellGraph &g, const SliceHeader
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const double wt = sell_weight(g, w_s, w, (rec[u] >> 2) & SELL_WID_MASK);
+      const double wt = sell_weight(g, w_s, w, sell_unary_wid(rec[u]));
       const double t = FV == FV_ONE ? wt : __dmul_rn(wt, fv[u]);  // w * (+-1 * fv) == +-(w * fv) exactly
       pos = __dadd_rn(pos, sell_term(rec[u] & 3u, t));
       if (!ANTISYM) neg = __dadd_rn(neg, sell_term(rec[u] >> 26, t));
@@ -321,15 +321,19 @@ k_sell_infer(const SellGraph g, const SellState st, const SweepParams p) {
 //    records are then read with conflict-free LDS; what is left on the critical path of a slice
 //    is shared-memory latency, the L2 gather of neighbour chain bytes (issued before the unary
 //    records are summed) and arithmetic.  A slice longer than a stage (rare: the stage size is
-//    picked to hold >= 97 % of the slices) is staged up to the stage's end and read from HBM.
-//  * weights with id < n_tab are staged as a SIGNED table of four entries per weight
-//    (-w, 0, +w, 0): a record's sign code indexes the table, so a term costs one mask, one LDS.64
-//    and one DADD instead of compares and selects, and (ALLHOT) no hot/cold branch exists at all
-//    when every weight fits.  (+-w) * fv == +-(w * fv) and x + (+-0) == x: the sums are the
-//    direct kernel's bit for bit.
+//    picked to hold >= 99.5 % of the slices) is staged up to the stage's end and read from HBM.
+//  * weights with id < n_tab are staged as a SIGNED table of three planes (-w | 0 | +w, n_tab
+//    entries each): a record's sign code picks the plane, so a term costs two masks, one IMAD,
+//    one LDS.64 and one DADD instead of compares and selects (bank conflicts as for a plain
+//    table: the planes are a multiple of 128 B apart), and (ALLHOT) no hot/cold branch exists
+//    at all when every weight fits.  (+-w) * fv == +-(w * fv) and x + (+-0) == x: the sums are
+//    the direct kernel's bit for bit.
+//  * the uniform of the draw (Philox) is computed and the neighbour chain bytes of the NEXT
+//    slice (other colour classes: constant during the launch) are requested before the current
+//    slice's records are summed, so the L2 gather is off the critical path too.
 constexpr int SELL_MAX_STAGES = 4;
 constexpr int SELL_STAGED_THREADS = 384;  // 12 warps, 2 CTAs per SM, <= 85 registers
-constexpr uint32_t SELL_MAX_TAB = 1024;   // weights in the signed table (32 B each)
+constexpr uint32_t SELL_MAX_TAB = 2048;   // weights in the signed table (3 planes x 8 B each)
 
 __device__ __forceinline__ uint32_t sell_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sell_mbar_init(uint32_t bar, uint32_t count) {
@@ -362,7 +366,8 @@ __device__ __forceinline__ void sell_bulk_g2s(uint32_t dst, const void *src, uin
 
 // shared-memory plan of the staged kernel (host and device agree through these):
 // signed weight table | one mbarrier per (warp, stage) | the rings
-__host__ __device__ inline uint32_t sell_staged_bar_off(uint32_t n_tab) { return n_tab * 32u; }
+__host__ __device__ inline uint32_t sell_tab_plane(uint32_t n_tab) { return (n_tab * 8u + 127u) & ~127u; }  // bytes
+__host__ __device__ inline uint32_t sell_staged_bar_off(uint32_t n_tab) { return 3u * sell_tab_plane(n_tab); }
 __host__ __device__ inline uint32_t sell_staged_ring_off(uint32_t n_tab, uint32_t stages) {
   return (sell_staged_bar_off(n_tab) + (SELL_STAGED_THREADS / 32) * stages * 8u + 127u) & ~127u;
 }
@@ -396,31 +401,31 @@ __device__ __forceinline__ double sell_fv_s(const uint32_t *sm, uint32_t fvb, ui
   return 1.0;
 }
 
-// sign * weight of table entry idx = wid << 2 | code
+// sign * weight: plane `code` (0 -> -w, 1 -> 0, 2 -> +w) of the signed table, wid8 = 8 * weight id
 template <bool ALLHOT>
-__device__ __forceinline__ double sell_signed_weight(const SellGraph &g, const double *tab_s, const double *w,
-                                                     uint32_t idx) {
-  if (ALLHOT || idx < 4u * g.n_tab) return tab_s[idx];
-  return sell_term(idx & 3u, __ldg(w + (idx >> 2)));
+__device__ __forceinline__ double sell_signed_weight(const SellGraph &g, const unsigned char *tab_s, uint32_t plane,
+                                                     const double *w, uint32_t code, uint32_t wid8) {
+  if (ALLHOT || wid8 < 8u * g.n_tab) return *reinterpret_cast<const double *>(tab_s + (code * plane + wid8));
+  return sell_term(code, __ldg(w + (wid8 >> 3)));
 }
 
 // one unary record of a staged slice into pos / neg (same arithmetic and order as sell_unary)
 template <int FV, bool ANTISYM, bool ALLHOT>
-__device__ __forceinline__ void sell_unary_rec(const SellGraph &g, const double *tab_s, const double *w, uint32_t rec,
-                                               double fv, double &pos, double &neg) {
-  const uint32_t idx = rec & SELL_UN_IDX_MASK;
-  const double t1 = sell_signed_weight<ALLHOT>(g, tab_s, w, idx);
+__device__ __forceinline__ void sell_unary_rec(const SellGraph &g, const unsigned char *tab_s, uint32_t plane,
+                                               const double *w, uint32_t rec, double fv, double &pos, double &neg) {
+  const uint32_t wid8 = rec & SELL_UN_WID8_MASK;
+  const double t1 = sell_signed_weight<ALLHOT>(g, tab_s, plane, w, rec & 3u, wid8);
   pos = __dadd_rn(pos, FV == FV_ONE ? t1 : __dmul_rn(t1, fv));
   if (!ANTISYM) {
-    const double t0 = sell_signed_weight<ALLHOT>(g, tab_s, w, (idx & ~3u) | (rec >> 26));
+    const double t0 = sell_signed_weight<ALLHOT>(g, tab_s, plane, w, rec >> 26, wid8);
     neg = __dadd_rn(neg, FV == FV_ONE ? t0 : __dmul_rn(t0, fv));
   }
 }
 
 template <int FV, bool ANTISYM, bool ALLHOT>
 __device__ __forceinline__ void sell_unary_s(const SellGraph &g, const uint32_t *sm, uint32_t b, uint32_t n_un,
-                                             const double *tab_s, const double *w, uint32_t lane, double &pos,
-                                             double &neg) {
+                                             const unsigned char *tab_s, uint32_t plane, const double *w,
+                                             uint32_t lane, double &pos, double &neg) {
   constexpr uint32_t U = 4;
   const uint32_t un = b + SH_WORDS + lane, fvb = b + SH_WORDS + 32u * n_un;
   uint32_t j0 = 0;
@@ -433,10 +438,11 @@ __device__ __forceinline__ void sell_unary_s(const SellGraph &g, const uint32_t 
       fv[u] = sell_fv_s<FV>(sm, fvb, j0 + u, lane);
     }
 #pragma unroll
-    for (uint32_t u = 0; u < U; ++u) sell_unary_rec<FV, ANTISYM, ALLHOT>(g, tab_s, w, rec[u], fv[u], pos, neg);
+    for (uint32_t u = 0; u < U; ++u) sell_unary_rec<FV, ANTISYM, ALLHOT>(g, tab_s, plane, w, rec[u], fv[u], pos, neg);
   }
   for (; j0 < n_un; ++j0)
-    sell_unary_rec<FV, ANTISYM, ALLHOT>(g, tab_s, w, sm[un + 32u * j0], sell_fv_s<FV>(sm, fvb, j0, lane), pos, neg);
+    sell_unary_rec<FV, ANTISYM, ALLHOT>(g, tab_s, plane, w, sm[un + 32u * j0], sell_fv_s<FV>(sm, fvb, j0, lane), pos,
+                                        neg);
   if (ANTISYM) neg = -pos;
 }
 
@@ -447,7 +453,8 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
   extern __shared__ __align__(128) unsigned char sell_smem[];
   constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
   constexpr uint32_t MC = 2;  // binary records handled together
-  double *tab_s = reinterpret_cast<double *>(sell_smem);
+  const unsigned char *tab_s = sell_smem;
+  const uint32_t plane = sell_tab_plane(g.n_tab);
   const uint32_t *sm = reinterpret_cast<const uint32_t *>(sell_smem);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t bar0 = sell_smem_addr(sell_smem) + sell_staged_bar_off(g.n_tab) + warp * stages * 8u;
@@ -458,7 +465,9 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (uint32_t i = threadIdx.x; i < g.n_tab; i += blockDim.x) {
     const double w = __ldg(st.weights + i);
-    tab_s[4 * i] = -w; tab_s[4 * i + 1] = 0.0; tab_s[4 * i + 2] = w; tab_s[4 * i + 3] = 0.0;
+    *reinterpret_cast<double *>(sell_smem + 8u * i) = -w;
+    *reinterpret_cast<double *>(sell_smem + plane + 8u * i) = 0.0;
+    *reinterpret_cast<double *>(sell_smem + 2u * plane + 8u * i) = w;
   }
   __syncthreads();
 
@@ -496,19 +505,45 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
     }
   };
 
+  // wait for the slice in `stage` and request the chain bytes of the other variables of its first MC
+  // binary records (raw bytes and equal_to bits: compared when the slice is sampled)
+  auto front = [&](uint32_t stage, uint32_t parity, uint32_t (&av)[MC], uint32_t &eq) {
+    sell_mbar_wait(bar0 + 8u * stage, parity);
+    if (!MULTI) return;
+    const uint32_t b = ringw + stage * stage_words;
+    const uint4 h0 = *reinterpret_cast<const uint4 *>(sm + b);
+    const uint32_t flags = sm[b + SH_FLAGS];
+    eq = 0;
+    if ((flags & SF_BINARY) && SH_WORDS + 32u * ((h0.x + h0.y) * (1 + FVW) + h0.z) <= stage_words) {
+      const uint32_t oth = b + SH_WORDS + 32u * (h0.x + h0.y) * (1 + FVW) + lane;
+#pragma unroll
+      for (uint32_t u = 0; u < MC; ++u) {
+        const uint32_t ow = u < h0.y ? sm[oth + 32u * u] : 0u;
+        av[u] = st.assign_evid[ow >> 1];
+        eq |= (ow & 1u) << u;
+      }
+    }
+  };
+
   const uint32_t pre = n_my < stages ? n_my : stages;
   for (uint32_t k = 0; k < pre; ++k) issue(k, k);
   uint32_t stage = 0, parity = 0;  // of iteration k
+  uint32_t av[MC] = {}, eq = 0, nav[MC] = {}, neq = 0;
+  front(0, 0, av, eq);
   uint64_t s64 = s0;
   for (uint32_t k = 0; k < n_my; ++k, s64 += step) {
-    sell_mbar_wait(bar0 + 8u * stage, parity);
+    uint32_t nstage = stage + 1, nparity = parity;
+    if (nstage == stages) { nstage = 0; nparity ^= 1u; }
+    const uint32_t d = (uint32_t)s64 * 32u + lane;
+    double r0, r1;
+    dev_uniforms(p, d, r0, r1);
+    if (k + 1 < n_my) front(nstage, nparity, nav, neq);
     const uint32_t b = ringw + stage * stage_words;
     const uint4 h0 = *reinterpret_cast<const uint4 *>(sm + b);      // n_un, n_mu, n_oc, evid
     const uint4 h1 = *reinterpret_cast<const uint4 *>(sm + b + 4);  // pad, evval, flags, own offset
     const uint32_t n_un = h0.x, n_mu = h0.y, flags = h1.z;
     // gibbs_sampler.h:157 -- a slice with nothing to sample is skipped
     const uint32_t active = ~h1.x & (p.sample_evidence ? 0xffffffffu : ~h0.w);
-    const uint32_t d = (uint32_t)s64 * 32u + lane;
     if (active) {
       // FactorGraph::potential for proposals 1 and 0 (src/factor_graph.h:127-145)
       double pos = 0.0, neg = 0.0;
@@ -518,35 +553,30 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
         const uint32_t mu = b + SH_WORDS + 32u * n_un * (1 + FVW) + lane;
         const uint32_t mufv = b + SH_WORDS + 32u * n_un * (1 + FVW) + 32u * n_mu;
         const uint32_t oth = mu + 32u * n_mu * (1 + FVW);
-        const bool binary = MULTI && (flags & SF_BINARY);
-        // the neighbour chain bytes of the first binary records travel while the unary records are summed
-        uint32_t ow[MC], av[MC];
-        if (binary) {
-#pragma unroll
-          for (uint32_t u = 0; u < MC; ++u) ow[u] = u < n_mu ? sm[oth + 32u * u] : 0u;
-#pragma unroll
-          for (uint32_t u = 0; u < MC; ++u) av[u] = st.assign_evid[ow[u] >> 1];
-        }
-        if (flags & SF_ANTISYM) sell_unary_s<FV, true, ALLHOT>(g, sm, b, n_un, tab_s, st.weights, lane, pos, neg);
-        else sell_unary_s<FV, false, ALLHOT>(g, sm, b, n_un, tab_s, st.weights, lane, pos, neg);
-        if (binary) {
+        if (flags & SF_ANTISYM) sell_unary_s<FV, true, ALLHOT>(g, sm, b, n_un, tab_s, plane, st.weights, lane, pos, neg);
+        else sell_unary_s<FV, false, ALLHOT>(g, sm, b, n_un, tab_s, plane, st.weights, lane, pos, neg);
+        if (MULTI && (flags & SF_BINARY)) {
           // record j owns others word j; its tag is the factor's sign table code(x, sat) at bits
           // 2 (2 x + sat): x = 1 feeds pos, x = 0 feeds neg
           for (uint32_t j0 = 0; j0 < n_mu; j0 += MC) {
             if (j0) {
+              uint32_t ow[MC];
+              eq = 0;
 #pragma unroll
               for (uint32_t u = 0; u < MC; ++u) ow[u] = j0 + u < n_mu ? sm[oth + 32u * (j0 + u)] : 0u;
 #pragma unroll
               for (uint32_t u = 0; u < MC; ++u) av[u] = st.assign_evid[ow[u] >> 1];
+#pragma unroll
+              for (uint32_t u = 0; u < MC; ++u) eq |= (ow[u] & 1u) << u;
             }
 #pragma unroll
             for (uint32_t u = 0; u < MC; ++u) {
               const bool ok = j0 + u < n_mu;
               const uint32_t rec = ok ? sm[mu + 32u * (j0 + u)] : (SELL_BINARY_NOP << 24);
-              const uint32_t sat = av[u] == (ow[u] & 1u) ? 1u : 0u;
-              const uint32_t codes = rec >> (24u + 2u * sat), wid4 = (rec & SELL_WID_MASK) << 2;
-              double t1 = sell_signed_weight<ALLHOT>(g, tab_s, st.weights, wid4 | ((codes >> 4) & 3u));
-              double t0 = sell_signed_weight<ALLHOT>(g, tab_s, st.weights, wid4 | (codes & 3u));
+              const uint32_t sat = av[u] == ((eq >> u) & 1u) ? 1u : 0u;
+              const uint32_t codes = rec >> (24u + 2u * sat), wid8 = (rec & SELL_WID_MASK) << 3;
+              double t1 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, (codes >> 4) & 3u, wid8);
+              double t0 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, codes & 3u, wid8);
               if (FV != FV_ONE) {
                 const double fv = ok ? sell_fv_s<FV>(sm, mufv, j0 + u, lane) : 0.0;
                 t1 = __dmul_rn(t1, fv);
@@ -567,8 +597,6 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
         }
       }
       if ((active >> lane) & 1u) {
-        double r0, r1;
-        dev_uniforms(p, d, r0, r1);
         const uint32_t prop = sell_draw_boolean(pos, neg, r0);
         st.assign_evid[d] = (uint8_t)prop;
         if (prop) atomicAdd(st.tallies + d, 1u);  // gibbs_sampler.h:163-167
@@ -576,7 +604,10 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
     }
     __syncwarp();  // every lane is done with this stage before the next copy lands in it
     if (k + stages < n_my) issue(k + stages, stage);
-    if (++stage == stages) { stage = 0; parity ^= 1u; }
+    stage = nstage; parity = nparity;
+#pragma unroll
+    for (uint32_t u = 0; u < MC; ++u) av[u] = nav[u];
+    eq = neq;
   }
 }
 
@@ -637,7 +668,7 @@ k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
         if (!learn || pf == ev) continue;
         const int cf = (int)(pf ? rec & 3u : rec >> 26), ce = (int)(ev ? rec & 3u : rec >> 26);
         if (cf == ce) continue;
-        sell_grad(g, st, acc_s, (rec >> 2) & SELL_WID_MASK, rec & SELL_UN_FIXED_BIT,
+        sell_grad(g, st, acc_s, sell_unary_wid(rec), rec & SELL_UN_FIXED_BIT,
                   __dmul_rn((double)(cf - ce), sell_fv<FV, LD_CACHED>(h.un, h.n_un, j, lane)));
       }
     }

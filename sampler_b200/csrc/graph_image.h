@@ -48,10 +48,10 @@ constexpr uint8_t VF_PAD = 0x80;      // filler slot that rounds a colour class 
 // records come first, then the multi-variable ones, each group in ascending factor id (the
 // CSR stream keeps construct_index's pure factor-id order; the two sums agree to fp64
 // reassociation).  Sign codes: 0 -> -1, 1 -> 0, 2 -> +1.
-//   unary record:  code(variable = 1) | wid << 2 | weight_is_fixed << 25 | code(variable = 0) << 26,
-//               so that  rec & SELL_UN_IDX_MASK  is the record's entry in the kernels' signed weight
-//               table (4 entries per weight: -w, 0, +w, 0).  Padding records are SELL_UNARY_NOP
-//               (weight 0, both codes 1: adds +0.0).
+//   unary record:  code(variable = 1) | weight_is_fixed << 2 | wid << 3 | code(variable = 0) << 26,
+//               so that  rec & SELL_UN_WID8_MASK  is the byte offset of the weight in an f64 table and
+//               code * plane + that offset its entry in the staged kernel's signed weight table (three
+//               planes: -w, 0, +w).  Padding records are SELL_UNARY_NOP (weight 0, both codes 1: adds +0.0).
 //   multi record:  wid[22:0] | weight_is_fixed << 23 | tag << 24
 //   multi tag : slices flagged SF_BINARY (every multi record has exactly one other variable,
 //               record j owns others column j): the factor's whole sign table,
@@ -70,11 +70,12 @@ constexpr uint32_t SF_ANTISYM = 1;  // every unary record has sign(1) == -sign(0
 constexpr uint32_t SF_BINARY = 2;   // every multi record has exactly one other variable
 constexpr uint32_t SELL_WID_MASK = 0x7fffffu, SELL_FIXED_BIT = 0x800000u;  // multi records
 constexpr uint32_t SELL_BINARY_NOP = 0x55u;                                // tag of a padding binary record
-constexpr uint32_t SELL_UN_IDX_MASK = 0x1ffffffu, SELL_UN_FIXED_BIT = 1u << 25;
+constexpr uint32_t SELL_UN_WID8_MASK = 0x3fffff8u, SELL_UN_FIXED_BIT = 1u << 2;
 constexpr uint32_t SELL_UNARY_NOP = 1u | (1u << 26);                       // a whole padding unary record
 inline constexpr uint32_t sell_unary_record(uint32_t wid, bool fixed, uint32_t code1, uint32_t code0) {
-  return code1 | (wid << 2) | (fixed ? SELL_UN_FIXED_BIT : 0u) | (code0 << 26);
+  return code1 | (fixed ? SELL_UN_FIXED_BIT : 0u) | (wid << 3) | (code0 << 26);
 }
+inline constexpr uint32_t sell_unary_wid(uint32_t rec) { return (rec & SELL_UN_WID8_MASK) >> 3; }
 constexpr uint64_t SELL_MAX_WEIGHTS = 1ull << 23;
 
 // weights with internal id < n_hot are staged in shared memory by the sweep kernels

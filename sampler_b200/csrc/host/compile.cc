@@ -20,6 +20,7 @@
 
 #include "../../../include/dwg.h"
 #include "../graph_image.h"
+#include "parallel.h"
 
 namespace dwg {
 
@@ -176,30 +177,56 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   std::vector<uint32_t> edense(nedge);  // FactorToVariable::dense_equal_to
   std::vector<uint32_t> deg(nvar + 1, 0);
   bool coupled = false, eq_is_bit = true;
-  for (uint64_t f = 0; f < nfac; ++f) {
-    if (func_code(raw.fac_func[f]) < 0)
-      return "factor " + std::to_string(f) + ": unsupported FACTOR_FUNCTION_TYPE = " +
-             std::to_string(raw.fac_func[f]);
-    uint64_t a = raw.fac_ptr[f], b = raw.fac_ptr[f + 1];
-    // (a zero-arity factor is legal input: it sits in no adjacency list and is never evaluated)
-    if (raw.fac_wid[f] >= nweight) return "factor " + std::to_string(f) + " refers to an unknown weight";
-    if (b - a > 1) g->has_multi = true;
-    for (uint64_t e = a; e < b; ++e) {
-      uint64_t v = raw.edge_vid[e];
-      if (v >= nvar) return "factor " + std::to_string(f) + " refers to an unknown variable";  // :159
-      uint64_t d = dom.lookup(v, raw.edge_eq[e]);
-      if (d == INVALID)
-        return "factor " + std::to_string(f) + ": value " + std::to_string(raw.edge_eq[e]) +
-               " is not in the domain of variable " + std::to_string(v);
-      if (d >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "equal_to value >= 2^32"; }
-      edense[e] = (uint32_t)d;
-      if (d > 1) eq_is_bit = false;
-      if (v != raw.edge_vid[a]) coupled = true;
-      // the reference asserts value_dense < cardinality in construct_index (:186)
-      if (g->var_dtype[v] && d >= raw.var_card[v])
-        return "factor " + std::to_string(f) + ": value index out of range for variable " + std::to_string(v);
-      ++deg[v + 1];
+  {
+    // factor ranges in parallel; the error reported is the one of the lowest factor id, as a
+    // sequential scan would find it
+    struct Part {
+      uint64_t bad_f = INVALID;
+      std::string msg;
+      int code = DWG_ERR_INVALID;
+      bool coupled = false, eq_is_bit = true, multi = false;
+    };
+    const unsigned T = host_threads();
+    std::vector<Part> parts(T);
+    parallel_ranges(nfac, T, [&](uint64_t f0, uint64_t f1, unsigned p) {
+      Part &P = parts[p];
+      auto bad = [&](uint64_t f, std::string m, int code = DWG_ERR_INVALID) {
+        P.bad_f = f; P.msg = std::move(m); P.code = code;
+      };
+      for (uint64_t f = f0; f < f1; ++f) {
+        if (func_code(raw.fac_func[f]) < 0)
+          return bad(f, "factor " + std::to_string(f) + ": unsupported FACTOR_FUNCTION_TYPE = " +
+                            std::to_string(raw.fac_func[f]));
+        uint64_t a = raw.fac_ptr[f], b = raw.fac_ptr[f + 1];
+        // (a zero-arity factor is legal input: it sits in no adjacency list and is never evaluated)
+        if (raw.fac_wid[f] >= nweight) return bad(f, "factor " + std::to_string(f) + " refers to an unknown weight");
+        if (b - a > 1) P.multi = true;
+        for (uint64_t e = a; e < b; ++e) {
+          uint64_t v = raw.edge_vid[e];
+          if (v >= nvar) return bad(f, "factor " + std::to_string(f) + " refers to an unknown variable");  // :159
+          uint64_t d = dom.lookup(v, raw.edge_eq[e]);
+          if (d == INVALID)
+            return bad(f, "factor " + std::to_string(f) + ": value " + std::to_string(raw.edge_eq[e]) +
+                              " is not in the domain of variable " + std::to_string(v));
+          if (d >= U32_LIMIT) return bad(f, "equal_to value >= 2^32", DWG_ERR_UNSUPPORTED);
+          edense[e] = (uint32_t)d;
+          if (d > 1) P.eq_is_bit = false;
+          if (v != raw.edge_vid[a]) P.coupled = true;
+          // the reference asserts value_dense < cardinality in construct_index (:186)
+          if (g->var_dtype[v] && d >= raw.var_card[v])
+            return bad(f, "factor " + std::to_string(f) + ": value index out of range for variable " +
+                              std::to_string(v));
+          __atomic_fetch_add(&deg[v + 1], 1u, __ATOMIC_RELAXED);
+        }
+      }
+    });
+    const Part *first_bad = nullptr;
+    for (const Part &P : parts) {
+      if (P.bad_f != INVALID && (!first_bad || P.bad_f < first_bad->bad_f)) first_bad = &P;
+      coupled |= P.coupled; eq_is_bit &= P.eq_is_bit;
+      if (P.multi) g->has_multi = true;
     }
+    if (first_bad) { *err = first_bad->code; return first_bad->msg; }
   }
   for (uint64_t v = 0; v < nvar; ++v) deg[v + 1] += deg[v];
 
@@ -208,24 +235,28 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   std::vector<Inc> inc(nedge);
   {
     std::vector<uint32_t> fill(deg.begin(), deg.end() - 1);
-    for (uint64_t f = 0; f < nfac; ++f)
-      for (uint64_t e = raw.fac_ptr[f]; e < raw.fac_ptr[f + 1]; ++e) {
-        uint64_t v = raw.edge_vid[e];
-        inc[fill[v]++] = {g->var_dtype[v] ? edense[e] : 0u, (uint32_t)f};
-      }
+    parallel_for(nfac, [&](uint64_t f0, uint64_t f1) {
+      for (uint64_t f = f0; f < f1; ++f)
+        for (uint64_t e = raw.fac_ptr[f]; e < raw.fac_ptr[f + 1]; ++e) {
+          uint64_t v = raw.edge_vid[e];
+          inc[__atomic_fetch_add(&fill[v], 1u, __ATOMIC_RELAXED)] = {g->var_dtype[v] ? edense[e] : 0u, (uint32_t)f};
+        }
+    });
   }
-  // factor ids arrive ascending per variable, so only categorical lists need the (value, fid)
-  // sort; then drop consecutive duplicates (same factor under the same value)
+  // per variable: entries sorted by (value, factor id) -- the parallel fill leaves a list in
+  // arrival order, and equal (value, factor) entries are interchangeable -- then consecutive
+  // duplicates dropped (same factor under the same value, :179-195)
   std::vector<uint32_t> inc_end(nvar);
-  for (uint64_t v = 0; v < nvar; ++v) {
-    Inc *a = inc.data() + deg[v], *b = inc.data() + deg[v + 1];
-    if (g->var_dtype[v])
-      std::stable_sort(a, b, [](const Inc &x, const Inc &y) { return x.key < y.key; });
-    Inc *o = a;
-    for (Inc *p = a; p != b; ++p)
-      if (o == a || o[-1].key != p->key || o[-1].fid != p->fid) *o++ = *p;
-    inc_end[v] = (uint32_t)(o - inc.data());
-  }
+  parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+    for (uint64_t v = v0; v < v1; ++v) {
+      Inc *a = inc.data() + deg[v], *b = inc.data() + deg[v + 1];
+      std::sort(a, b, [](const Inc &x, const Inc &y) { return x.key != y.key ? x.key < y.key : x.fid < y.fid; });
+      Inc *o = a;
+      for (Inc *q = a; q != b; ++q)
+        if (o == a || o[-1].key != q->key || o[-1].fid != q->fid) *o++ = *q;
+      inc_end[v] = (uint32_t)(o - inc.data());
+    }
+  });
 
   pt.lap("adjacency + index");
   // ---- rows in ORIGINAL order (var_val_base, values, truthiness) ----
@@ -288,6 +319,36 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       *err = DWG_ERR_UNSUPPORTED;
       return "chromatic schedule: factor arities too large to colour; use the hogwild schedule";
     }
+    // conflict lists (the other variables of every incident factor; repeats are harmless), built
+    // in parallel; the two greedy passes below then touch nothing but these and color[]
+    std::vector<uint64_t> nb_ptr(nvar + 1, 0);
+    auto for_neighbours = [&](uint64_t v, auto &&fn) {
+      uint32_t last_f = 0xffffffffu;
+      for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
+        uint32_t f = inc[i].fid;
+        if (f == last_f) continue;
+        last_f = f;
+        const uint64_t a = raw.fac_ptr[f], b = raw.fac_ptr[f + 1];
+        if (b - a < 2) continue;
+        for (uint64_t e = a; e < b; ++e)
+          if (raw.edge_vid[e] != v) fn((uint32_t)raw.edge_vid[e]);
+      }
+    };
+    parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+      for (uint64_t v = v0; v < v1; ++v) {
+        uint64_t n = 0;
+        for_neighbours(v, [&](uint32_t) { ++n; });
+        nb_ptr[v + 1] = n;
+      }
+    });
+    for (uint64_t v = 0; v < nvar; ++v) nb_ptr[v + 1] += nb_ptr[v];
+    std::vector<uint32_t> nb(nb_ptr[nvar]);
+    parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+      for (uint64_t v = v0; v < v1; ++v) {
+        uint64_t o = nb_ptr[v];
+        for_neighbours(v, [&](uint32_t u) { nb[o++] = u; });
+      }
+    });
     // Pass 1, first fit, finds how many colours K the graph needs; pass 2 recolours with the
     // least-loaded admissible colour among those K, so that every class is large enough to
     // fill the GPU (first fit alone leaves a tail of tiny classes = latency-bound launches).
@@ -300,16 +361,10 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       load.assign(K + 1, 0);
       ncolor = 1;
       for (uint64_t v = 0; v < nvar; ++v) {
-        uint32_t last_f = 0xffffffffu;
-        for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
-          uint32_t f = inc[i].fid;
-          if (f == last_f) continue;
-          last_f = f;
-          for (uint64_t e = raw.fac_ptr[f]; e < raw.fac_ptr[f + 1]; ++e) {
-            uint32_t c = color[raw.edge_vid[e]];
-            if (c == 0xffffffffu) continue;
-            stamp[c] = (uint32_t)v + 1;
-          }
+        for (uint64_t i = nb_ptr[v]; i < nb_ptr[v + 1]; ++i) {
+          uint32_t c = color[nb[i]];
+          if (c == 0xffffffffu) continue;
+          stamp[c] = (uint32_t)v + 1;
         }
         uint32_t c = 0xffffffffu;
         if (pass == 0) {
@@ -382,31 +437,54 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   if (g->sell) {
     struct Key { uint64_t k; uint32_t v; };
     std::vector<Key> keys(nvar);
-    for (uint64_t v = 0; v < nvar; ++v) {
-      uint64_t n_un = 0, n_mu = 0, ow = 0;
-      for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
-        uint32_t f = inc[i].fid;
-        uint64_t n = raw.fac_ptr[f + 1] - raw.fac_ptr[f];
-        int form = edge_form(v, f, 0, false, nullptr);
-        if (form == 0) { ++n_un; continue; }
-        ++n_mu;
-        ow += form == (int)FORM_GENERAL ? 1 + n : (uint64_t)form;
+    parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+      for (uint64_t v = v0; v < v1; ++v) {
+        uint64_t n_un = 0, n_mu = 0, ow = 0;
+        for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
+          uint32_t f = inc[i].fid;
+          uint64_t n = raw.fac_ptr[f + 1] - raw.fac_ptr[f];
+          int form = edge_form(v, f, 0, false, nullptr);
+          if (form == 0) { ++n_un; continue; }
+          ++n_mu;
+          ow += form == (int)FORM_GENERAL ? 1 + n : (uint64_t)form;
+        }
+        n_un = std::min<uint64_t>(n_un, (1u << 16) - 1);
+        n_mu = std::min<uint64_t>(n_mu, (1u << 12) - 1);
+        ow = std::min<uint64_t>(ow, (1u << 20) - 1);
+        keys[v] = {((uint64_t)color[v] << 49) | ((uint64_t)g->var_is_evid[v] << 48) | (n_un << 32) | (n_mu << 20) | ow,
+                   (uint32_t)v};
       }
-      n_un = std::min<uint64_t>(n_un, (1u << 16) - 1);
-      n_mu = std::min<uint64_t>(n_mu, (1u << 12) - 1);
-      ow = std::min<uint64_t>(ow, (1u << 20) - 1);
-      keys[v] = {((uint64_t)color[v] << 49) | ((uint64_t)g->var_is_evid[v] << 48) | (n_un << 32) | (n_mu << 20) | ow,
-                 (uint32_t)v};
-    }
-    std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
-      return a.k != b.k ? a.k < b.k : a.v < b.v;
     });
-    std::vector<uint32_t> fill(g->color_start.begin(), g->color_start.end() - 1);
-    for (auto &kv : keys) {
-      uint32_t d = fill[color[kv.v]]++;
-      g->perm[d] = kv.v;
-      g->inv[kv.v] = d;
+    // sorted runs in parallel, then pairwise merges (the order is total: ties broken by id)
+    auto less = [](const Key &a, const Key &b) { return a.k != b.k ? a.k < b.k : a.v < b.v; };
+    {
+      unsigned runs = 1;
+      while (runs * 2 <= host_threads() && nvar / (runs * 2) >= (1u << 16)) runs *= 2;
+      auto bound = [&](unsigned r) { return keys.begin() + (std::ptrdiff_t)(nvar * r / runs); };
+      parallel_ranges(runs, runs, [&](uint64_t r0, uint64_t r1, unsigned) {
+        for (uint64_t r = r0; r < r1; ++r) std::sort(bound((unsigned)r), bound((unsigned)r + 1), less);
+      }, 1);
+      for (unsigned width = 1; width < runs; width *= 2) {
+        const unsigned pairs = runs / (2 * width);
+        parallel_ranges(pairs, pairs, [&](uint64_t p0, uint64_t p1, unsigned) {
+          for (uint64_t q = p0; q < p1; ++q) {
+            const unsigned lo = (unsigned)q * 2 * width;
+            std::inplace_merge(bound(lo), bound(lo + width), bound(lo + 2 * width), less);
+          }
+        }, 1);
+      }
     }
+    // keys are colour-major: position in the sorted order -> slot of the (padded) class
+    std::vector<uint64_t> class_first(ncolor + 1, 0);
+    for (uint32_t c = 0; c < ncolor; ++c) class_first[c + 1] = class_first[c] + class_count[c];
+    parallel_for(nvar, [&](uint64_t i0, uint64_t i1) {
+      for (uint64_t i = i0; i < i1; ++i) {
+        const uint32_t v = keys[i].v, c = color[v];
+        const uint32_t d = (uint32_t)(g->color_start[c] + (i - class_first[c]));
+        g->perm[d] = v;
+        g->inv[v] = d;
+      }
+    });
   } else {
     std::vector<uint32_t> fill(g->color_start.begin(), g->color_start.end() - 1);
     for (uint64_t v = 0; v < nvar; ++v) {
@@ -433,71 +511,111 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   g->e_wid.resize(nindex); g->e_tag.resize(nindex);
   if (g->fv_mode == FV_F32) g->e_fv32.resize(nindex);
   if (g->fv_mode == FV_F64) g->e_fv64.resize(nindex);
-  g->oth.clear();
   const int ow = g->oth_packed ? 1 : 2;  // words per others entry
-  auto push_oth = [&](uint32_t d, uint32_t eq) {
-    if (g->oth_packed) g->oth.push_back((d << 1) | eq);
-    else { g->oth.push_back(d); g->oth.push_back(eq); }
+  // Two passes over contiguous blocks of schedule positions, both in parallel: pass 1 sizes each
+  // block (rows, edge records, others entries), a prefix sum places it, pass 2 writes it.
+  struct Block {
+    uint64_t rows = 0, edges = 0, oth = 0;   // sizes, then (after the prefix sum) start offsets
+    uint64_t bad_d = INVALID;
+    const char *msg = nullptr;
+    double b_all = 0, b_query = 0, b_learn = 0;
   };
-  uint64_t row = 0, ei = 0;
-  double b_all = 0, b_query = 0, b_learn = 0;
-  for (uint64_t d = 0; d < nvar_pad; ++d) {
-    uint64_t v = g->perm[d];
-    if (v == 0xffffffffu) {  // pad: an empty row
-      g->row_ptr[row] = (uint32_t)ei;
-      if (g->has_multi) g->row_oth[row] = (uint32_t)(g->oth.size() / ow);
-      ++row;
-      continue;
-    }
-    bool cat = g->var_dtype[v];
-    uint64_t K = cat ? raw.var_card[v] : 1;
-    g->var_flags[d] = (g->var_is_evid[v] ? VF_EVID : 0) | (cat ? VF_CATEGORICAL : 0) |
-                      (has_truth[v] ? VF_TRUTHINESS : 0);
-    if (adense[v] >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "initial value >= 2^32"; }
-    g->evid_val[d] = (uint32_t)adense[v];
-    if (g->has_categorical) g->var_row[d] = (uint32_t)row;
-    double vb = 13.0 + (cat ? 4.0 * K : 0.0), vl = 2.0;
-    uint32_t i = deg[v];
-    for (uint64_t k = 0; k < K; ++k, ++row) {
-      g->row_of_value[g->value_base[v] + k] = (uint32_t)row;
-      if (g->has_truthiness) g->truthiness[row] = truth_orig[g->value_base[v] + k];
-      g->row_ptr[row] = (uint32_t)ei;
-      if (g->has_multi) g->row_oth[row] = (uint32_t)(g->oth.size() / ow);
-      for (; i < inc_end[v] && inc[i].key == k; ++i, ++ei) {
+  const unsigned NB = nvar_pad >= (1u << 12) ? host_threads() * 4 : 1;
+  std::vector<Block> blk(NB + 1);
+  parallel_ranges(nvar_pad, NB, [&](uint64_t d0, uint64_t d1, unsigned p) {
+    Block &B = blk[p];
+    for (uint64_t d = d0; d < d1; ++d) {
+      uint64_t v = g->perm[d];
+      if (v == 0xffffffffu) { ++B.rows; continue; }  // pad: an empty row
+      bool cat = g->var_dtype[v];
+      B.rows += cat ? raw.var_card[v] : 1;
+      if (adense[v] >= U32_LIMIT && B.bad_d == INVALID) { B.bad_d = d; B.msg = "initial value >= 2^32"; }
+      for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
         uint32_t f = inc[i].fid;
-        uint64_t a = raw.fac_ptr[f], b = raw.fac_ptr[f + 1], n = b - a;
-        g->e_wid[ei] = (uint32_t)raw.fac_wid[f];
-        if (g->fv_mode == FV_F32) g->e_fv32[ei] = (float)raw.fac_fv[f];
-        if (g->fv_mode == FV_F64) g->e_fv64[ei] = raw.fac_fv[f];
-        uint8_t tag = (uint8_t)func_code(raw.fac_func[f]);
-        uint64_t self_pos = 0;
-        int form = edge_form(v, f, k, cat, &self_pos);
-        if (form != (int)FORM_GENERAL) {
-          if (!cat && edense[a + self_pos] == 1) tag |= TAG_SELF_EQ1;
-          if (self_pos == n - 1) tag |= TAG_SELF_HEAD;
-          tag |= (uint8_t)(form << TAG_FORM_SHIFT);
-          for (uint64_t e = a; e < b; ++e)
-            if (raw.edge_vid[e] != v) push_oth(g->inv[raw.edge_vid[e]], edense[e]);
-        } else {
-          // general form: length word, then every position (self included) in order
-          tag |= (uint8_t)(FORM_GENERAL << TAG_FORM_SHIFT);
-          if (n >= (g->oth_packed ? (1ull << 31) : U32_LIMIT)) {
-            *err = DWG_ERR_UNSUPPORTED; return "factor arity too large";
-          }
-          if (g->oth_packed) g->oth.push_back((uint32_t)n);
-          else { g->oth.push_back((uint32_t)n); g->oth.push_back(0); }
-          for (uint64_t e = a; e < b; ++e) push_oth(g->inv[raw.edge_vid[e]], edense[e]);
+        uint64_t n = raw.fac_ptr[f + 1] - raw.fac_ptr[f];
+        int form = edge_form(v, f, inc[i].key, cat, nullptr);
+        if (form == (int)FORM_GENERAL && n >= (g->oth_packed ? (1ull << 31) : U32_LIMIT) && B.bad_d == INVALID) {
+          B.bad_d = d; B.msg = "factor arity too large";
         }
-        g->e_tag[ei] = tag;
-        vb += 9.0 + 5.0 * (double)(n - 1);
-        vl += 1.0 * (double)(n - 1);
+        B.oth += form != (int)FORM_GENERAL ? (uint64_t)form : 1 + n;
+        ++B.edges;
       }
-      if (g->oth.size() / ow >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "others stream >= 2^32 entries"; }
     }
-    b_all += vb;
-    if (!g->var_is_evid[v]) b_query += vb;
-    b_learn += vb + vl;
+  });
+  {
+    uint64_t rows = 0, edges = 0, oth = 0;
+    for (unsigned p = 0; p <= NB; ++p) {
+      if (p < NB && blk[p].bad_d != INVALID) { *err = DWG_ERR_UNSUPPORTED; return blk[p].msg; }
+      uint64_t r = blk[p].rows, e = blk[p].edges, o = blk[p].oth;
+      blk[p].rows = rows; blk[p].edges = edges; blk[p].oth = oth;
+      rows += r; edges += e; oth += o;
+    }
+    if (blk[NB].oth >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "others stream >= 2^32 entries"; }
+    g->oth.assign(blk[NB].oth * ow, 0);
   }
+  parallel_ranges(nvar_pad, NB, [&](uint64_t d0, uint64_t d1, unsigned p) {
+    Block &B = blk[p];
+    uint64_t row = B.rows, ei = B.edges, oc = B.oth;
+    auto put_oth = [&](uint32_t a, uint32_t eq) {
+      if (g->oth_packed) g->oth[oc] = (a << 1) | eq;
+      else { g->oth[2 * oc] = a; g->oth[2 * oc + 1] = eq; }
+      ++oc;
+    };
+    for (uint64_t d = d0; d < d1; ++d) {
+      uint64_t v = g->perm[d];
+      if (v == 0xffffffffu) {  // pad: an empty row
+        g->row_ptr[row] = (uint32_t)ei;
+        if (g->has_multi) g->row_oth[row] = (uint32_t)oc;
+        ++row;
+        continue;
+      }
+      bool cat = g->var_dtype[v];
+      uint64_t K = cat ? raw.var_card[v] : 1;
+      g->var_flags[d] = (g->var_is_evid[v] ? VF_EVID : 0) | (cat ? VF_CATEGORICAL : 0) |
+                        (has_truth[v] ? VF_TRUTHINESS : 0);
+      g->evid_val[d] = (uint32_t)adense[v];
+      if (g->has_categorical) g->var_row[d] = (uint32_t)row;
+      double vb = 13.0 + (cat ? 4.0 * K : 0.0), vl = 2.0;
+      uint32_t i = deg[v];
+      for (uint64_t k = 0; k < K; ++k, ++row) {
+        g->row_of_value[g->value_base[v] + k] = (uint32_t)row;
+        if (g->has_truthiness) g->truthiness[row] = truth_orig[g->value_base[v] + k];
+        g->row_ptr[row] = (uint32_t)ei;
+        if (g->has_multi) g->row_oth[row] = (uint32_t)oc;
+        for (; i < inc_end[v] && inc[i].key == k; ++i, ++ei) {
+          uint32_t f = inc[i].fid;
+          uint64_t a = raw.fac_ptr[f], b = raw.fac_ptr[f + 1], n = b - a;
+          g->e_wid[ei] = (uint32_t)raw.fac_wid[f];
+          if (g->fv_mode == FV_F32) g->e_fv32[ei] = (float)raw.fac_fv[f];
+          if (g->fv_mode == FV_F64) g->e_fv64[ei] = raw.fac_fv[f];
+          uint8_t tag = (uint8_t)func_code(raw.fac_func[f]);
+          uint64_t self_pos = 0;
+          int form = edge_form(v, f, k, cat, &self_pos);
+          if (form != (int)FORM_GENERAL) {
+            if (!cat && edense[a + self_pos] == 1) tag |= TAG_SELF_EQ1;
+            if (self_pos == n - 1) tag |= TAG_SELF_HEAD;
+            tag |= (uint8_t)(form << TAG_FORM_SHIFT);
+            for (uint64_t e = a; e < b; ++e)
+              if (raw.edge_vid[e] != v) put_oth(g->inv[raw.edge_vid[e]], edense[e]);
+          } else {
+            // general form: length word, then every position (self included) in order
+            tag |= (uint8_t)(FORM_GENERAL << TAG_FORM_SHIFT);
+            put_oth((uint32_t)n >> (g->oth_packed ? 1 : 0), g->oth_packed ? (uint32_t)n & 1u : 0u);  // the word n
+            for (uint64_t e = a; e < b; ++e) put_oth(g->inv[raw.edge_vid[e]], edense[e]);
+          }
+          g->e_tag[ei] = tag;
+          vb += 9.0 + 5.0 * (double)(n - 1);
+          vl += 1.0 * (double)(n - 1);
+        }
+      }
+      B.b_all += vb;
+      if (!g->var_is_evid[v]) B.b_query += vb;
+      B.b_learn += vb + vl;
+    }
+  });
+  const uint64_t ei = blk[NB].edges;
+  double b_all = 0, b_query = 0, b_learn = 0;
+  for (unsigned p = 0; p < NB; ++p) { b_all += blk[p].b_all; b_query += blk[p].b_query; b_learn += blk[p].b_learn; }
   g->row_ptr[ndrow] = (uint32_t)ei;
   if (g->has_multi) g->row_oth[ndrow] = (uint32_t)(g->oth.size() / ow);
   if (g->has_categorical) g->var_row[nvar_pad] = (uint32_t)ndrow;
@@ -510,14 +628,27 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   // ---- internal weight ids: hottest first, so that ids < n_hot can live in shared memory ----
   g->w_perm.resize(nweight); g->w_inv.resize(nweight);
   {
-    std::vector<uint64_t> cnt(nweight, 0);
-    for (uint64_t e = 0; e < nindex; ++e) ++cnt[g->e_wid[e]];
     std::iota(g->w_perm.begin(), g->w_perm.end(), 0u);
-    if (nweight > DWG_HOT_WEIGHTS)
+    if (nweight > DWG_HOT_WEIGHTS) {
+      // use counts: one histogram per thread, summed (integers: any order gives the same counts)
+      const unsigned T = host_threads();
+      std::vector<std::vector<uint32_t>> part(T);
+      parallel_ranges(nindex, T, [&](uint64_t e0, uint64_t e1, unsigned p) {
+        part[p].assign(nweight, 0);
+        for (uint64_t e = e0; e < e1; ++e) ++part[p][g->e_wid[e]];
+      });
+      std::vector<uint64_t> cnt(nweight, 0);
+      for (unsigned p = 0; p < T; ++p)
+        if (!part[p].empty())
+          for (uint64_t w = 0; w < nweight; ++w) cnt[w] += part[p][w];
       std::stable_sort(g->w_perm.begin(), g->w_perm.end(),
                        [&](uint32_t a, uint32_t b) { return cnt[a] > cnt[b]; });
+    }
     for (uint64_t i = 0; i < nweight; ++i) g->w_inv[g->w_perm[i]] = (uint32_t)i;
-    for (uint64_t e = 0; e < nindex; ++e) g->e_wid[e] = g->w_inv[g->e_wid[e]];
+    if (nweight > DWG_HOT_WEIGHTS)
+      parallel_for(nindex, [&](uint64_t e0, uint64_t e1) {
+        for (uint64_t e = e0; e < e1; ++e) g->e_wid[e] = g->w_inv[g->e_wid[e]];
+      });
     g->n_hot = (uint32_t)std::min<uint64_t>(nweight, DWG_HOT_WEIGHTS);
   }
 
@@ -559,7 +690,11 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         fn(w, std::fabs(fv) * srange(tag & TAG_FUNC_MASK, n));
       }
     };
-    for (uint32_t c = 0; c < ncolor; ++c) {
+    // every class owns its row of the tables: classes in parallel (the float sums of a row keep
+    // their sequential order); a shared row is filled by one thread
+    parallel_ranges(ncolor, g->cls_shared ? 1u : std::min<unsigned>(ncolor, host_threads()),
+                    [&](uint64_t c0, uint64_t c1, unsigned) {
+    for (uint64_t c = c0; c < c1; ++c) {
       uint64_t base = g->cls_shared ? 0 : (uint64_t)c * nweight;
       for (uint64_t d = g->color_start[c]; d < g->color_start[c + 1]; ++d) {
         uint64_t v = g->perm[d];
@@ -578,6 +713,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         });
       }
     }
+    }, 1);
     if (g->cls_shared)
       for (uint64_t w = 0; w < nweight; ++w) {
         g->cls_N_evid[w] /= ncolor; g->cls_Q_evid[w] /= ncolor; g->cls_H_evid[w] /= ncolor;
@@ -597,16 +733,21 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     // slice shapes
     std::vector<uint32_t> s_un(nslice), s_mu(nslice), s_oc(nslice);
     uint64_t words = 0;
-    for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
-      uint32_t un = 0, mu = 0, oc = 0;
-      for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
-        uint32_t u = 0;
-        for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) u += is_unary(e);
-        un = std::max(un, u);
-        mu = std::max<uint32_t>(mu, g->row_ptr[d + 1] - g->row_ptr[d] - u);
-        if (g->has_multi) oc = std::max(oc, g->row_oth[d + 1] - g->row_oth[d]);
+    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
+      for (uint64_t sidx = a0; sidx < a1; ++sidx) {
+        uint32_t un = 0, mu = 0, oc = 0;
+        for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
+          uint32_t u = 0;
+          for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) u += is_unary(e);
+          un = std::max(un, u);
+          mu = std::max<uint32_t>(mu, g->row_ptr[d + 1] - g->row_ptr[d] - u);
+          if (g->has_multi) oc = std::max(oc, g->row_oth[d + 1] - g->row_oth[d]);
+        }
+        s_un[sidx] = un; s_mu[sidx] = mu; s_oc[sidx] = oc;
       }
-      s_un[sidx] = un; s_mu[sidx] = mu; s_oc[sidx] = oc;
+    });
+    for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
+      const uint32_t un = s_un[sidx], mu = s_mu[sidx], oc = s_oc[sidx];
       g->sl_off[sidx] = (uint32_t)(words / 8);
       uint64_t w = SH_WORDS + 32ull * ((uint64_t)(un + mu) * (1 + fvw) + oc);
       g->sell_max_words = (uint32_t)std::max<uint64_t>(g->sell_max_words, std::min<uint64_t>(w, U32_LIMIT));
@@ -639,7 +780,8 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       if (g->fv_mode == FV_F32) std::memcpy(slot, &g->e_fv32[e], 4);
       else if (g->fv_mode == FV_F64) std::memcpy(slot, &g->e_fv64[e], 8);
     };
-    for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
+    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
+    for (uint64_t sidx = a0; sidx < a1; ++sidx) {
       uint32_t *h = g->blob.data() + (uint64_t)g->sl_off[sidx] * 8;
       const uint32_t un = s_un[sidx], mu = s_mu[sidx], oc = s_oc[sidx];
       const uint64_t o_un = SH_WORDS, o_unfv = o_un + 32ull * un, o_mu = o_unfv + 32ull * un * fvw,
@@ -700,6 +842,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       }
       h[SH_FLAGS] = (antisym ? SF_ANTISYM : 0u) | (binary ? SF_BINARY : 0u);
     }
+    });
   }
   pt.lap("sliced-ELL blob");
   *err = DWG_OK;

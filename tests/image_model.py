@@ -141,7 +141,7 @@ class ImageModel:
         antisym = True
         for j in range(h["n_un"]):
             rec = int(self.blob[h["un"] + 32 * j + lane])
-            wid = (rec >> 2) & 0x7FFFFF  # unary record: code(1) | wid << 2 | fixed << 25 | code(0) << 26
+            wid = (rec >> 3) & 0x7FFFFF  # unary record: code(1) | fixed << 2 | wid << 3 | code(0) << 26
             w = float(weights[wid])
             fv = self._sell_fv(h["un"], h["n_un"], j, lane, h["fvw"])
             s1, s0 = code(rec & 3), code((rec >> 26) & 3)
@@ -205,8 +205,8 @@ class ImageModel:
             h = self.slice_header(s)
             recs = self.blob[h["un"]:h["un"] + 32 * h["n_un"]]
             real = recs != 0x04000001  # SELL_UNARY_NOP
-            bits = (recs >> 25) & 1
-            if not np.array_equal(bits[real], fixed[((recs >> 2) & 0x7FFFFF).astype(np.int64)][real]) or bits[~real].any():
+            bits = (recs >> 2) & 1
+            if not np.array_equal(bits[real], fixed[((recs >> 3) & 0x7FFFFF).astype(np.int64)][real]) or bits[~real].any():
                 return False
             nop = 0x55 if h["flags"] & 2 else 0
             recs = self.blob[h["mu"]:h["mu"] + 32 * h["n_mu"]]

@@ -189,3 +189,40 @@ def test_no_device_is_a_loud_error():
     g = sb.Graph.from_raw(load_golden_graph("biased_coin"))
     with pytest.raises(sb.DwgError, match="no CUDA device"):
         sb.Sampler(g)
+
+
+IMAGE_ARRAYS = ("perm", "inv", "color_start", "var_flags", "evid_val", "var_row", "row_ptr", "row_oth",
+                "truthiness", "e_wid", "e_fv32", "e_fv64", "e_tag", "oth", "row_of_value", "values",
+                "value_base", "w_perm", "w_inv", "sl_off", "blob", "cls_N_evid", "cls_Q_evid", "cls_H_evid",
+                "cls_N_all", "cls_Q_all", "cls_H_all")
+
+
+@pytest.mark.parametrize("shape", ["c2", "c3", "mixed", "zipf"])
+def test_compiled_image_does_not_depend_on_the_thread_count(shape, monkeypatch):
+    """compile.cc fans every O(edges) phase out over host threads (host/parallel.h): the image --
+    schedule, CSR stream, sliced-ELL blob, learning statistics -- is the same byte for byte with
+    1, 3 and 8 threads (graphs large enough that the parallel paths really split)"""
+    from sampler_b200 import graphgen
+    rng = np.random.default_rng(99)
+    if shape == "c2":
+        raw = graphgen.c2_boolean(150_000, nweight=300)
+    elif shape == "c3":
+        raw = graphgen.c3_categorical(40_000, nweight=200)
+    elif shape == "zipf":
+        raw = graphgen.unary_boolean(100_000, 12, 20_000, p_evid=0.9, zipf=1.1, real_features=True)
+    else:
+        raw = random_graph(rng, nvar=6_000, nfac=16_000, nweight=300, max_arity=4)
+    ref = None
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("DWG_COMPILE_THREADS", threads)
+        g = sb.Graph.from_raw(raw, sb.SCHED_CHROMATIC)
+        img = {name: g.image(name).copy() for name in IMAGE_ARRAYS}
+        info = g.info
+        meta = (info.num_colors, info.schedule, info.num_index_entries, info.num_other_refs, info.bytes_per_sweep_infer,
+                info.bytes_per_sweep_learn, info.bytes_per_sweep_infer_query)
+        if ref is None:
+            ref = (img, meta)
+            continue
+        assert meta == ref[1]
+        for name in IMAGE_ARRAYS:
+            assert img[name].dtype == ref[0][name].dtype and np.array_equal(img[name].view(np.uint8), ref[0][name].view(np.uint8)), (name, threads)
