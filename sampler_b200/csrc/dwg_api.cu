@@ -65,7 +65,29 @@ struct dwg_graph {
       reg(img.e_fv32.data(), img.e_fv32.size() * 4);
       reg(img.e_fv64.data(), img.e_fv64.size() * 8);
     }
+    reg(img.row_of_value.data(), img.row_of_value.size() * 4);
     if (pinned.empty()) pinned.push_back(nullptr);  // tried
+  }
+  // per colour class: the first slice from which every slice holds evidence / padding only
+  // (slices are sorted non-evidence first inside a class, compile.cc); computed once per graph
+  mutable std::vector<uint32_t> cls_query_end;
+  const std::vector<uint32_t> &query_end() const {
+    std::lock_guard<std::mutex> lk(pin_mu);
+    if (!cls_query_end.empty() || !img.sell) return cls_query_end;
+    const uint32_t nc = img.ncolor();
+    cls_query_end.assign(nc, 0);
+    for (uint32_t c = 0; c < nc; ++c) {
+      const uint32_t sb = img.color_start[c] / 32, se = img.color_start[c + 1] / 32;
+      uint32_t qe = sb;
+      for (uint32_t sl = se; sl > sb && qe == sb; --sl) {  // from the evidence tail backwards
+        bool query = false;
+        for (uint32_t d = (sl - 1) * 32; d < sl * 32 && !query; ++d)
+          query = !(img.var_flags[d] & (VF_EVID | VF_PAD));
+        if (query) qe = sl;
+      }
+      cls_query_end[c] = qe;
+    }
+    return cls_query_end;
   }
   ~dwg_graph() {
     for (const void *p : pinned)
@@ -139,6 +161,9 @@ struct dwg_handle {
   DevBuf<uint32_t> assign_free32, assign_evid32, tallies;
   DevBuf<double> r_free, r_evid;  // parity hook
   bool explicit_r = false, sequential = false;
+  // the last operation enqueued on the stream was a staged inference launch of this handle (the
+  // next one may be a programmatic dependent launch); cleared by every other entry point
+  bool chain_open = false;
   uint64_t sweep_counter = 0, infer_sweeps = 0;
   std::vector<uint64_t> extra_nsamples;  // from dwg_add_tallies
   DevGraph dg{};
@@ -187,7 +212,10 @@ int sell_setup_t(dwg_handle *h) {
   const char *direct = getenv("DWG_SELL_DIRECT");
   if (direct && *direct == '1') return DWG_OK;
   const size_t budget = 112 * 1024;  // per CTA, two per SM out of 228 KB (1 KB reserved each)
-  uint32_t max_stages = SELL_MAX_STAGES;
+  // measured on C2 / C5 (profiles/r1_v4_ab.txt): with neighbour gathers in the loop two deep stages
+  // beat three or four shallow ones (fewer slices fall out of their stage), unary-only graphs
+  // gain a little from the deeper ring
+  uint32_t max_stages = MULTI ? 2 : SELL_MAX_STAGES;
   if (const char *e = getenv("DWG_SELL_STAGES")) max_stages = std::max(2, std::min(SELL_MAX_STAGES, atoi(e)));
   const uint32_t nwarp = SELL_STAGED_THREADS / 32;
   const uint32_t n_tab = (uint32_t)std::min<uint64_t>({h->img->nweight, n_hot, SELL_MAX_TAB});
@@ -220,15 +248,23 @@ int sell_setup_t(dwg_handle *h) {
   return DWG_OK;
 }
 template <bool MULTI, int FV>
-void sell_launch_t(dwg_handle *h, bool learn, bool staged, uint32_t blocks, const SellGraph &sg,
+void sell_launch_t(dwg_handle *h, bool learn, bool staged, bool pdl, uint32_t blocks, const SellGraph &sg,
                    const SweepParams &p) {
   const size_t n_hot = h->img->n_hot;
   if (staged) {
-    const size_t smem = sell_staged_smem(sg.n_tab, h->sell_stages, h->sell_stage_words);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(SELL_STAGED_THREADS);
+    cfg.dynamicSmemBytes = sell_staged_smem(sg.n_tab, h->sell_stages, h->sell_stage_words);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;  // only behind another launch of this kernel (see launch_sweep)
     if (h->img->nweight <= sg.n_tab)
-      k_sell_infer_staged<MULTI, FV, true><<<blocks, SELL_STAGED_THREADS, smem, h->stream>>>(sg, h->ss, p, h->sell_stages, h->sell_stage_words);
+      cudaLaunchKernelEx(&cfg, k_sell_infer_staged<MULTI, FV, true>, sg, h->ss, p, h->sell_stages, h->sell_stage_words);
     else
-      k_sell_infer_staged<MULTI, FV, false><<<blocks, SELL_STAGED_THREADS, smem, h->stream>>>(sg, h->ss, p, h->sell_stages, h->sell_stage_words);
+      cudaLaunchKernelEx(&cfg, k_sell_infer_staged<MULTI, FV, false>, sg, h->ss, p, h->sell_stages, h->sell_stage_words);
   } else if (learn) k_sell_learn<MULTI, FV><<<blocks, SELL_THREADS, 16 * n_hot, h->stream>>>(sg, h->ss, p);
   else k_sell_infer<MULTI, FV><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
 }
@@ -250,10 +286,10 @@ int sell_setup(dwg_handle *h) {
 #undef CALL
   return rc;
 }
-void sell_launch(dwg_handle *h, bool learn, bool staged, uint32_t blocks, const SellGraph &sg,
+void sell_launch(dwg_handle *h, bool learn, bool staged, bool pdl, uint32_t blocks, const SellGraph &sg,
                  const SweepParams &p) {
   const GraphImage &m = *h->img;
-#define CALL(MU, FV) sell_launch_t<MU, FV>(h, learn, staged, blocks, sg, p)
+#define CALL(MU, FV) sell_launch_t<MU, FV>(h, learn, staged, pdl, blocks, sg, p)
   SELL_SWITCH(CALL)
 #undef CALL
 }
@@ -337,7 +373,7 @@ static size_t image_device_bytes(const GraphImage &m) {
     b += m.e_tag.size() + 4 * (m.var_row.size() + m.row_ptr.size() + m.row_oth.size() + m.e_wid.size() + m.oth.size());
     b += 4 * m.e_fv32.size() + 8 * m.e_fv64.size() + 8 * m.truthiness.size();
   }
-  b += 4 * m.ndrow;        // tallies
+  b += 4 * m.ndrow + 4 * m.row_of_value.size();  // tallies, their ABI-order map
   b += 8 * 3 * m.nweight;  // weights + prev + gradient sums
   b += 4 * 3 * (m.cls_N_evid.size());
   return b;
@@ -501,6 +537,7 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     CU(h->assign_evid32.alloc(m.nvar_pad));
   }
   CU(h->tallies.alloc(m.ndrow));
+  CU(h->row_of_value.upload(m.row_of_value, s));  // dwg_get_tallies: schedule order -> ABI order on the device
   CU(h->w_fixed.upload(fixed_dev, s));
   CU(h->weights.upload(w_dev, s));
   CU(h->prev_weights.upload(w_dev, s));
@@ -549,19 +586,7 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     ss.weights = h->weights.p; ss.grad_acc = h->grad_acc.p; ss.tallies = h->tallies.p;
     rc = sell_setup(h.get());
     if (rc) return rc;
-    const uint32_t nc = m.ncolor();
-    h->cls_query_end.assign(nc, 0);
-    for (uint32_t c = 0; c < nc; ++c) {
-      const uint32_t sb = m.color_start[c] / 32, se = m.color_start[c + 1] / 32;
-      uint32_t qe = sb;
-      for (uint32_t sl = sb; sl < se; ++sl) {
-        bool query = false;
-        for (uint32_t d = sl * 32; d < sl * 32 + 32 && !query; ++d)
-          query = !(m.var_flags[d] & (VF_EVID | VF_PAD));
-        if (query) qe = sl + 1;
-      }
-      h->cls_query_end[c] = qe;
-    }
+    h->cls_query_end = g->query_end();
   }
   *out = h.release();
   return DWG_OK;
@@ -636,7 +661,10 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
         const uint32_t wpb = (staged ? SELL_STAGED_THREADS : SELL_THREADS) / 32;
         const uint32_t need = (n_sl + wpb - 1) / wpb;
         const uint32_t cap = (uint32_t)(staged ? h->sell_blocks_staged : learn ? h->sell_blocks_learn : h->sell_blocks_infer);
-        sell_launch(h, learn, staged, std::min<uint32_t>(need, cap), sg, p);
+        // programmatic dependent launch behind the previous colour class of an inference run
+        const bool pdl = staged && h->chain_open && !getenv("DWG_SELL_NO_PDL");
+        sell_launch(h, learn, staged, pdl, std::min<uint32_t>(need, cap), sg, p);
+        h->chain_open = staged;
       } else {
         uint32_t blocks = (my_units * 32 + SWEEP_THREADS - 1) / SWEEP_THREADS;
         uint32_t threads = SWEEP_THREADS;
@@ -688,17 +716,22 @@ int dwg_infer_epochs(dwg_handle *h, uint64_t n) {
 
 int dwg_sync(dwg_handle *h) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  h->chain_open = false;
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   return DWG_OK;
 }
 
-void *dwg_stream(dwg_handle *h) { return h ? (void *)h->stream : nullptr; }
+void *dwg_stream(dwg_handle *h) {
+  if (h) h->chain_open = false;  // the caller may enqueue anything behind our launches
+  return h ? (void *)h->stream : nullptr;
+}
 void *dwg_weights_device_ptr(dwg_handle *h) { return h ? (void *)h->weights.p : nullptr; }
 void *dwg_tallies_device_ptr(dwg_handle *h) { return h ? (void *)h->tallies.p : nullptr; }
 
 int dwg_clear_tallies(dwg_handle *h) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  h->chain_open = false;
   CU(cudaSetDevice(h->device));
   CU(cudaMemsetAsync(h->tallies.p, 0, 4 * h->img->ndrow, h->stream));
   h->infer_sweeps = 0;
@@ -708,12 +741,12 @@ int dwg_clear_tallies(dwg_handle *h) {
 
 int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   if (tallies && m.nrow) {
     // schedule order -> ABI order on the device, one DMA into page-locked memory, widen on the host
     if (!h->tallies_host) {
-      CU(h->row_of_value.upload(m.row_of_value, h->stream));
       CU(h->tallies_abi.alloc(m.nrow));
       CU(cudaHostAlloc((void **)&h->tallies_host, 4 * m.nrow, cudaHostAllocDefault));
     }
@@ -740,6 +773,7 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
 
 int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsamples) {
   if (!h || !tallies || !nsamples) return fail(DWG_ERR_INVALID, "null argument");
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<uint32_t> t(m.ndrow, 0);
@@ -758,6 +792,7 @@ int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsam
 
 int dwg_get_weights(dwg_handle *h, double *out) {
   if (!h || !out) return fail(DWG_ERR_INVALID, "null argument");
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<double> t(m.nweight);
@@ -769,6 +804,7 @@ int dwg_get_weights(dwg_handle *h, double *out) {
 
 int dwg_set_weights(dwg_handle *h, const double *in) {
   if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<double> t(m.nweight);
@@ -781,6 +817,7 @@ int dwg_set_weights(dwg_handle *h, const double *in) {
 
 int dwg_set_weight_sum(dwg_handle *h, const double *in) {
   if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<double> t(m.nweight);
@@ -792,6 +829,7 @@ int dwg_set_weight_sum(dwg_handle *h, const double *in) {
 
 int dwg_get_assignments(dwg_handle *h, int evid_chain, uint64_t *out) {
   if (!h || !out) return fail(DWG_ERR_INVALID, "null argument");
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   const void *src = evid_chain ? h->ds.assign_evid : h->ds.assign_free;
@@ -811,6 +849,7 @@ int dwg_get_assignments(dwg_handle *h, int evid_chain, uint64_t *out) {
 
 int dwg_set_assignments(dwg_handle *h, int evid_chain, const uint64_t *in) {
   if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   void *dst = evid_chain ? h->ds.assign_evid : h->ds.assign_free;
@@ -830,6 +869,7 @@ int dwg_set_assignments(dwg_handle *h, int evid_chain, const uint64_t *in) {
 
 int dwg_finish_weight_average(dwg_handle *h, int n_replicas, double *lmax, double *l2) {
   if (!h || n_replicas < 1) return fail(DWG_ERR_INVALID, "bad argument");
+  h->chain_open = false;
   const uint32_t n = (uint32_t)h->img->nweight;
   CU(cudaSetDevice(h->device));
   CU(cudaMemsetAsync(h->norms.p, 0, 16, h->stream));
@@ -915,6 +955,7 @@ int dwg_comm_destroy(void *comm) {
 
 int dwg_average_weights_nccl(dwg_handle *h, void *comm, int n_replicas, double *lmax, double *l2) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  h->chain_open = false;
   if (n_replicas > 1) {
     if (!comm) return fail(DWG_ERR_INVALID, "null communicator");
     NcclApi &api = nccl();
@@ -992,6 +1033,7 @@ int dwg_reduce_tallies_multi(dwg_handle *const *hs, void *const *comms, int n) {
 int dwg_eval_potentials(dwg_handle *h, uint64_t n, const uint64_t *vids, const uint64_t *proposals,
                         int evid_chain, double *out) {
   if (!h || !vids || !proposals || !out) return fail(DWG_ERR_INVALID, "null argument");
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   {
@@ -1063,6 +1105,7 @@ int dwg_logadd(int device, uint64_t n, const double *a, const double *b, double 
 
 int dwg_debug_set_uniforms(dwg_handle *h, const double *r_free, const double *r_evid) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   if (!r_free) { h->explicit_r = false; return DWG_OK; }
@@ -1081,6 +1124,7 @@ int dwg_debug_set_uniforms(dwg_handle *h, const double *r_free, const double *r_
 
 int dwg_debug_set_sequential(dwg_handle *h, int on) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  h->chain_open = false;
   h->sequential = on != 0;
   return DWG_OK;
 }

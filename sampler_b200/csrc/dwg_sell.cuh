@@ -453,6 +453,11 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
   extern __shared__ __align__(128) unsigned char sell_smem[];
   constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
   constexpr uint32_t MC = 2;  // binary records handled together
+  // Programmatic dependent launch: the launch of the next colour class may start as soon as SMs
+  // free up, run its prologue (weight table, mbarriers, slice offsets, the first bulk copies --
+  // all of it data no sweep writes) and park at griddepcontrol.wait below until this class is
+  // complete and visible.  Fills the tail of one class with the ramp of the next.
+  asm volatile("griddepcontrol.launch_dependents;");
   const unsigned char *tab_s = sell_smem;
   const uint32_t plane = sell_tab_plane(g.n_tab);
   const uint32_t *sm = reinterpret_cast<const uint32_t *>(sell_smem);
@@ -529,6 +534,8 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
   for (uint32_t k = 0; k < pre; ++k) issue(k, k);
   uint32_t stage = 0, parity = 0;  // of iteration k
   uint32_t av[MC] = {}, eq = 0, nav[MC] = {}, neq = 0;
+  // from here on the kernel reads and writes the chains and tallies: the previous class must be done
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   front(0, 0, av, eq);
   uint64_t s64 = s0;
   for (uint32_t k = 0; k < n_my; ++k, s64 += step) {

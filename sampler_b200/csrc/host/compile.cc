@@ -420,7 +420,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
 
   pt.lap("layout knobs");
   // ---- schedule order: colour-major; SELL graphs additionally sort each class by
-  // (is_evidence, degree, others words) so that a 32-variable slice is uniform, and pad every
+  // (is_evidence, degree and others words descending) so that a 32-variable slice is uniform, and pad every
   // class to a multiple of 32 ----
   std::vector<uint32_t> class_count(ncolor, 0);
   for (uint64_t v = 0; v < nvar; ++v) ++class_count[color[v]];
@@ -451,7 +451,10 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         n_un = std::min<uint64_t>(n_un, (1u << 16) - 1);
         n_mu = std::min<uint64_t>(n_mu, (1u << 12) - 1);
         ow = std::min<uint64_t>(ow, (1u << 20) - 1);
-        keys[v] = {((uint64_t)color[v] << 49) | ((uint64_t)g->var_is_evid[v] << 48) | (n_un << 32) | (n_mu << 20) | ow,
+        // longest rows first inside (class, evidence): a launch walks its slices in this order, so the
+        // heavy slices start early and the tail of the launch is made of the light ones
+        keys[v] = {((uint64_t)color[v] << 49) | ((uint64_t)g->var_is_evid[v] << 48) | ((0xffffull - n_un) << 32) |
+                       ((0xfffull - n_mu) << 20) | (0xfffffull - ow),
                    (uint32_t)v};
       }
     });

@@ -19,12 +19,33 @@
 
 #include "../../../include/dwg.h"
 #include "cmd_parser.h"
+#include "parallel.h"
 
 namespace dwg {
 int text2bin_main(const CmdParser &args);
 int bin2text_main(const CmdParser &args);
 
 namespace {
+
+// Text dump of n items: ranges are formatted on the host threads into their own buffers and the
+// buffers written in order -- the file is byte for byte the sequential one (dump_*_in_text,
+// src/inference_result.cc:101-105,211-243, one ostream << per field there).
+template <typename Fmt>
+bool dump_lines(const std::string &fn, uint64_t n, Fmt fmt) {
+  FILE *f = std::fopen(fn.c_str(), "w");
+  if (!f) return false;
+  const unsigned parts = n >= (1u << 16) ? host_threads() * 4 : 1;
+  std::vector<std::string> buf(parts);
+  parallel_ranges(n, parts, [&](uint64_t a, uint64_t b, unsigned p) {
+    std::string &out = buf[p];
+    out.reserve((b - a) * 24);
+    char line[96];
+    for (uint64_t i = a; i < b; ++i) fmt(i, out, line);
+  });
+  bool ok = true;
+  for (const std::string &b : buf) ok = ok && std::fwrite(b.data(), 1, b.size(), f) == b.size();
+  return std::fclose(f) == 0 && ok;
+}
 
 struct Timer {  // src/timer.cc:21-28 (CLOCK_MONOTONIC stopwatch, float seconds)
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -186,13 +207,12 @@ int gibbs(const CmdParser &args) {
   {
     std::string fn = args.output_folder + "/inference_result.out.weights.text";
     std::cout << "DUMPING... TEXT    : " << fn << std::endl;
-    FILE *f = std::fopen(fn.c_str(), "w");
-    if (!f) {
+    if (!dump_lines(fn, nweight, [&](uint64_t j, std::string &out, char *line) {
+          out.append(line, (size_t)std::snprintf(line, 96, "%llu %g\n", (unsigned long long)j, w[j]));
+        })) {
       std::cerr << "[ERROR] cannot write " << fn << std::endl;
       return 1;
     }
-    for (uint64_t j = 0; j < nweight; ++j) std::fprintf(f, "%llu %g\n", (unsigned long long)j, w[j]);
-    std::fclose(f);
   }
 
   // ---- inference, :121-160.  --burn_in (parsed but unused by the reference) discards that many
@@ -250,23 +270,20 @@ int gibbs(const CmdParser &args) {
     }
     std::string fn = args.output_folder + "/inference_result.out.text";
     std::cout << "DUMPING... TEXT    : " << fn << std::endl;
-    FILE *f = std::fopen(fn.c_str(), "w");
-    if (!f) {
+    // dump_marginals_in_text, inference_result.cc:211-243
+    if (!dump_lines(fn, nvar, [&](uint64_t v, std::string &out, char *line) {
+          if (is_evid[v] && !args.should_sample_evidence) return;
+          if (!dtype[v]) {
+            out.append(line, (size_t)std::snprintf(line, 96, "%llu 1 %g\n", (unsigned long long)v, prob(v, 0)));
+          } else {
+            for (uint64_t k = 0; k < value_base[v + 1] - value_base[v]; ++k)
+              out.append(line, (size_t)std::snprintf(line, 96, "%llu %llu %g\n", (unsigned long long)v,
+                                                     (unsigned long long)values[value_base[v] + k], prob(v, k)));
+          }
+        })) {
       std::cerr << "[ERROR] cannot write " << fn << std::endl;
       return 1;
     }
-    // dump_marginals_in_text, inference_result.cc:211-243
-    for (uint64_t v = 0; v < nvar; ++v) {
-      if (is_evid[v] && !args.should_sample_evidence) continue;
-      if (!dtype[v]) {
-        std::fprintf(f, "%llu 1 %g\n", (unsigned long long)v, prob(v, 0));
-      } else {
-        for (uint64_t k = 0; k < value_base[v + 1] - value_base[v]; ++k)
-          std::fprintf(f, "%llu %llu %g\n", (unsigned long long)v,
-                       (unsigned long long)values[value_base[v] + k], prob(v, k));
-      }
-    }
-    std::fclose(f);
     if (progress) {  // show_marginal_histogram, inference_result.cc:171-209
       const size_t bins = 10;
       std::cout << "INFERENCE CALIBRATION (QUERY BINS):" << std::endl;

@@ -2,11 +2,14 @@
 //
 // Replaces read_meta / FactorGraph::load_{weights,variables,domains,factors}
 // (src/binary_format.cc:23-226).  Big-endian records; every input may be a pipe
-// (test/run_end_to_end.sh:18-23 passes <(cat ...)), so files are slurped sequentially and
-// decoded from memory, one thread per file like parallel_load (:38-46).  With several
+// (test/run_end_to_end.sh:18-23 passes <(cat ...)), so files are slurped sequentially, one
+// thread per file like parallel_load (:38-46), and decoded from memory by all host threads:
+// fixed-size records by ranges, the variable-length factor records after one light pass that
+// finds block boundaries (the arity is the only variable-length field).  With several
 // factor files the reference numbers factors in thread-arrival order (:146); here ids
 // follow the order of the -f flags, which is the single-file order when one file is given.
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,35 +17,76 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "../../../include/dwg.h"
 #include "../graph_image.h"
+#include "parallel.h"
 
 namespace dwg {
 namespace {
 
-bool slurp(const std::string &path, std::vector<uint8_t> *buf, std::string *msg) {
-  FILE *f = std::fopen(path.c_str(), "rb");
-  if (!f) {
+// One input, in memory: a regular file is mapped (no copy: records are decoded straight from
+// the page cache), anything else (pipe, /dev/fd/N) is read to its end into a heap buffer.
+struct FileBuf {
+  const uint8_t *ptr = nullptr;
+  size_t len = 0;
+  bool mapped = false;
+  std::vector<uint8_t> heap;
+  FileBuf() = default;
+  FileBuf(const FileBuf &) = delete;
+  FileBuf &operator=(const FileBuf &) = delete;
+  ~FileBuf() {
+    if (mapped && ptr) munmap(const_cast<uint8_t *>(ptr), len);
+  }
+  size_t size() const { return len; }
+  const uint8_t *data() const { return ptr; }
+  const uint8_t &operator[](size_t i) const { return ptr[i]; }
+};
+
+bool slurp(const std::string &path, FileBuf *buf, std::string *msg) {
+  int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) {
     *msg = "cannot open " + path;
     return false;
   }
-  buf->clear();
-  size_t cap = 1 << 20, len = 0;
-  buf->resize(cap);
-  for (;;) {
-    size_t n = std::fread(buf->data() + len, 1, cap - len, f);
-    len += n;
-    if (n == 0) break;
-    if (len == cap) {
-      cap *= 2;
-      buf->resize(cap);
+  struct stat st;
+  if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+    if (st.st_size == 0) { close(fd); return true; }
+    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    if (m != MAP_FAILED) {
+      madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+      buf->ptr = static_cast<const uint8_t *>(m);
+      buf->len = (size_t)st.st_size;
+      buf->mapped = true;
+      close(fd);
+      return true;
     }
   }
-  bool bad = std::ferror(f);
-  std::fclose(f);
-  buf->resize(len);
-  if (bad) *msg = "read error on " + path;
-  return !bad;
+  size_t cap = 1 << 20, len = 0;
+  buf->heap.resize(cap);
+  for (;;) {
+    ssize_t n = read(fd, buf->heap.data() + len, cap - len);
+    if (n < 0) {
+      close(fd);
+      *msg = "read error on " + path;
+      return false;
+    }
+    if (n == 0) break;
+    len += (size_t)n;
+    if (len == cap) {
+      cap *= 2;
+      buf->heap.resize(cap);
+    }
+  }
+  close(fd);
+  buf->heap.resize(len);
+  buf->ptr = buf->heap.data();
+  buf->len = len;
+  return true;
 }
 
 inline uint64_t be64(const uint8_t *p) {
@@ -63,10 +107,10 @@ inline double bef64(const uint8_t *p) {
 // numWeights,numVariables,numFactors,numEdges[,ignored...]; atoll on the first four
 // comma-separated fields (src/binary_format.cc:23-36)
 std::string read_meta(const std::string &path, MetaCounts *m) {
-  std::vector<uint8_t> buf;
+  FileBuf buf;
   std::string msg;
   if (!slurp(path, &buf, &msg)) return msg;
-  std::string s(buf.begin(), buf.end());
+  std::string s(buf.data(), buf.data() + buf.size());
   uint64_t vals[4] = {0, 0, 0, 0};
   size_t pos = 0;
   for (int i = 0; i < 4; ++i) {
@@ -85,9 +129,16 @@ std::string load_raw(const MetaCounts &meta, const std::vector<std::string> &var
                      const std::vector<std::string> &fac_files,
                      const std::vector<std::string> &wgt_files, RawGraph *out, int *err) {
   *err = DWG_ERR_IO;
+  const bool timing = getenv("DWG_COMPILE_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    auto n = std::chrono::steady_clock::now();
+    if (timing) fprintf(stderr, "[load]    %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t_prev).count());
+    t_prev = n;
+  };
   // slurp everything, one thread per file
   std::vector<const std::vector<std::string> *> kinds = {&var_files, &dom_files, &fac_files, &wgt_files};
-  std::vector<std::vector<std::vector<uint8_t>>> data(4);
+  std::vector<std::vector<FileBuf>> data(4);
   std::vector<std::string> msgs;
   {
     std::vector<std::thread> th;
@@ -97,10 +148,10 @@ std::string load_raw(const MetaCounts &meta, const std::vector<std::string> &var
     m.resize(total);
     size_t idx = 0;
     for (int k = 0; k < 4; ++k) {
-      data[k].resize(kinds[k]->size());
+      data[k] = std::vector<FileBuf>(kinds[k]->size());
       for (size_t i = 0; i < kinds[k]->size(); ++i, ++idx) {
         const std::string &path = (*kinds[k])[i];
-        std::vector<uint8_t> *dst = &data[k][i];
+        FileBuf *dst = &data[k][i];
         std::string *mm = &m[idx];
         th.emplace_back([path, dst, mm]() { slurp(path, dst, mm); });
       }
@@ -109,6 +160,7 @@ std::string load_raw(const MetaCounts &meta, const std::vector<std::string> &var
     for (auto &s : m)
       if (!s.empty()) return s;
   }
+  lap("read files");
   *err = DWG_ERR_INVALID;
   RawGraph &r = *out;
   r = RawGraph();
@@ -121,16 +173,26 @@ std::string load_raw(const MetaCounts &meta, const std::vector<std::string> &var
     uint64_t count = 0;
     for (auto &b : data[0]) {
       if (b.size() % 27) return "variables file: truncated record";
-      for (size_t p = 0; p < b.size(); p += 27) {
-        uint64_t vid = be64(&b[p]);
-        if (vid >= meta.nvar) return "variable id " + std::to_string(vid) + " out of range";
-        r.var_role[vid] = b[p + 8];
-        r.var_init[vid] = be64(&b[p + 9]);
-        r.var_dtype[vid] = be16(&b[p + 17]);
-        r.var_card[vid] = be64(&b[p + 19]);
-        seen[vid] = 1;
-        ++count;
-      }
+      const uint64_t nrec = b.size() / 27;
+      std::atomic<uint64_t> bad{~0ull};  // lowest record index with an id out of range
+      parallel_for(nrec, [&](uint64_t i0, uint64_t i1) {
+        for (uint64_t i = i0; i < i1; ++i) {
+          const uint8_t *q = &b[i * 27];
+          uint64_t vid = be64(q);
+          if (vid >= meta.nvar) {
+            uint64_t cur = bad.load();
+            while (i < cur && !bad.compare_exchange_weak(cur, i)) {}
+            return;
+          }
+          r.var_role[vid] = q[8];
+          r.var_init[vid] = be64(q + 9);
+          r.var_dtype[vid] = be16(q + 17);
+          r.var_card[vid] = be64(q + 19);
+          seen[vid] = 1;
+        }
+      });
+      if (bad.load() != ~0ull) return "variable id " + std::to_string(be64(&b[bad.load() * 27])) + " out of range";
+      count += nrec;
     }
     // safety_check: counts equal meta and ids dense (src/factor_graph.cc:203-218)
     if (count != meta.nvar) return "number of variables (" + std::to_string(count) + ") != meta (" + std::to_string(meta.nvar) + ")";
@@ -175,30 +237,54 @@ std::string load_raw(const MetaCounts &meta, const std::vector<std::string> &var
       r.dom_ptr.push_back(r.dom_val.size());
     }
   }
-  // factors (:143-181)
-  r.fac_func.reserve(meta.nfac); r.fac_wid.reserve(meta.nfac); r.fac_fv.reserve(meta.nfac);
-  r.fac_ptr.reserve(meta.nfac + 1); r.edge_vid.reserve(meta.nedge); r.edge_eq.reserve(meta.nedge);
+  lap("variables, weights, domains");
+  // factors (:143-181).  Pass 1 walks the arities and notes where every block of 2^16 records
+  // starts (byte offset, factor index, edge index); pass 2 decodes the blocks in parallel.
+  struct FBlock { const FileBuf *buf; size_t p; uint64_t f, e, nrec; };
+  std::vector<FBlock> blocks;
+  uint64_t nfac = 0, nedge = 0;
   for (auto &b : data[2]) {
     size_t p = 0;
     while (p < b.size()) {
+      if ((nfac & 0xffff) == 0 || blocks.empty() || blocks.back().buf != &b) blocks.push_back({&b, p, nfac, nedge, 0});
       if (p + 10 > b.size()) return "factors file: truncated record";
-      uint16_t func = be16(&b[p]);
       uint64_t arity = be64(&b[p + 2]);
       p += 10;
       if (arity > (b.size() - p) / 16 || b.size() - p - 16 * arity < 16) return "factors file: truncated record";
-      r.fac_func.push_back((int32_t)(int16_t)func == -1 ? -1 : (int32_t)func);
-      for (uint64_t i = 0; i < arity; ++i, p += 16) {
-        r.edge_vid.push_back(be64(&b[p]));
-        r.edge_eq.push_back(be64(&b[p + 8]));
-      }
-      r.fac_ptr.push_back(r.edge_vid.size());
-      r.fac_wid.push_back(be64(&b[p]));
-      r.fac_fv.push_back(bef64(&b[p + 8]));
-      p += 16;
+      p += 16 * arity + 16;
+      nedge += arity;
+      ++nfac;
+      ++blocks.back().nrec;
     }
   }
-  if (r.fac_func.size() != meta.nfac) return "number of factors (" + std::to_string(r.fac_func.size()) + ") != meta (" + std::to_string(meta.nfac) + ")";
-  if (r.edge_vid.size() != meta.nedge) return "number of edges (" + std::to_string(r.edge_vid.size()) + ") != meta (" + std::to_string(meta.nedge) + ")";
+  if (nfac != meta.nfac) return "number of factors (" + std::to_string(nfac) + ") != meta (" + std::to_string(meta.nfac) + ")";
+  if (nedge != meta.nedge) return "number of edges (" + std::to_string(nedge) + ") != meta (" + std::to_string(meta.nedge) + ")";
+  lap("factor boundaries");
+  r.fac_func.resize(nfac); r.fac_wid.resize(nfac); r.fac_fv.resize(nfac);
+  r.fac_ptr.resize(nfac + 1); r.edge_vid.resize(nedge); r.edge_eq.resize(nedge);
+  r.fac_ptr[0] = 0;
+  parallel_ranges(blocks.size(), host_threads(), [&](uint64_t b0, uint64_t b1, unsigned) {
+    for (uint64_t bi = b0; bi < b1; ++bi) {
+      const FBlock &B = blocks[bi];
+      const uint8_t *q = B.buf->data() + B.p;
+      uint64_t e = B.e;
+      for (uint64_t f = B.f; f < B.f + B.nrec; ++f) {
+        uint16_t func = be16(q);
+        uint64_t arity = be64(q + 2);
+        q += 10;
+        r.fac_func[f] = (int32_t)(int16_t)func == -1 ? -1 : (int32_t)func;
+        for (uint64_t i = 0; i < arity; ++i, q += 16, ++e) {
+          r.edge_vid[e] = be64(q);
+          r.edge_eq[e] = be64(q + 8);
+        }
+        r.fac_ptr[f + 1] = e;
+        r.fac_wid[f] = be64(q);
+        r.fac_fv[f] = bef64(q + 8);
+        q += 16;
+      }
+    }
+  }, 1);
+  lap("factor decode");
   *err = DWG_OK;
   return "";
 }
