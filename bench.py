@@ -152,7 +152,7 @@ def reference_arm(args):
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     if r is None or len(r["infer"]) < args.warmup + 1:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/dw missing or produced no epochs"}))
+        args.emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/dw missing or produced no epochs"}))
         return 0
     timed = r["infer"][args.warmup:]
     # whole-run throughput over the timed epochs: total samples / total time
@@ -169,7 +169,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "variable-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    args.emit(json.dumps(line))
     return 0
 
 
@@ -351,10 +351,23 @@ def ours(args):
                   "epochs": n_learn, "hbm_gbs": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9},
         "gpu_launches": int(launches), "clocks": clk, "frac_true": frac1,
     }
-    print(json.dumps(line))
+    args.emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 while the bench runs
+    (NCCL's version banner, library chatter) goes to stderr.  Returns a writer for the line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str):
+        sys.stdout.flush()
+        os.write(saved, (line + "\n").encode())
+    return emit
 
 
 def main():
@@ -369,6 +382,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.emit = _claim_stdout()
     if args.impl == "reference":
         return reference_arm(args)
     return ours(args)

@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <algorithm>
 #include <cstdio>
@@ -23,6 +24,7 @@
 #include "dwg_kernels.cuh"
 #include "dwg_sell.cuh"
 #include "graph_image.h"
+#include "host/parallel.h"
 
 using namespace dwg;
 
@@ -95,21 +97,6 @@ struct dwg_graph {
   }
 };
 
-namespace {
-// split [0, n) over a few host threads (the un-permute / widen loops of the getters)
-template <typename F>
-void parallel_for(uint64_t n, F f) {
-  unsigned nt = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
-  if (n < (1u << 20) || nt == 1) { f(0, n); return; }
-  std::vector<std::thread> th;
-  const uint64_t per = (n + nt - 1) / nt;
-  for (unsigned t = 0; t < nt; ++t) {
-    const uint64_t a = t * per, b = std::min(n, a + per);
-    if (a < b) th.emplace_back([=] { f(a, b); });
-  }
-  for (auto &x : th) x.join();
-}
-}  // namespace
 
 namespace {
 template <typename T>
@@ -131,6 +118,26 @@ struct DevBuf {
   }
   size_t bytes() const { return n * sizeof(T); }
 };
+}  // namespace
+
+namespace {
+// Page-locked landing buffer of the getters, one per process: page-locking costs more than the
+// transfers it serves, so it is paid once, not per handle.  Held for the duration of a download.
+struct LandingBuffer {
+  std::mutex mu;
+  uint32_t *buf = nullptr;
+  size_t words = 0;
+  uint32_t *get(size_t w) {
+    if (w > words) {
+      if (buf) cudaFreeHost(buf);
+      buf = nullptr; words = 0;
+      if (cudaHostAlloc((void **)&buf, w * 4, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      words = w;
+    }
+    return buf;
+  }
+};
+LandingBuffer g_landing;
 }  // namespace
 
 struct dwg_handle {
@@ -173,18 +180,19 @@ struct dwg_handle {
   int sell_blocks_infer = 0, sell_blocks_learn = 0;
   // bulk-async staged inference kernel (dwg_sell.cuh): ring depth, stage capacity in words,
   // grid cap; 0 stages = not available (DWG_SELL_DIRECT=1, or no room for two stages)
-  uint32_t sell_stages = 0, sell_stage_words = 0;
+  uint32_t sell_stages = 0, sell_stage_words = 0, sell_staged_warps = 0;
   int sell_blocks_staged = 0;
   // per colour class: the first slice from which every slice holds evidence / padding only
   // (slices are sorted non-evidence first inside a class, compile.cc)
   std::vector<uint32_t> cls_query_end;
   size_t device_bytes = 0;
-  // tally download: device row of every (variable, value) in ABI order, the gathered tallies and a
-  // page-locked landing buffer (all created on the first dwg_get_tallies)
+  // tally download: device row of every (variable, value) in ABI order (uploaded with the graph) and
+  // the gathered tallies; the page-locked landing pieces are the process's (g_landing)
   DevBuf<uint32_t> row_of_value, tallies_abi;
-  uint32_t *tallies_host = nullptr;
+  cudaEvent_t piece_done[2] = {nullptr, nullptr};
   ~dwg_handle() {
-    if (tallies_host) cudaFreeHost(tallies_host);
+    for (cudaEvent_t e : piece_done)
+      if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -213,11 +221,14 @@ int sell_setup_t(dwg_handle *h) {
   if (direct && *direct == '1') return DWG_OK;
   const size_t budget = 112 * 1024;  // per CTA, two per SM out of 228 KB (1 KB reserved each)
   // measured on C2 / C5 (profiles/r1_v4_ab.txt): with neighbour gathers in the loop two deep stages
-  // beat three or four shallow ones (fewer slices fall out of their stage), unary-only graphs
-  // gain a little from the deeper ring
+  // beat three or four shallow ones (a deeper prefetch queues the latency-critical L2 gathers behind
+  // bulk traffic), unary-only graphs gain from the deeper ring
   uint32_t max_stages = MULTI ? 2 : SELL_MAX_STAGES;
   if (const char *e = getenv("DWG_SELL_STAGES")) max_stages = std::max(2, std::min(SELL_MAX_STAGES, atoi(e)));
-  const uint32_t nwarp = SELL_STAGED_THREADS / 32;
+  // measured (profiles/r1_v4_ab.txt): with neighbour gathers in the loop 8 warps x <= 128 registers per
+  // CTA win (more loads in flight per warp beat more warps), unary-only graphs stream best with 16 x 64
+  uint32_t nwarp = MULTI ? 8 : 16;
+  if (const char *e = getenv("DWG_SELL_WARPS")) nwarp = atoi(e) == 16 ? 16 : 8;
   const uint32_t n_tab = (uint32_t)std::min<uint64_t>({h->img->nweight, n_hot, SELL_MAX_TAB});
   // the deepest ring (<= SELL_MAX_STAGES, two CTAs per SM) whose stage holds at least 99.5 % of the
   // slices whole (90 % for the two-stage ring); the rare longer slice is staged up to its stage's
@@ -227,7 +238,7 @@ int sell_setup_t(dwg_handle *h) {
   const uint32_t want = (h->img->sell_max_words + 3u) & ~3u;
   uint32_t stages = 0, words = 0;
   for (uint32_t st = max_stages; st >= 2 && !stages; --st) {
-    const size_t fixed = sell_staged_ring_off(n_tab, st);
+    const size_t fixed = sell_staged_ring_off(n_tab, st, nwarp);
     uint32_t cap = (uint32_t)((budget - fixed) / (nwarp * st * 4)) & ~3u;
     if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) cap = std::min<uint32_t>(cap, std::max(8, atoi(e)) & ~3u);  // tests
     size_t fit = 0;
@@ -237,11 +248,14 @@ int sell_setup_t(dwg_handle *h) {
   // slices too long for even a two-stage ring (e.g. 20 f64-valued features per variable): the
   // direct kernel streams them from HBM
   if (!stages) return DWG_OK;
-  const size_t smem = sell_staged_smem(n_tab, stages, words);
-  rc = h->img->nweight <= n_tab
-           ? sell_grid(k_sell_infer_staged<MULTI, FV, true>, smem, h->num_sms, &h->sell_blocks_staged, SELL_STAGED_THREADS)
-           : sell_grid(k_sell_infer_staged<MULTI, FV, false>, smem, h->num_sms, &h->sell_blocks_staged, SELL_STAGED_THREADS);
+  const size_t smem = sell_staged_smem(n_tab, stages, words, nwarp);
+  const bool allhot = h->img->nweight <= n_tab;
+#define STAGED_GRID(AH, NT) sell_grid(k_sell_infer_staged<MULTI, FV, AH, NT>, smem, h->num_sms, &h->sell_blocks_staged, NT)
+  rc = nwarp == 16 ? (allhot ? STAGED_GRID(true, 512) : STAGED_GRID(false, 512))
+                   : (allhot ? STAGED_GRID(true, 256) : STAGED_GRID(false, 256));
+#undef STAGED_GRID
   if (rc) return rc;
+  h->sell_staged_warps = nwarp;
   h->sg.n_tab = n_tab;
   h->sell_stages = stages;
   h->sell_stage_words = words;
@@ -253,18 +267,20 @@ void sell_launch_t(dwg_handle *h, bool learn, bool staged, bool pdl, uint32_t bl
   const size_t n_hot = h->img->n_hot;
   if (staged) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(SELL_STAGED_THREADS);
-    cfg.dynamicSmemBytes = sell_staged_smem(sg.n_tab, h->sell_stages, h->sell_stage_words);
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(h->sell_staged_warps * 32);
+    cfg.dynamicSmemBytes = sell_staged_smem(sg.n_tab, h->sell_stages, h->sell_stage_words, h->sell_staged_warps);
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;  // only behind another launch of this kernel (see launch_sweep)
-    if (h->img->nweight <= sg.n_tab)
-      cudaLaunchKernelEx(&cfg, k_sell_infer_staged<MULTI, FV, true>, sg, h->ss, p, h->sell_stages, h->sell_stage_words);
-    else
-      cudaLaunchKernelEx(&cfg, k_sell_infer_staged<MULTI, FV, false>, sg, h->ss, p, h->sell_stages, h->sell_stage_words);
+    const bool allhot = h->img->nweight <= sg.n_tab;
+#define STAGED_LAUNCH(AH, NT) \
+  cudaLaunchKernelEx(&cfg, k_sell_infer_staged<MULTI, FV, AH, NT>, sg, h->ss, p, h->sell_stages, h->sell_stage_words)
+    if (h->sell_staged_warps == 16) { if (allhot) STAGED_LAUNCH(true, 512); else STAGED_LAUNCH(false, 512); }
+    else { if (allhot) STAGED_LAUNCH(true, 256); else STAGED_LAUNCH(false, 256); }
+#undef STAGED_LAUNCH
   } else if (learn) k_sell_learn<MULTI, FV><<<blocks, SELL_THREADS, 16 * n_hot, h->stream>>>(sg, h->ss, p);
   else k_sell_infer<MULTI, FV><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
 }
@@ -639,7 +655,11 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
     // a learning sweep of a class runs as `chunks` strided parts with a weight update after each
     uint32_t chunks = 1;
     if (learn && !p.sequential) {
-      chunks = h->opts.learn_chunks > 0 ? (uint32_t)h->opts.learn_chunks : (32 + m.ncolor() - 1) / m.ncolor();
+      // auto: ~32 weight updates per sweep, shared out by class size (a class of a few hundred
+      // variables -- the overflow class of the balanced colouring -- gets one launch, not six)
+      chunks = h->opts.learn_chunks > 0
+                   ? (uint32_t)h->opts.learn_chunks
+                   : (uint32_t)std::llround(32.0 * (double)n / (double)std::max<uint64_t>(1, m.nvar_pad));
       chunks = std::max(1u, std::min(chunks, units));
     }
     for (uint32_t b = 0; b < chunks; ++b) {
@@ -658,7 +678,7 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
           if (!n_sl) continue;
         }
         const bool staged = !learn && h->sell_stages;
-        const uint32_t wpb = (staged ? SELL_STAGED_THREADS : SELL_THREADS) / 32;
+        const uint32_t wpb = staged ? h->sell_staged_warps : SELL_THREADS / 32;
         const uint32_t need = (n_sl + wpb - 1) / wpb;
         const uint32_t cap = (uint32_t)(staged ? h->sell_blocks_staged : learn ? h->sell_blocks_learn : h->sell_blocks_infer);
         // programmatic dependent launch behind the previous colour class of an inference run
@@ -744,19 +764,50 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
   h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
+  const bool timing = getenv("DWG_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    auto n = std::chrono::steady_clock::now();
+    if (timing) fprintf(stderr, "[get_tallies] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t_prev).count());
+    t_prev = n;
+  };
   if (tallies && m.nrow) {
-    // schedule order -> ABI order on the device, one DMA into page-locked memory, widen on the host
-    if (!h->tallies_host) {
+    // schedule order -> ABI order on the device, then 4 MB pieces through two small page-locked
+    // buffers: the DMA of piece c overlaps the widening of piece c - 1 on the host threads (page-locking
+    // a buffer for the whole vector would cost more than the transfer)
+    constexpr uint64_t PIECE = 1u << 20;  // tallies per piece
+    std::lock_guard<std::mutex> pool_lock(g_landing.mu);
+    uint32_t *landing = g_landing.get(2 * PIECE);
+    if (!landing) return fail(DWG_ERR_CUDA, "cannot page-lock the tally landing buffer");
+    if (!h->tallies_abi.p) {
       CU(h->tallies_abi.alloc(m.nrow));
-      CU(cudaHostAlloc((void **)&h->tallies_host, 4 * m.nrow, cudaHostAllocDefault));
+      CU(cudaEventCreateWithFlags(&h->piece_done[0], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&h->piece_done[1], cudaEventDisableTiming));
     }
+    lap("buffers");
     k_gather_u32<<<(uint32_t)((m.nrow + 255) / 256), 256, 0, h->stream>>>(h->tallies_abi.p, h->tallies.p,
                                                                          h->row_of_value.p, (uint32_t)m.nrow);
     ++g_launches;
-    CU(cudaMemcpyAsync(h->tallies_host, h->tallies_abi.p, 4 * m.nrow, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    const uint32_t *t = h->tallies_host;
-    parallel_for(m.nrow, [=](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; ++i) tallies[i] = t[i]; });
+    const uint64_t npiece = (m.nrow + PIECE - 1) / PIECE;
+    auto widen = [&](uint64_t c) {
+      const uint64_t base = c * PIECE, cnt = std::min(PIECE, m.nrow - base);
+      const uint32_t *t = landing + (c & 1) * PIECE;
+      uint64_t *out = tallies + base;
+      parallel_for(cnt, [=](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; ++i) out[i] = t[i]; });
+    };
+    for (uint64_t c = 0; c < npiece; ++c) {
+      const uint64_t base = c * PIECE, cnt = std::min(PIECE, m.nrow - base);
+      CU(cudaMemcpyAsync(landing + (c & 1) * PIECE, h->tallies_abi.p + base, 4 * cnt, cudaMemcpyDeviceToHost,
+                         h->stream));
+      CU(cudaEventRecord(h->piece_done[c & 1], h->stream));
+      if (c) {
+        CU(cudaEventSynchronize(h->piece_done[(c - 1) & 1]));
+        widen(c - 1);
+      }
+    }
+    CU(cudaEventSynchronize(h->piece_done[(npiece - 1) & 1]));
+    widen(npiece - 1);
+    lap("widen");
   }
   if (nsamples) {
     // ++agg_nsamples for every sampled variable every sweep (src/gibbs_sampler.h:157,163)
@@ -767,6 +818,7 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
     parallel_for(m.nvar, [=](uint64_t a, uint64_t b) {
       for (uint64_t v = a; v < b; ++v) nsamples[v] = ((!ev[v] || all) ? sweeps : 0) + (extra ? extra[v] : 0);
     });
+    lap("nsamples");
   }
   return DWG_OK;
 }

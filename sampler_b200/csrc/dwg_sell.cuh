@@ -332,7 +332,6 @@ k_sell_infer(const SellGraph g, const SellState st, const SweepParams p) {
 //    slice (other colour classes: constant during the launch) are requested before the current
 //    slice's records are summed, so the L2 gather is off the critical path too.
 constexpr int SELL_MAX_STAGES = 4;
-constexpr int SELL_STAGED_THREADS = 384;  // 12 warps, 2 CTAs per SM, <= 85 registers
 constexpr uint32_t SELL_MAX_TAB = 2048;   // weights in the signed table (3 planes x 8 B each)
 
 __device__ __forceinline__ uint32_t sell_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -368,11 +367,12 @@ __device__ __forceinline__ void sell_bulk_g2s(uint32_t dst, const void *src, uin
 // signed weight table | one mbarrier per (warp, stage) | the rings
 __host__ __device__ inline uint32_t sell_tab_plane(uint32_t n_tab) { return (n_tab * 8u + 127u) & ~127u; }  // bytes
 __host__ __device__ inline uint32_t sell_staged_bar_off(uint32_t n_tab) { return 3u * sell_tab_plane(n_tab); }
-__host__ __device__ inline uint32_t sell_staged_ring_off(uint32_t n_tab, uint32_t stages) {
-  return (sell_staged_bar_off(n_tab) + (SELL_STAGED_THREADS / 32) * stages * 8u + 127u) & ~127u;
+__host__ __device__ inline uint32_t sell_staged_ring_off(uint32_t n_tab, uint32_t stages, uint32_t nwarp) {
+  return (sell_staged_bar_off(n_tab) + nwarp * stages * 8u + 127u) & ~127u;
 }
-__host__ __device__ inline uint32_t sell_staged_smem(uint32_t n_tab, uint32_t stages, uint32_t stage_words) {
-  return sell_staged_ring_off(n_tab, stages) + (SELL_STAGED_THREADS / 32) * stages * stage_words * 4u;
+__host__ __device__ inline uint32_t sell_staged_smem(uint32_t n_tab, uint32_t stages, uint32_t stage_words,
+                                                     uint32_t nwarp) {
+  return sell_staged_ring_off(n_tab, stages, nwarp) + nwarp * stages * stage_words * 4u;
 }
 
 // the rare slice that is longer than a stage: potentials straight from HBM, as the direct kernel
@@ -446,8 +446,8 @@ __device__ __forceinline__ void sell_unary_s(const SellGraph &g, const uint32_t 
   if (ANTISYM) neg = -pos;
 }
 
-template <bool MULTI, int FV, bool ALLHOT>
-__global__ void __launch_bounds__(SELL_STAGED_THREADS, 2)
+template <bool MULTI, int FV, bool ALLHOT, int NT>
+__global__ void __launch_bounds__(NT, 2)
 k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, const uint32_t stages,
                     const uint32_t stage_words) {
   extern __shared__ __align__(128) unsigned char sell_smem[];
@@ -463,7 +463,7 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
   const uint32_t *sm = reinterpret_cast<const uint32_t *>(sell_smem);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t bar0 = sell_smem_addr(sell_smem) + sell_staged_bar_off(g.n_tab) + warp * stages * 8u;
-  const uint32_t ringw = sell_staged_ring_off(g.n_tab, stages) / 4u + warp * stages * stage_words;  // word index
+  const uint32_t ringw = sell_staged_ring_off(g.n_tab, stages, NT / 32) / 4u + warp * stages * stage_words;  // word index
   const uint32_t ring0 = sell_smem_addr(sell_smem) + ringw * 4u;
   if (lane == 0)
     for (uint32_t i = 0; i < stages; ++i) sell_mbar_init(bar0 + 8u * i, 1u);

@@ -225,7 +225,7 @@ def test_parallel_chromatic_inference_is_exact_gibbs(seed):
     assert np.array_equal(t, o.tallies) and np.array_equal(n, o.nsamples)
 
 
-SELL_VARIANTS = [{"DWG_SELL_DIRECT": "1"}, {}, {"DWG_SELL_WARPS": "16"}, {"DWG_SELL_STAGES": "2"},
+SELL_VARIANTS = [{"DWG_SELL_DIRECT": "1"}, {}, {"DWG_SELL_WARPS": "16"}, {"DWG_SELL_WARPS": "8"}, {"DWG_SELL_STAGES": "4"},
                  {"DWG_SELL_STAGE_WORDS": "200"}, {"DWG_SELL_STAGE_WORDS": "8", "DWG_SELL_STAGES": "3"}]
 
 
