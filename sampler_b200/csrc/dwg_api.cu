@@ -72,14 +72,17 @@ struct dwg_graph {
   }
   // per colour class: the first slice from which every slice holds evidence / padding only
   // (slices are sorted non-evidence first inside a class, compile.cc); computed once per graph
-  mutable std::vector<uint32_t> cls_query_end;
+  mutable std::vector<uint32_t> cls_query_end, cls_max_words;  // the latter: longest slice of the class
   const std::vector<uint32_t> &query_end() const {
     std::lock_guard<std::mutex> lk(pin_mu);
     if (!cls_query_end.empty() || !img.sell) return cls_query_end;
     const uint32_t nc = img.ncolor();
     cls_query_end.assign(nc, 0);
+    cls_max_words.assign(nc, 0);
     for (uint32_t c = 0; c < nc; ++c) {
       const uint32_t sb = img.color_start[c] / 32, se = img.color_start[c + 1] / 32;
+      for (uint32_t sl = sb; sl < se; ++sl)
+        cls_max_words[c] = std::max(cls_max_words[c], (img.sl_off[sl + 1] - img.sl_off[sl]) * 8u);
       uint32_t qe = sb;
       for (uint32_t sl = se; sl > sb && qe == sb; --sl) {  // from the evidence tail backwards
         bool query = false;
@@ -170,7 +173,7 @@ struct dwg_handle {
   bool explicit_r = false, sequential = false;
   // the last operation enqueued on the stream was a staged inference launch of this handle (the
   // next one may be a programmatic dependent launch); cleared by every other entry point
-  bool chain_open = false;
+  bool chain_open = false, learn_chain_open = false;
   uint64_t sweep_counter = 0, infer_sweeps = 0;
   std::vector<uint64_t> extra_nsamples;  // from dwg_add_tallies
   DevGraph dg{};
@@ -184,7 +187,10 @@ struct dwg_handle {
   int sell_blocks_staged = 0;
   // per colour class: the first slice from which every slice holds evidence / padding only
   // (slices are sorted non-evidence first inside a class, compile.cc)
-  std::vector<uint32_t> cls_query_end;
+  std::vector<uint32_t> cls_query_end, cls_max_words;
+  // staged learning kernel: ring depth (0 = unavailable), stage capacity in words, grid cap
+  uint32_t learn_stages = 0, learn_stage_words = 0;
+  int sell_blocks_learn_staged = 0;
   size_t device_bytes = 0;
   // tally download: device row of every (variable, value) in ABI order (uploaded with the graph) and
   // the gathered tallies; the page-locked landing pieces are the process's (g_landing)
@@ -215,11 +221,26 @@ int sell_setup_t(dwg_handle *h) {
   if (rc) return rc;
   rc = sell_grid(k_sell_learn<MULTI, FV>, 16 * n_hot, h->num_sms, &h->sell_blocks_learn);
   if (rc) return rc;
-  // staged (bulk-async) inference kernel: ring geometry for this graph
+  // staged (bulk-async) kernels: ring geometry for this graph
   h->sell_stages = 0;
+  h->learn_stages = 0;
   const char *direct = getenv("DWG_SELL_DIRECT");
   if (direct && *direct == '1') return DWG_OK;
-  const size_t budget = 112 * 1024;  // per CTA, two per SM out of 228 KB (1 KB reserved each)
+  size_t budget = 112 * 1024;  // per CTA, two per SM out of 228 KB (1 KB reserved each)
+  {  // learning: two stages of whatever fits beside the weight and gradient tables; classes whose
+     // longest slice does not fit a stage take the direct kernel (launch_sweep)
+    const size_t fixed = sell_learn_ring_off((uint32_t)n_hot, 2);
+    if (fixed + (SELL_LEARN_STAGED_THREADS / 32) * 2 * 4 * 64 <= budget) {
+      uint32_t cap = (uint32_t)((budget - fixed) / ((SELL_LEARN_STAGED_THREADS / 32) * 2 * 4)) & ~3u;
+      if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) cap = std::min<uint32_t>(cap, std::max(8, atoi(e)) & ~3u);  // tests
+      const uint32_t words = std::min(cap, (h->img->sell_max_words + 3u) & ~3u);
+      rc = sell_grid(k_sell_learn_staged<MULTI, FV>, sell_learn_smem((uint32_t)n_hot, 2, words), h->num_sms,
+                     &h->sell_blocks_learn_staged, SELL_LEARN_STAGED_THREADS);
+      if (rc) return rc;
+      h->learn_stages = 2;
+      h->learn_stage_words = words;
+    }
+  }
   // measured on C2 / C5 (profiles/r1_v4_ab.txt): with neighbour gathers in the loop two deep stages
   // beat three or four shallow ones (a deeper prefetch queues the latency-critical L2 gathers behind
   // bulk traffic), unary-only graphs gain from the deeper ring
@@ -252,7 +273,7 @@ int sell_setup_t(dwg_handle *h) {
   const bool allhot = h->img->nweight <= n_tab;
 #define STAGED_GRID(AH, NT) sell_grid(k_sell_infer_staged<MULTI, FV, AH, NT>, smem, h->num_sms, &h->sell_blocks_staged, NT)
   rc = nwarp == 16 ? (allhot ? STAGED_GRID(true, 512) : STAGED_GRID(false, 512))
-                   : (allhot ? STAGED_GRID(true, 256) : STAGED_GRID(false, 256));
+                    : (allhot ? STAGED_GRID(true, 256) : STAGED_GRID(false, 256));
 #undef STAGED_GRID
   if (rc) return rc;
   h->sell_staged_warps = nwarp;
@@ -262,10 +283,12 @@ int sell_setup_t(dwg_handle *h) {
   return DWG_OK;
 }
 template <bool MULTI, int FV>
+// staged: the bulk-async kernel of the sweep kind (inference / learning); pdl: programmatic
+// dependent launch behind the previous inference launch
 void sell_launch_t(dwg_handle *h, bool learn, bool staged, bool pdl, uint32_t blocks, const SellGraph &sg,
                    const SweepParams &p) {
   const size_t n_hot = h->img->n_hot;
-  if (staged) {
+  if (staged && !learn) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(h->sell_staged_warps * 32);
     cfg.dynamicSmemBytes = sell_staged_smem(sg.n_tab, h->sell_stages, h->sell_stage_words, h->sell_staged_warps);
@@ -281,6 +304,17 @@ void sell_launch_t(dwg_handle *h, bool learn, bool staged, bool pdl, uint32_t bl
     if (h->sell_staged_warps == 16) { if (allhot) STAGED_LAUNCH(true, 512); else STAGED_LAUNCH(false, 512); }
     else { if (allhot) STAGED_LAUNCH(true, 256); else STAGED_LAUNCH(false, 256); }
 #undef STAGED_LAUNCH
+  } else if (learn && staged) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(SELL_LEARN_STAGED_THREADS);
+    cfg.dynamicSmemBytes = sell_learn_smem((uint32_t)n_hot, h->learn_stages, h->learn_stage_words);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;  // only behind the k_apply_weights of another staged learning launch
+    cudaLaunchKernelEx(&cfg, k_sell_learn_staged<MULTI, FV>, sg, h->ss, p, h->learn_stages, h->learn_stage_words);
   } else if (learn) k_sell_learn<MULTI, FV><<<blocks, SELL_THREADS, 16 * n_hot, h->stream>>>(sg, h->ss, p);
   else k_sell_infer<MULTI, FV><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
 }
@@ -603,6 +637,7 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     rc = sell_setup(h.get());
     if (rc) return rc;
     h->cls_query_end = g->query_end();
+    h->cls_max_words = g->cls_max_words;
   }
   *out = h.release();
   return DWG_OK;
@@ -663,6 +698,7 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
       chunks = std::max(1u, std::min(chunks, units));
     }
     for (uint32_t b = 0; b < chunks; ++b) {
+      bool chained_apply = false;  // k_apply_weights as a dependent launch of a staged learning launch
       const uint32_t my_units = (units - b + chunks - 1) / chunks;
       p.unit_stride = chunks;
       p.unit_phase = b;
@@ -678,13 +714,19 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
           if (!n_sl) continue;
         }
         const bool staged = !learn && h->sell_stages;
-        const uint32_t wpb = staged ? h->sell_staged_warps : SELL_THREADS / 32;
+        const bool learn_staged = learn && h->learn_stages && h->cls_max_words[c] <= h->learn_stage_words;
+        const uint32_t wpb = staged ? h->sell_staged_warps : learn_staged ? SELL_LEARN_STAGED_THREADS / 32 : SELL_THREADS / 32;
         const uint32_t need = (n_sl + wpb - 1) / wpb;
-        const uint32_t cap = (uint32_t)(staged ? h->sell_blocks_staged : learn ? h->sell_blocks_learn : h->sell_blocks_infer);
-        // programmatic dependent launch behind the previous colour class of an inference run
-        const bool pdl = staged && h->chain_open && !getenv("DWG_SELL_NO_PDL");
-        sell_launch(h, learn, staged, pdl, std::min<uint32_t>(need, cap), sg, p);
+        const uint32_t cap = (uint32_t)(staged ? h->sell_blocks_staged : learn_staged ? h->sell_blocks_learn_staged
+                                        : learn ? h->sell_blocks_learn : h->sell_blocks_infer);
+        // programmatic dependent launch: behind the previous colour class of an inference run, or
+        // behind the k_apply_weights of the previous staged learning launch
+        const bool pdl = !getenv("DWG_SELL_NO_PDL") &&
+                         ((staged && h->chain_open) || (learn_staged && h->learn_chain_open));
+        sell_launch(h, learn, staged || learn_staged, pdl, std::min<uint32_t>(need, cap), sg, p);
         h->chain_open = staged;
+        h->learn_chain_open = false;
+        chained_apply = learn_staged && !getenv("DWG_SELL_NO_PDL");
       } else {
         uint32_t blocks = (my_units * 32 + SWEEP_THREADS - 1) / SWEEP_THREADS;
         uint32_t threads = SWEEP_THREADS;
@@ -702,10 +744,19 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
         // integrate this launch's SGD steps (k_apply_weights): the sliced-ELL kernel sums bare
         // gradients (decay from the static update counts), the CSR kernel sums gradient + decay
         const size_t row = m.cls_shared ? 0 : (size_t)c * m.nweight;
-        k_apply_weights<<<(uint32_t)((m.nweight + 255) / 256), 256, 0, h->stream>>>(
-            h->weights.p, h->grad_acc.p, h->cls_N.p + row, h->cls_Q.p + row, h->cls_H.p + row, h->w_fixed.p,
-            (uint32_t)m.nweight, stepsize, h->opts.reg_param, p.reg_l1, use_sell ? 0 : 1,
-            (double)my_units / (double)units);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((uint32_t)((m.nweight + 255) / 256)); cfg.blockDim = dim3(256);
+        cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = chained_apply ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, k_apply_weights, h->weights.p, h->grad_acc.p, (const float *)(h->cls_N.p + row),
+                           (const float *)(h->cls_Q.p + row), (const float *)(h->cls_H.p + row),
+                           (const uint8_t *)h->w_fixed.p, (uint32_t)m.nweight, stepsize, h->opts.reg_param,
+                           (int)p.reg_l1, use_sell ? 0 : 1, (double)my_units / (double)units);
+        h->learn_chain_open = chained_apply;
         ++g_launches;
       }
     }
@@ -736,14 +787,14 @@ int dwg_infer_epochs(dwg_handle *h, uint64_t n) {
 
 int dwg_sync(dwg_handle *h) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   return DWG_OK;
 }
 
 void *dwg_stream(dwg_handle *h) {
-  if (h) h->chain_open = false;  // the caller may enqueue anything behind our launches
+  if (h) h->chain_open = h->learn_chain_open = false;  // the caller may enqueue anything behind our launches
   return h ? (void *)h->stream : nullptr;
 }
 void *dwg_weights_device_ptr(dwg_handle *h) { return h ? (void *)h->weights.p : nullptr; }
@@ -751,7 +802,7 @@ void *dwg_tallies_device_ptr(dwg_handle *h) { return h ? (void *)h->tallies.p : 
 
 int dwg_clear_tallies(dwg_handle *h) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   CU(cudaSetDevice(h->device));
   CU(cudaMemsetAsync(h->tallies.p, 0, 4 * h->img->ndrow, h->stream));
   h->infer_sweeps = 0;
@@ -761,7 +812,7 @@ int dwg_clear_tallies(dwg_handle *h) {
 
 int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   const bool timing = getenv("DWG_TIMING") != nullptr;
@@ -825,7 +876,7 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
 
 int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsamples) {
   if (!h || !tallies || !nsamples) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<uint32_t> t(m.ndrow, 0);
@@ -844,7 +895,7 @@ int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsam
 
 int dwg_get_weights(dwg_handle *h, double *out) {
   if (!h || !out) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<double> t(m.nweight);
@@ -856,7 +907,7 @@ int dwg_get_weights(dwg_handle *h, double *out) {
 
 int dwg_set_weights(dwg_handle *h, const double *in) {
   if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<double> t(m.nweight);
@@ -869,7 +920,7 @@ int dwg_set_weights(dwg_handle *h, const double *in) {
 
 int dwg_set_weight_sum(dwg_handle *h, const double *in) {
   if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<double> t(m.nweight);
@@ -881,7 +932,7 @@ int dwg_set_weight_sum(dwg_handle *h, const double *in) {
 
 int dwg_get_assignments(dwg_handle *h, int evid_chain, uint64_t *out) {
   if (!h || !out) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   const void *src = evid_chain ? h->ds.assign_evid : h->ds.assign_free;
@@ -901,7 +952,7 @@ int dwg_get_assignments(dwg_handle *h, int evid_chain, uint64_t *out) {
 
 int dwg_set_assignments(dwg_handle *h, int evid_chain, const uint64_t *in) {
   if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   void *dst = evid_chain ? h->ds.assign_evid : h->ds.assign_free;
@@ -921,7 +972,7 @@ int dwg_set_assignments(dwg_handle *h, int evid_chain, const uint64_t *in) {
 
 int dwg_finish_weight_average(dwg_handle *h, int n_replicas, double *lmax, double *l2) {
   if (!h || n_replicas < 1) return fail(DWG_ERR_INVALID, "bad argument");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   const uint32_t n = (uint32_t)h->img->nweight;
   CU(cudaSetDevice(h->device));
   CU(cudaMemsetAsync(h->norms.p, 0, 16, h->stream));
@@ -1007,7 +1058,7 @@ int dwg_comm_destroy(void *comm) {
 
 int dwg_average_weights_nccl(dwg_handle *h, void *comm, int n_replicas, double *lmax, double *l2) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   if (n_replicas > 1) {
     if (!comm) return fail(DWG_ERR_INVALID, "null communicator");
     NcclApi &api = nccl();
@@ -1085,7 +1136,7 @@ int dwg_reduce_tallies_multi(dwg_handle *const *hs, void *const *comms, int n) {
 int dwg_eval_potentials(dwg_handle *h, uint64_t n, const uint64_t *vids, const uint64_t *proposals,
                         int evid_chain, double *out) {
   if (!h || !vids || !proposals || !out) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   {
@@ -1157,7 +1208,7 @@ int dwg_logadd(int device, uint64_t n, const double *a, const double *b, double 
 
 int dwg_debug_set_uniforms(dwg_handle *h, const double *r_free, const double *r_evid) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   if (!r_free) { h->explicit_r = false; return DWG_OK; }
@@ -1176,7 +1227,7 @@ int dwg_debug_set_uniforms(dwg_handle *h, const double *r_free, const double *r_
 
 int dwg_debug_set_sequential(dwg_handle *h, int on) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = false;
+  h->chain_open = h->learn_chain_open = false;
   h->sequential = on != 0;
   return DWG_OK;
 }

@@ -188,9 +188,10 @@ __device__ __forceinline__ void sell_general_signs(const SliceHeader &h, uint32_
 }
 
 // number of others words behind a general-slice record (to skip it)
+template <int LD>
 __device__ __forceinline__ uint32_t sell_general_span(const SliceHeader &h, uint32_t tag, uint32_t lane, uint32_t oc) {
   const uint32_t form = tag >> TAG_FORM_SHIFT;
-  return form != FORM_GENERAL ? form : 1u + __ldg(h.oth + (size_t)oc * 32 + lane);
+  return form != FORM_GENERAL ? form : 1u + sell_ld<LD>(h.oth + (size_t)oc * 32 + lane);
 }
 
 template <int FV, int LD>
@@ -626,6 +627,105 @@ __device__ __forceinline__ void sell_grad(const SellGraph &g, const SellState &s
   else atomicAdd(st.grad_acc + wid, grad);
 }
 
+// The update of weight i after a learning launch (see k_apply_weights below for the scheme).
+__device__ __forceinline__ void sell_apply_weight(uint32_t i, double *w, double *grad_acc, const float *N,
+                                                  const float *Q, const float *H, const uint8_t *fixed, double step,
+                                                  double reg, int reg_l1, int decay_in_acc, double share) {
+  if (fixed[i]) return;
+  const double nn = (double)N[i] * share;  // this launch swept `share` of the class
+  const double acc = __ldcg(grad_acc + i);  // summed by atomics in L2
+  if (nn == 0.0 && acc == 0.0) return;
+  grad_acc[i] = 0.0;
+  const double x = w[i];
+  const double r = reg_l1 ? 0.0 : reg * step / (1.0 + reg * step);
+  double S = acc;
+  if (!decay_in_acc) S += reg_l1 ? -nn * reg * (x < 0 ? 1.0 : 0.0) / step : nn * (r / step) * x;
+  // curvature D: the weight's own (diagonal) bound H where the joint step is provably
+  // non-expansive with it, i.e. step * phi(step * D) * R <= 1 with R the row-sum majorizer;
+  // otherwise the smallest D that is (fixed point of D = R (1 - exp(-step D)), approached from above)
+  const double Rk = (double)Q[i] * share, Hk = (double)H[i] * share;
+  double D = Hk;
+  if (Rk * -expm1(-step * D) > D) {
+    D = Rk;
+    for (int it = 0; it < 12; ++it) D = Rk * -expm1(-step * D);
+  }
+  const double z = step * D + nn * r;
+  const double phi = z > 1e-8 ? -expm1(-z) / z : 1.0 - 0.5 * z;
+  w[i] = x - step * S * phi;
+}
+
+// One variable per lane of one slice of a learning sweep (sample_sgd_single_variable,
+// gibbs_sampler.h:127-149): both chains, then the SGD gradients of the lane's records into the
+// launch's accumulators.  LD: where the slice is read from (HBM through L1, or a staged copy).
+template <bool MULTI, int FV, int LD>
+__device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellState &st, const SweepParams &p,
+                                                 const SliceHeader &h, const double *w_s, double *acc_s,
+                                                 uint32_t lane, uint32_t d) {
+  const bool pad = (h.pad >> lane) & 1u, evid = (h.evid >> lane) & 1u;
+  const uint32_t ev = (h.evval >> lane) & 1u;  // Variable::assignment_dense
+  double r0, r1;
+  dev_uniforms(p, d, r0, r1);
+  // free chain: every variable, evidence included (gibbs_sampler.h:137-139)
+  double pos, neg;
+  sell_potentials<MULTI, FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_free, pos, neg);
+  const uint32_t pf = sell_draw_boolean(pos, neg, r0);
+  if (!pad) st.assign_free[d] = (uint8_t)pf;
+  // evid chain (sample_evid, gibbs_sampler.h:171-190): clamp hard evidence, else a Gibbs draw
+  // (Boolean variables carry no truthiness, so --noise_aware makes evidence variables draw too)
+  uint32_t pe = ev;
+  const uint32_t draw_evid = ~h.pad & (p.noise_aware ? 0xffffffffu : ~h.evid);
+  if (draw_evid) {
+    if (MULTI && h.n_mu)  // unary-only slices: both chains see identical potentials
+      sell_potentials<MULTI, FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_evid, pos, neg);
+    if ((draw_evid >> lane) & 1u) pe = sell_draw_boolean(pos, neg, r1);
+  }
+  if (!pad) st.assign_evid[d] = (uint8_t)pe;
+  // which variables learn (gibbs_sampler.h:144-146); Boolean has_truthiness() is false
+  const bool learn = !pad && (p.learn_non_evidence || (!p.noise_aware && evid));
+  if (!__any_sync(0xffffffffu, learn)) return;
+  // sgd_on_variable (factor_graph.cc:262-277): evidence_value = assignment_dense, free = pf.
+  // grad = sign_free * fv - sign_evid * fv == (code_free - code_evid) * fv exactly.
+  if (__any_sync(0xffffffffu, learn && pf != ev)) {  // unary: same value on both chains = zero gradient
+    for (uint32_t j = 0; j < h.n_un; ++j) {
+      const uint32_t rec = sell_ld<LD>(h.un + (size_t)32 * j + lane);
+      if (!learn || pf == ev) continue;
+      const int cf = (int)(pf ? rec & 3u : rec >> 26), ce = (int)(ev ? rec & 3u : rec >> 26);
+      if (cf == ce) continue;
+      sell_grad(g, st, acc_s, sell_unary_wid(rec), rec & SELL_UN_FIXED_BIT,
+                __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.un, h.n_un, j, lane)));
+    }
+  }
+  if (!MULTI || !h.n_mu) return;
+  if (h.flags & SF_BINARY) {
+    for (uint32_t j = 0; j < h.n_mu; ++j) {
+      const uint32_t rec = sell_ld<LD>(h.mu + (size_t)32 * j + lane);
+      const uint32_t ow = sell_ld<LD>(h.oth + (size_t)32 * j + lane);
+      if (!learn) continue;
+      const uint32_t tag = rec >> 24, od = ow >> 1, eq = ow & 1u;
+      const uint32_t sf = st.assign_free[od] == eq, se = st.assign_evid[od] == eq;
+      const int cf = (int)((tag >> (4u * pf + 2u * sf)) & 3u), ce = (int)((tag >> (4u * ev + 2u * se)) & 3u);
+      if (cf == ce) continue;
+      sell_grad(g, st, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
+                __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.mu, h.n_mu, j, lane)));
+    }
+  } else {
+    uint32_t oc = 0;
+    for (uint32_t j = 0; j < h.n_mu; ++j) {
+      const uint32_t rec = sell_ld<LD>(h.mu + (size_t)32 * j + lane);
+      const uint32_t tag = rec >> 24;
+      if ((tag >> TAG_FORM_SHIFT) == 0) continue;
+      if (!learn) { oc += sell_general_span<LD>(h, tag, lane, oc); continue; }
+      uint32_t oc2 = oc;
+      double f0, f1, e0, e1;
+      sell_general_signs<LD>(h, tag, d, lane, oc, st.assign_free, f0, f1);
+      sell_general_signs<LD>(h, tag, d, lane, oc2, st.assign_evid, e0, e1);
+      const double fv = sell_fv<FV, LD>(h.mu, h.n_mu, j, lane);
+      sell_grad(g, st, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
+                __dsub_rn(__dmul_rn(pf ? f1 : f0, fv), __dmul_rn(ev ? e1 : e0, fv)));
+    }
+  }
+}
+
 // One learning sweep over a colour class.  Weights are FROZEN for the launch; the gradient
 // of every SGD step (pot_free - pot_evid, src/factor_graph.cc:255-258) is summed per weight
 // into grad_acc (hot weights pre-aggregated in shared memory), and k_apply_weights turns the
@@ -644,69 +744,104 @@ k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
        s64 < g.slice_end; s64 += (uint64_t)warps * g.slice_stride) {
     const uint32_t s = (uint32_t)s64;
     const SliceHeader h = sell_header<FV>(g, s);
-    const uint32_t d = s * 32u + lane;
-    const bool pad = (h.pad >> lane) & 1u, evid = (h.evid >> lane) & 1u;
-    const uint32_t ev = (h.evval >> lane) & 1u;  // Variable::assignment_dense
-    double r0, r1;
-    dev_uniforms(p, d, r0, r1);
-    // free chain: every variable, evidence included (gibbs_sampler.h:137-139)
-    double pos, neg;
-    sell_potentials<MULTI, FV, LD_CACHED>(g, h, w_s, st.weights, lane, d, st.assign_free, pos, neg);
-    const uint32_t pf = sell_draw_boolean(pos, neg, r0);
-    if (!pad) st.assign_free[d] = (uint8_t)pf;
-    // evid chain (sample_evid, gibbs_sampler.h:171-190): clamp hard evidence, else a Gibbs draw
-    // (Boolean variables carry no truthiness, so --noise_aware makes evidence variables draw too)
-    uint32_t pe = ev;
-    const uint32_t draw_evid = ~h.pad & (p.noise_aware ? 0xffffffffu : ~h.evid);
-    if (draw_evid) {
-      if (MULTI && h.n_mu)  // unary-only slices: both chains see identical potentials
-        sell_potentials<MULTI, FV, LD_CACHED>(g, h, w_s, st.weights, lane, d, st.assign_evid, pos, neg);
-      if ((draw_evid >> lane) & 1u) pe = sell_draw_boolean(pos, neg, r1);
+    sell_learn_slice<MULTI, FV, LD_CACHED>(g, st, p, h, w_s, acc_s, lane, s * 32u + lane);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) {
+    const double a = acc_s[i];
+    if (a != 0.0) atomicAdd(st.grad_acc + i, a);
+  }
+}
+
+// The same sweep with the slices staged through a per-warp ring of bulk-async copies, like
+// k_sell_infer_staged (8 warps per CTA, two stages): a learning launch covers 1/chunks of a
+// class, i.e. a handful of slices per warp, so the 4-deep dependent HBM chain of the direct
+// kernel (offset -> header -> records -> second pass) was most of its duration.  The host only
+// picks this kernel for classes whose longest slice fits a stage.
+constexpr int SELL_LEARN_STAGED_THREADS = 256;
+__host__ __device__ inline uint32_t sell_learn_bar_off(uint32_t n_hot) { return (16u * n_hot + 15u) & ~15u; }
+__host__ __device__ inline uint32_t sell_learn_ring_off(uint32_t n_hot, uint32_t stages) {
+  return (sell_learn_bar_off(n_hot) + (SELL_LEARN_STAGED_THREADS / 32) * stages * 8u + 127u) & ~127u;
+}
+__host__ __device__ inline uint32_t sell_learn_smem(uint32_t n_hot, uint32_t stages, uint32_t stage_words) {
+  return sell_learn_ring_off(n_hot, stages) + (SELL_LEARN_STAGED_THREADS / 32) * stages * stage_words * 4u;
+}
+
+template <bool MULTI, int FV>
+__global__ void __launch_bounds__(SELL_LEARN_STAGED_THREADS, 2)
+k_sell_learn_staged(const SellGraph g, const SellState st, const SweepParams p, const uint32_t stages,
+                    const uint32_t stage_words) {
+  extern __shared__ __align__(128) unsigned char sell_smem[];
+  constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
+  // programmatic dependent launch (learning launch -> k_apply_weights -> next learning launch):
+  // everything up to griddepcontrol.wait touches nothing the previous two kernels write
+  asm volatile("griddepcontrol.launch_dependents;");
+  double *w_s = reinterpret_cast<double *>(sell_smem), *acc_s = w_s + g.n_hot;
+  const uint32_t *sm = reinterpret_cast<const uint32_t *>(sell_smem);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t bar0 = sell_smem_addr(sell_smem) + sell_learn_bar_off(g.n_hot) + warp * stages * 8u;
+  const uint32_t ringw = sell_learn_ring_off(g.n_hot, stages) / 4u + warp * stages * stage_words;  // word index
+  const uint32_t ring0 = sell_smem_addr(sell_smem) + ringw * 4u;
+  if (lane == 0)
+    for (uint32_t i = 0; i < stages; ++i) sell_mbar_init(bar0 + 8u * i, 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) acc_s[i] = 0.0;
+  __syncthreads();  // mbarriers initialised before any lane waits on one
+
+  const uint64_t step = (uint64_t)((gridDim.x * blockDim.x) >> 5) * g.slice_stride;
+  const uint64_t s0 = g.slice_begin + (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * g.slice_stride;
+  const uint32_t n_my = s0 < g.slice_end ? (uint32_t)((g.slice_end - 1 - s0) / step) + 1u : 0u;
+  const uint64_t pol = sell_policy_evict_first();
+  uint32_t cur_lo = 0, cur_hi = 0, nxt_lo = 0, nxt_hi = 0;
+  auto fetch_offsets = [&](uint32_t kb, uint32_t &lo, uint32_t &hi) {
+    const uint32_t k = kb + lane;
+    if (k < n_my) {
+      const uint32_t *o = g.sl_off + (s0 + (uint64_t)k * step);
+      lo = __ldg(o);
+      hi = __ldg(o + 1);
     }
-    if (!pad) st.assign_evid[d] = (uint8_t)pe;
-    // which variables learn (gibbs_sampler.h:144-146); Boolean has_truthiness() is false
-    const bool learn = !pad && (p.learn_non_evidence || (!p.noise_aware && evid));
-    if (!__any_sync(0xffffffffu, learn)) continue;
-    // sgd_on_variable (factor_graph.cc:262-277): evidence_value = assignment_dense, free = pf.
-    // grad = sign_free * fv - sign_evid * fv == (code_free - code_evid) * fv exactly.
-    if (__any_sync(0xffffffffu, learn && pf != ev)) {  // unary: same value on both chains = zero gradient
-      for (uint32_t j = 0; j < h.n_un; ++j) {
-        const uint32_t rec = __ldg(h.un + (size_t)32 * j + lane);
-        if (!learn || pf == ev) continue;
-        const int cf = (int)(pf ? rec & 3u : rec >> 26), ce = (int)(ev ? rec & 3u : rec >> 26);
-        if (cf == ce) continue;
-        sell_grad(g, st, acc_s, sell_unary_wid(rec), rec & SELL_UN_FIXED_BIT,
-                  __dmul_rn((double)(cf - ce), sell_fv<FV, LD_CACHED>(h.un, h.n_un, j, lane)));
-      }
+  };
+  auto issue = [&](uint32_t k, uint32_t stage) {
+    const uint32_t j = k & 31u;
+    if (j == 0 && k) {
+      cur_lo = nxt_lo; cur_hi = nxt_hi;
+      fetch_offsets(k + 32, nxt_lo, nxt_hi);
     }
-    if (!MULTI || !h.n_mu) continue;
-    if (h.flags & SF_BINARY) {
-      for (uint32_t j = 0; j < h.n_mu; ++j) {
-        const uint32_t rec = __ldg(h.mu + (size_t)32 * j + lane);
-        const uint32_t ow = __ldg(h.oth + (size_t)32 * j + lane);
-        if (!learn) continue;
-        const uint32_t tag = rec >> 24, od = ow >> 1, eq = ow & 1u;
-        const uint32_t sf = st.assign_free[od] == eq, se = st.assign_evid[od] == eq;
-        const int cf = (int)((tag >> (4u * pf + 2u * sf)) & 3u), ce = (int)((tag >> (4u * ev + 2u * se)) & 3u);
-        if (cf == ce) continue;
-        sell_grad(g, st, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
-                  __dmul_rn((double)(cf - ce), sell_fv<FV, LD_CACHED>(h.mu, h.n_mu, j, lane)));
-      }
-    } else {
-      uint32_t oc = 0;
-      for (uint32_t j = 0; j < h.n_mu; ++j) {
-        const uint32_t rec = __ldg(h.mu + (size_t)32 * j + lane);
-        const uint32_t tag = rec >> 24;
-        if ((tag >> TAG_FORM_SHIFT) == 0) continue;
-        if (!learn) { oc += sell_general_span(h, tag, lane, oc); continue; }
-        uint32_t oc2 = oc;
-        double f0, f1, e0, e1;
-        sell_general_signs<LD_CACHED>(h, tag, d, lane, oc, st.assign_free, f0, f1);
-        sell_general_signs<LD_CACHED>(h, tag, d, lane, oc2, st.assign_evid, e0, e1);
-        const double fv = sell_fv<FV, LD_CACHED>(h.mu, h.n_mu, j, lane);
-        sell_grad(g, st, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
-                  __dsub_rn(__dmul_rn(pf ? f1 : f0, fv), __dmul_rn(ev ? e1 : e0, fv)));
-      }
+    const uint32_t off = __shfl_sync(0xffffffffu, cur_lo, j);
+    const uint32_t bytes = (__shfl_sync(0xffffffffu, cur_hi, j) - off) * 32u;  // fits: the host checked the class
+    if (lane == 0) {
+      sell_mbar_expect_tx(bar0 + 8u * stage, bytes);
+      sell_bulk_g2s(ring0 + stage * stage_words * 4u, g.blob + (size_t)off * 8, bytes, bar0 + 8u * stage, pol);
+    }
+  };
+  if (n_my) {  // the blob is static: the first copies go out before the previous launch is known to be done
+    fetch_offsets(0, cur_lo, cur_hi);
+    fetch_offsets(32, nxt_lo, nxt_hi);
+    const uint32_t pre = n_my < stages ? n_my : stages;
+    for (uint32_t k = 0; k < pre; ++k) issue(k, k);
+  }
+  // from here on: the chains the previous learning launch wrote and the weights k_apply_weights updated
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  sell_stage_weights(g, st.weights, w_s);
+  __syncthreads();
+  if (n_my) {
+    uint32_t stage = 0, parity = 0;
+    uint64_t s64 = s0;
+    for (uint32_t k = 0; k < n_my; ++k, s64 += step) {
+      sell_mbar_wait(bar0 + 8u * stage, parity);
+      const uint32_t *b = sm + ringw + stage * stage_words;
+      const uint4 h0 = *reinterpret_cast<const uint4 *>(b);
+      const uint4 h1 = *reinterpret_cast<const uint4 *>(b + 4);
+      SliceHeader h;
+      h.n_un = h0.x; h.n_mu = h0.y; h.n_oc = h0.z; h.evid = h0.w;
+      h.pad = h1.x; h.evval = h1.y; h.flags = h1.z;
+      h.un = b + SH_WORDS;
+      h.mu = h.un + 32u * h.n_un * (1 + FVW);
+      h.oth = h.mu + 32u * h.n_mu * (1 + FVW);
+      sell_learn_slice<MULTI, FV, LD_SMEM>(g, st, p, h, w_s, acc_s, lane, (uint32_t)s64 * 32u + lane);
+      __syncwarp();  // every lane is done with this stage before the next copy lands in it
+      if (k + stages < n_my) issue(k + stages, stage);
+      if (++stage == stages) { stage = 0; parity ^= 1u; }
     }
   }
   __syncthreads();
@@ -730,28 +865,12 @@ k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
 __global__ void k_apply_weights(double *w, double *grad_acc, const float *N, const float *Q, const float *H,
                                 const uint8_t *fixed, uint32_t n, double step, double reg, int reg_l1,
                                 int decay_in_acc, double share) {
+  // chained by programmatic dependent launch between two learning launches: lets the next one
+  // start its prologue, then waits for the gradient sums of the previous one
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || fixed[i]) return;
-  const double nn = (double)N[i] * share;  // this launch swept `share` of the class
-  const double acc = grad_acc[i];
-  if (nn == 0.0 && acc == 0.0) return;
-  grad_acc[i] = 0.0;
-  const double x = w[i];
-  const double r = reg_l1 ? 0.0 : reg * step / (1.0 + reg * step);
-  double S = acc;
-  if (!decay_in_acc) S += reg_l1 ? -nn * reg * (x < 0 ? 1.0 : 0.0) / step : nn * (r / step) * x;
-  // curvature D: the weight's own (diagonal) bound H where the joint step is provably
-  // non-expansive with it, i.e. step * phi(step * D) * R <= 1 with R the row-sum majorizer;
-  // otherwise the smallest D that is (fixed point of D = R (1 - exp(-step D)), approached from above)
-  const double Rk = (double)Q[i] * share, Hk = (double)H[i] * share;
-  double D = Hk;
-  if (Rk * -expm1(-step * D) > D) {
-    D = Rk;
-    for (int it = 0; it < 12; ++it) D = Rk * -expm1(-step * D);
-  }
-  const double z = step * D + nn * r;
-  const double phi = z > 1e-8 ? -expm1(-z) / z : 1.0 - 0.5 * z;
-  w[i] = x - step * S * phi;
+  if (i < n) sell_apply_weight(i, w, grad_acc, N, Q, H, fixed, step, reg, reg_l1, decay_in_acc, share);
 }
 
 }  // namespace dwg

@@ -279,6 +279,51 @@ def test_staged_and_direct_inference_kernels_agree(shape, monkeypatch):
         assert np.array_equal(s.tallies()[0], o.tallies)
 
 
+@pytest.mark.parametrize("shape", ["binary", "general", "c2", "unary_f32"])
+def test_staged_and_direct_learning_kernels_agree(shape, monkeypatch):
+    """k_sell_learn_staged against k_sell_learn: with every weight fixed (no update, so no
+    floating-point summation order in play) both chains are identical after several learning
+    sweeps; with free weights the learned weights agree to summation-order rounding"""
+    import copy
+    from sampler_b200 import graphgen
+    rng = np.random.default_rng(777)
+    if shape == "c2":
+        raw = graphgen.c2_boolean(50_000, nweight=200)
+    elif shape == "binary":
+        raw = random_graph(rng, nvar=5000, nfac=15000, nweight=60, p_cat=0.0, max_arity=2)
+    elif shape == "general":
+        raw = random_graph(rng, nvar=4000, nfac=9000, nweight=60, p_cat=0.0, max_arity=4)
+    else:
+        raw = graphgen.unary_boolean(30_000, 12, 300, p_evid=0.7)
+    variants = [{"DWG_SELL_DIRECT": "1"}, {}, {"DWG_SELL_STAGE_WORDS": "300"}]
+    keys = ("DWG_SELL_DIRECT", "DWG_SELL_STAGE_WORDS")
+    fixed = copy.deepcopy(raw)
+    fixed.w_fixed[:] = 1
+    fixed.w_init[:] = rng.normal(0, 1, len(fixed.w_init))
+    for graph_raw, free in ((fixed, False), (raw, True)):
+        g = sb.Graph.from_raw(graph_raw, sb.SCHED_CHROMATIC)
+        ref = None
+        for env in variants:
+            for k in keys:
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            s = sb.Sampler(g, seed=31, learn_non_evidence=(shape == "general"))
+            step = 0.01
+            for _ in range(3):
+                s.learn_epoch(step)
+                step *= 0.9
+            got = (s.assignments(0), s.assignments(1), s.weights())
+            s.close()
+            if ref is None:
+                ref = got
+            elif not free:
+                assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), env
+                assert np.array_equal(got[2], ref[2])
+            else:
+                assert np.allclose(got[2], ref[2], rtol=0, atol=1e-9), (env, np.abs(got[2] - ref[2]).max())
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_parallel_learning_with_exact_arithmetic(seed):
     """parallel learning launches under the chromatic schedule: with fixed weights both chains
