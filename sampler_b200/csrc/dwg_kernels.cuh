@@ -56,8 +56,9 @@ k_sweep_infer(const DevGraph g, const DevState st, const SweepParams p) {
     a[d] = (AssignT)prop;  // :160
     // agg_nsamples is implicit (every sampled variable gains one per sweep, :163);
     // Boolean: tally only proposal == 1 at the single row; categorical: row of the value (:164-167)
-    if (cat) st.tallies[row0 + prop] += 1u;
-    else if (prop == 1u) st.tallies[row0] += 1u;
+    // (a RED: nothing waits for the old count)
+    if (cat) atomicAdd(st.tallies + row0 + prop, 1u);
+    else if (prop == 1u) atomicAdd(st.tallies + row0, 1u);
   }
 }
 

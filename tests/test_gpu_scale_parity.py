@@ -130,3 +130,38 @@ def test_mid_size_graph_vs_reference(name):
     assert np.quantile(d, 0.99) <= max(0.15, 1.5 * q_ref), (np.quantile(d, 0.99), q_ref)
     print("%s: weights mean|d| %.4f (ref -t8 %.4f, noise %.4f) slope %.3f; marginals mean|d| %.4f (ref -t8 %.4f, noise %.4f)"
           % (name, d_ours, d_ref, noise_w, slope, d.mean(), dm_ref, noise.mean()))
+
+
+def test_full_size_c2_invariants(monkeypatch):
+    """BASELINE.json configs[1] at its full size (10 M variables, 10^8 edge records), through
+    size-independent properties: the staged and the direct inference kernels make identical chains
+    and tallies; the same seed reproduces them; evidence variables keep their value and are never
+    tallied without --sample_evidence; every tally is bounded by the sweep count; learning moves
+    only non-fixed weights and keeps them finite"""
+    raw = graphgen.c2_boolean(10_000_000)
+    g = sb.Graph.from_raw(raw)
+    assert g.info.schedule == sb.SCHED_CHROMATIC and g.info.num_index_entries == 100_000_000
+    is_evid = raw.var_role > 0
+    runs = []
+    for env in ({}, {}, {"DWG_SELL_DIRECT": "1"}):
+        monkeypatch.delenv("DWG_SELL_DIRECT", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s = sb.Sampler(g, sample_evidence=False, seed=2024)
+        s.learn_epoch(0.01)
+        w = s.weights()
+        s.clear_tallies()
+        s.infer_epochs(4)
+        a = s.assignments(1)
+        t, n = s.tallies()
+        s.close()
+        runs.append((a, t, n, w))
+    a, t, n, w = runs[0]
+    assert np.array_equal(a, runs[1][0]) and np.array_equal(t, runs[1][1])      # same seed, same run
+    assert np.array_equal(a, runs[2][0]) and np.array_equal(t, runs[2][1])      # staged == direct
+    assert np.allclose(w, runs[2][3], rtol=0, atol=1e-9) and np.isfinite(w).all() and np.abs(w).max() > 0
+    assert set(np.unique(a).tolist()) <= {0, 1}
+    assert np.array_equal(a[is_evid], raw.var_init[is_evid])                    # evidence stays clamped
+    assert (n[is_evid] == 0).all() and (n[~is_evid] == 4).all()
+    assert (t[is_evid] == 0).all() and (t <= 4).all()
+    assert 0.05 < t[~is_evid].sum() / (4.0 * (~is_evid).sum()) < 0.95
