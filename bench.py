@@ -272,18 +272,15 @@ def ours(args):
     value = nvar * world * args.steps / (total_ms * 1e-3)
     clk = clocks.stop(t_wall0, t_wall1) if clocks else None
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-
     t, ns = smp.tallies()
     assert int(ns[0]) == args.steps
-    frac1 = float(t.sum()) / (float(nvar) * args.steps * world)
+    frac1 = float(t.sum()) / (float(nvar) * args.steps * world) if rank == 0 else 0.0
 
-    # ---- e2e through the C ABI from host buffers: create (H2D) + K sweeps + tallies (D2H) ----
+    # ---- e2e through the C ABI from host buffers, every replica at once: create (H2D) + K sweeps +
+    # tallies (D2H); whole-job value = all replicas' samples / the slowest replica's wall time ----
     smp.close()
     torch.cuda.synchronize()
+    barrier()
     t0 = time.time()
     s2 = sb.Sampler(graph, device=local, sample_evidence=True, reg_param=LEARN["reg_param"], seed=99, replica=rank)
     t_up = time.time()
@@ -293,9 +290,17 @@ def ours(args):
     t2, n2 = s2.tallies()
     t_end = time.time()
     e2e_s = t_end - t0
-    e2e_value = nvar * args.steps / e2e_s
-    e2e_parts = "upload %.1f ms, sweeps %.1f ms, tallies %.1f ms" % (1e3 * (t_up - t0), 1e3 * (t_sw - t_up), 1e3 * (t_end - t_sw))
+    et = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_value = nvar * world * args.steps / float(et.item())
+    e2e_parts = "upload %.1f ms, sweeps %.1f ms, tallies %.1f ms (rank 0)" % (1e3 * (t_up - t0), 1e3 * (t_sw - t_up), 1e3 * (t_end - t_sw))
     s2.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
 
     # ---- the reference's CPU path on this host, bounded sample ----
     cpu = None

@@ -567,7 +567,15 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const GraphImage &m = g->img;
   cudaStream_t s = h->stream;
+  const bool timing = getenv("DWG_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    auto n = std::chrono::steady_clock::now();
+    if (timing) fprintf(stderr, "[create] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t_prev).count());
+    t_prev = n;
+  };
   g->pin();
+  lap("page-lock (first create only)");
   CU(h->var_flags.upload(m.var_flags, s));
   if (m.has_categorical) CU(h->var_row.upload(m.var_row, s));
   std::vector<uint8_t> ev8, fixed_dev(m.nweight);
@@ -606,9 +614,11 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     // Boolean variables have no truthiness: under --noise_aware only --learn_non_evidence learns
     h->learns = h->opts.learn_non_evidence || !h->opts.noise_aware;
   }
+  lap("allocations + copies queued");
   int rc = init_state(h.get());
   if (rc) return rc;
   CU(cudaStreamSynchronize(s));  // the staging vectors go out of scope
+  lap("copies done");
   h->device_bytes = image_device_bytes(m);
 
   DevGraph &dg = h->dg;
@@ -639,6 +649,7 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     h->cls_query_end = g->query_end();
     h->cls_max_words = g->cls_max_words;
   }
+  lap("kernel setup");
   *out = h.release();
   return DWG_OK;
 }
