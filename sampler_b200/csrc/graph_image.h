@@ -9,7 +9,9 @@
 #ifndef DWG_GRAPH_IMAGE_H_
 #define DWG_GRAPH_IMAGE_H_
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace dwg {
@@ -150,6 +152,20 @@ struct GraphImage {
   uint32_t ncolor() const { return (uint32_t)color_start.size() - 1; }
 };
 
+// std::vector whose resize() leaves new elements uninitialised: the big per-factor / per-edge
+// arrays are sized once and then filled by parallel ranges, so a zero-fill would be a second,
+// single-threaded pass over gigabytes (and would fault every page in on one thread)
+template <typename T>
+struct NoInitAlloc : std::allocator<T> {
+  template <typename U> struct rebind { using other = NoInitAlloc<U>; };
+  template <typename U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+  template <typename U, typename... A> void construct(U *p, A &&...a) {
+    ::new (static_cast<void *>(p)) U(std::forward<A>(a)...);
+  }
+};
+template <typename T>
+using BulkVec = std::vector<T, NoInitAlloc<T>>;
+
 // decoded input records (owning)
 struct RawGraph {
   std::vector<uint8_t> var_role;
@@ -158,9 +174,9 @@ struct RawGraph {
   std::vector<uint64_t> var_card;
   std::vector<uint64_t> dom_vid, dom_ptr{0}, dom_val;
   std::vector<double> dom_truth;
-  std::vector<int32_t> fac_func;
-  std::vector<uint64_t> fac_ptr{0}, edge_vid, edge_eq, fac_wid;
-  std::vector<double> fac_fv;
+  BulkVec<int32_t> fac_func;
+  BulkVec<uint64_t> fac_ptr{0}, edge_vid, edge_eq, fac_wid;
+  BulkVec<double> fac_fv;
   std::vector<double> w_init;
   std::vector<uint8_t> w_fixed;
 };

@@ -174,7 +174,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
 
   pt.lap("variables + domains");
   // ---- factors (src/binary_format.cc:128-190) ----
-  std::vector<uint32_t> edense(nedge);  // FactorToVariable::dense_equal_to
+  BulkVec<uint32_t> edense(nedge);  // FactorToVariable::dense_equal_to (every entry written below)
   std::vector<uint32_t> deg(nvar + 1, 0);
   bool coupled = false, eq_is_bit = true;
   {
@@ -232,7 +232,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
 
   pt.lap("factors");
   // ---- adjacency + construct_index (src/factor_graph.cc:131-199) ----
-  std::vector<Inc> inc(nedge);
+  BulkVec<Inc> inc(nedge);
   {
     std::vector<uint32_t> fill(deg.begin(), deg.end() - 1);
     parallel_for(nfac, [&](uint64_t f0, uint64_t f1) {
@@ -342,7 +342,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       }
     });
     for (uint64_t v = 0; v < nvar; ++v) nb_ptr[v + 1] += nb_ptr[v];
-    std::vector<uint32_t> nb(nb_ptr[nvar]);
+    BulkVec<uint32_t> nb(nb_ptr[nvar]);
     parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
       for (uint64_t v = v0; v < v1; ++v) {
         uint64_t o = nb_ptr[v];
@@ -436,7 +436,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   g->inv.resize(nvar);
   if (g->sell) {
     struct Key { uint64_t k; uint32_t v; };
-    std::vector<Key> keys(nvar);
+    BulkVec<Key> keys(nvar);
     parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
       for (uint64_t v = v0; v < v1; ++v) {
         uint64_t n_un = 0, n_mu = 0, ow = 0;
