@@ -1,25 +1,28 @@
 // dwg_sell.cuh -- the production sweep kernels for Boolean graphs (sm_100a): one warp per
 // 32-variable slice of the sliced-ELL blob (graph_image.h), lane = variable.
 //
-//   k_sell_infer   GibbsSamplerThread::sample        (src/gibbs_sampler.cc:65-69,
-//                                                      src/gibbs_sampler.h:151-169,192-215)
-//   k_sell_learn   GibbsSamplerThread::sample_sgd    (src/gibbs_sampler.cc:71-75,
-//                  src/gibbs_sampler.h:127-149,171-190; sgd_on_variable/-factor,
-//                  src/factor_graph.cc:243-314)
-//   k_apply_weights  the weight update of one learning launch (update_weight,
-//                  src/inference_result.h:66-85, as a semi-implicit mini-batch step)
+//   k_sell_infer_staged  GibbsSamplerThread::sample   (src/gibbs_sampler.cc:65-69,
+//   k_sell_infer                                        src/gibbs_sampler.h:151-169,192-215)
+//   k_sell_learn_staged  GibbsSamplerThread::sample_sgd (src/gibbs_sampler.cc:71-75,
+//   k_sell_learn           src/gibbs_sampler.h:127-149,171-190; sgd_on_variable/-factor,
+//                          src/factor_graph.cc:243-314)
+//   k_apply_weights      the weight update of one learning launch (update_weight,
+//                          src/inference_result.h:66-85, as a semi-implicit mini-batch step)
 //
 // Memory behaviour (HBM-bound by design): a slice is one contiguous run of words, read exactly
-// once per sweep with warp-wide 128 B requests; all record loads of a slice (unary chunk,
-// multi chunk, others words) are issued before the first dependent use, so every warp keeps
-// ~1.5 KB in flight and an SM (32 warps) ~50 KB -- what 6.5 TB/s x ~1 us of latency needs.
-// Per variable besides the records: 1 B chain write, 8 B tally read-modify-write; evidence /
-// padding / evidence-value bits ride in the slice header.  Gathers that stay on chip: weights
-// (ids < n_hot from shared memory, the rest through L1/L2) and the u8 chain values of other
-// variables (L2).  The fast paths are branch-free: a unary record carries its two sign codes,
-// a record of a two-variable factor carries the factor's whole 2x2 sign table, so no
-// factor-function switch runs per edge.  Persistent CTAs (2 per SM) walk the slices of a colour
-// class with a grid stride so the shared-memory weight table is staged once per CTA.
+// once per sweep.  The *_staged kernels (the default) move it with one 1-D bulk-async copy
+// (cp.async.bulk + mbarrier, the TMA unit) into a per-warp ring in shared memory, one or more
+// slices ahead of the one being sampled, and read records with conflict-free LDS; the direct
+// kernels (fallback for slices longer than a ring stage) read it with warp-wide 128 B global
+// loads issued before their first dependent use.  Per variable besides the records: 1 B chain
+// write, a tally RED; evidence / padding / evidence-value bits ride in the slice header.
+// Gathers that stay on chip: weights (shared memory: a signed table -w | 0 | +w in the staged
+// inference kernel, a plain one elsewhere; ids beyond it through L1/L2) and the u8 chain
+// values of other variables (L2).  The fast paths are branch-free: a unary record carries its
+// two sign codes, a record of a two-variable factor carries the factor's whole 2x2 sign table,
+// so no factor-function switch runs per edge.  Persistent CTAs (2 per SM) walk the slices of a
+// launch with a grid stride, so the weight table is staged once per CTA; consecutive launches
+// are chained by programmatic dependent launch (their prologues overlap the previous tail).
 // No tensor cores: O(1) flop per 4..12 B of edge data.
 #ifndef DWG_SELL_CUH_
 #define DWG_SELL_CUH_
@@ -253,13 +256,37 @@ __device__ __forceinline__ void sell_binary_acc(const SellGraph &g, const SliceH
   }
 }
 
+// The multi-variable records of a slice added to (pos, neg), the other variables read from chain
+// `a`.  first / first_sat: the slice's first binary chunk when the caller already loaded it.
+template <int FV, int LD>
+__device__ __forceinline__ void sell_multi(const SellGraph &g, const SliceHeader &h, const double *w_s,
+                                           const double *w, uint32_t lane, uint32_t self, const uint8_t *a,
+                                           const BinaryChunk *first, uint32_t first_sat, double &pos, double &neg) {
+  if (h.flags & SF_BINARY) {
+    BinaryChunk c;
+    uint32_t sat;
+    if (first) { c = *first; sat = first_sat; }
+    else { sell_binary_load<LD>(h, 0, lane, c); sat = sell_binary_sat(c, a); }
+    sell_binary_acc<FV, LD>(g, h, w_s, w, 0, lane, c, sat, pos, neg);
+    for (uint32_t j0 = SELL_MCHUNK; j0 < h.n_mu; j0 += SELL_MCHUNK) {
+      sell_binary_load<LD>(h, j0, lane, c);
+      sat = sell_binary_sat(c, a);
+      sell_binary_acc<FV, LD>(g, h, w_s, w, j0, lane, c, sat, pos, neg);
+    }
+  } else if (h.n_mu) {
+    sell_general_multi<FV, LD>(g, h, w_s, w, lane, self, a, pos, neg);
+  }
+}
+
 // FactorGraph::potential for proposals 1 and 0 of the lane's variable on chain `a`
-// (src/factor_graph.h:127-145); `first` = the slice's first binary chunk, loaded by the caller
-// ahead of the unary records so that its gathers overlap them
+// (src/factor_graph.h:127-145).  The slice's first binary chunk is loaded ahead of the unary
+// records so that its gathers overlap them.  upos / uneg (optional): the sums after the unary
+// records -- they do not depend on the chain, so a second chain continues from them (sell_multi).
 template <bool MULTI, int FV, int LD>
 __device__ __forceinline__ void sell_potentials(const SellGraph &g, const SliceHeader &h, const double *w_s,
                                                 const double *w, uint32_t lane, uint32_t self,
-                                                const uint8_t *a, double &pos, double &neg) {
+                                                const uint8_t *a, double &pos, double &neg,
+                                                double *upos = nullptr, double *uneg = nullptr) {
   pos = 0.0; neg = 0.0;
   BinaryChunk c;
   uint32_t sat = 0;
@@ -270,17 +297,9 @@ __device__ __forceinline__ void sell_potentials(const SellGraph &g, const SliceH
   }
   if (h.flags & SF_ANTISYM) sell_unary<FV, LD, true>(g, h, w_s, w, lane, pos, neg);
   else sell_unary<FV, LD, false>(g, h, w_s, w, lane, pos, neg);
+  if (upos) { *upos = pos; *uneg = neg; }
   if (!MULTI) return;
-  if (binary) {
-    sell_binary_acc<FV, LD>(g, h, w_s, w, 0, lane, c, sat, pos, neg);
-    for (uint32_t j0 = SELL_MCHUNK; j0 < h.n_mu; j0 += SELL_MCHUNK) {
-      sell_binary_load<LD>(h, j0, lane, c);
-      sat = sell_binary_sat(c, a);
-      sell_binary_acc<FV, LD>(g, h, w_s, w, j0, lane, c, sat, pos, neg);
-    }
-  } else if (h.n_mu) {
-    sell_general_multi<FV, LD>(g, h, w_s, w, lane, self, a, pos, neg);
-  }
+  sell_multi<FV, LD>(g, h, w_s, w, lane, self, a, binary ? &c : nullptr, sat, pos, neg);
 }
 
 template <bool MULTI, int FV>
@@ -666,8 +685,8 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
   double r0, r1;
   dev_uniforms(p, d, r0, r1);
   // free chain: every variable, evidence included (gibbs_sampler.h:137-139)
-  double pos, neg;
-  sell_potentials<MULTI, FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_free, pos, neg);
+  double pos, neg, upos, uneg;
+  sell_potentials<MULTI, FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_free, pos, neg, &upos, &uneg);
   const uint32_t pf = sell_draw_boolean(pos, neg, r0);
   if (!pad) st.assign_free[d] = (uint8_t)pf;
   // evid chain (sample_evid, gibbs_sampler.h:171-190): clamp hard evidence, else a Gibbs draw
@@ -675,8 +694,10 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
   uint32_t pe = ev;
   const uint32_t draw_evid = ~h.pad & (p.noise_aware ? 0xffffffffu : ~h.evid);
   if (draw_evid) {
-    if (MULTI && h.n_mu)  // unary-only slices: both chains see identical potentials
-      sell_potentials<MULTI, FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_evid, pos, neg);
+    if (MULTI && h.n_mu) {  // unary-only slices: both chains see identical potentials
+      pos = upos; neg = uneg;  // the unary sums are the same on both chains: continue from them
+      sell_multi<FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_evid, nullptr, 0u, pos, neg);
+    }
     if ((draw_evid >> lane) & 1u) pe = sell_draw_boolean(pos, neg, r1);
   }
   if (!pad) st.assign_evid[d] = (uint8_t)pe;
