@@ -68,6 +68,9 @@ struct dwg_graph {
       reg(img.e_fv64.data(), img.e_fv64.size() * 8);
     }
     reg(img.row_of_value.data(), img.row_of_value.size() * 4);
+    reg(img.var_flags.data(), img.var_flags.size());
+    reg(img.evid_val8.data(), img.evid_val8.size());
+    reg(img.sl_off.data(), img.sl_off.size() * 4);
     if (pinned.empty()) pinned.push_back(nullptr);  // tried
   }
   // per colour class: the first slice from which every slice holds evidence / padding only
@@ -578,15 +581,14 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
   lap("page-lock (first create only)");
   CU(h->var_flags.upload(m.var_flags, s));
   if (m.has_categorical) CU(h->var_row.upload(m.var_row, s));
-  std::vector<uint8_t> ev8, fixed_dev(m.nweight);
+  std::vector<uint8_t> fixed_dev(m.nweight);
   std::vector<double> w_dev(m.nweight);
   for (uint64_t i = 0; i < m.nweight; ++i) {
     w_dev[i] = m.w_init[m.w_perm[i]];
     fixed_dev[i] = m.w_fixed[m.w_perm[i]];
   }
   if (m.assign_bytes == 1) {
-    ev8.assign(m.evid_val.begin(), m.evid_val.end());
-    CU(h->evid_val8.upload(ev8, s));
+    CU(h->evid_val8.upload(m.evid_val8, s));
     CU(h->assign_free8.alloc(m.nvar_pad));
     CU(h->assign_evid8.alloc(m.nvar_pad));
   } else {

@@ -108,6 +108,7 @@ struct GraphImage {
   // per variable (d order)
   std::vector<uint8_t> var_flags;   // [nvar]
   std::vector<uint32_t> evid_val;   // [nvar] Variable::assignment_dense
+  std::vector<uint8_t> evid_val8;   // the same as bytes when assign_bytes == 1 (what the device holds)
   std::vector<uint32_t> var_row;    // [nvar+1] first row of each variable (only if has_categorical)
 
   // per row = (variable, dense value); Boolean variables own one row

@@ -627,6 +627,12 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   g->bytes_infer_query = b_query;
   g->bytes_learn = b_learn;
 
+  if (g->assign_bytes == 1) {
+    g->evid_val8.resize(nvar_pad);
+    parallel_for(nvar_pad, [&](uint64_t a, uint64_t b) {
+      for (uint64_t d = a; d < b; ++d) g->evid_val8[d] = (uint8_t)g->evid_val[d];
+    });
+  }
   pt.lap("emit CSR");
   // ---- internal weight ids: hottest first, so that ids < n_hot can live in shared memory ----
   g->w_perm.resize(nweight); g->w_inv.resize(nweight);
