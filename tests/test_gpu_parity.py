@@ -560,6 +560,33 @@ def test_reference_check_results_scripts(tmp_path):
                 assert abs(p - want[k]) <= 0.04, (k, p)
 
 
+def test_cli_outputs_do_not_depend_on_host_threads(tmp_path, monkeypatch):
+    """`dw gibbs` from binary files on a graph large enough for the parallel host paths (mmap
+    loader with block-parallel factor decode, parallel compile, parallel text dump): the two
+    output files are byte-identical with 1 and with 8 host threads and hold one line per variable /
+    weight in id order"""
+    from sampler_b200 import graphgen
+    raw = graphgen.c2_boolean(150_000, nweight=100)
+    paths = gio.write_binary(raw, str(tmp_path))
+    outs = []
+    for threads in ("1", "8"):
+        monkeypatch.setenv("DWG_COMPILE_THREADS", threads)
+        out = tmp_path / ("out" + threads)
+        out.mkdir()
+        argv = ["dw", "gibbs", "-m", paths["meta"], "-v", paths["variables"], "-f", paths["factors"],
+                "-w", paths["weights"], "-o", str(out), "--quiet", "-l", "3", "-i", "10", "--alpha", "0.01",
+                "--sample_evidence"]
+        assert sb.dw_main(argv) == 0
+        outs.append(((out / "inference_result.out.text").read_bytes(),
+                     (out / "inference_result.out.weights.text").read_bytes()))
+    assert outs[0] == outs[1]
+    lines = outs[0][0].decode().splitlines()
+    assert len(lines) == 150_000 and lines[0].split()[:2] == ["0", "1"] and lines[-1].split()[0] == "149999"
+    probs = np.array([float(x.split()[2]) for x in lines])
+    assert ((probs >= 0) & (probs <= 1)).all() and 0.2 < probs.mean() < 0.8
+    assert len(outs[0][1].decode().splitlines()) == 100
+
+
 # ---------------------------------------------------------------- replicas
 def test_two_replicas_one_gpu_average_and_aggregate():
     """the -c N plumbing with both replicas on one device and no NCCL: weights are averaged
