@@ -10,6 +10,8 @@
 // follow the order of the -f flags, which is the single-file order when one file is given.
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -238,52 +240,98 @@ std::string load_raw(const MetaCounts &meta, const std::vector<std::string> &var
     }
   }
   lap("variables, weights, domains");
-  // factors (:143-181).  Pass 1 walks the arities and notes where every block of 2^16 records
-  // starts (byte offset, factor index, edge index); pass 2 decodes the blocks in parallel.
+  // factors (:143-181).  One thread walks the arities and hands out blocks of 2^16 records (byte
+  // offset, factor index, edge index) as it finds them; the other host threads decode the blocks
+  // while the walk goes on.  The arrays are sized from the meta counts, which the walk confirms
+  // (a block that would overrun them is never handed out).
   struct FBlock { const FileBuf *buf; size_t p; uint64_t f, e, nrec; };
-  std::vector<FBlock> blocks;
+  r.fac_func.resize(meta.nfac); r.fac_wid.resize(meta.nfac); r.fac_fv.resize(meta.nfac);
+  r.fac_ptr.resize(meta.nfac + 1); r.edge_vid.resize(meta.nedge); r.edge_eq.resize(meta.nedge);
+  r.fac_ptr[0] = 0;
+  auto decode = [&](const FBlock &B) {
+    const uint8_t *q = B.buf->data() + B.p;
+    uint64_t e = B.e;
+    for (uint64_t f = B.f; f < B.f + B.nrec; ++f) {
+      uint16_t func = be16(q);
+      uint64_t arity = be64(q + 2);
+      q += 10;
+      r.fac_func[f] = (int32_t)(int16_t)func == -1 ? -1 : (int32_t)func;
+      for (uint64_t i = 0; i < arity; ++i, q += 16, ++e) {
+        r.edge_vid[e] = be64(q);
+        r.edge_eq[e] = be64(q + 8);
+      }
+      r.fac_ptr[f + 1] = e;
+      r.fac_wid[f] = be64(q);
+      r.fac_fv[f] = bef64(q + 8);
+      q += 16;
+    }
+  };
+  std::mutex qmu;
+  std::condition_variable qcv;
+  std::vector<FBlock> queue;  // blocks found so far
+  size_t next_block = 0;      // first block no worker has taken
+  bool walk_done = false;
+  std::vector<std::thread> workers;
+  const unsigned nworkers = std::max(1u, host_threads() - 1);
+  for (unsigned t = 0; t < nworkers; ++t)
+    workers.emplace_back([&] {
+      for (;;) {
+        FBlock B;
+        {
+          std::unique_lock<std::mutex> lk(qmu);
+          qcv.wait(lk, [&] { return next_block < queue.size() || walk_done; });
+          if (next_block >= queue.size()) return;
+          B = queue[next_block++];
+        }
+        decode(B);
+      }
+    });
+  std::string walk_error;
   uint64_t nfac = 0, nedge = 0;
-  for (auto &b : data[2]) {
-    size_t p = 0;
-    while (p < b.size()) {
-      if ((nfac & 0xffff) == 0 || blocks.empty() || blocks.back().buf != &b) blocks.push_back({&b, p, nfac, nedge, 0});
-      if (p + 10 > b.size()) return "factors file: truncated record";
-      uint64_t arity = be64(&b[p + 2]);
-      p += 10;
-      if (arity > (b.size() - p) / 16 || b.size() - p - 16 * arity < 16) return "factors file: truncated record";
-      p += 16 * arity + 16;
-      nedge += arity;
-      ++nfac;
-      ++blocks.back().nrec;
+  {
+    FBlock cur{nullptr, 0, 0, 0, 0};
+    auto hand_out = [&]() {
+      if (!cur.nrec) return;
+      {
+        std::lock_guard<std::mutex> lk(qmu);
+        queue.push_back(cur);
+      }
+      qcv.notify_one();
+      cur.nrec = 0;
+    };
+    for (auto &b : data[2]) {
+      size_t p = 0;
+      while (p < b.size() && walk_error.empty()) {
+        if (!cur.nrec) cur = FBlock{&b, p, nfac, nedge, 0};
+        if (p + 10 > b.size()) { walk_error = "factors file: truncated record"; break; }
+        uint64_t arity = be64(&b[p + 2]);
+        p += 10;
+        if (arity > (b.size() - p) / 16 || b.size() - p - 16 * arity < 16) { walk_error = "factors file: truncated record"; break; }
+        if (nfac + 1 > meta.nfac || nedge + arity > meta.nedge) {  // more than the meta file announced: reported below
+          nfac += 1; nedge += arity;
+          p += 16 * arity + 16;
+          cur.nrec = 0;  // never decoded: it would not fit the arrays
+          continue;
+        }
+        p += 16 * arity + 16;
+        nedge += arity;
+        ++nfac;
+        if (++cur.nrec == (1u << 16)) hand_out();
+      }
+      if (nfac <= meta.nfac && nedge <= meta.nedge) hand_out();  // a block does not span files
+      cur.nrec = 0;
     }
   }
+  {
+    std::lock_guard<std::mutex> lk(qmu);
+    walk_done = true;
+  }
+  qcv.notify_all();
+  lap("factor boundaries (decode running)");
+  for (auto &t : workers) t.join();
+  if (!walk_error.empty()) return walk_error;
   if (nfac != meta.nfac) return "number of factors (" + std::to_string(nfac) + ") != meta (" + std::to_string(meta.nfac) + ")";
   if (nedge != meta.nedge) return "number of edges (" + std::to_string(nedge) + ") != meta (" + std::to_string(meta.nedge) + ")";
-  lap("factor boundaries");
-  r.fac_func.resize(nfac); r.fac_wid.resize(nfac); r.fac_fv.resize(nfac);
-  r.fac_ptr.resize(nfac + 1); r.edge_vid.resize(nedge); r.edge_eq.resize(nedge);
-  r.fac_ptr[0] = 0;
-  parallel_ranges(blocks.size(), host_threads(), [&](uint64_t b0, uint64_t b1, unsigned) {
-    for (uint64_t bi = b0; bi < b1; ++bi) {
-      const FBlock &B = blocks[bi];
-      const uint8_t *q = B.buf->data() + B.p;
-      uint64_t e = B.e;
-      for (uint64_t f = B.f; f < B.f + B.nrec; ++f) {
-        uint16_t func = be16(q);
-        uint64_t arity = be64(q + 2);
-        q += 10;
-        r.fac_func[f] = (int32_t)(int16_t)func == -1 ? -1 : (int32_t)func;
-        for (uint64_t i = 0; i < arity; ++i, q += 16, ++e) {
-          r.edge_vid[e] = be64(q);
-          r.edge_eq[e] = be64(q + 8);
-        }
-        r.fac_ptr[f + 1] = e;
-        r.fac_wid[f] = be64(q);
-        r.fac_fv[f] = bef64(q + 8);
-        q += 16;
-      }
-    }
-  }, 1);
   lap("factor decode");
   *err = DWG_OK;
   return "";

@@ -164,6 +164,14 @@ def test_errors_are_codes_not_aborts(tmp_path):
     open(paths["meta"], "w").write("1,18,17,18")
     with pytest.raises(sb.DwgError, match="number of factors"):
         sb.Graph.from_files(paths["meta"], [paths["variables"]], [], [paths["factors"]], [paths["weights"]])
+    open(paths["meta"], "w").write("1,18,19,19")  # announces more than the file holds
+    with pytest.raises(sb.DwgError, match="number of factors"):
+        sb.Graph.from_files(paths["meta"], [paths["variables"]], [], [paths["factors"]], [paths["weights"]])
+    open(paths["meta"], "w").write("1,18,18,18")
+    whole = open(paths["factors"], "rb").read()
+    open(paths["factors"] + ".cut", "wb").write(whole[:-5])
+    with pytest.raises(sb.DwgError, match="truncated record"):
+        sb.Graph.from_files(paths["meta"], [paths["variables"]], [], [paths["factors"] + ".cut"], [paths["weights"]])
     with pytest.raises(sb.DwgError, match="cannot open"):
         sb.Graph.from_files(paths["meta"], ["/nonexistent"], [], [paths["factors"]], [paths["weights"]])
     # meta with trailing junk / no newline parses like atoll on 4 comma fields
