@@ -361,6 +361,9 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       load.assign(K + 1, 0);
       ncolor = 1;
       for (uint64_t v = 0; v < nvar; ++v) {
+        // the colours of the neighbours are random reads: ask for those of variable v + 16 now
+        if (v + 16 < nvar)
+          for (uint64_t i = nb_ptr[v + 16]; i < nb_ptr[v + 17]; ++i) __builtin_prefetch(&color[nb[i]]);
         for (uint64_t i = nb_ptr[v]; i < nb_ptr[v + 1]; ++i) {
           uint32_t c = color[nb[i]];
           if (c == 0xffffffffu) continue;
