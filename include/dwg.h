@@ -108,6 +108,11 @@ int dwg_graph_from_files(const char *meta, int n_var, const char *const *var_fil
                          const char *const *dom_files, int n_fac, const char *const *fac_files,
                          int n_wgt, const char *const *wgt_files, int schedule, dwg_graph **out);
 void dwg_graph_free(dwg_graph *g);
+/* The compiled image is page-locked on the first dwg_create so that every replica's upload is a
+ * DMA at the PCIe rate (the reference deep-copies the FactorGraph per NUMA node,
+ * src/dimmwitted.cc:113-116).  Page-locking costs about three pageable uploads: a host that
+ * creates ONE replica and exits (dw gibbs -c 1) turns it off. */
+int dwg_graph_set_page_locking(dwg_graph *g, int on);
 
 typedef struct dwg_graph_info {
   uint64_t num_variables, num_factors, num_weights, num_edges, num_values;

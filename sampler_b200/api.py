@@ -78,6 +78,7 @@ def load(build: bool = False):
     L.dwg_graph_from_raw.argtypes = [C.POINTER(Raw), i32, C.POINTER(vp)]
     L.dwg_graph_from_files.argtypes = [C.c_char_p] + [i32, C.POINTER(C.c_char_p)] * 4 + [i32, C.POINTER(vp)]
     L.dwg_graph_free.argtypes = [vp]
+    L.dwg_graph_set_page_locking.argtypes = [vp, i32]
     L.dwg_graph_info.argtypes = [vp, C.POINTER(GraphInfo)]
     L.dwg_graph_var_meta.argtypes = [vp, vp, vp, vp, vp]
     L.dwg_debug_schedule.argtypes = [vp, vp, vp]

@@ -49,9 +49,10 @@ struct dwg_graph {
   // a bounce through the driver's staging buffers; undone by dwg_graph_free
   mutable std::mutex pin_mu;
   mutable std::vector<const void *> pinned;
+  mutable bool pin_wanted = true;  // dwg_graph_set_page_locking
   void pin() const {
     std::lock_guard<std::mutex> lk(pin_mu);
-    if (!pinned.empty()) return;
+    if (!pinned.empty() || !pin_wanted) return;
     auto reg = [&](const void *p, size_t bytes) {
       if (bytes < (1u << 20)) return;
       if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) pinned.push_back(p);
@@ -415,6 +416,13 @@ int dwg_graph_from_files(const char *meta, int n_var, const char *const *var_fil
 }
 
 void dwg_graph_free(dwg_graph *g) { delete g; }
+
+int dwg_graph_set_page_locking(dwg_graph *g, int on) {
+  if (!g) return fail(DWG_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(g->pin_mu);
+  g->pin_wanted = on != 0;
+  return DWG_OK;
+}
 
 static size_t image_device_bytes(const GraphImage &m) {
   size_t b = 0;

@@ -9,10 +9,12 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime_api.h>
@@ -99,6 +101,16 @@ int gibbs(const CmdParser &args) {
   }
 
   Replicas R;
+  // DWG_COMPILE_TIMING=1: wall time of the application's phases on stderr, like the loader's and compiler's
+  const bool timing = getenv("DWG_COMPILE_TIMING") != nullptr;
+  Timer t_phase;
+  auto lap = [&](const char *what) {
+    if (timing) std::fprintf(stderr, "[app]     %-28s %8.1f ms\n", what, 1e3 * t_phase.elapsed());
+    t_phase.restart();
+  };
+  // the CUDA context comes up (0.3-0.5 s) on a second thread while the graph is loaded and compiled
+  std::thread cuda_up([] { cudaFree(nullptr); });
+  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } cuda_up_joiner{cuda_up};
   std::cout << "\tloading factor graph..." << std::endl;
   auto cptr = [](const std::vector<std::string> &v) {
     std::vector<const char *> p;
@@ -111,6 +123,7 @@ int gibbs(const CmdParser &args) {
   TRY(dwg_graph_from_files(args.fg_file.c_str(), (int)args.variable_file.size(), vf.data(),
                            (int)args.domain_file.size(), df.data(), (int)args.factor_file.size(),
                            ff.data(), (int)args.weight_file.size(), wf.data(), args.schedule, &R.graph));
+  lap("load + compile");
   dwg_graph_info_t info;
   TRY(dwg_graph_info(R.graph, &info));
   std::cout << "Factor graph loaded:\t";
@@ -142,6 +155,7 @@ int gibbs(const CmdParser &args) {
   // the reference seeds from un-seeded rand() (gibbs_sampler.cc:49): a fixed default; --seed varies it
   opts.seed = args.seed;
   opts.learn_chunks = args.learn_chunks;
+  if (n_samplers == 1) TRY(dwg_graph_set_page_locking(R.graph, 0));  // one upload: not worth locking 0.6 GB
   for (size_t i = 0; i < n_samplers; ++i) {
     std::cout << "CREATE CFG ON GPU ... " << i << std::endl;
     opts.replica = (uint32_t)i;
@@ -194,6 +208,7 @@ int gibbs(const CmdParser &args) {
     }
     for (auto *h : R.hs) TRY(dwg_sync(h));
     std::cout << "TOTAL LEARNING TIME: " << t_total.elapsed() << " sec." << std::endl;
+    lap("replicas up + learning");
   }
 
   // ---- dump_weights, :245-258 (written even with -l 0) ----
@@ -240,6 +255,7 @@ int gibbs(const CmdParser &args) {
     }
     for (auto *h : R.hs) TRY(dwg_sync(h));
     std::cout << "TOTAL INFERENCE TIME: " << t_total.elapsed() << " sec." << std::endl;
+    lap("weights dump + inference");
   }
 
   if (args.n_inference_epoch > 0) {  // :89-92
@@ -300,6 +316,7 @@ int gibbs(const CmdParser &args) {
         std::printf("PROB BIN %.1f~%.1f  -->  # %zu\n", (float)i / bins, (float)(i + 1) / bins, abc[i]);
     }
   }
+  lap("tallies + marginal dump");
   return 0;
 }
 

@@ -31,12 +31,12 @@ def main():
         cmd = [_build.DW, "gibbs", "-m", paths["meta"], "-v", paths["variables"], "-f", paths["factors"],
                "-w", paths["weights"], "-o", d, "-l", "20", "-i", "100", "--alpha", "0.01", "--diminish", "0.95",
                "--reg_param", "0.01", "--sample_evidence", "-q"]
-        env = dict(os.environ, DWG_COMPILE_TIMING="1")
+        env = dict(os.environ, DWG_COMPILE_TIMING="1", DWG_TIMING="1")
         t0 = time.time()
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
         wall = time.time() - t0
-        phases = {m.group(1).strip(): float(m.group(2)) for m in
-                  re.finditer(r"\[(?:load|compile)\]\s+(.*?)\s+([0-9.]+) ms", r.stderr)}
+        phases = {m.group(1) + ": " + m.group(2).strip(): float(m.group(3)) for m in
+                  re.finditer(r"\[(load|compile|app|create)\]\s+(.*?)\s+([0-9.]+) ms", r.stderr)}
         out = r.stdout
         learn = re.search(r"TOTAL LEARNING TIME: ([0-9.eE+-]+)", out)
         infer = re.search(r"TOTAL INFERENCE TIME: ([0-9.eE+-]+)", out)
@@ -45,10 +45,9 @@ def main():
         print(json.dumps({
             "workload": "C2, %d variables, -l 20 -i 100 --sample_evidence" % args.nvar, "rc": r.returncode,
             "wall_s": wall, "input_bytes": sum(sizes.values()), "write_inputs_s": t_write,
-            "load_ms": sum(v for k, v in phases.items() if k in ("read files", "variables, weights, domains",
-                                                                  "factor boundaries", "factor decode")),
-            "compile_ms": sum(v for k, v in phases.items() if k not in ("read files", "variables, weights, domains",
-                                                                     "factor boundaries", "factor decode")),
+            "load_ms": sum(v for k, v in phases.items() if k.startswith("load:")),
+            "compile_ms": sum(v for k, v in phases.items() if k.startswith("compile:")),
+            "app_ms": {k[5:]: v for k, v in phases.items() if k.startswith("app:")},
             "learning_s": float(learn.group(1)) if learn else None,
             "inference_s": float(infer.group(1)) if infer else None,
             "marginal_lines": sum(1 for _ in open(res)) if os.path.exists(res) else 0,
