@@ -420,6 +420,19 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     bool compact = nself == 1 && n <= 3 && (cat ? self_eq == k : self_eq <= 1);
     return compact ? (int)(n - 1) : (int)FORM_GENERAL;
   };
+  // ... evaluated ONCE per incidence (a random read of the factor each time), kept as
+  // form | self position << 2 for the three phases that need it (sort keys, sizing, CSR fill)
+  BulkVec<uint8_t> finfo(nedge);
+  parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+    for (uint64_t v = v0; v < v1; ++v) {
+      const bool cat = g->var_dtype[v];
+      for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
+        uint64_t self_pos = 0;
+        const int form = edge_form(v, inc[i].fid, inc[i].key, cat, &self_pos);
+        finfo[i] = (uint8_t)(form | ((form != (int)FORM_GENERAL ? self_pos : 0) << 2));
+      }
+    }
+  });
 
   pt.lap("layout knobs");
   // ---- schedule order: colour-major; SELL graphs additionally sort each class by
@@ -446,7 +459,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
           uint32_t f = inc[i].fid;
           uint64_t n = raw.fac_ptr[f + 1] - raw.fac_ptr[f];
-          int form = edge_form(v, f, 0, false, nullptr);
+          int form = finfo[i] & 3;
           if (form == 0) { ++n_un; continue; }
           ++n_mu;
           ow += form == (int)FORM_GENERAL ? 1 + n : (uint64_t)form;
@@ -539,7 +552,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
         uint32_t f = inc[i].fid;
         uint64_t n = raw.fac_ptr[f + 1] - raw.fac_ptr[f];
-        int form = edge_form(v, f, inc[i].key, cat, nullptr);
+        int form = finfo[i] & 3;
         if (form == (int)FORM_GENERAL && n >= (g->oth_packed ? (1ull << 31) : U32_LIMIT) && B.bad_d == INVALID) {
           B.bad_d = d; B.msg = "factor arity too large";
         }
@@ -595,8 +608,8 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
           if (g->fv_mode == FV_F32) g->e_fv32[ei] = (float)raw.fac_fv[f];
           if (g->fv_mode == FV_F64) g->e_fv64[ei] = raw.fac_fv[f];
           uint8_t tag = (uint8_t)func_code(raw.fac_func[f]);
-          uint64_t self_pos = 0;
-          int form = edge_form(v, f, k, cat, &self_pos);
+          const uint64_t self_pos = finfo[i] >> 2;
+          int form = finfo[i] & 3;
           if (form != (int)FORM_GENERAL) {
             if (!cat && edense[a + self_pos] == 1) tag |= TAG_SELF_EQ1;
             if (self_pos == n - 1) tag |= TAG_SELF_HEAD;
