@@ -234,3 +234,25 @@ def test_compiled_image_does_not_depend_on_the_thread_count(shape, monkeypatch):
         assert meta == ref[1]
         for name in IMAGE_ARRAYS:
             assert img[name].dtype == ref[0][name].dtype and np.array_equal(img[name].view(np.uint8), ref[0][name].view(np.uint8)), (name, threads)
+
+
+def test_loader_blocks_match_in_memory_graph(tmp_path, monkeypatch):
+    """the file path (mmap, one thread walking the factor arities while the others decode blocks of
+    2^16 records, two factor files) builds the image the in-memory records build, with 1 and with 8
+    host threads"""
+    from sampler_b200 import graphgen
+    raw = graphgen.c2_boolean(120_000, nweight=64)
+    ref = sb.Graph.from_raw(raw, sb.SCHED_CHROMATIC)
+    paths = gio.write_binary(raw, str(tmp_path))
+    whole = open(paths["factors"], "rb").read()
+    cut = 0  # split the factor file at a record boundary, after 500 000 records
+    for _ in range(500_000):
+        cut += 26 + 16 * int.from_bytes(whole[cut + 2:cut + 10], "big")
+    open(paths["factors"] + ".a", "wb").write(whole[:cut])
+    open(paths["factors"] + ".b", "wb").write(whole[cut:])
+    for threads in ("1", "8"):
+        monkeypatch.setenv("DWG_COMPILE_THREADS", threads)
+        for files in ([paths["factors"]], [paths["factors"] + ".a", paths["factors"] + ".b"]):
+            g = sb.Graph.from_files(paths["meta"], [paths["variables"]], [], files, [paths["weights"]], sb.SCHED_CHROMATIC)
+            for name in IMAGE_ARRAYS:
+                assert np.array_equal(g.image(name), ref.image(name)), (name, threads, len(files))
