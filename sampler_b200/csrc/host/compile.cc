@@ -352,9 +352,63 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     // Pass 1, first fit, finds how many colours K the graph needs; pass 2 recolours with the
     // least-loaded admissible colour among those K, so that every class is large enough to
     // fill the GPU (first fit alone leaves a tail of tiny classes = latency-bound launches).
+    // Pass 1 in parallel wavefronts.  The first-fit colour of v depends only on the colours of its
+    // lower-numbered neighbours, so colouring v once all of those are coloured gives exactly the
+    // sequential result, whatever the interleaving: every round colours the pending variables that
+    // are ready (in id order inside each thread's range), the rest wait for the next round.  Graphs
+    // with long id-ordered dependency chains (v coupled to v+1) make little progress per round:
+    // the remainder is then finished sequentially.
+    {
+      std::fill(color.begin(), color.end(), 0xffffffffu);
+      auto first_fit = [&](uint32_t v, std::vector<uint32_t> &stamp) -> bool {  // false: not ready yet
+        for (uint64_t i = nb_ptr[v]; i < nb_ptr[v + 1]; ++i) {
+          const uint32_t u = nb[i];
+          const uint32_t c = __atomic_load_n(&color[u], __ATOMIC_ACQUIRE);
+          if (c == 0xffffffffu) {
+            if (u < v) return false;
+            continue;
+          }
+          if (c >= stamp.size()) stamp.resize(c + 2, 0);
+          stamp[c] = v + 1;
+        }
+        uint32_t c = 0;
+        while (c < stamp.size() && stamp[c] == v + 1) ++c;
+        __atomic_store_n(&color[v], c, __ATOMIC_RELEASE);
+        return true;
+      };
+      const unsigned T = host_threads();
+      std::vector<uint32_t> pending(nvar);
+      std::iota(pending.begin(), pending.end(), 0u);
+      while (!pending.empty()) {
+        if (T == 1 || pending.size() < (1u << 14)) {
+          std::vector<uint32_t> stamp(ncolor + 2, 0);
+          for (uint32_t v : pending) first_fit(v, stamp);  // in id order every variable is ready
+          break;
+        }
+        std::vector<std::vector<uint32_t>> later(T);
+        parallel_ranges(pending.size(), T, [&](uint64_t i0, uint64_t i1, unsigned t) {
+          std::vector<uint32_t> stamp(64, 0);
+          for (uint64_t i = i0; i < i1; ++i)
+            if (!first_fit(pending[i], stamp)) later[t].push_back(pending[i]);
+        });
+        std::vector<uint32_t> rest;
+        for (auto &l : later) rest.insert(rest.end(), l.begin(), l.end());  // still ascending
+        const bool stalled = rest.size() * 8 > pending.size() * 7;
+        pending.swap(rest);
+        if (stalled && !pending.empty()) {
+          std::vector<uint32_t> stamp(64, 0);
+          for (uint32_t v : pending) first_fit(v, stamp);
+          break;
+        }
+      }
+      uint32_t mx = 0;
+      for (uint64_t v = 0; v < nvar; ++v) mx = std::max(mx, color[v]);
+      ncolor = mx + 1;
+    }
+    // Pass 2 (sequential: the least-loaded choice depends on every earlier one)
     std::vector<uint32_t> stamp;  // stamp[c] == v+1 : colour c is taken by a neighbour of v
     std::vector<uint64_t> load;
-    for (int pass = 0; pass < 2; ++pass) {
+    {
       const uint32_t K = ncolor;
       std::fill(color.begin(), color.end(), 0xffffffffu);
       stamp.assign(K + 1, 0);
@@ -370,16 +424,11 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
           stamp[c] = (uint32_t)v + 1;
         }
         uint32_t c = 0xffffffffu;
-        if (pass == 0) {
-          c = 0;
+        for (uint32_t k = 0; k < K; ++k)
+          if (stamp[k] != (uint32_t)v + 1 && (c == 0xffffffffu || load[k] < load[c])) c = k;
+        if (c == 0xffffffffu) {  // every planned colour is taken around v: open a new one
+          c = K;
           while (c < stamp.size() && stamp[c] == (uint32_t)v + 1) ++c;
-        } else {
-          for (uint32_t k = 0; k < K; ++k)
-            if (stamp[k] != (uint32_t)v + 1 && (c == 0xffffffffu || load[k] < load[c])) c = k;
-          if (c == 0xffffffffu) {  // every planned colour is taken around v: open a new one
-            c = K;
-            while (c < stamp.size() && stamp[c] == (uint32_t)v + 1) ++c;
-          }
         }
         if (c + 1 >= stamp.size()) { stamp.resize(c + 2, 0); load.resize(c + 2, 0); }
         color[v] = c;
