@@ -256,3 +256,32 @@ def test_loader_blocks_match_in_memory_graph(tmp_path, monkeypatch):
             g = sb.Graph.from_files(paths["meta"], [paths["variables"]], [], files, [paths["weights"]], sb.SCHED_CHROMATIC)
             for name in IMAGE_ARRAYS:
                 assert np.array_equal(g.image(name), ref.image(name)), (name, threads, len(files))
+
+
+@pytest.mark.parametrize("shape", ["c2", "c3"])
+def test_large_chromatic_schedule_is_a_proper_colouring(shape, monkeypatch):
+    """the parallel wavefront first-fit pass + sequential balancing pass on graphs large enough to
+    split across threads (random couplings: c2; id-ordered chains, the stalled path: c3): no factor
+    joins two variables of one colour class, the classes are balanced, every variable is scheduled"""
+    from sampler_b200 import graphgen
+    monkeypatch.setenv("DWG_COMPILE_THREADS", "8")
+    raw = graphgen.c2_boolean(200_000, nweight=64) if shape == "c2" else graphgen.c3_categorical(60_000, nweight=64)
+    g = sb.Graph.from_raw(raw, sb.SCHED_CHROMATIC)
+    perm, cs = g.schedule()
+    nvar = len(raw.var_role)
+    color = np.full(nvar, -1, np.int64)
+    for c in range(len(cs) - 1):
+        members = perm[int(cs[c]):int(cs[c + 1])]
+        members = members[members != 0xFFFFFFFF].astype(np.int64)
+        color[members] = c
+    assert (color >= 0).all()
+    ptr = raw.fac_ptr.astype(np.int64)
+    arity = np.diff(ptr)
+    assert arity.max() <= 2
+    two = np.nonzero(arity == 2)[0]
+    a, b = raw.edge_vid[ptr[two]].astype(np.int64), raw.edge_vid[ptr[two] + 1].astype(np.int64)
+    distinct = a != b
+    assert (color[a[distinct]] != color[b[distinct]]).all(), "two variables of one factor share a colour"
+    sizes = np.bincount(color)
+    big = sizes[sizes > 0.01 * nvar]
+    assert big.max() <= 1.05 * big.min() + 64, sizes
