@@ -65,9 +65,9 @@ typedef struct dwg_opts {
   int schedule;            /* DWG_SCHED_*          */
   uint64_t seed;           /* counter-based RNG key (the reference: rand(), gibbs_sampler.cc:49) */
   uint32_t replica;        /* RNG stream of this replica (== nodeid, gibbs_sampler.h:34) */
-  int learn_chunks;        /* parallel schedules: weight updates per colour class and learning sweep
-                              (the class is swept in that many strided parts, the weights move after
-                              each); 0 = auto (about 32 updates per sweep) */
+  int learn_chunks;        /* categorical graphs (CSR learning kernels) only: batch weight updates per colour
+                              class and learning sweep; 0 = auto (about 32 updates per sweep).  Boolean
+                              graphs learn with live weights and ignore it */
 } dwg_opts_t;
 void dwg_opts_default(dwg_opts_t *o);
 
@@ -205,6 +205,9 @@ int dwg_debug_set_uniforms(dwg_handle *h, const double *r_free, const double *r_
 int dwg_debug_set_sequential(dwg_handle *h, int on);
 /* schedule order: perm[d] = original vid; color_start[num_colors+1] */
 int dwg_debug_schedule(const dwg_graph *g, uint64_t *perm, uint64_t *color_start);
+/* the order in which a LEARNING sweep of the parallel schedules visits the variables (slices in
+ * ascending id block; the sequential / CSR schedules: schedule order); perm[num_variables] */
+int dwg_debug_learn_order(const dwg_graph *g, uint64_t *perm, uint64_t *n_out);
 /* borrow one array of the compiled image by name ("row_ptr", "e_wid", "e_tag", "oth", ...) so
  * CPU tests can check the device layout without a device; *elem_size in bytes */
 int dwg_debug_image(const dwg_graph *g, const char *name, const void **data, uint64_t *count,

@@ -82,6 +82,7 @@ def load(build: bool = False):
     L.dwg_graph_info.argtypes = [vp, C.POINTER(GraphInfo)]
     L.dwg_graph_var_meta.argtypes = [vp, vp, vp, vp, vp]
     L.dwg_debug_schedule.argtypes = [vp, vp, vp]
+    L.dwg_debug_learn_order.argtypes = [vp, vp, vp]
     L.dwg_debug_image.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(u64), C.POINTER(C.c_uint32)]
     L.dwg_create.argtypes = [vp, C.POINTER(Opts), i32, C.POINTER(vp)]
     L.dwg_destroy.argtypes = [vp]
@@ -195,6 +196,14 @@ class Graph:
         cs = np.zeros(self.info.num_colors + 1, np.uint64)
         _check(load().dwg_debug_schedule(self._h, _ptr(perm), _ptr(cs)))
         return perm, cs
+
+    def learn_order(self) -> np.ndarray:
+        """original ids in the order a learning sweep of the parallel schedules visits them"""
+        perm = np.zeros(self.info.num_variables, np.uint64)
+        n = C.c_uint64()
+        _check(load().dwg_debug_learn_order(self._h, _ptr(perm), C.byref(n)))
+        assert n.value == len(perm)
+        return perm
 
 
 class Sampler:

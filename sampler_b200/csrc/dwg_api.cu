@@ -177,7 +177,7 @@ struct dwg_handle {
   bool explicit_r = false, sequential = false;
   // the last operation enqueued on the stream was a staged inference launch of this handle (the
   // next one may be a programmatic dependent launch); cleared by every other entry point
-  bool chain_open = false, learn_chain_open = false;
+  bool chain_open = false;
   uint64_t sweep_counter = 0, infer_sweeps = 0;
   std::vector<uint64_t> extra_nsamples;  // from dwg_add_tallies
   DevGraph dg{};
@@ -191,10 +191,12 @@ struct dwg_handle {
   int sell_blocks_staged = 0;
   // per colour class: the first slice from which every slice holds evidence / padding only
   // (slices are sorted non-evidence first inside a class, compile.cc)
-  std::vector<uint32_t> cls_query_end, cls_max_words;
-  // staged learning kernel: ring depth (0 = unavailable), stage capacity in words, grid cap
-  uint32_t learn_stages = 0, learn_stage_words = 0;
-  int sell_blocks_learn_staged = 0;
+  std::vector<uint32_t> cls_query_end;
+  // learning sweeps of sliced-ELL graphs (k_sell_learn_live): visit order, per-weight statistics
+  // in internal weight order (device: cls_N / cls_H; host: curvatures sorted for the epoch plan)
+  DevBuf<uint32_t> learn_visit;
+  std::vector<float> learn_H_sorted;   // curvature bounds of the learnable weights, ascending
+  double learn_rho = 1.0;              // coupling: learnable records per learning variable / 10
   size_t device_bytes = 0;
   // tally download: device row of every (variable, value) in ABI order (uploaded with the graph) and
   // the gathered tallies; the page-locked landing pieces are the process's (g_landing)
@@ -223,28 +225,14 @@ int sell_setup_t(dwg_handle *h) {
   const size_t n_hot = h->img->n_hot;
   int rc = sell_grid(k_sell_infer<MULTI, FV>, 8 * n_hot, h->num_sms, &h->sell_blocks_infer);
   if (rc) return rc;
-  rc = sell_grid(k_sell_learn<MULTI, FV>, 16 * n_hot, h->num_sms, &h->sell_blocks_learn);
+  rc = sell_grid(k_sell_learn_live<MULTI, FV>, sell_learn_smem((uint32_t)n_hot), h->num_sms, &h->sell_blocks_learn,
+                 SELL_LEARN_THREADS);
   if (rc) return rc;
-  // staged (bulk-async) kernels: ring geometry for this graph
+  // staged (bulk-async) inference kernel: ring geometry for this graph
   h->sell_stages = 0;
-  h->learn_stages = 0;
   const char *direct = getenv("DWG_SELL_DIRECT");
   if (direct && *direct == '1') return DWG_OK;
   size_t budget = 112 * 1024;  // per CTA, two per SM out of 228 KB (1 KB reserved each)
-  {  // learning: two stages of whatever fits beside the weight and gradient tables; classes whose
-     // longest slice does not fit a stage take the direct kernel (launch_sweep)
-    const size_t fixed = sell_learn_ring_off((uint32_t)n_hot, 2);
-    if (fixed + (SELL_LEARN_STAGED_THREADS / 32) * 2 * 4 * 64 <= budget) {
-      uint32_t cap = (uint32_t)((budget - fixed) / ((SELL_LEARN_STAGED_THREADS / 32) * 2 * 4)) & ~3u;
-      if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) cap = std::min<uint32_t>(cap, std::max(8, atoi(e)) & ~3u);  // tests
-      const uint32_t words = std::min(cap, (h->img->sell_max_words + 3u) & ~3u);
-      rc = sell_grid(k_sell_learn_staged<MULTI, FV>, sell_learn_smem((uint32_t)n_hot, 2, words), h->num_sms,
-                     &h->sell_blocks_learn_staged, SELL_LEARN_STAGED_THREADS);
-      if (rc) return rc;
-      h->learn_stages = 2;
-      h->learn_stage_words = words;
-    }
-  }
   // measured on C2 / C5 (profiles/r1_v4_ab.txt): with neighbour gathers in the loop two deep stages
   // beat three or four shallow ones (a deeper prefetch queues the latency-critical L2 gathers behind
   // bulk traffic), unary-only graphs gain from the deeper ring
@@ -287,12 +275,11 @@ int sell_setup_t(dwg_handle *h) {
   return DWG_OK;
 }
 template <bool MULTI, int FV>
-// staged: the bulk-async kernel of the sweep kind (inference / learning); pdl: programmatic
-// dependent launch behind the previous inference launch
-void sell_launch_t(dwg_handle *h, bool learn, bool staged, bool pdl, uint32_t blocks, const SellGraph &sg,
-                   const SweepParams &p) {
+// staged: the bulk-async inference kernel; pdl: programmatic dependent launch behind the previous
+// inference launch
+void sell_launch_t(dwg_handle *h, bool staged, bool pdl, uint32_t blocks, const SellGraph &sg, const SweepParams &p) {
   const size_t n_hot = h->img->n_hot;
-  if (staged && !learn) {
+  if (staged) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(h->sell_staged_warps * 32);
     cfg.dynamicSmemBytes = sell_staged_smem(sg.n_tab, h->sell_stages, h->sell_stage_words, h->sell_staged_warps);
@@ -308,19 +295,11 @@ void sell_launch_t(dwg_handle *h, bool learn, bool staged, bool pdl, uint32_t bl
     if (h->sell_staged_warps == 16) { if (allhot) STAGED_LAUNCH(true, 512); else STAGED_LAUNCH(false, 512); }
     else { if (allhot) STAGED_LAUNCH(true, 256); else STAGED_LAUNCH(false, 256); }
 #undef STAGED_LAUNCH
-  } else if (learn && staged) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(SELL_LEARN_STAGED_THREADS);
-    cfg.dynamicSmemBytes = sell_learn_smem((uint32_t)n_hot, h->learn_stages, h->learn_stage_words);
-    cfg.stream = h->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;  // only behind the k_apply_weights of another staged learning launch
-    cudaLaunchKernelEx(&cfg, k_sell_learn_staged<MULTI, FV>, sg, h->ss, p, h->learn_stages, h->learn_stage_words);
-  } else if (learn) k_sell_learn<MULTI, FV><<<blocks, SELL_THREADS, 16 * n_hot, h->stream>>>(sg, h->ss, p);
-  else k_sell_infer<MULTI, FV><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
+  } else k_sell_infer<MULTI, FV><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
+}
+template <bool MULTI, int FV>
+void sell_learn_launch_t(dwg_handle *h, uint32_t blocks, uint32_t threads, const SweepParams &p, const SellLearn &L) {
+  k_sell_learn_live<MULTI, FV><<<blocks, threads, sell_learn_smem(h->img->n_hot), h->stream>>>(h->sg, h->ss, p, L);
 }
 #define SELL_SWITCH(CALL)                                                      \
   if (m.has_multi) {                                                           \
@@ -340,10 +319,15 @@ int sell_setup(dwg_handle *h) {
 #undef CALL
   return rc;
 }
-void sell_launch(dwg_handle *h, bool learn, bool staged, bool pdl, uint32_t blocks, const SellGraph &sg,
-                 const SweepParams &p) {
+void sell_launch(dwg_handle *h, bool staged, bool pdl, uint32_t blocks, const SellGraph &sg, const SweepParams &p) {
   const GraphImage &m = *h->img;
-#define CALL(MU, FV) sell_launch_t<MU, FV>(h, learn, staged, pdl, blocks, sg, p)
+#define CALL(MU, FV) sell_launch_t<MU, FV>(h, staged, pdl, blocks, sg, p)
+  SELL_SWITCH(CALL)
+#undef CALL
+}
+void sell_learn_launch(dwg_handle *h, uint32_t blocks, uint32_t threads, const SweepParams &p, const SellLearn &L) {
+  const GraphImage &m = *h->img;
+#define CALL(MU, FV) sell_learn_launch_t<MU, FV>(h, blocks, threads, p, L)
   SELL_SWITCH(CALL)
 #undef CALL
 }
@@ -487,6 +471,28 @@ int dwg_debug_schedule(const dwg_graph *g, uint64_t *perm, uint64_t *color_start
   return DWG_OK;
 }
 
+int dwg_debug_learn_order(const dwg_graph *g, uint64_t *perm, uint64_t *n_out) {
+  if (!g) return fail(DWG_ERR_INVALID, "null argument");
+  const GraphImage &m = g->img;
+  uint64_t k = 0;
+  if (m.sell) {
+    for (uint32_t sl : m.learn_visit)
+      for (uint64_t d = (uint64_t)sl * 32; d < (uint64_t)sl * 32 + 32; ++d)
+        if (m.perm[d] != 0xffffffffu) {
+          if (perm) perm[k] = m.perm[d];
+          ++k;
+        }
+  } else {
+    for (uint64_t d = 0; d < m.nvar_pad; ++d)
+      if (m.perm[d] != 0xffffffffu) {
+        if (perm) perm[k] = m.perm[d];
+        ++k;
+      }
+  }
+  if (n_out) *n_out = k;
+  return DWG_OK;
+}
+
 int dwg_debug_image(const dwg_graph *g, const char *name, const void **data, uint64_t *count,
                     uint32_t *elem_size) {
   if (!g || !name || !data || !count || !elem_size) return fail(DWG_ERR_INVALID, "null argument");
@@ -501,7 +507,7 @@ int dwg_debug_image(const dwg_graph *g, const char *name, const void **data, uin
   ARR(perm) ARR(inv) ARR(color_start) ARR(var_flags) ARR(evid_val) ARR(var_row) ARR(row_ptr)
   ARR(row_oth) ARR(truthiness) ARR(e_wid) ARR(e_fv32) ARR(e_fv64) ARR(e_tag) ARR(oth) ARR(w_init)
   ARR(w_fixed) ARR(row_of_value) ARR(values) ARR(value_base) ARR(w_perm) ARR(w_inv)
-  ARR(sl_off) ARR(blob)
+  ARR(sl_off) ARR(blob) ARR(learn_visit)
   ARR(cls_N_evid) ARR(cls_Q_evid) ARR(cls_N_all) ARR(cls_Q_all) ARR(cls_H_evid) ARR(cls_H_all)
 #undef ARR
   if (n == "oth_packed") {
@@ -621,8 +627,21 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
   if (m.sell) {
     CU(h->sl_off.upload(m.sl_off, s));
     CU(h->blob.upload(m.blob, s));
+    CU(h->learn_visit.upload(m.learn_visit, s));
     // Boolean variables have no truthiness: under --noise_aware only --learn_non_evidence learns
     h->learns = h->opts.learn_non_evidence || !h->opts.noise_aware;
+    // the epoch plan of launch_learn_sell: curvature bounds of the learnable weights, sorted, and
+    // the coupling factor (SGD steps of one variable move all its weights together)
+    const bool all = h->opts.learn_non_evidence;
+    const std::vector<float> &N = all ? m.cls_N_all : m.cls_N_evid, &H = all ? m.cls_H_all : m.cls_H_evid;
+    double updates = 0;
+    for (uint64_t i = 0; i < m.nweight; ++i) {
+      updates += N[i];
+      if (H[i] > 0) h->learn_H_sorted.push_back(H[i]);
+    }
+    std::sort(h->learn_H_sorted.begin(), h->learn_H_sorted.end());
+    const double learners = (double)std::max<uint64_t>(1, all ? m.nvar : m.nvar_evid);
+    h->learn_rho = std::max(1.0, updates / learners / 10.0);
   }
   lap("allocations + copies queued");
   int rc = init_state(h.get());
@@ -657,7 +676,6 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     rc = sell_setup(h.get());
     if (rc) return rc;
     h->cls_query_end = g->query_end();
-    h->cls_max_words = g->cls_max_words;
   }
   lap("kernel setup");
   *out = h.release();
@@ -692,6 +710,88 @@ static SweepParams make_params(dwg_handle *h, double stepsize) {
   return p;
 }
 
+static double env_double(const char *name, double dflt) {
+  const char *e = getenv(name);
+  return e && *e ? atof(e) : dflt;
+}
+
+// One learning sweep of a sliced-ELL graph (k_sell_learn_live, dwg_sell.cuh): the plan of the epoch.
+//   H_k   curvature bound of weight k over a sweep (sum of 1/4 (|feature| x sign range)^2 over its
+//         learnable records): stepsize x H_k = relaxation times weight k goes through per sweep
+//   x_k   = stepsize x H_k x rho x (slices in flight / slices): step mass in flight; a weight keeps
+//         the reference's step while x_k <= cap, beyond that its step is scaled by cap / x_k
+// The tail (the last c relaxation times of the median fast weight, at least 12 rounds) runs on as
+// few warps as keep the 90th-percentile weight at x <= cap with s = 1; the head runs on every SM.
+// A sweep short enough for the narrow grid (<= rounds_max rounds) is all tail.
+static int launch_learn_sell(dwg_handle *h, SweepParams &p, double stepsize) {
+  const GraphImage &m = *h->img;
+  const uint32_t nslice = (uint32_t)m.learn_visit.size();
+  if (!nslice) return DWG_OK;
+  const double cap = env_double("DWG_LEARN_XCAP", 0.25), tail_c = env_double("DWG_LEARN_TAILC", 3.0);
+  const uint32_t rounds_max = (uint32_t)env_double("DWG_LEARN_ROUNDS", 96), period_wide = (uint32_t)env_double("DWG_LEARN_PERIOD", 4);
+  const uint32_t max_warps = (uint32_t)h->sell_blocks_learn * (SELL_LEARN_THREADS / 32);
+  const std::vector<float> &Hs = h->learn_H_sorted;
+  const double a = stepsize > 0 ? stepsize : 0.0, rho = h->learn_rho;
+  // warps that keep weight curvature H at x <= cap with one slice per warp in flight
+  auto narrow_warps = [&](double H) -> uint32_t {
+    if (!(a * H * rho > 0)) return max_warps;
+    return (uint32_t)std::max(1.0, std::min((double)max_warps, std::floor(cap * nslice / (a * H * rho))));
+  };
+  // A learning sweep is Hogwild across colour classes (like the reference's threads): the slices in
+  // flight must stay a small part of the graph, or neighbouring variables are resampled in lockstep
+  // from each other's old values (synchronous Gibbs: on a strongly coupled graph the free chain
+  // then never settles).  At most 1/16 of the slices on the narrow grid, 1/4 on the wide one.
+  const uint32_t narrow_max = std::max(1u, nslice / 16), wide_warps = std::max(1u, std::min(max_warps, nslice / 4));
+  uint32_t tail_slices = 0, tail_warps = std::min(max_warps, narrow_max);
+  if (const char *e = getenv("DWG_LEARN_WARPS")) {  // tests: 1 = one warp walks the visit order slice by slice
+    tail_slices = nslice;
+    tail_warps = (uint32_t)std::max(1, atoi(e));
+  } else if (h->learns && !Hs.empty() && a > 0) {
+    const size_t n = Hs.size();
+    const uint32_t g_all = std::min(narrow_max, narrow_warps(Hs[(size_t)(0.9 * (n - 1))]));
+    if ((nslice + g_all - 1) / g_all <= rounds_max) {
+      tail_slices = nslice; tail_warps = g_all;  // short sweep: all of it at the reference's step
+    } else {
+      const size_t lo = std::lower_bound(Hs.begin(), Hs.end(), (float)(1.0 / a)) - Hs.begin();  // fast: stepsize x H > 1
+      if (lo < n) {
+        const double h_med = Hs[lo + (n - lo) / 2], h_ref = Hs[lo + (size_t)(0.9 * (n - 1 - lo))];
+        tail_warps = std::min(narrow_max, narrow_warps(h_ref));
+        const double f = std::min(1.0, tail_c / (a * h_med));
+        tail_slices = (uint32_t)std::min<double>(nslice, std::max(std::ceil(f * nslice), 12.0 * tail_warps));
+        tail_warps = std::max(1u, std::min(tail_warps, tail_slices / 12u));
+      }
+    }
+  }
+  SellLearn L{};
+  L.visit = h->learn_visit.p;
+  L.step = a;
+  L.decay = !h->learns ? 0.0 : p.reg_l1 ? h->opts.reg_param : h->opts.reg_param * a;
+  L.inv_nslice = 1.0 / nslice;
+  L.reg_l1 = p.reg_l1;
+  L.w_N = h->cls_N.p; L.w_H = h->cls_H.p;
+  L.weights = h->weights.p;
+  auto launch = [&](uint32_t vb, uint32_t ve, uint32_t warps, uint32_t period) {
+    if (ve <= vb) return;
+    const uint32_t wpc = SELL_LEARN_THREADS / 32;
+    warps = std::max(1u, std::min(warps, ve - vb));
+    uint32_t threads = SELL_LEARN_THREADS, blocks = warps / wpc;
+    if (warps < wpc) { threads = warps * 32; blocks = 1; }
+    const uint32_t grid_warps = blocks * (threads / 32);
+    L.vbegin = vb; L.vend = ve; L.period = std::max(1u, period);
+    const double inflight = std::min(1.0, (double)grid_warps * L.period / nslice);
+    // one warp cannot be narrowed further: it keeps the reference's step whatever x is
+    L.xcap_inv = grid_warps == 1 ? 0.0 : a * rho * inflight / cap;
+    sell_learn_launch(h, blocks, threads, p, L);
+    ++g_launches;
+  };
+  launch(0, nslice - tail_slices, wide_warps, period_wide);
+  launch(nslice - tail_slices, nslice, tail_warps, 1);
+  if (getenv("DWG_TIMING"))
+    fprintf(stderr, "[learn] step %.4g: %u slices, head %u on %u warps (period %u), tail %u on %u warps\n", a, nslice,
+            nslice - tail_slices, wide_warps, period_wide, tail_slices, tail_warps);
+  return DWG_OK;
+}
+
 static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
@@ -702,52 +802,48 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
     int rc = ensure_csr(h);
     if (rc) return rc;
   }
+  if (use_sell && learn) {
+    h->chain_open = false;
+    int rc = launch_learn_sell(h, p, stepsize);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    return DWG_OK;
+  }
   for (uint32_t c = 0; c < m.ncolor(); ++c) {
     p.d_begin = m.color_start[c];
     p.d_end = m.color_start[c + 1];
     const uint32_t n = p.d_end - p.d_begin;
     if (!n) continue;
     const uint32_t units = (n + 31) / 32;  // 32-variable units (= slices of the sliced-ELL stream)
-    // a learning sweep of a class runs as `chunks` strided parts with a weight update after each
+    // CSR (categorical) learning: a sweep of a class runs as `chunks` strided parts with a batch
+    // weight update (k_apply_weights) after each
     uint32_t chunks = 1;
     if (learn && !p.sequential) {
-      // auto: ~32 weight updates per sweep, shared out by class size (a class of a few hundred
-      // variables -- the overflow class of the balanced colouring -- gets one launch, not six)
       chunks = h->opts.learn_chunks > 0
                    ? (uint32_t)h->opts.learn_chunks
                    : (uint32_t)std::llround(32.0 * (double)n / (double)std::max<uint64_t>(1, m.nvar_pad));
       chunks = std::max(1u, std::min(chunks, units));
     }
     for (uint32_t b = 0; b < chunks; ++b) {
-      bool chained_apply = false;  // k_apply_weights as a dependent launch of a staged learning launch
       const uint32_t my_units = (units - b + chunks - 1) / chunks;
       p.unit_stride = chunks;
       p.unit_phase = b;
       if (use_sell) {
         SellGraph sg = h->sg;
-        sg.slice_begin = p.d_begin / 32 + b;
+        sg.slice_begin = p.d_begin / 32;
         sg.slice_end = p.d_end / 32;
-        sg.slice_stride = chunks;
-        uint32_t n_sl = my_units;
-        if (!learn && !p.sample_evidence) {  // gibbs_sampler.h:157: the evidence tail of the class is not read at all
-          sg.slice_end = h->cls_query_end[c];
-          n_sl = sg.slice_end - sg.slice_begin;
-          if (!n_sl) continue;
-        }
-        const bool staged = !learn && h->sell_stages;
-        const bool learn_staged = learn && h->learn_stages && h->cls_max_words[c] <= h->learn_stage_words;
-        const uint32_t wpb = staged ? h->sell_staged_warps : learn_staged ? SELL_LEARN_STAGED_THREADS / 32 : SELL_THREADS / 32;
+        sg.slice_stride = 1;
+        if (!p.sample_evidence) sg.slice_end = h->cls_query_end[c];  // gibbs_sampler.h:157: the evidence tail of the class is not read at all
+        const uint32_t n_sl = sg.slice_end - sg.slice_begin;
+        if (!n_sl) continue;
+        const bool staged = h->sell_stages != 0;
+        const uint32_t wpb = staged ? h->sell_staged_warps : SELL_THREADS / 32;
         const uint32_t need = (n_sl + wpb - 1) / wpb;
-        const uint32_t cap = (uint32_t)(staged ? h->sell_blocks_staged : learn_staged ? h->sell_blocks_learn_staged
-                                        : learn ? h->sell_blocks_learn : h->sell_blocks_infer);
-        // programmatic dependent launch: behind the previous colour class of an inference run, or
-        // behind the k_apply_weights of the previous staged learning launch
-        const bool pdl = !getenv("DWG_SELL_NO_PDL") &&
-                         ((staged && h->chain_open) || (learn_staged && h->learn_chain_open));
-        sell_launch(h, learn, staged || learn_staged, pdl, std::min<uint32_t>(need, cap), sg, p);
+        const uint32_t cap = (uint32_t)(staged ? h->sell_blocks_staged : h->sell_blocks_infer);
+        // programmatic dependent launch behind the previous colour class of an inference run
+        const bool pdl = !getenv("DWG_SELL_NO_PDL") && staged && h->chain_open;
+        sell_launch(h, staged, pdl, std::min<uint32_t>(need, cap), sg, p);
         h->chain_open = staged;
-        h->learn_chain_open = false;
-        chained_apply = learn_staged && !getenv("DWG_SELL_NO_PDL");
       } else {
         uint32_t blocks = (my_units * 32 + SWEEP_THREADS - 1) / SWEEP_THREADS;
         uint32_t threads = SWEEP_THREADS;
@@ -761,23 +857,13 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
         }
       }
       ++g_launches;
-      if (learn && !p.sequential && m.nweight && (!use_sell || h->learns)) {
-        // integrate this launch's SGD steps (k_apply_weights): the sliced-ELL kernel sums bare
-        // gradients (decay from the static update counts), the CSR kernel sums gradient + decay
+      if (learn && !p.sequential && m.nweight) {
+        // integrate this launch's SGD steps (k_apply_weights): the CSR kernel sums gradient + decay
         const size_t row = m.cls_shared ? 0 : (size_t)c * m.nweight;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((uint32_t)((m.nweight + 255) / 256)); cfg.blockDim = dim3(256);
-        cfg.stream = h->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = chained_apply ? 1 : 0;
-        cudaLaunchKernelEx(&cfg, k_apply_weights, h->weights.p, h->grad_acc.p, (const float *)(h->cls_N.p + row),
-                           (const float *)(h->cls_Q.p + row), (const float *)(h->cls_H.p + row),
-                           (const uint8_t *)h->w_fixed.p, (uint32_t)m.nweight, stepsize, h->opts.reg_param,
-                           (int)p.reg_l1, use_sell ? 0 : 1, (double)my_units / (double)units);
-        h->learn_chain_open = chained_apply;
+        k_apply_weights<<<(uint32_t)((m.nweight + 255) / 256), 256, 0, h->stream>>>(
+            h->weights.p, h->grad_acc.p, (const float *)(h->cls_N.p + row), (const float *)(h->cls_Q.p + row),
+            (const float *)(h->cls_H.p + row), (const uint8_t *)h->w_fixed.p, (uint32_t)m.nweight, stepsize,
+            h->opts.reg_param, (int)p.reg_l1, 1, (double)my_units / (double)units);
         ++g_launches;
       }
     }
@@ -808,14 +894,14 @@ int dwg_infer_epochs(dwg_handle *h, uint64_t n) {
 
 int dwg_sync(dwg_handle *h) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   return DWG_OK;
 }
 
 void *dwg_stream(dwg_handle *h) {
-  if (h) h->chain_open = h->learn_chain_open = false;  // the caller may enqueue anything behind our launches
+  if (h) h->chain_open = false;  // the caller may enqueue anything behind our launches
   return h ? (void *)h->stream : nullptr;
 }
 void *dwg_weights_device_ptr(dwg_handle *h) { return h ? (void *)h->weights.p : nullptr; }
@@ -823,7 +909,7 @@ void *dwg_tallies_device_ptr(dwg_handle *h) { return h ? (void *)h->tallies.p : 
 
 int dwg_clear_tallies(dwg_handle *h) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   CU(cudaSetDevice(h->device));
   CU(cudaMemsetAsync(h->tallies.p, 0, 4 * h->img->ndrow, h->stream));
   h->infer_sweeps = 0;
@@ -833,7 +919,7 @@ int dwg_clear_tallies(dwg_handle *h) {
 
 int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   const bool timing = getenv("DWG_TIMING") != nullptr;
@@ -897,7 +983,7 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
 
 int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsamples) {
   if (!h || !tallies || !nsamples) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<uint32_t> t(m.ndrow, 0);
@@ -916,7 +1002,7 @@ int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsam
 
 int dwg_get_weights(dwg_handle *h, double *out) {
   if (!h || !out) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<double> t(m.nweight);
@@ -928,7 +1014,7 @@ int dwg_get_weights(dwg_handle *h, double *out) {
 
 int dwg_set_weights(dwg_handle *h, const double *in) {
   if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<double> t(m.nweight);
@@ -941,7 +1027,7 @@ int dwg_set_weights(dwg_handle *h, const double *in) {
 
 int dwg_set_weight_sum(dwg_handle *h, const double *in) {
   if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   std::vector<double> t(m.nweight);
@@ -953,7 +1039,7 @@ int dwg_set_weight_sum(dwg_handle *h, const double *in) {
 
 int dwg_get_assignments(dwg_handle *h, int evid_chain, uint64_t *out) {
   if (!h || !out) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   const void *src = evid_chain ? h->ds.assign_evid : h->ds.assign_free;
@@ -973,7 +1059,7 @@ int dwg_get_assignments(dwg_handle *h, int evid_chain, uint64_t *out) {
 
 int dwg_set_assignments(dwg_handle *h, int evid_chain, const uint64_t *in) {
   if (!h || !in) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   void *dst = evid_chain ? h->ds.assign_evid : h->ds.assign_free;
@@ -993,7 +1079,7 @@ int dwg_set_assignments(dwg_handle *h, int evid_chain, const uint64_t *in) {
 
 int dwg_finish_weight_average(dwg_handle *h, int n_replicas, double *lmax, double *l2) {
   if (!h || n_replicas < 1) return fail(DWG_ERR_INVALID, "bad argument");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   const uint32_t n = (uint32_t)h->img->nweight;
   CU(cudaSetDevice(h->device));
   CU(cudaMemsetAsync(h->norms.p, 0, 16, h->stream));
@@ -1079,7 +1165,7 @@ int dwg_comm_destroy(void *comm) {
 
 int dwg_average_weights_nccl(dwg_handle *h, void *comm, int n_replicas, double *lmax, double *l2) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   if (n_replicas > 1) {
     if (!comm) return fail(DWG_ERR_INVALID, "null communicator");
     NcclApi &api = nccl();
@@ -1157,7 +1243,7 @@ int dwg_reduce_tallies_multi(dwg_handle *const *hs, void *const *comms, int n) {
 int dwg_eval_potentials(dwg_handle *h, uint64_t n, const uint64_t *vids, const uint64_t *proposals,
                         int evid_chain, double *out) {
   if (!h || !vids || !proposals || !out) return fail(DWG_ERR_INVALID, "null argument");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   {
@@ -1229,7 +1315,7 @@ int dwg_logadd(int device, uint64_t n, const double *a, const double *b, double 
 
 int dwg_debug_set_uniforms(dwg_handle *h, const double *r_free, const double *r_evid) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   if (!r_free) { h->explicit_r = false; return DWG_OK; }
@@ -1248,7 +1334,7 @@ int dwg_debug_set_uniforms(dwg_handle *h, const double *r_free, const double *r_
 
 int dwg_debug_set_sequential(dwg_handle *h, int on) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
-  h->chain_open = h->learn_chain_open = false;
+  h->chain_open = false;
   h->sequential = on != 0;
   return DWG_OK;
 }

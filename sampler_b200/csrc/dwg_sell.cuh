@@ -3,11 +3,10 @@
 //
 //   k_sell_infer_staged  GibbsSamplerThread::sample   (src/gibbs_sampler.cc:65-69,
 //   k_sell_infer                                        src/gibbs_sampler.h:151-169,192-215)
-//   k_sell_learn_staged  GibbsSamplerThread::sample_sgd (src/gibbs_sampler.cc:71-75,
-//   k_sell_learn           src/gibbs_sampler.h:127-149,171-190; sgd_on_variable/-factor,
-//                          src/factor_graph.cc:243-314)
-//   k_apply_weights      the weight update of one learning launch (update_weight,
-//                          src/inference_result.h:66-85, as a semi-implicit mini-batch step)
+//   k_sell_learn_live    GibbsSamplerThread::sample_sgd (src/gibbs_sampler.cc:71-75,
+//                          src/gibbs_sampler.h:127-149,171-190; sgd_on_variable/-factor,
+//                          src/factor_graph.cc:243-314; update_weight, src/inference_result.h:66-85)
+//   k_apply_weights      the batch weight update of the CSR (categorical) learning launches
 //
 // Memory behaviour (HBM-bound by design): a slice is one contiguous run of words, read exactly
 // once per sweep.  The *_staged kernels (the default) move it with one 1-D bulk-async copy
@@ -93,13 +92,25 @@ __device__ __forceinline__ double sell_fv(const uint32_t *sec, uint32_t ncol, ui
   return 1.0;
 }
 
+// chain value of another variable: a learning sweep is Hogwild (the variable may be resampled by
+// another SM during the launch), so it reads L2; a colour class of an inference sweep never
+// writes what it gathers
+template <int LD>
+__device__ __forceinline__ uint32_t sell_chain(const uint8_t *a, uint32_t d) {
+  return LD == LD_CACHED ? (uint32_t)__ldcg(a + d) : (uint32_t)a[d];
+}
+
 // sign code (0,1,2) -> the term  sign * t  with t = weight * feature value
 __device__ __forceinline__ double sell_term(uint32_t code, double t) {
   return code == 2u ? t : (code == 0u ? -t : 0.0);
 }
 
+// LD_CACHED marks a learning sweep: its weights beyond the shared-memory copy are LIVE (other CTAs
+// move them with atomics while the launch runs), so they are read from L2, not through the
+// non-coherent path
+template <int LD>
 __device__ __forceinline__ double sell_weight(const SellGraph &g, const double *w_s, const double *w, uint32_t wid) {
-  return wid < g.n_hot ? w_s[wid] : __ldg(w + wid);
+  return wid < g.n_hot ? w_s[wid] : (LD == 0 ? __ldcg(w + wid) : __ldg(w + wid));
 }
 
 __device__ __forceinline__ void sell_stage_weights(const SellGraph &g, const double *w, double *w_s) {
@@ -135,7 +146,7 @@ __device__ __forceinline__ void sell_unary(const SellGraph &g, const SliceHeader
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const double wt = sell_weight(g, w_s, w, sell_unary_wid(rec[u]));
+      const double wt = sell_weight<LD>(g, w_s, w, sell_unary_wid(rec[u]));
       const double t = FV == FV_ONE ? wt : __dmul_rn(wt, fv[u]);  // w * (+-1 * fv) == +-(w * fv) exactly
       pos = __dadd_rn(pos, sell_term(rec[u] & 3u, t));
       if (!ANTISYM) neg = __dadd_rn(neg, sell_term(rec[u] >> 26, t));
@@ -159,7 +170,7 @@ __device__ __forceinline__ void sell_general_signs(const SliceHeader &h, uint32_
     bool head_oth = false;
     for (uint32_t j = 0; j < form; ++j) {
       const uint32_t w = sell_ld<LD>(o + (size_t)(oc + j) * 32);
-      const bool s = (uint32_t)a[w >> 1] == (w & 1u);
+      const bool s = sell_chain<LD>(a, w >> 1) == (w & 1u);
       if (!self_head && j == form - 1) head_oth = s;
       else nsb += s;
     }
@@ -181,7 +192,7 @@ __device__ __forceinline__ void sell_general_signs(const SliceHeader &h, uint32_
     const uint32_t d = w >> 1, eq = w & 1u;
     bool t0, t1;
     if (d == self) { t0 = eq == 0u; t1 = eq == 1u; }
-    else { t0 = t1 = (uint32_t)a[d] == eq; }
+    else { t0 = t1 = sell_chain<LD>(a, d) == eq; }
     if (i == n - 1) { h0 = t0; h1 = t1; }
     else { nsb0 += t0; nsb1 += t1; }
   }
@@ -206,7 +217,7 @@ __device__ __forceinline__ void sell_general_multi(const SellGraph &g, const Sli
     const uint32_t rec = sell_ld<LD>(h.mu + (size_t)32 * j + lane);
     const uint32_t tag = rec >> 24;
     if ((tag >> TAG_FORM_SHIFT) == 0) continue;  // padding
-    const double wt = sell_weight(g, w_s, w, rec & SELL_WID_MASK);
+    const double wt = sell_weight<LD>(g, w_s, w, rec & SELL_WID_MASK);
     const double fv = sell_fv<FV, LD>(h.mu, h.n_mu, j, lane);
     double s0, s1;
     sell_general_signs<LD>(h, tag, self, lane, oc, a, s0, s1);
@@ -232,10 +243,11 @@ __device__ __forceinline__ void sell_binary_load(const SliceHeader &h, uint32_t 
 }
 
 // bit u: the other variable of record u satisfies its equal_to on chain `a`
+template <int LD>
 __device__ __forceinline__ uint32_t sell_binary_sat(const BinaryChunk &c, const uint8_t *a) {
   uint32_t av[SELL_MCHUNK], sat = 0;
 #pragma unroll
-  for (int u = 0; u < SELL_MCHUNK; ++u) av[u] = a[c.ow[u] >> 1];
+  for (int u = 0; u < SELL_MCHUNK; ++u) av[u] = sell_chain<LD>(a, c.ow[u] >> 1);
 #pragma unroll
   for (int u = 0; u < SELL_MCHUNK; ++u) sat |= (av[u] == (c.ow[u] & 1u) ? 1u : 0u) << u;
   return sat;
@@ -247,7 +259,7 @@ __device__ __forceinline__ void sell_binary_acc(const SellGraph &g, const SliceH
                                                 const BinaryChunk &c, uint32_t sat, double &pos, double &neg) {
 #pragma unroll
   for (int u = 0; u < SELL_MCHUNK; ++u) {
-    const double wt = sell_weight(g, w_s, w, c.rec[u] & SELL_WID_MASK);
+    const double wt = sell_weight<LD>(g, w_s, w, c.rec[u] & SELL_WID_MASK);
     double t = wt;
     if (FV != FV_ONE) t = __dmul_rn(wt, j0 + u < h.n_mu ? sell_fv<FV, LD>(h.mu, h.n_mu, j0 + u, lane) : 0.0);
     const uint32_t tab = (c.rec[u] >> 24) >> (2u * ((sat >> u) & 1u));
@@ -266,11 +278,11 @@ __device__ __forceinline__ void sell_multi(const SellGraph &g, const SliceHeader
     BinaryChunk c;
     uint32_t sat;
     if (first) { c = *first; sat = first_sat; }
-    else { sell_binary_load<LD>(h, 0, lane, c); sat = sell_binary_sat(c, a); }
+    else { sell_binary_load<LD>(h, 0, lane, c); sat = sell_binary_sat<LD>(c, a); }
     sell_binary_acc<FV, LD>(g, h, w_s, w, 0, lane, c, sat, pos, neg);
     for (uint32_t j0 = SELL_MCHUNK; j0 < h.n_mu; j0 += SELL_MCHUNK) {
       sell_binary_load<LD>(h, j0, lane, c);
-      sat = sell_binary_sat(c, a);
+      sat = sell_binary_sat<LD>(c, a);
       sell_binary_acc<FV, LD>(g, h, w_s, w, j0, lane, c, sat, pos, neg);
     }
   } else if (h.n_mu) {
@@ -293,7 +305,7 @@ __device__ __forceinline__ void sell_potentials(const SellGraph &g, const SliceH
   const bool binary = MULTI && (h.flags & SF_BINARY);
   if (binary) {
     sell_binary_load<LD>(h, 0, lane, c);
-    sat = sell_binary_sat(c, a);
+    sat = sell_binary_sat<LD>(c, a);
   }
   if (h.flags & SF_ANTISYM) sell_unary<FV, LD, true>(g, h, w_s, w, lane, pos, neg);
   else sell_unary<FV, LD, false>(g, h, w_s, w, lane, pos, neg);
@@ -638,12 +650,55 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
   }
 }
 
-// gradient of one SGD step into the launch's accumulators (hot weights: shared memory)
-__device__ __forceinline__ void sell_grad(const SellGraph &g, const SellState &st, double *acc_s, uint32_t wid,
+// ---- learning sweep (sample_sgd, src/gibbs_sampler.cc:71-75) --------------------------------
+// The reference's SGD is per sample: every variable moves its weights at once
+// (src/inference_result.h:66-85) and the next variable of the id-order scan draws with the moved
+// weights.  Two things follow (tests/sim/): (1) the learned weights weight the
+// variables visited LAST most (relaxation time 1/(stepsize x curvature) updates), so a sweep must
+// visit the variables in ascending id like the reference -- SellLearn::visit, slices in ascending
+// id block; (2) only about cap/stepsize updates of a weight may be in flight before its step has
+// to shrink to stay stable.  One kernel, launched twice per epoch by the host:
+//   wide  every SM, the head of the visit order: fast, steps of heavily shared weights scaled down
+//         (s_k = min(1, cap / (stepsize x in-flight curvature of k))); brings every weight near its
+//         fixed point and keeps both chains moving;
+//   tail  the last few relaxation times of the visit order on as few warps as the cap allows with
+//         s_k = 1: the reference's own recursion up to a Hogwild staleness of a few dozen updates
+//         (its -t N threads have N).
+// A CTA keeps a copy of the hot weights in shared memory and refreshes it from the live global
+// vector every `period` slices per warp: draws of a period see the weights as of its start,
+// gradients of the period are pre-summed in shared memory and pushed with one atomic per weight.
+struct SellLearn {
+  const uint32_t *visit;      // slice indices in learning order
+  uint32_t vbegin, vend;      // positions of this launch
+  uint32_t period;            // slices per warp between two refreshes of the CTA's weight copy
+  double step;                // stepsize of this epoch
+  double xcap_inv;            // (stepsize x in-flight fraction x coupling) / cap: s_k = min(1, 1 / (xcap_inv * H_k))
+  double decay;               // reg * step (l2) or reg (l1, sic: no stepsize, src/inference_result.h:77)
+  double inv_nslice;          // 1 / slices of the whole visit order
+  int reg_l1;
+  const float *w_N, *w_H;     // per weight: SGD updates / curvature bound of one whole sweep
+  double *weights;            // live
+};
+
+// step scale of weight k (1 = the reference's step)
+__device__ __forceinline__ double sell_step_scale(const SellLearn &L, uint32_t wid) {
+  const double x = L.xcap_inv * (double)__ldg(L.w_H + wid);
+  return x > 1.0 ? 1.0 / x : 1.0;
+}
+
+// gradient of one SGD step: hot weights into the CTA's accumulator of the period, others straight
+// into the live vector together with the step's decay (update_weight, src/inference_result.h:66-85)
+__device__ __forceinline__ void sell_grad(const SellGraph &g, const SellLearn &L, double *acc_s, uint32_t wid,
                                           bool fixed, double grad) {
-  if (grad == 0.0 || fixed) return;  // factor_graph.cc:247
-  if (wid < g.n_hot) atomicAdd(acc_s + wid, grad);
-  else atomicAdd(st.grad_acc + wid, grad);
+  if (fixed) return;  // factor_graph.cc:247
+  if (wid < g.n_hot) {
+    if (grad != 0.0) atomicAdd(acc_s + wid, grad);
+    return;
+  }
+  const double sc = sell_step_scale(L, wid), x = __ldcg(L.weights + wid);
+  const double dec = L.reg_l1 ? L.decay * (x < 0 ? 1.0 : 0.0) : -x * (L.decay * sc) / (1.0 + L.decay * sc);
+  const double d = dec - L.step * sc * grad;
+  if (d != 0.0) atomicAdd(L.weights + wid, d);
 }
 
 // The update of weight i after a learning launch (see k_apply_weights below for the scheme).
@@ -678,8 +733,9 @@ __device__ __forceinline__ void sell_apply_weight(uint32_t i, double *w, double 
 // launch's accumulators.  LD: where the slice is read from (HBM through L1, or a staged copy).
 template <bool MULTI, int FV, int LD>
 __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellState &st, const SweepParams &p,
-                                                 const SliceHeader &h, const double *w_s, double *acc_s,
-                                                 uint32_t lane, uint32_t d) {
+                                                 const SellLearn &L, const SliceHeader &h, const double *w_s,
+                                                 double *acc_s, uint32_t lane, uint32_t d) {
+  const bool cold = g.nweight > g.n_hot;  // weights outside the shared copy: their decay rides on every visited record
   const bool pad = (h.pad >> lane) & 1u, evid = (h.evid >> lane) & 1u;
   const uint32_t ev = (h.evval >> lane) & 1u;  // Variable::assignment_dense
   double r0, r1;
@@ -706,14 +762,14 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
   if (!__any_sync(0xffffffffu, learn)) return;
   // sgd_on_variable (factor_graph.cc:262-277): evidence_value = assignment_dense, free = pf.
   // grad = sign_free * fv - sign_evid * fv == (code_free - code_evid) * fv exactly.
-  if (__any_sync(0xffffffffu, learn && pf != ev)) {  // unary: same value on both chains = zero gradient
+  if (cold || __any_sync(0xffffffffu, learn && pf != ev)) {  // unary: same value on both chains = zero gradient
     for (uint32_t j = 0; j < h.n_un; ++j) {
       const uint32_t rec = sell_ld<LD>(h.un + (size_t)32 * j + lane);
-      if (!learn || pf == ev) continue;
+      if (!learn || rec == SELL_UNARY_NOP) continue;
       const int cf = (int)(pf ? rec & 3u : rec >> 26), ce = (int)(ev ? rec & 3u : rec >> 26);
-      if (cf == ce) continue;
-      sell_grad(g, st, acc_s, sell_unary_wid(rec), rec & SELL_UN_FIXED_BIT,
-                __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.un, h.n_un, j, lane)));
+      if (cf == ce && !cold) continue;
+      sell_grad(g, L, acc_s, sell_unary_wid(rec), rec & SELL_UN_FIXED_BIT,
+                cf == ce ? 0.0 : __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.un, h.n_un, j, lane)));
     }
   }
   if (!MULTI || !h.n_mu) return;
@@ -723,11 +779,11 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
       const uint32_t ow = sell_ld<LD>(h.oth + (size_t)32 * j + lane);
       if (!learn) continue;
       const uint32_t tag = rec >> 24, od = ow >> 1, eq = ow & 1u;
-      const uint32_t sf = st.assign_free[od] == eq, se = st.assign_evid[od] == eq;
+      const uint32_t sf = sell_chain<LD>(st.assign_free, od) == eq, se = sell_chain<LD>(st.assign_evid, od) == eq;
       const int cf = (int)((tag >> (4u * pf + 2u * sf)) & 3u), ce = (int)((tag >> (4u * ev + 2u * se)) & 3u);
-      if (cf == ce) continue;
-      sell_grad(g, st, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
-                __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.mu, h.n_mu, j, lane)));
+      if ((cf == ce && !cold) || tag == SELL_BINARY_NOP) continue;
+      sell_grad(g, L, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
+                cf == ce ? 0.0 : __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.mu, h.n_mu, j, lane)));
     }
   } else {
     uint32_t oc = 0;
@@ -741,134 +797,64 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
       sell_general_signs<LD>(h, tag, d, lane, oc, st.assign_free, f0, f1);
       sell_general_signs<LD>(h, tag, d, lane, oc2, st.assign_evid, e0, e1);
       const double fv = sell_fv<FV, LD>(h.mu, h.n_mu, j, lane);
-      sell_grad(g, st, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
+      sell_grad(g, L, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
                 __dsub_rn(__dmul_rn(pf ? f1 : f0, fv), __dmul_rn(ev ? e1 : e0, fv)));
     }
   }
 }
 
-// One learning sweep over a colour class.  Weights are FROZEN for the launch; the gradient
-// of every SGD step (pot_free - pot_evid, src/factor_graph.cc:255-258) is summed per weight
-// into grad_acc (hot weights pre-aggregated in shared memory), and k_apply_weights turns the
-// sums into the weight change afterwards.
-template <bool MULTI, int FV>
-__global__ void __launch_bounds__(SELL_THREADS, 2)
-k_sell_learn(const SellGraph g, const SellState st, const SweepParams p) {
-  extern __shared__ double smem[];
-  double *w_s = smem, *acc_s = smem + g.n_hot;
-  sell_stage_weights(g, st.weights, w_s);
-  for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) acc_s[i] = 0.0;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint64_t s64 = g.slice_begin + (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * g.slice_stride;
-       s64 < g.slice_end; s64 += (uint64_t)warps * g.slice_stride) {
-    const uint32_t s = (uint32_t)s64;
-    const SliceHeader h = sell_header<FV>(g, s);
-    sell_learn_slice<MULTI, FV, LD_CACHED>(g, st, p, h, w_s, acc_s, lane, s * 32u + lane);
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) {
-    const double a = acc_s[i];
-    if (a != 0.0) atomicAdd(st.grad_acc + i, a);
-  }
-}
-
-// The same sweep with the slices staged through a per-warp ring of bulk-async copies, like
-// k_sell_infer_staged (8 warps per CTA, two stages): a learning launch covers 1/chunks of a
-// class, i.e. a handful of slices per warp, so the 4-deep dependent HBM chain of the direct
-// kernel (offset -> header -> records -> second pass) was most of its duration.  The host only
-// picks this kernel for classes whose longest slice fits a stage.
-constexpr int SELL_LEARN_STAGED_THREADS = 256;
-__host__ __device__ inline uint32_t sell_learn_bar_off(uint32_t n_hot) { return (16u * n_hot + 15u) & ~15u; }
-__host__ __device__ inline uint32_t sell_learn_ring_off(uint32_t n_hot, uint32_t stages) {
-  return (sell_learn_bar_off(n_hot) + (SELL_LEARN_STAGED_THREADS / 32) * stages * 8u + 127u) & ~127u;
-}
-__host__ __device__ inline uint32_t sell_learn_smem(uint32_t n_hot, uint32_t stages, uint32_t stage_words) {
-  return sell_learn_ring_off(n_hot, stages) + (SELL_LEARN_STAGED_THREADS / 32) * stages * stage_words * 4u;
-}
+// One launch of a learning sweep: positions [vbegin, vend) of the visit order, dealt to the warps
+// of the grid round-robin (position vbegin + round * warps + warp: the whole grid moves through the
+// order together, so "later in the order" is "later in time").
+constexpr int SELL_LEARN_THREADS = 256;
+__host__ __device__ inline size_t sell_learn_smem(uint32_t n_hot) { return (size_t)n_hot * 24; }
 
 template <bool MULTI, int FV>
-__global__ void __launch_bounds__(SELL_LEARN_STAGED_THREADS, 2)
-k_sell_learn_staged(const SellGraph g, const SellState st, const SweepParams p, const uint32_t stages,
-                    const uint32_t stage_words) {
+__global__ void __launch_bounds__(SELL_LEARN_THREADS, 2)
+k_sell_learn_live(const SellGraph g, const SellState st, const SweepParams p, const SellLearn L) {
   extern __shared__ __align__(128) unsigned char sell_smem[];
-  constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
-  // programmatic dependent launch (learning launch -> k_apply_weights -> next learning launch):
-  // everything up to griddepcontrol.wait touches nothing the previous two kernels write
-  asm volatile("griddepcontrol.launch_dependents;");
   double *w_s = reinterpret_cast<double *>(sell_smem), *acc_s = w_s + g.n_hot;
-  const uint32_t *sm = reinterpret_cast<const uint32_t *>(sell_smem);
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  const uint32_t bar0 = sell_smem_addr(sell_smem) + sell_learn_bar_off(g.n_hot) + warp * stages * 8u;
-  const uint32_t ringw = sell_learn_ring_off(g.n_hot, stages) / 4u + warp * stages * stage_words;  // word index
-  const uint32_t ring0 = sell_smem_addr(sell_smem) + ringw * 4u;
-  if (lane == 0)
-    for (uint32_t i = 0; i < stages; ++i) sell_mbar_init(bar0 + 8u * i, 1u);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) acc_s[i] = 0.0;
-  __syncthreads();  // mbarriers initialised before any lane waits on one
-
-  const uint64_t step = (uint64_t)((gridDim.x * blockDim.x) >> 5) * g.slice_stride;
-  const uint64_t s0 = g.slice_begin + (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * g.slice_stride;
-  const uint32_t n_my = s0 < g.slice_end ? (uint32_t)((g.slice_end - 1 - s0) / step) + 1u : 0u;
-  const uint64_t pol = sell_policy_evict_first();
-  uint32_t cur_lo = 0, cur_hi = 0, nxt_lo = 0, nxt_hi = 0;
-  auto fetch_offsets = [&](uint32_t kb, uint32_t &lo, uint32_t &hi) {
-    const uint32_t k = kb + lane;
-    if (k < n_my) {
-      const uint32_t *o = g.sl_off + (s0 + (uint64_t)k * step);
-      lo = __ldg(o);
-      hi = __ldg(o + 1);
-    }
-  };
-  auto issue = [&](uint32_t k, uint32_t stage) {
-    const uint32_t j = k & 31u;
-    if (j == 0 && k) {
-      cur_lo = nxt_lo; cur_hi = nxt_hi;
-      fetch_offsets(k + 32, nxt_lo, nxt_hi);
-    }
-    const uint32_t off = __shfl_sync(0xffffffffu, cur_lo, j);
-    const uint32_t bytes = (__shfl_sync(0xffffffffu, cur_hi, j) - off) * 32u;  // fits: the host checked the class
-    if (lane == 0) {
-      sell_mbar_expect_tx(bar0 + 8u * stage, bytes);
-      sell_bulk_g2s(ring0 + stage * stage_words * 4u, g.blob + (size_t)off * 8, bytes, bar0 + 8u * stage, pol);
-    }
-  };
-  if (n_my) {  // the blob is static: the first copies go out before the previous launch is known to be done
-    fetch_offsets(0, cur_lo, cur_hi);
-    fetch_offsets(32, nxt_lo, nxt_hi);
-    const uint32_t pre = n_my < stages ? n_my : stages;
-    for (uint32_t k = 0; k < pre; ++k) issue(k, k);
-  }
-  // from here on: the chains the previous learning launch wrote and the weights k_apply_weights updated
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  sell_stage_weights(g, st.weights, w_s);
-  __syncthreads();
-  if (n_my) {
-    uint32_t stage = 0, parity = 0;
-    uint64_t s64 = s0;
-    for (uint32_t k = 0; k < n_my; ++k, s64 += step) {
-      sell_mbar_wait(bar0 + 8u * stage, parity);
-      const uint32_t *b = sm + ringw + stage * stage_words;
-      const uint4 h0 = *reinterpret_cast<const uint4 *>(b);
-      const uint4 h1 = *reinterpret_cast<const uint4 *>(b + 4);
-      SliceHeader h;
-      h.n_un = h0.x; h.n_mu = h0.y; h.n_oc = h0.z; h.evid = h0.w;
-      h.pad = h1.x; h.evval = h1.y; h.flags = h1.z;
-      h.un = b + SH_WORDS;
-      h.mu = h.un + 32u * h.n_un * (1 + FVW);
-      h.oth = h.mu + 32u * h.n_mu * (1 + FVW);
-      sell_learn_slice<MULTI, FV, LD_SMEM>(g, st, p, h, w_s, acc_s, lane, (uint32_t)s64 * 32u + lane);
-      __syncwarp();  // every lane is done with this stage before the next copy lands in it
-      if (k + stages < n_my) issue(k + stages, stage);
-      if (++stage == stages) { stage = 0; parity ^= 1u; }
-    }
-  }
-  __syncthreads();
+  float *as_s = reinterpret_cast<float *>(acc_s + g.n_hot), *lam_s = as_s + g.n_hot;
+  __shared__ uint32_t cnt_s;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t npos = L.vend - L.vbegin, rounds = (npos + warps - 1) / warps;
+  // per hot weight: step of one update (stepsize x scale) and its decay per slice of the sweep
+  // (N_k / slices updates per slice, each  w <- w / (1 + reg step)  resp.  w += reg (w < 0))
   for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) {
-    const double a = acc_s[i];
-    if (a != 0.0) atomicAdd(st.grad_acc + i, a);
+    const double sc = sell_step_scale(L, i);
+    as_s[i] = (float)(L.step * sc);
+    const double per_update = L.reg_l1 ? L.decay : log1p(L.decay * sc);  // (1 + reg step)^-n = exp(-n log1p(reg step))
+    lam_s[i] = (float)((double)__ldg(L.w_N + i) * L.inv_nslice * per_update);
+    acc_s[i] = 0.0;
+  }
+  for (uint32_t r0 = 0; r0 < rounds; r0 += L.period) {
+    __syncthreads();  // the previous flush is done with w_s / acc_s
+    for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) w_s[i] = __ldcg(L.weights + i);
+    if (threadIdx.x == 0) cnt_s = 0;
+    __syncthreads();
+    uint32_t mine = 0;
+    const uint32_t r1 = min(rounds, r0 + L.period);
+    for (uint32_t r = r0; r < r1; ++r) {
+      const uint32_t pos = r * warps + gw;
+      if (pos >= npos) break;
+      const uint32_t s = __ldg(L.visit + L.vbegin + pos);
+      const SliceHeader h = sell_header<FV>(g, s);
+      sell_learn_slice<MULTI, FV, LD_CACHED>(g, st, p, L, h, w_s, acc_s, lane, s * 32u + lane);
+      ++mine;
+    }
+    // slices this CTA swept in the period (for the decay of the updates it made)
+    if (lane == 0 && mine) atomicAdd(&cnt_s, mine);
+    __syncthreads();
+    const uint32_t cnt = cnt_s;
+    for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) {
+      const double a = acc_s[i], x = w_s[i];
+      acc_s[i] = 0.0;
+      const double lam = (double)lam_s[i] * (double)cnt;
+      const double dec = L.reg_l1 ? lam * (x < 0 ? 1.0 : 0.0) : x * expm1(-lam);
+      const double d = dec - (double)as_s[i] * a;
+      if (d != 0.0) atomicAdd(L.weights + i, d);
+    }
   }
 }
 

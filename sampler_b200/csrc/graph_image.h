@@ -128,6 +128,10 @@ struct GraphImage {
   std::vector<uint32_t> sl_off;    // [nslice+1] first word of each slice / 8
   std::vector<uint32_t> blob;
   uint32_t sell_max_words = 0;     // longest slice, in words
+  // Learning sweeps visit the slices in ascending id block of their variables (classes
+  // interleaved: Hogwild, like the reference's threads), inference sweeps class by class.
+  uint32_t id_block = 0;               // variables per id block (compile.cc)
+  std::vector<uint32_t> learn_visit;   // [nslice] slice indices in learning order
 
   // weights: ABI order is the original id; the device uses internal ids, hottest first
   std::vector<double> w_init;      // original order

@@ -453,7 +453,9 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     else g->fv_mode = FV_F64;
   }
   // Boolean-only graphs under a parallel schedule get the sliced-ELL stream (graph_image.h)
-  g->sell = !g->has_categorical && schedule != DWG_SCHED_SEQUENTIAL && nweight <= SELL_MAX_WEIGHTS;
+  // (a Boolean edge with equal_to >= 2 -- legal input, never satisfied -- needs two-word others
+  // entries, which only the CSR kernels read)
+  g->sell = !g->has_categorical && g->oth_packed && schedule != DWG_SCHED_SEQUENTIAL && nweight <= SELL_MAX_WEIGHTS;
   for (uint64_t v = 0; v < nvar && g->sell; ++v)
     if (adense[v] > 1) g->sell = false;  // a Boolean evidence value outside {0,1}: CSR kernels only
 
@@ -472,16 +474,23 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   // ... evaluated ONCE per incidence (a random read of the factor each time), kept as
   // form | self position << 2 for the three phases that need it (sort keys, sizing, CSR fill)
   BulkVec<uint8_t> finfo(nedge);
+  int general_seen = 0;
   parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+    bool any_general = false;
     for (uint64_t v = v0; v < v1; ++v) {
       const bool cat = g->var_dtype[v];
       for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
         uint64_t self_pos = 0;
         const int form = edge_form(v, inc[i].fid, inc[i].key, cat, &self_pos);
         finfo[i] = (uint8_t)(form | ((form != (int)FORM_GENERAL ? self_pos : 0) << 2));
+        any_general |= form == (int)FORM_GENERAL;
       }
+      if (any_general) __atomic_store_n(&general_seen, 1, __ATOMIC_RELAXED);
     }
   });
+  // a general-form record walks the others stream even when its factor has one variable (a Boolean
+  // edge with equal_to >= 2, a variable twice in a factor): the stream and its row offsets must exist
+  if (general_seen) g->has_multi = true;
 
   pt.lap("layout knobs");
   // ---- schedule order: colour-major; SELL graphs additionally sort each class by
@@ -500,7 +509,17 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   g->perm.assign(nvar_pad, 0xffffffffu);
   g->inv.resize(nvar);
   if (g->sell) {
-    struct Key { uint64_t k; uint32_t v; };
+    // Order inside a class: (is_evidence, id block, then unary / multi / others counts DESCENDING).
+    // Evidence last: the evidence tail of a class is one range a query-only sweep never reads.  Id
+    // blocks ascending: a LEARNING sweep visits the slices in ascending id block (learn_visit
+    // below), because per-sample SGD weights the most recently visited variables most: the
+    // reference's results are those of the id-order scan (src/gibbs_sampler.cc:52-54,71-75), and a
+    // sweep in another order converges to measurably different weights.  Counts
+    // descending inside a block: the 32 variables of a slice have rows of similar length.
+    uint64_t id_block = 256;
+    while (id_block * 1024 < nvar && id_block < 65536) id_block <<= 1;
+    g->id_block = (uint32_t)id_block;
+    struct Key { uint64_t hi, lo; uint32_t v; };
     BulkVec<Key> keys(nvar);
     parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
       for (uint64_t v = v0; v < v1; ++v) {
@@ -516,15 +535,14 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         n_un = std::min<uint64_t>(n_un, (1u << 16) - 1);
         n_mu = std::min<uint64_t>(n_mu, (1u << 12) - 1);
         ow = std::min<uint64_t>(ow, (1u << 20) - 1);
-        // longest rows first inside (class, evidence): a launch walks its slices in this order, so the
-        // heavy slices start early and the tail of the launch is made of the light ones
-        keys[v] = {((uint64_t)color[v] << 49) | ((uint64_t)g->var_is_evid[v] << 48) | ((0xffffull - n_un) << 32) |
-                       ((0xfffull - n_mu) << 20) | (0xfffffull - ow),
-                   (uint32_t)v};
+        keys[v] = {((uint64_t)color[v] << 32) | ((uint64_t)g->var_is_evid[v] << 31) | (v / id_block),
+                   ((0xffffull - n_un) << 32) | ((0xfffull - n_mu) << 20) | (0xfffffull - ow), (uint32_t)v};
       }
     });
     // sorted runs in parallel, then pairwise merges (the order is total: ties broken by id)
-    auto less = [](const Key &a, const Key &b) { return a.k != b.k ? a.k < b.k : a.v < b.v; };
+    auto less = [](const Key &a, const Key &b) {
+      return a.hi != b.hi ? a.hi < b.hi : a.lo != b.lo ? a.lo < b.lo : a.v < b.v;
+    };
     {
       unsigned runs = 1;
       while (runs * 2 <= host_threads() && nvar / (runs * 2) >= (1u << 16)) runs *= 2;
@@ -732,7 +750,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   // q = (fv * sign range)^2 / 4 >= Var(f | rest): the conditional is a Bernoulli. ----
   {
     uint64_t cells = (uint64_t)ncolor * nweight;
-    g->cls_shared = cells > (64ull << 20);  // too many cells: one class-averaged row
+    g->cls_shared = g->sell || cells > (64ull << 20);  // sell: whole-graph sums; too many cells: one class-averaged row
     uint64_t rows_n = g->cls_shared ? 1 : ncolor;
     g->cls_N_evid.assign(rows_n * nweight, 0.f); g->cls_Q_evid.assign(rows_n * nweight, 0.f);
     g->cls_N_all.assign(rows_n * nweight, 0.f); g->cls_Q_all.assign(rows_n * nweight, 0.f);
@@ -764,6 +782,42 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         fn(w, std::fabs(fv) * srange(tag & TAG_FUNC_MASK, n));
       }
     };
+    if (g->sell) {
+      // Sliced-ELL graphs learn in ONE visit order over all classes (learn_visit below): whole-graph
+      // sums, one row.  Accumulated as 2^-20 fixed point with integer atomics: the result does not
+      // depend on the thread count or the interleaving.
+      g->cls_shared = true;
+      std::vector<uint64_t> acc(6 * nweight, 0);
+      auto fx = [](double x) { return (uint64_t)std::llround(x * 1048576.0); };
+      parallel_for(nvar_pad, [&](uint64_t d0, uint64_t d1) {
+        for (uint64_t d = d0; d < d1; ++d) {
+          uint64_t v = g->perm[d];
+          if (v == 0xffffffffu) continue;
+          const bool ev = g->var_is_evid[v];
+          double rowsum = 0;
+          walk_row(d, [&](uint32_t, double delta) { rowsum += delta; });
+          walk_row(d, [&](uint32_t w, double delta) {
+            const uint64_t q = fx(0.25 * delta * rowsum), hd = fx(0.25 * delta * delta);
+            __atomic_fetch_add(&acc[0 * nweight + w], 1ull << 20, __ATOMIC_RELAXED);
+            __atomic_fetch_add(&acc[1 * nweight + w], q, __ATOMIC_RELAXED);
+            __atomic_fetch_add(&acc[2 * nweight + w], hd, __ATOMIC_RELAXED);
+            if (ev) {
+              __atomic_fetch_add(&acc[3 * nweight + w], 1ull << 20, __ATOMIC_RELAXED);
+              __atomic_fetch_add(&acc[4 * nweight + w], q, __ATOMIC_RELAXED);
+              __atomic_fetch_add(&acc[5 * nweight + w], hd, __ATOMIC_RELAXED);
+            }
+          });
+        }
+      });
+      for (uint64_t w = 0; w < nweight; ++w) {
+        g->cls_N_all[w] = (float)((double)acc[0 * nweight + w] / 1048576.0);
+        g->cls_Q_all[w] = (float)((double)acc[1 * nweight + w] / 1048576.0);
+        g->cls_H_all[w] = (float)((double)acc[2 * nweight + w] / 1048576.0);
+        g->cls_N_evid[w] = (float)((double)acc[3 * nweight + w] / 1048576.0);
+        g->cls_Q_evid[w] = (float)((double)acc[4 * nweight + w] / 1048576.0);
+        g->cls_H_evid[w] = (float)((double)acc[5 * nweight + w] / 1048576.0);
+      }
+    } else {
     // every class owns its row of the tables: classes in parallel (the float sums of a row keep
     // their sequential order); a shared row is filled by one thread
     parallel_ranges(ncolor, g->cls_shared ? 1u : std::min<unsigned>(ncolor, host_threads()),
@@ -788,11 +842,12 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       }
     }
     }, 1);
-    if (g->cls_shared)
+    if (g->cls_shared && !g->sell)
       for (uint64_t w = 0; w < nweight; ++w) {
         g->cls_N_evid[w] /= ncolor; g->cls_Q_evid[w] /= ncolor; g->cls_H_evid[w] /= ncolor;
         g->cls_N_all[w] /= ncolor; g->cls_Q_all[w] /= ncolor; g->cls_H_all[w] /= ncolor;
       }
+    }
   }
 
   pt.lap("class statistics");
@@ -830,6 +885,25 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     }
     g->sl_off[nslice] = (uint32_t)(words / 8);
     g->blob.assign(words, 0);
+    {  // learning order: by id block of the slice's first variable, then by class, then by position
+      std::vector<uint64_t> vk(nslice);
+      parallel_for(ncolor, [&](uint64_t c0, uint64_t c1) {
+        for (uint64_t c = c0; c < c1; ++c)
+          for (uint64_t sidx = g->color_start[c] / 32; sidx < g->color_start[c + 1] / 32; ++sidx) {
+            uint64_t v = 0;
+            for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d)
+              if (g->perm[d] != 0xffffffffu) { v = g->perm[d]; break; }
+            vk[sidx] = ((v / g->id_block) << 40) | (c << 24 & 0xffff000000ull) | (sidx & 0xffffffu);
+          }
+      });
+      // (the low fields only break ties; the slice index is recovered from a parallel array)
+      g->learn_visit.resize(nslice);
+      std::iota(g->learn_visit.begin(), g->learn_visit.end(), 0u);
+      std::stable_sort(g->learn_visit.begin(), g->learn_visit.end(), [&](uint32_t a, uint32_t b) {
+        const uint64_t ka = vk[a] >> 24, kb = vk[b] >> 24;
+        return ka != kb ? ka < kb : a < b;
+      });
+    }
     // sign tables (host mirror of dev_sign, dwg_device.cuh): codes 0 -> -1, 1 -> 0, 2 -> +1
     auto sign2 = [](uint32_t fc, uint32_t nsb, bool head) -> int {  // arity 2
       const bool body_all = nsb == 1;

@@ -1,7 +1,11 @@
 #!/usr/bin/env python
-"""Learning fidelity at mid size: learned weights of the parallel schedules vs the UNMODIFIED
-reference's (tests/golden/c{2,3,4}_small.npz: mean over 5 reference seeds), for several
---learn_chunks settings.  Needs a GPU.  Prints one line per (graph, chunks)."""
+"""Learning fidelity at mid size: learned weights / marginals of the parallel learning sweeps vs the
+UNMODIFIED reference's -t 1 results (tests/golden/c{2,3,4}_small.npz), for several settings of the
+epoch plan (environment knobs of launch_learn_sell, dwg_api.cu).  Needs a GPU.
+
+  python scripts/learn_fidelity.py [graph ...] [--variants "K=V,K=V;K=V"] [--seeds N] [--top N]
+"""
+import argparse
 import json
 import os
 import sys
@@ -16,37 +20,69 @@ from helpers import GOLDEN, parse_dw_args  # noqa: E402
 from sampler_b200 import graphgen  # noqa: E402
 
 
-def run(raw, a, seed, chunks, sched=sb.SCHED_AUTO):
-    s = sb.Sampler(sb.Graph.from_raw(raw, sched), sample_evidence=a["sample_evidence"], reg_param=a["reg_param"],
-                   seed=seed, learn_chunks=chunks)
+def run(graph, a, seed, infer):
+    s = sb.Sampler(graph, sample_evidence=a["sample_evidence"], reg_param=a["reg_param"], seed=seed)
     step = a["stepsize"]
     for _ in range(a["n_learn"]):
         s.learn_epoch(step)
         step *= a["decay"]
-    return s.weights()
+    w = s.weights()
+    t = n = None
+    if infer:
+        s.clear_tallies()
+        s.infer_epochs(a["n_infer"])
+        t, n = s.tallies()
+    s.close()
+    return w, t, n
 
 
 def main():
-    names = sys.argv[1:] or ["c2_small", "c3_small", "c4_small"]
-    for name in names:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("graphs", nargs="*", default=["c2_small", "c4_small"])
+    ap.add_argument("--variants", default="")
+    ap.add_argument("--seeds", type=int, default=8)
+    ap.add_argument("--top", type=int, default=0, help="print the N most used weights")
+    args = ap.parse_args()
+    variants = [dict(kv.split("=") for kv in v.split(",") if kv) for v in args.variants.split(";")] if args.variants else [{}]
+    for name in args.graphs:
         z = np.load(os.path.join(GOLDEN, name + ".npz"))
         raw = getattr(graphgen, str(z["generator"]))(**json.loads(str(z["kwargs"])))
         a = parse_dw_args(str(z["dw_args"]).split())
         wref, wstd = z["weights_mean"], z["weights_std"]
-        tol = np.maximum(0.05 * np.abs(wref), 0.03 + 2 * wstd)
+        mref = z["marginals_mean"].astype(np.float64)
         nref = float(z["nseeds"])
-        for chunks in (0, 1, 4, 16, 64):
-            runs = np.array([run(raw, a, seed, chunks) for seed in range(1, 17)])
-            w = runs.mean(0)
-            own_std = runs.std(0).mean()
-            floor = np.sqrt(2 / np.pi) * np.sqrt(wstd ** 2 / nref + runs.std(0) ** 2 / len(runs)).mean()
+        graph = sb.Graph.from_raw(raw)
+        boolean = raw.var_dtype.max() == 0
+        use = np.bincount(raw.fac_wid.astype(np.int64), minlength=raw.nweight)
+        for env in variants:
+            for k in list(os.environ):
+                if k.startswith("DWG_LEARN_"):
+                    del os.environ[k]
+            os.environ.update(env)
+            ws, ms = [], []
+            for seed in range(1, args.seeds + 1):
+                w, t, n = run(graph, a, seed, boolean)
+                ws.append(w)
+                if boolean:
+                    vid = z["marginal_keys"][:, 0]
+                    _, _, base, _ = graph.var_meta()
+                    ms.append(t[base[vid].astype(np.int64)] / n[vid].astype(np.float64))
+            w = np.mean(ws, 0)
+            sig = wstd * np.sqrt(1.0 / nref + 1.0 / args.seeds)
+            tol = np.maximum(0.05 * np.abs(wref), 0.03) + 3 * sig
             err = np.abs(w - wref)
             big = np.abs(wref) > 0.1
             slope = float(np.dot(w[big], wref[big]) / np.dot(wref[big], wref[big])) if big.any() else float("nan")
-            print("%-9s chunks=%-3d bad=%.3f  max_err=%.3f  mean_err=%.4f (noise floor %.4f)  shrink=%.3f  "
-                  "seed-std ours %.4f ref %.4f  (|wref| mean %.3f)"
-                  % (name, chunks, float((err > tol).mean()), err.max(), err.mean(), floor, slope, own_std,
-                     wstd.mean(), np.abs(wref).mean()), flush=True)
+            line = "%-9s %-40s bad=%.4f mean|dw|=%.4f (noise %.4f) slope=%.3f" % (
+                name, json.dumps(env), float((err > tol).mean()), err.mean(), np.sqrt(2 / np.pi) * sig.mean(), slope)
+            if ms:
+                m = np.mean(ms, 0)
+                line += " mean|dm|=%.4f shift=%+.4f" % (np.abs(m - mref).mean(), m.mean() - mref.mean())
+            print(line, flush=True)
+            if args.top:
+                for k in np.argsort(-use)[:args.top]:
+                    print("    w[%d] uses %d: ours %+.4f ref %+.4f (t8 %+.4f) std %.4f tol %.4f %s" % (
+                        k, use[k], w[k], wref[k], z["weights_mean_t8"][k], wstd[k], tol[k], "BAD" if err[k] > tol[k] else ""))
 
 
 if __name__ == "__main__":

@@ -279,78 +279,39 @@ def test_staged_and_direct_inference_kernels_agree(shape, monkeypatch):
         assert np.array_equal(s.tallies()[0], o.tallies)
 
 
-@pytest.mark.parametrize("shape", ["binary", "general", "c2", "unary_f32"])
-def test_staged_and_direct_learning_kernels_agree(shape, monkeypatch):
-    """k_sell_learn_staged against k_sell_learn: with every weight fixed (no update, so no
-    floating-point summation order in play) both chains are identical after several learning
-    sweeps; with free weights the learned weights agree to summation-order rounding"""
-    import copy
-    from sampler_b200 import graphgen
-    rng = np.random.default_rng(777)
-    if shape == "c2":
-        raw = graphgen.c2_boolean(50_000, nweight=200)
-    elif shape == "binary":
-        raw = random_graph(rng, nvar=5000, nfac=15000, nweight=60, p_cat=0.0, max_arity=2)
-    elif shape == "general":
-        raw = random_graph(rng, nvar=4000, nfac=9000, nweight=60, p_cat=0.0, max_arity=4)
-    else:
-        raw = graphgen.unary_boolean(30_000, 12, 300, p_evid=0.7)
-    variants = [{"DWG_SELL_DIRECT": "1"}, {}, {"DWG_SELL_STAGE_WORDS": "300"}]
-    keys = ("DWG_SELL_DIRECT", "DWG_SELL_STAGE_WORDS")
-    fixed = copy.deepcopy(raw)
-    fixed.w_fixed[:] = 1
-    fixed.w_init[:] = rng.normal(0, 1, len(fixed.w_init))
-    for graph_raw, free in ((fixed, False), (raw, True)):
-        g = sb.Graph.from_raw(graph_raw, sb.SCHED_CHROMATIC)
-        ref = None
-        for env in variants:
-            for k in keys:
-                monkeypatch.delenv(k, raising=False)
-            for k, v in env.items():
-                monkeypatch.setenv(k, v)
-            s = sb.Sampler(g, seed=31, learn_non_evidence=(shape == "general"))
-            step = 0.01
-            for _ in range(3):
-                s.learn_epoch(step)
-                step *= 0.9
-            got = (s.assignments(0), s.assignments(1), s.weights())
-            s.close()
-            if ref is None:
-                ref = got
-            elif not free:
-                assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), env
-                assert np.array_equal(got[2], ref[2])
-            else:
-                assert np.allclose(got[2], ref[2], rtol=0, atol=1e-9), (env, np.abs(got[2] - ref[2]).max())
+def _learn_order(g):
+    """order in which a learning sweep visits the variables: slices in ascending id block for
+    sliced-ELL (Boolean) graphs, schedule order for the CSR (categorical) kernels"""
+    return g.learn_order()
 
 
 @pytest.mark.parametrize("seed", range(4))
-def test_parallel_learning_with_exact_arithmetic(seed):
-    """parallel learning launches under the chromatic schedule: with fixed weights both chains
-    (free-chain draws of every variable, evid-chain clamps / draws) must equal the sequential
-    reference in schedule order exactly"""
+def test_parallel_learning_with_exact_arithmetic(seed, monkeypatch):
+    """a learning sweep on ONE warp (DWG_LEARN_WARPS=1) walks the visit order slice by slice: with
+    fixed weights both chains (free-chain draws of every variable, evid-chain clamps / draws) must
+    equal the sequential reference run in that order exactly.  (Categorical graphs: the chromatic
+    CSR launches, schedule order.)"""
+    monkeypatch.setenv("DWG_LEARN_WARPS", "1")
     rng = np.random.default_rng(800 + seed)
     raw = random_graph(rng, nvar=2000, nfac=5000, nweight=30, p_cat=[0.0, 0.5][seed % 2], max_arity=3)
     raw.fac_fv[:] = rng.choice([1.0, 0.5, 2.0, -1.0], raw.nfac)
     raw.w_fixed[:] = 1  # fixed weights: the launch cannot perturb its own draws
     g, s, o = _mk(raw, sb.SCHED_CHROMATIC, reg_param=0.0, learn_non_evidence=True)
-    perm, _ = g.schedule()
+    order = _learn_order(g)
     for ep in range(3):
         r0, r1 = rng.random(o.nvar), rng.random(o.nvar)
         s.set_uniforms(r0, r1)
         s.learn_epoch(2.0 ** -6)
-        o.sweep_learn_seq(2.0 ** -6, perm, r0, r1)
+        o.sweep_learn_seq(2.0 ** -6, order, r0, r1)
         _same_state(s, o)
 
 
-def test_learning_launch_integrates_the_gradient_sum():
-    """A parallel learning launch freezes the weights, sums the gradients of its SGD steps per
-    weight (shared-memory pre-aggregation + atomics) and applies them in k_apply_weights as
-        w <- w - step * S * (1 - exp(-z)) / z,   z = step * H     (reg = 0, one chunk per sweep,
-                                                 H = the weight's own curvature bound)
-    On a unary all-evidence graph with dyadic step / feature values the sum S is exact and equals
-    what the sequential reference accumulates (its draws use the same potentials as long as no
-    draw sits within the weight drift of a decision boundary)."""
+def test_learning_sweep_sums_the_reference_steps():
+    """With a vanishing step the weights of a learning sweep end at  w0 - step * (sum of the
+    reference's SGD gradients): full-width launch, shared-memory pre-aggregation, atomics into the
+    live weight vector, step scale 1.  Unary all-evidence graph with dyadic step / feature values:
+    the sums are exact, and the draws do not depend on the visit order (no factor couples two
+    variables; draws are kept away from the decision boundary)."""
     rng = np.random.default_rng(11)
     nvar, nw, deg = 20000, 64, 6
     func = np.full(nvar * deg, gio.FUNC_ISTRUE, np.int32)
@@ -362,9 +323,8 @@ def test_learning_launch_integrates_the_gradient_sum():
                        rng.choice([1.0, 0.5, 2.0], nvar * deg), rng.normal(0, 1, nw),
                        np.zeros(nw, np.uint8)).normalized()
     g = sb.Graph.from_raw(raw, sb.SCHED_AUTO)
-    s, o = sb.Sampler(g, reg_param=0.0, learn_chunks=1), ol.Oracle(raw, reg_param=0.0)
+    s, o = sb.Sampler(g, reg_param=0.0), ol.Oracle(raw, reg_param=0.0)
     assert g.info.schedule == sb.SCHED_HOGWILD
-    perm, _ = g.schedule()
     step = 2.0 ** -20
     r0 = rng.random(nvar)
     for v in range(nvar):  # keep draws away from the decision boundary
@@ -374,23 +334,48 @@ def test_learning_launch_integrates_the_gradient_sum():
             r0[v] = (p1 + 0.5) % 1.0
     s.set_uniforms(r0, np.zeros(nvar))
     s.learn_epoch(step)
-    o.sweep_learn_seq(step, perm, r0, np.zeros(nvar))
+    o.sweep_learn_seq(step, _learn_order(g), r0, np.zeros(nvar))
     _same_state(s, o)
-    S = (raw.w_init - o.weights) / step          # the reference's gradient sums (exact: dyadic)
-    H = g.image("cls_H_evid").astype(np.float64)[g.image("w_inv").astype(np.int64)]
-    z = step * H
-    want = raw.w_init - step * S * (-np.expm1(-z) / z)
     w = s.weights()
-    assert np.allclose(w, want, rtol=0, atol=1e-13)
+    assert np.allclose(w, o.weights, rtol=0, atol=1e-12)
     assert np.abs(w - raw.w_init).max() > 100 * step  # something was learnt
 
 
+def test_learning_decay_follows_the_update_counts():
+    """l2 decay of a sweep: every SGD step of a weight multiplies it by 1 / (1 + reg * step)
+    (src/inference_result.h:75); a parallel sweep applies the decay of the steps each CTA made per
+    period.  With zero gradients (every variable's free draw forced to its evidence value) the
+    weights must end at  w0 * (1 + reg * step)^(-N_k)  to first order in reg * step."""
+    rng = np.random.default_rng(12)
+    nvar, nw, deg = 30000, 40, 5
+    func = np.full(nvar * deg, gio.FUNC_ISTRUE, np.int32)
+    ptr = np.arange(nvar * deg + 1, dtype=np.uint64)
+    evid = np.repeat(np.arange(nvar, dtype=np.uint64), deg)
+    label = rng.integers(0, 2, nvar)
+    wid = rng.integers(0, nw, nvar * deg)
+    raw = gio.RawGraph(np.ones(nvar, np.uint8), label, np.zeros(nvar, np.uint16), np.full(nvar, 2, np.uint64),
+                       *gio.empty_domains(), func, ptr, evid, np.ones(nvar * deg, np.uint64), wid,
+                       np.ones(nvar * deg), np.full(nw, 0.5), np.zeros(nw, np.uint8)).normalized()
+    g = sb.Graph.from_raw(raw, sb.SCHED_AUTO)
+    reg, step = 0.05, 2.0 ** -12
+    s = sb.Sampler(g, reg_param=reg)
+    s.set_uniforms(np.where(label == 1, 0.0, 1.0 - 1e-9), np.zeros(nvar))  # r = 0 draws 1, r -> 1 draws 0
+    s.learn_epoch(step)
+    assert np.array_equal(s.assignments(0), label.astype(np.uint64))
+    n_k = np.bincount(wid, minlength=nw)
+    want = 0.5 * (1.0 + reg * step) ** (-n_k.astype(np.float64))
+    assert np.abs(want - 0.5).min() > 0.01  # the decay is visible
+    assert np.allclose(s.weights(), want, rtol=1e-3), (s.weights()[:4], want[:4])
+
+
 @pytest.mark.parametrize("seed", range(6))
-def test_parallel_learning_gradient_sums_on_coupled_graphs(seed):
-    """The gradient a parallel learning launch accumulates per weight (sliced-ELL sign codes and
-    2x2 sign tables, general records, CSR records for categorical graphs) must be the sum of the
-    reference's SGD gradients.  With a vanishing dyadic step the weights do not move the draws,
-    phi(z) = 1 to 1e-5, and  w0 - w  =  step * sum of gradients  on both sides."""
+def test_parallel_learning_gradient_sums_on_coupled_graphs(seed, monkeypatch):
+    """The gradient a learning sweep accumulates per weight (sliced-ELL sign codes and 2x2 sign
+    tables, general records, CSR records for categorical graphs) must be the sum of the
+    reference's SGD gradients.  With a vanishing dyadic step the weights do not move the draws and
+    w0 - w  =  step * sum of gradients  on both sides; one warp (DWG_LEARN_WARPS=1) keeps the
+    chains those of the sequential reference run in visit order."""
+    monkeypatch.setenv("DWG_LEARN_WARPS", "1")
     rng = np.random.default_rng(900 + seed)
     raw = random_graph(rng, nvar=1500, nfac=4000, nweight=24, p_cat=[0.0, 0.0, 0.5][seed % 3],
                        max_arity=[2, 3, 3][seed % 3])
@@ -401,7 +386,7 @@ def test_parallel_learning_gradient_sums_on_coupled_graphs(seed):
         g = sb.Graph.from_raw(raw, sched)
         s = sb.Sampler(g, learn_chunks=[1, 3][seed % 2], **kw)
         o = ol.Oracle(raw, **kw)
-        perm, _ = g.schedule()
+        order = _learn_order(g)
         step = 2.0 ** -30
         for ep in range(2):
             r0, r1 = rng.random(o.nvar), rng.random(o.nvar)
@@ -410,11 +395,36 @@ def test_parallel_learning_gradient_sums_on_coupled_graphs(seed):
             o.weights[:] = w0
             s.set_uniforms(r0, r1)
             s.learn_epoch(step)
-            o.sweep_learn_seq(step, perm, r0, r1)
+            o.sweep_learn_seq(step, order, r0, r1)
             _same_state(s, o)
             got, want = (w0 - s.weights()) / step, (w0 - o.weights) / step
             assert np.abs(want).max() > 10  # gradients were summed
             assert np.allclose(got, want, rtol=1e-4, atol=1e-6), (got, want)
+
+
+def test_wide_learning_sweep_keeps_chains_and_weights_valid():
+    """a full-width Hogwild learning sweep (every SM, classes interleaved in id-block order): chain
+    values stay in {0, 1}, evidence stays clamped on the evid chain, fixed weights do not move,
+    free weights stay finite and move; the same on the direct and the staged inference kernels
+    afterwards is covered by test_staged_and_direct_inference_kernels_agree"""
+    from sampler_b200 import graphgen
+    raw = graphgen.c2_boolean(300_000, nweight=500)
+    raw.w_fixed[::7] = 1
+    raw.w_init[::7] = 0.25
+    g = sb.Graph.from_raw(raw, sb.SCHED_AUTO)
+    s = sb.Sampler(g, seed=5)
+    step = 0.01
+    for _ in range(4):
+        s.learn_epoch(step)
+        step *= 0.9
+    w = s.weights()
+    assert np.isfinite(w).all() and (w[::7] == 0.25).all()
+    free = np.ones(len(w), bool); free[::7] = False
+    assert np.abs(w[free]).max() > 0.05 and np.abs(w).max() < 10
+    a0, a1 = s.assignments(0), s.assignments(1)
+    assert set(np.unique(a0).tolist()) <= {0, 1} and set(np.unique(a1).tolist()) <= {0, 1}
+    ev = raw.var_role > 0
+    assert np.array_equal(a1[ev], raw.var_init[ev])
 
 
 # ---------------------------------------------------------------- RNG
@@ -496,13 +506,10 @@ def test_end_to_end_vs_reference_results(name):
 
 @pytest.mark.parametrize("name", GRAPHS)
 def test_end_to_end_parallel_schedules(name):
-    """the PARALLEL kernels (full-width launches, Philox, atomic SGD) on the same graphs: chromatic
-    everywhere, hogwild where no factor couples two variables.  Marginals must meet the 0.02 gate.
-    Weights: a launch is a mini-batch (every variable of a colour class reads the weights of the
-    launch start), the reference updates after every variable; with 18 variables and steps of 0.1
-    that changes the transient, so graphs whose weights have a fixed point meet the 5 % gate and
-    partial_observation (weights grow until the step size has decayed away: no fixed point, 7 %
-    seed-to-seed spread in the reference itself) gets 10 %."""
+    """the PARALLEL kernels (Philox, live weights, atomic SGD) on the same graphs: chromatic
+    everywhere, hogwild where no factor couples two variables.  Marginals must meet the 0.02 gate,
+    weights the 5 % gate (a sweep this small runs on one warp: the 32 draws of a slice see the same
+    weights, the SGD steps follow at once, slices in ascending id order)."""
     a = parse_dw_args(dw_args(name))
     exp = expected(name)
     raw = load_golden_graph(name)
@@ -514,8 +521,7 @@ def test_end_to_end_parallel_schedules(name):
             ws.append(w); ms.append(m)
         w = np.mean(ws, axis=0)
         wref = np.array(exp["weights_mean"])
-        rel = 0.10 if name == "partial_observation" else 0.05
-        tol = np.maximum(rel * np.abs(wref), 0.05 * (np.abs(wref) < 1.0))
+        tol = np.maximum(0.05 * np.abs(wref), 0.05 * (np.abs(wref) < 1.0))
         assert (np.abs(w - wref) <= tol).all(), (sched, w, wref)
         keys = exp["marginal_keys"]
         m = np.array([np.mean([mm[tuple(int(x) for x in k.split())] for mm in ms]) for k in keys])

@@ -93,73 +93,67 @@ def test_mid_size_graph_vs_reference(name):
     w, m = np.mean(ws, 0), np.mean(ms, 0)
     wref, mref = z["weights_mean"], z["marginals_mean"].astype(np.float64)
     nref = float(z["nseeds"])
-    # Learned weights within 5 % of the reference.  Three facts shape the gate.  (1) Both sides
-    # are noisy estimates (the reference's seed-to-seed std on these graphs is 0.01..0.08 per
-    # weight).  (2) The reference's per-sample SGD with these step sizes has an O(stepsize)
-    # stationary offset that depends on the update order: its OWN results move when it runs with
-    # -t 8 instead of -t 1 (golden *_t8: mean |dw| 0.035 on c2_small, 0.025 on c3_small).  A
-    # parallel sweep cannot be closer to the -t 1 numbers than the reference's own parallel mode
-    # is.  (3) What noise and order effects do not hide is under- or over-convergence: the
-    # regression slope of our weights on the reference's, which is held to 5 %.
+    # Learned weights within 5 % of the reference's -t 1 -c 1 results averaged over seeds.  Both
+    # sides are means over a finite number of noisy runs: a weight passes when it is within 5 %
+    # (absolute 0.03 for weights near zero) plus three standard errors of the difference of the two
+    # means; at most 2 % of the weights may miss, the regression slope of ours on the reference's
+    # is held to 5 % and the mean absolute difference to the noise floor + 0.01.
     sig = z["weights_std"] * np.sqrt(1.0 / nref + 1.0 / NSEEDS)
-    d_ref = float(np.abs(z["weights_mean_t8"] - wref).mean())
-    d_ours = float(np.abs(w - wref).mean())
-    noise_w = float(np.sqrt(2 / np.pi) * sig.mean())
-    assert d_ours <= max(1.25 * d_ref, 1.5 * noise_w + 0.003), (d_ours, d_ref, noise_w)
-    tol = np.maximum(0.05 * np.abs(wref), 0.03 + 2 * sig + np.abs(z["weights_mean_t8"] - wref))
+    tol = np.maximum(0.05 * np.abs(wref), 0.03) + 3 * sig
     bad = np.abs(w - wref) > tol
-    assert bad.mean() <= 0.05, (bad.mean(), np.nonzero(bad)[0][:10], w[bad][:10], wref[bad][:10])
+    assert bad.mean() <= 0.02, (bad.mean(), np.nonzero(bad)[0][:10], w[bad][:10], wref[bad][:10])
     big = np.abs(wref) > 0.1
     slope = float(np.dot(w[big], wref[big]) / np.dot(wref[big], wref[big]))
     assert abs(slope - 1.0) <= 0.05, slope
-    # Marginals: each seed's estimate carries sampling noise AND the noise of its own learned
-    # weights; the reference's per-variable seed-to-seed std measures both.  Gate: the mean
-    # absolute difference exceeds what that noise explains by at most 0.02, or stays within twice
-    # the reference's own -t 8 vs -t 1 distance (c2_small: ours 0.06, the reference's 0.04 -- a
-    # marginal there sums ten learned weights, so the order-dependent weight offsets of (2) add up).
+    noise_w = float(np.sqrt(2 / np.pi) * sig.mean())
+    d_ours = float(np.abs(w - wref).mean())
+    assert d_ours <= noise_w + 0.01, (d_ours, noise_w)
+    # Marginals within 0.02 absolute: mean absolute difference at most 0.02 on top of the sampling
+    # noise of the two means (each seed's estimate carries the noise of its own learned weights;
+    # the reference's per-variable seed-to-seed std measures it), mean marginal within 0.02.
     noise = np.sqrt(2 / np.pi) * z["marginals_std"].astype(np.float64) * np.sqrt(1.0 / nref + 1.0 / NSEEDS)
     d = np.abs(m - mref)
-    dm_ref = float(np.abs(z["marginals_mean_t8"].astype(np.float64) - mref).mean())
-    assert d.mean() <= max(0.02 + noise.mean(), 2.0 * dm_ref), (d.mean(), noise.mean(), dm_ref)
-    # the mean marginal: on the coupled graph the reference's own -t 8 run moves it by 0.031 from
-    # its -t 1 run (same order-dependent offsets, all of one sign); same 2 x yardstick as above
-    shift_ref = abs(float(z["marginals_mean_t8"].astype(np.float64).mean()) - float(mref.mean()))
-    assert abs(m.mean() - mref.mean()) <= max(0.005, 2.0 * shift_ref), (m.mean(), mref.mean(), shift_ref)
-    # tail: the reference's -t 8 run is itself 0.165 from its -t 1 run at the 99th percentile on c2_small
-    q_ref = float(np.quantile(np.abs(z["marginals_mean_t8"].astype(np.float64) - mref), 0.99))
-    assert np.quantile(d, 0.99) <= max(0.15, 1.5 * q_ref), (np.quantile(d, 0.99), q_ref)
-    print("%s: weights mean|d| %.4f (ref -t8 %.4f, noise %.4f) slope %.3f; marginals mean|d| %.4f (ref -t8 %.4f, noise %.4f)"
-          % (name, d_ours, d_ref, noise_w, slope, d.mean(), dm_ref, noise.mean()))
+    assert d.mean() <= 0.02 + noise.mean(), (d.mean(), noise.mean())
+    assert abs(m.mean() - mref.mean()) <= 0.02, (m.mean(), mref.mean())
+    assert np.quantile(d, 0.99) <= 0.15, np.quantile(d, 0.99)
+    print("%s: weights mean|d| %.4f (noise %.4f) slope %.3f bad %.3f; marginals mean|d| %.4f (noise %.4f) shift %.4f"
+          % (name, d_ours, noise_w, slope, bad.mean(), d.mean(), noise.mean(), m.mean() - mref.mean()))
 
 
 def test_full_size_c2_invariants(monkeypatch):
     """BASELINE.json configs[1] at its full size (10 M variables, 10^8 edge records), through
     size-independent properties: the staged and the direct inference kernels make identical chains
     and tallies; the same seed reproduces them; evidence variables keep their value and are never
-    tallied without --sample_evidence; every tally is bounded by the sweep count; learning moves
-    only non-fixed weights and keeps them finite"""
+    tallied without --sample_evidence; every tally is bounded by the sweep count; a learning sweep
+    (wide head + narrow tail) moves the weights and keeps them finite"""
     raw = graphgen.c2_boolean(10_000_000)
     g = sb.Graph.from_raw(raw)
     assert g.info.schedule == sb.SCHED_CHROMATIC and g.info.num_index_entries == 100_000_000
     is_evid = raw.var_role > 0
+    # a learning sweep is Hogwild like the reference's threads (not reproducible bit for bit): learn
+    # once, then pin the learned weights for the reproducibility checks of the inference kernels
+    s = sb.Sampler(g, sample_evidence=False, seed=2024)
+    w0 = s.weights()
+    s.learn_epoch(0.01)
+    w = s.weights()
+    s.close()
+    assert np.isfinite(w).all() and np.abs(w).max() > 0.01 and np.abs(w).max() < 10 and (w0 == 0).all()
     runs = []
     for env in ({}, {}, {"DWG_SELL_DIRECT": "1"}):
         monkeypatch.delenv("DWG_SELL_DIRECT", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         s = sb.Sampler(g, sample_evidence=False, seed=2024)
-        s.learn_epoch(0.01)
-        w = s.weights()
+        s.set_weights(w)
         s.clear_tallies()
         s.infer_epochs(4)
         a = s.assignments(1)
         t, n = s.tallies()
         s.close()
-        runs.append((a, t, n, w))
-    a, t, n, w = runs[0]
+        runs.append((a, t, n))
+    a, t, n = runs[0]
     assert np.array_equal(a, runs[1][0]) and np.array_equal(t, runs[1][1])      # same seed, same run
     assert np.array_equal(a, runs[2][0]) and np.array_equal(t, runs[2][1])      # staged == direct
-    assert np.allclose(w, runs[2][3], rtol=0, atol=1e-9) and np.isfinite(w).all() and np.abs(w).max() > 0
     assert set(np.unique(a).tolist()) <= {0, 1}
     assert np.array_equal(a[is_evid], raw.var_init[is_evid])                    # evidence stays clamped
     assert (n[is_evid] == 0).all() and (n[~is_evid] == 4).all()
