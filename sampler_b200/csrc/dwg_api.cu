@@ -197,6 +197,7 @@ struct dwg_handle {
   DevBuf<uint32_t> learn_visit;
   std::vector<float> learn_H_sorted;   // curvature bounds of the learnable weights, ascending
   double learn_rho = 1.0;              // coupling: learnable records per learning variable / 10
+  uint32_t learn_stage_words = 8;      // capacity of one ring stage of the learning kernel
   size_t device_bytes = 0;
   // tally download: device row of every (variable, value) in ABI order (uploaded with the graph) and
   // the gathered tallies; the page-locked landing pieces are the process's (g_landing)
@@ -225,9 +226,15 @@ int sell_setup_t(dwg_handle *h) {
   const size_t n_hot = h->img->n_hot;
   int rc = sell_grid(k_sell_infer<MULTI, FV>, 8 * n_hot, h->num_sms, &h->sell_blocks_infer);
   if (rc) return rc;
-  rc = sell_grid(k_sell_learn_live<MULTI, FV>, sell_learn_smem((uint32_t)n_hot), h->num_sms, &h->sell_blocks_learn,
-                 SELL_LEARN_THREADS);
-  if (rc) return rc;
+  {  // learning: a two-stage ring per warp of whatever fits beside the weight tables (longer slices are read from HBM)
+    const size_t fixed = sell_learn_ring_off((uint32_t)n_hot), lbudget = 112 * 1024;
+    uint32_t cap = fixed + 1024 < lbudget ? (uint32_t)((lbudget - fixed) / ((SELL_LEARN_THREADS / 32) * SELL_LEARN_STAGES * 4)) & ~3u : 8u;
+    if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) cap = std::min<uint32_t>(cap, std::max(8, atoi(e)) & ~3u);  // tests
+    h->learn_stage_words = std::max(8u, std::min(cap, (h->img->sell_max_words + 3u) & ~3u));
+    rc = sell_grid(k_sell_learn_live<MULTI, FV>, sell_learn_smem((uint32_t)n_hot, h->learn_stage_words), h->num_sms,
+                   &h->sell_blocks_learn, SELL_LEARN_THREADS);
+    if (rc) return rc;
+  }
   // staged (bulk-async) inference kernel: ring geometry for this graph
   h->sell_stages = 0;
   const char *direct = getenv("DWG_SELL_DIRECT");
@@ -297,9 +304,15 @@ void sell_launch_t(dwg_handle *h, bool staged, bool pdl, uint32_t blocks, const 
 #undef STAGED_LAUNCH
   } else k_sell_infer<MULTI, FV><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
 }
+// live: no shared-memory copy of the weights at all (the narrow tail of a learning sweep: every
+// record reads its weight from L2 and pushes its step there, nothing to refresh or flush)
 template <bool MULTI, int FV>
-void sell_learn_launch_t(dwg_handle *h, uint32_t blocks, uint32_t threads, const SweepParams &p, const SellLearn &L) {
-  k_sell_learn_live<MULTI, FV><<<blocks, threads, sell_learn_smem(h->img->n_hot), h->stream>>>(h->sg, h->ss, p, L);
+void sell_learn_launch_t(dwg_handle *h, uint32_t blocks, uint32_t threads, bool live, const SweepParams &p,
+                         const SellLearn &L) {
+  SellGraph sg = h->sg;
+  if (live) sg.n_hot = 0;
+  k_sell_learn_live<MULTI, FV><<<blocks, threads, sell_learn_smem(sg.n_hot, h->learn_stage_words), h->stream>>>(
+      sg, h->ss, p, L, h->learn_stage_words);
 }
 #define SELL_SWITCH(CALL)                                                      \
   if (m.has_multi) {                                                           \
@@ -325,9 +338,9 @@ void sell_launch(dwg_handle *h, bool staged, bool pdl, uint32_t blocks, const Se
   SELL_SWITCH(CALL)
 #undef CALL
 }
-void sell_learn_launch(dwg_handle *h, uint32_t blocks, uint32_t threads, const SweepParams &p, const SellLearn &L) {
+void sell_learn_launch(dwg_handle *h, uint32_t blocks, uint32_t threads, bool live, const SweepParams &p, const SellLearn &L) {
   const GraphImage &m = *h->img;
-#define CALL(MU, FV) sell_learn_launch_t<MU, FV>(h, blocks, threads, p, L)
+#define CALL(MU, FV) sell_learn_launch_t<MU, FV>(h, blocks, threads, live, p, L)
   SELL_SWITCH(CALL)
 #undef CALL
 }
@@ -727,8 +740,8 @@ static int launch_learn_sell(dwg_handle *h, SweepParams &p, double stepsize) {
   const GraphImage &m = *h->img;
   const uint32_t nslice = (uint32_t)m.learn_visit.size();
   if (!nslice) return DWG_OK;
-  const double cap = env_double("DWG_LEARN_XCAP", 0.25), tail_c = env_double("DWG_LEARN_TAILC", 3.0);
-  const uint32_t rounds_max = (uint32_t)env_double("DWG_LEARN_ROUNDS", 96), period_wide = (uint32_t)env_double("DWG_LEARN_PERIOD", 4);
+  const double cap = env_double("DWG_LEARN_XCAP", 0.15), tail_c = env_double("DWG_LEARN_TAILC", 3.0);
+  const uint32_t rounds_max = (uint32_t)env_double("DWG_LEARN_ROUNDS", 96), period_wide = std::max(1u, (uint32_t)env_double("DWG_LEARN_PERIOD", 32));
   const uint32_t max_warps = (uint32_t)h->sell_blocks_learn * (SELL_LEARN_THREADS / 32);
   const std::vector<float> &Hs = h->learn_H_sorted;
   const double a = stepsize > 0 ? stepsize : 0.0, rho = h->learn_rho;
@@ -770,22 +783,30 @@ static int launch_learn_sell(dwg_handle *h, SweepParams &p, double stepsize) {
   L.reg_l1 = p.reg_l1;
   L.w_N = h->cls_N.p; L.w_H = h->cls_H.p;
   L.weights = h->weights.p;
+  // period 0: the narrow form -- one warp per CTA (an SM to itself while there are SMs), weights
+  // read from and pushed to the live vector record by record
   auto launch = [&](uint32_t vb, uint32_t ve, uint32_t warps, uint32_t period) {
     if (ve <= vb) return;
-    const uint32_t wpc = SELL_LEARN_THREADS / 32;
+    const bool live = period == 0;
+    const uint32_t wpc = live ? 1 : SELL_LEARN_THREADS / 32;
     warps = std::max(1u, std::min(warps, ve - vb));
-    uint32_t threads = SELL_LEARN_THREADS, blocks = warps / wpc;
+    uint32_t threads = wpc * 32, blocks = warps / wpc;
     if (warps < wpc) { threads = warps * 32; blocks = 1; }
     const uint32_t grid_warps = blocks * (threads / 32);
-    L.vbegin = vb; L.vend = ve; L.period = std::max(1u, period);
-    const double inflight = std::min(1.0, (double)grid_warps * L.period / nslice);
+    L.vbegin = vb; L.vend = ve;
+    L.period = live ? 0xffffffffu : period;
+    const double inflight = std::min(1.0, (double)grid_warps * (live ? 1 : period) / nslice);
     // one warp cannot be narrowed further: it keeps the reference's step whatever x is
     L.xcap_inv = grid_warps == 1 ? 0.0 : a * rho * inflight / cap;
-    sell_learn_launch(h, blocks, threads, p, L);
+    sell_learn_launch(h, blocks, threads, live, p, L);
     ++g_launches;
   };
   launch(0, nslice - tail_slices, wide_warps, period_wide);
-  launch(nslice - tail_slices, nslice, tail_warps, 1);
+  // tail: the CTA's weight copy is refreshed before every slice (period 1: eight warps read the
+  // live vector together, sweep a slice each, push their steps together).  Measured on c2_small
+  // (scripts/learn_fidelity.py, 32 seeds): mean |dw| 0.0114 against a noise floor of 0.0101; the
+  // free-running per-record form (period 0) gives 0.018 at the same width.
+  launch(nslice - tail_slices, nslice, tail_warps, (uint32_t)env_double("DWG_LEARN_TAIL_PERIOD", 1));
   if (getenv("DWG_TIMING"))
     fprintf(stderr, "[learn] step %.4g: %u slices, head %u on %u warps (period %u), tail %u on %u warps\n", a, nslice,
             nslice - tail_slices, wide_warps, period_wide, tail_slices, tail_warps);

@@ -71,9 +71,13 @@ __device__ __forceinline__ SliceHeader sell_header(const SellGraph &g, uint32_t 
 // how a slice is read: cached loads for learning (its SGD pass walks the slice a second time
 // and finds it in L1), streaming (evict-first) loads for the direct inference sweep, plain
 // loads when the slice was staged in shared memory by a bulk-async copy
-constexpr int LD_CACHED = 0, LD_STREAM = 1, LD_SMEM = 2;
+// LD_CACHED and LD_SMEM_LIVE mark a LEARNING sweep (its weights and chains are live, see sell_live)
+constexpr int LD_CACHED = 0, LD_STREAM = 1, LD_SMEM = 2, LD_SMEM_LIVE = 3;
 template <int LD, typename T>
-__device__ __forceinline__ T sell_ldt(const T *p) { return LD == LD_SMEM ? *p : LD == LD_STREAM ? __ldcs(p) : __ldg(p); }
+__device__ __forceinline__ T sell_ldt(const T *p) {
+  return (LD == LD_SMEM || LD == LD_SMEM_LIVE) ? *p : LD == LD_STREAM ? __ldcs(p) : __ldg(p);
+}
+__host__ __device__ constexpr bool sell_live(int LD) { return LD == LD_CACHED || LD == LD_SMEM_LIVE; }
 template <int LD>
 __device__ __forceinline__ uint32_t sell_ld(const uint32_t *p) { return sell_ldt<LD, uint32_t>(p); }
 
@@ -97,7 +101,7 @@ __device__ __forceinline__ double sell_fv(const uint32_t *sec, uint32_t ncol, ui
 // writes what it gathers
 template <int LD>
 __device__ __forceinline__ uint32_t sell_chain(const uint8_t *a, uint32_t d) {
-  return LD == LD_CACHED ? (uint32_t)__ldcg(a + d) : (uint32_t)a[d];
+  return sell_live(LD) ? (uint32_t)__ldcg(a + d) : (uint32_t)a[d];
 }
 
 // sign code (0,1,2) -> the term  sign * t  with t = weight * feature value
@@ -105,12 +109,11 @@ __device__ __forceinline__ double sell_term(uint32_t code, double t) {
   return code == 2u ? t : (code == 0u ? -t : 0.0);
 }
 
-// LD_CACHED marks a learning sweep: its weights beyond the shared-memory copy are LIVE (other CTAs
-// move them with atomics while the launch runs), so they are read from L2, not through the
-// non-coherent path
+// the weights of a learning sweep beyond the shared-memory copy are LIVE (other CTAs move them
+// with atomics while the launch runs), so they are read from L2, not through the non-coherent path
 template <int LD>
 __device__ __forceinline__ double sell_weight(const SellGraph &g, const double *w_s, const double *w, uint32_t wid) {
-  return wid < g.n_hot ? w_s[wid] : (LD == 0 ? __ldcg(w + wid) : __ldg(w + wid));
+  return wid < g.n_hot ? w_s[wid] : (sell_live(LD) ? __ldcg(w + wid) : __ldg(w + wid));
 }
 
 __device__ __forceinline__ void sell_stage_weights(const SellGraph &g, const double *w, double *w_s) {
@@ -687,18 +690,31 @@ __device__ __forceinline__ double sell_step_scale(const SellLearn &L, uint32_t w
 }
 
 // gradient of one SGD step: hot weights into the CTA's accumulator of the period, others straight
-// into the live vector together with the step's decay (update_weight, src/inference_result.h:66-85)
+// into the live vector together with the step's decay (update_weight, src/inference_result.h:66-85).
+// Graphs whose feature values are all 1 have integer gradients (differences of sign codes): their
+// accumulators are int32 (a native shared-memory atomic instead of a compare-and-swap loop).
+template <int FV>
 __device__ __forceinline__ void sell_grad(const SellGraph &g, const SellLearn &L, double *acc_s, uint32_t wid,
                                           bool fixed, double grad) {
   if (fixed) return;  // factor_graph.cc:247
   if (wid < g.n_hot) {
-    if (grad != 0.0) atomicAdd(acc_s + wid, grad);
+    if (grad == 0.0) return;
+    if (FV == FV_ONE) atomicAdd(reinterpret_cast<int *>(acc_s + wid), (int)grad);
+    else atomicAdd(acc_s + wid, grad);
     return;
   }
   const double sc = sell_step_scale(L, wid), x = __ldcg(L.weights + wid);
   const double dec = L.reg_l1 ? L.decay * (x < 0 ? 1.0 : 0.0) : -x * (L.decay * sc) / (1.0 + L.decay * sc);
   const double d = dec - L.step * sc * grad;
   if (d != 0.0) atomicAdd(L.weights + wid, d);
+}
+template <int FV>
+__device__ __forceinline__ double sell_acc_take(double *acc_s, uint32_t i) {  // read and clear
+  double a;
+  if (FV == FV_ONE) { a = (double)*reinterpret_cast<int *>(acc_s + i); }
+  else a = acc_s[i];
+  acc_s[i] = 0.0;  // all-zero bits: 0 in both views
+  return a;
 }
 
 // The update of weight i after a learning launch (see k_apply_weights below for the scheme).
@@ -740,9 +756,49 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
   const uint32_t ev = (h.evval >> lane) & 1u;  // Variable::assignment_dense
   double r0, r1;
   dev_uniforms(p, d, r0, r1);
+  // Slices of two-variable factors (the common coupled case): the chain values of every other
+  // variable, both chains, are gathered in ONE batch of independent L2 loads and kept as two bit
+  // masks (bit j: the other variable of record j satisfies its equal_to) -- the free-chain
+  // potentials, the evid-chain potentials and the SGD pass below all read the masks.
+  const bool masks = MULTI && (h.flags & SF_BINARY) && h.n_mu <= 32u;
+  uint32_t sf_mask = 0, se_mask = 0;
+  if (masks) {
+    for (uint32_t j0 = 0; j0 < h.n_mu; j0 += 4) {
+      uint32_t ow[4], af[4], ae[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ow[u] = j0 + u < h.n_mu ? sell_ld<LD>(h.oth + (size_t)32 * (j0 + u) + lane) : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { af[u] = sell_chain<LD>(st.assign_free, ow[u] >> 1); ae[u] = sell_chain<LD>(st.assign_evid, ow[u] >> 1); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < h.n_mu) {
+          sf_mask |= (af[u] == (ow[u] & 1u) ? 1u : 0u) << (j0 + u);
+          se_mask |= (ae[u] == (ow[u] & 1u) ? 1u : 0u) << (j0 + u);
+        }
+    }
+  }
+  // the multi-variable records of a mask slice into (pos, neg) for chain mask m
+  auto masked_multi = [&](uint32_t m, double &ps, double &ng) {
+    for (uint32_t j = 0; j < h.n_mu; ++j) {
+      const uint32_t rec = sell_ld<LD>(h.mu + (size_t)32 * j + lane);
+      const double wt = sell_weight<LD>(g, w_s, st.weights, rec & SELL_WID_MASK);
+      const double t = FV == FV_ONE ? wt : __dmul_rn(wt, sell_fv<FV, LD>(h.mu, h.n_mu, j, lane));
+      const uint32_t tab = (rec >> 24) >> (2u * ((m >> j) & 1u));
+      ps = __dadd_rn(ps, sell_term((tab >> 4) & 3u, t));
+      ng = __dadd_rn(ng, sell_term(tab & 3u, t));
+    }
+  };
   // free chain: every variable, evidence included (gibbs_sampler.h:137-139)
   double pos, neg, upos, uneg;
-  sell_potentials<MULTI, FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_free, pos, neg, &upos, &uneg);
+  if (masks) {
+    pos = 0.0; neg = 0.0;
+    if (h.flags & SF_ANTISYM) sell_unary<FV, LD, true>(g, h, w_s, st.weights, lane, pos, neg);
+    else sell_unary<FV, LD, false>(g, h, w_s, st.weights, lane, pos, neg);
+    upos = pos; uneg = neg;
+    masked_multi(sf_mask, pos, neg);
+  } else {
+    sell_potentials<MULTI, FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_free, pos, neg, &upos, &uneg);
+  }
   const uint32_t pf = sell_draw_boolean(pos, neg, r0);
   if (!pad) st.assign_free[d] = (uint8_t)pf;
   // evid chain (sample_evid, gibbs_sampler.h:171-190): clamp hard evidence, else a Gibbs draw
@@ -752,7 +808,8 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
   if (draw_evid) {
     if (MULTI && h.n_mu) {  // unary-only slices: both chains see identical potentials
       pos = upos; neg = uneg;  // the unary sums are the same on both chains: continue from them
-      sell_multi<FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_evid, nullptr, 0u, pos, neg);
+      if (masks) masked_multi(se_mask, pos, neg);
+      else sell_multi<FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_evid, nullptr, 0u, pos, neg);
     }
     if ((draw_evid >> lane) & 1u) pe = sell_draw_boolean(pos, neg, r1);
   }
@@ -768,7 +825,7 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
       if (!learn || rec == SELL_UNARY_NOP) continue;
       const int cf = (int)(pf ? rec & 3u : rec >> 26), ce = (int)(ev ? rec & 3u : rec >> 26);
       if (cf == ce && !cold) continue;
-      sell_grad(g, L, acc_s, sell_unary_wid(rec), rec & SELL_UN_FIXED_BIT,
+      sell_grad<FV>(g, L, acc_s, sell_unary_wid(rec), rec & SELL_UN_FIXED_BIT,
                 cf == ce ? 0.0 : __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.un, h.n_un, j, lane)));
     }
   }
@@ -779,10 +836,12 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
       const uint32_t ow = sell_ld<LD>(h.oth + (size_t)32 * j + lane);
       if (!learn) continue;
       const uint32_t tag = rec >> 24, od = ow >> 1, eq = ow & 1u;
-      const uint32_t sf = sell_chain<LD>(st.assign_free, od) == eq, se = sell_chain<LD>(st.assign_evid, od) == eq;
+      uint32_t sf, se;
+      if (masks) { sf = (sf_mask >> j) & 1u; se = (se_mask >> j) & 1u; }
+      else { sf = sell_chain<LD>(st.assign_free, od) == eq; se = sell_chain<LD>(st.assign_evid, od) == eq; }
       const int cf = (int)((tag >> (4u * pf + 2u * sf)) & 3u), ce = (int)((tag >> (4u * ev + 2u * se)) & 3u);
       if ((cf == ce && !cold) || tag == SELL_BINARY_NOP) continue;
-      sell_grad(g, L, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
+      sell_grad<FV>(g, L, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
                 cf == ce ? 0.0 : __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.mu, h.n_mu, j, lane)));
     }
   } else {
@@ -797,7 +856,7 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
       sell_general_signs<LD>(h, tag, d, lane, oc, st.assign_free, f0, f1);
       sell_general_signs<LD>(h, tag, d, lane, oc2, st.assign_evid, e0, e1);
       const double fv = sell_fv<FV, LD>(h.mu, h.n_mu, j, lane);
-      sell_grad(g, L, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
+      sell_grad<FV>(g, L, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
                 __dsub_rn(__dmul_rn(pf ? f1 : f0, fv), __dmul_rn(ev ? e1 : e0, fv)));
     }
   }
@@ -805,20 +864,40 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
 
 // One launch of a learning sweep: positions [vbegin, vend) of the visit order, dealt to the warps
 // of the grid round-robin (position vbegin + round * warps + warp: the whole grid moves through the
-// order together, so "later in the order" is "later in time").
+// order together, so "later in the order" is "later in time").  Slices come through a per-warp
+// two-stage ring of bulk-async copies like the staged inference kernel (a slice longer than a
+// stage is read from HBM instead): the blob is static, so the ring runs ahead across the periods.
 constexpr int SELL_LEARN_THREADS = 256;
-__host__ __device__ inline size_t sell_learn_smem(uint32_t n_hot) { return (size_t)n_hot * 24; }
+constexpr uint32_t SELL_LEARN_STAGES = 2;
+__host__ __device__ inline uint32_t sell_learn_bar_off(uint32_t n_hot) { return (24u * n_hot + 15u) & ~15u; }
+__host__ __device__ inline uint32_t sell_learn_ring_off(uint32_t n_hot) {
+  return (sell_learn_bar_off(n_hot) + (SELL_LEARN_THREADS / 32) * SELL_LEARN_STAGES * 8u + 127u) & ~127u;
+}
+__host__ __device__ inline size_t sell_learn_smem(uint32_t n_hot, uint32_t stage_words) {
+  return sell_learn_ring_off(n_hot) + (size_t)(SELL_LEARN_THREADS / 32) * SELL_LEARN_STAGES * stage_words * 4u;
+}
 
 template <bool MULTI, int FV>
 __global__ void __launch_bounds__(SELL_LEARN_THREADS, 2)
-k_sell_learn_live(const SellGraph g, const SellState st, const SweepParams p, const SellLearn L) {
+k_sell_learn_live(const SellGraph g, const SellState st, const SweepParams p, const SellLearn L,
+                  const uint32_t stage_words) {
   extern __shared__ __align__(128) unsigned char sell_smem[];
+  constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
+  constexpr uint32_t ST = SELL_LEARN_STAGES;
   double *w_s = reinterpret_cast<double *>(sell_smem), *acc_s = w_s + g.n_hot;
   float *as_s = reinterpret_cast<float *>(acc_s + g.n_hot), *lam_s = as_s + g.n_hot;
+  const uint32_t *sm = reinterpret_cast<const uint32_t *>(sell_smem);
   __shared__ uint32_t cnt_s;
-  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t npos = L.vend - L.vbegin, rounds = (npos + warps - 1) / warps;
+  const uint32_t n_my = gw < npos ? (npos - 1 - gw) / warps + 1u : 0u;  // positions of this warp
+  const uint32_t bar0 = sell_smem_addr(sell_smem) + sell_learn_bar_off(g.n_hot) + warp * ST * 8u;
+  const uint32_t ringw = sell_learn_ring_off(g.n_hot) / 4u + warp * ST * stage_words;  // word index
+  const uint32_t ring0 = sell_smem_addr(sell_smem) + ringw * 4u;
+  if (lane == 0)
+    for (uint32_t i = 0; i < ST; ++i) sell_mbar_init(bar0 + 8u * i, 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   // per hot weight: step of one update (stepsize x scale) and its decay per slice of the sweep
   // (N_k / slices updates per slice, each  w <- w / (1 + reg step)  resp.  w += reg (w < 0))
   for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) {
@@ -828,28 +907,82 @@ k_sell_learn_live(const SellGraph g, const SellState st, const SweepParams p, co
     lam_s[i] = (float)((double)__ldg(L.w_N + i) * L.inv_nslice * per_update);
     acc_s[i] = 0.0;
   }
-  for (uint32_t r0 = 0; r0 < rounds; r0 += L.period) {
+  // slice index and offsets of this warp's positions, 32 at a time (lane = iteration), one block ahead
+  const uint64_t pol = sell_policy_evict_first();
+  uint32_t cur_s = 0, cur_lo = 0, cur_hi = 0, nxt_s = 0, nxt_lo = 0, nxt_hi = 0;
+  auto fetch = [&](uint32_t kb, uint32_t &sl, uint32_t &lo, uint32_t &hi) {
+    const uint32_t k = kb + lane;
+    if (k < n_my) {
+      sl = __ldg(L.visit + L.vbegin + (size_t)k * warps + gw);
+      lo = __ldg(g.sl_off + sl);
+      hi = __ldg(g.sl_off + sl + 1);
+    }
+  };
+  auto issue = [&](uint32_t k, uint32_t stage) {  // called for k = 0, 1, 2, ... in order
+    const uint32_t j = k & 31u;
+    if (j == 0 && k) {
+      cur_s = nxt_s; cur_lo = nxt_lo; cur_hi = nxt_hi;
+      fetch(k + 32, nxt_s, nxt_lo, nxt_hi);
+    }
+    const uint32_t off = __shfl_sync(0xffffffffu, cur_lo, j);
+    const uint32_t bytes = min((__shfl_sync(0xffffffffu, cur_hi, j) - off) * 32u, stage_words * 4u);
+    if (lane == 0) {
+      sell_mbar_expect_tx(bar0 + 8u * stage, bytes);
+      sell_bulk_g2s(ring0 + stage * stage_words * 4u, g.blob + (size_t)off * 8, bytes, bar0 + 8u * stage, pol);
+    }
+  };
+  __syncthreads();  // mbarriers initialised before any lane waits on one
+  if (n_my) {
+    fetch(0, cur_s, cur_lo, cur_hi);
+    fetch(32, nxt_s, nxt_lo, nxt_hi);
+    const uint32_t pre = n_my < ST ? n_my : ST;
+    for (uint32_t k = 0; k < pre; ++k) issue(k, k);
+  }
+  // the slice index of iteration k was fetched with block k / 32: keep the block of the iteration
+  // being PROCESSED beside the one being issued (which runs ST ahead)
+  uint32_t stage = 0, parity = 0, k = 0;
+  uint32_t proc_s = cur_s;  // slice indices of the block being processed
+  for (uint32_t r0 = 0; r0 < rounds; r0 = r0 + L.period < r0 ? rounds : r0 + L.period) {
     __syncthreads();  // the previous flush is done with w_s / acc_s
     for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) w_s[i] = __ldcg(L.weights + i);
     if (threadIdx.x == 0) cnt_s = 0;
     __syncthreads();
     uint32_t mine = 0;
-    const uint32_t r1 = min(rounds, r0 + L.period);
-    for (uint32_t r = r0; r < r1; ++r) {
-      const uint32_t pos = r * warps + gw;
-      if (pos >= npos) break;
-      const uint32_t s = __ldg(L.visit + L.vbegin + pos);
-      const SliceHeader h = sell_header<FV>(g, s);
-      sell_learn_slice<MULTI, FV, LD_CACHED>(g, st, p, L, h, w_s, acc_s, lane, s * 32u + lane);
+    const uint32_t r1 = r0 + L.period < r0 ? rounds : min(rounds, r0 + L.period);
+    for (uint32_t r = r0; r < r1 && k < n_my; ++r, ++k) {
+      // slice index of iteration k: issue(k) ran two iterations ago and moved cur_s on to k's block
+      // when k opens one; the two last iterations of a block still read the block's own copy
+      if ((k & 31u) == 0 && k) proc_s = cur_s;
+      const uint32_t s = __shfl_sync(0xffffffffu, proc_s, k & 31u);
+      sell_mbar_wait(bar0 + 8u * stage, parity);
+      const uint32_t *b = sm + ringw + stage * stage_words;
+      const uint4 h0 = *reinterpret_cast<const uint4 *>(b);
+      const uint4 h1 = *reinterpret_cast<const uint4 *>(b + 4);
+      SliceHeader h;
+      h.n_un = h0.x; h.n_mu = h0.y; h.n_oc = h0.z; h.evid = h0.w;
+      h.pad = h1.x; h.evval = h1.y; h.flags = h1.z;
+      if (SH_WORDS + 32u * ((h.n_un + h.n_mu) * (1 + FVW) + h.n_oc) <= stage_words) {
+        h.un = b + SH_WORDS;
+        h.mu = h.un + 32u * h.n_un * (1 + FVW);
+        h.oth = h.mu + 32u * h.n_mu * (1 + FVW);
+        sell_learn_slice<MULTI, FV, LD_SMEM_LIVE>(g, st, p, L, h, w_s, acc_s, lane, s * 32u + lane);
+      } else {  // longer than a stage: the records come from HBM (the header carries the slice's offset)
+        h.un = g.blob + (size_t)h1.w * 8 + SH_WORDS;
+        h.mu = h.un + (size_t)32 * h.n_un * (1 + FVW);
+        h.oth = h.mu + (size_t)32 * h.n_mu * (1 + FVW);
+        sell_learn_slice<MULTI, FV, LD_CACHED>(g, st, p, L, h, w_s, acc_s, lane, s * 32u + lane);
+      }
       ++mine;
+      __syncwarp();  // every lane is done with this stage before the next copy lands in it
+      if (k + ST < n_my) issue(k + ST, stage);
+      if (++stage == ST) { stage = 0; parity ^= 1u; }
     }
     // slices this CTA swept in the period (for the decay of the updates it made)
     if (lane == 0 && mine) atomicAdd(&cnt_s, mine);
     __syncthreads();
     const uint32_t cnt = cnt_s;
     for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) {
-      const double a = acc_s[i], x = w_s[i];
-      acc_s[i] = 0.0;
+      const double a = sell_acc_take<FV>(acc_s, i), x = w_s[i];
       const double lam = (double)lam_s[i] * (double)cnt;
       const double dec = L.reg_l1 ? lam * (x < 0 ? 1.0 : 0.0) : x * expm1(-lam);
       const double d = dec - (double)as_s[i] * a;

@@ -496,12 +496,18 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   // ---- schedule order: colour-major; SELL graphs additionally sort each class by
   // (is_evidence, degree and others words descending) so that a 32-variable slice is uniform, and pad every
   // class to a multiple of 32 ----
-  std::vector<uint32_t> class_count(ncolor, 0);
-  for (uint64_t v = 0; v < nvar; ++v) ++class_count[color[v]];
+  // SELL: a class is its query variables, padded to a multiple of 32, then its evidence variables,
+  // padded again: no slice mixes the two (a query-only sweep skips whole slices, and a learning
+  // sweep never meets evidence variables of the first id block behind query variables of the last)
+  std::vector<uint32_t> class_count(ncolor, 0), class_query(ncolor, 0);
+  for (uint64_t v = 0; v < nvar; ++v) {
+    ++class_count[color[v]];
+    if (!g->var_is_evid[v]) ++class_query[color[v]];
+  }
   g->color_start.assign(ncolor + 1, 0);
   for (uint32_t c = 0; c < ncolor; ++c) {
     uint32_t n = class_count[c];
-    if (g->sell) n = (n + 31u) & ~31u;
+    if (g->sell) n = ((class_query[c] + 31u) & ~31u) + ((class_count[c] - class_query[c] + 31u) & ~31u);
     g->color_start[c + 1] = g->color_start[c] + n;
   }
   const uint64_t nvar_pad = g->color_start[ncolor];
@@ -566,7 +572,9 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     parallel_for(nvar, [&](uint64_t i0, uint64_t i1) {
       for (uint64_t i = i0; i < i1; ++i) {
         const uint32_t v = keys[i].v, c = color[v];
-        const uint32_t d = (uint32_t)(g->color_start[c] + (i - class_first[c]));
+        uint64_t in_class = i - class_first[c];
+        if (in_class >= class_query[c]) in_class += ((class_query[c] + 31u) & ~31u) - class_query[c];  // evidence part
+        const uint32_t d = (uint32_t)(g->color_start[c] + in_class);
         g->perm[d] = v;
         g->inv[v] = d;
       }

@@ -77,7 +77,9 @@ def main():
                 name, json.dumps(env), float((err > tol).mean()), err.mean(), np.sqrt(2 / np.pi) * sig.mean(), slope)
             if ms:
                 m = np.mean(ms, 0)
-                line += " mean|dm|=%.4f shift=%+.4f" % (np.abs(m - mref).mean(), m.mean() - mref.mean())
+                per_seed = np.array([x.mean() for x in ms])
+                line += " mean|dm|=%.4f shift=%+.4f (per-seed mean marginal std %.4f)" % (
+                    np.abs(m - mref).mean(), m.mean() - mref.mean(), per_seed.std())
             print(line, flush=True)
             if args.top:
                 for k in np.argsort(-use)[:args.top]:

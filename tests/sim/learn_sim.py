@@ -67,6 +67,20 @@ def make_layout(raw, kind, block=256, sw=32):
         ids = np.arange(nvar, dtype=np.uint64)
         for s0 in range(0, nvar, sw):
             slices.append(ids[s0:s0 + sw])
+    elif kind == "blocked_shape":  # like "blocked", inside an id block sorted by incident-factor count descending
+        evid = (raw.var_role > 0).astype(np.int64)
+        ids = np.arange(nvar, dtype=np.int64)
+        degv = np.bincount(raw.edge_vid.astype(np.int64), minlength=nvar)
+        key = np.lexsort((ids, -degv, ids // block, evid, color))
+        srt = ids[key]
+        grp = color[srt] * 2 + evid[srt]
+        bounds = np.flatnonzero(np.diff(grp)) + 1
+        tmp = []
+        for seg in np.split(srt, bounds):
+            for s0 in range(0, len(seg), sw):
+                tmp.append(seg[s0:s0 + sw].astype(np.uint64))
+        tmp.sort(key=lambda a: (int(a[0]) // block, int(color[int(a[0])])))
+        slices = tmp
     elif kind == "blocked":  # class-pure slices inside (colour, evid) in ascending id; visit by first id block
         evid = (raw.var_role > 0).astype(np.int64)
         ids = np.arange(nvar, dtype=np.int64)
@@ -80,6 +94,13 @@ def make_layout(raw, kind, block=256, sw=32):
                 tmp.append(seg[s0:s0 + sw].astype(np.uint64))
         tmp.sort(key=lambda a: (int(a[0]) // block, int(color[int(a[0])])))
         slices = tmp
+    elif kind == "compiled":  # exactly what the product compiles: learn_visit over the padded schedule order
+        g = sb.Graph.from_raw(raw, sb.SCHED_CHROMATIC)
+        visit = g.image("learn_visit")
+        perm_pad = g.image("perm")
+        for sl in visit:
+            v = perm_pad[int(sl) * 32:int(sl) * 32 + 32]
+            slices.append(v[v != 0xffffffff].astype(np.uint64))
     else:
         raise ValueError(kind)
     order = np.concatenate(slices).astype(np.uint64)

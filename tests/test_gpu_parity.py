@@ -285,13 +285,17 @@ def _learn_order(g):
     return g.learn_order()
 
 
+@pytest.mark.parametrize("stage_words", [None, "64"])
 @pytest.mark.parametrize("seed", range(4))
-def test_parallel_learning_with_exact_arithmetic(seed, monkeypatch):
+def test_parallel_learning_with_exact_arithmetic(seed, stage_words, monkeypatch):
     """a learning sweep on ONE warp (DWG_LEARN_WARPS=1) walks the visit order slice by slice: with
     fixed weights both chains (free-chain draws of every variable, evid-chain clamps / draws) must
-    equal the sequential reference run in that order exactly.  (Categorical graphs: the chromatic
-    CSR launches, schedule order.)"""
+    equal the sequential reference run in that order exactly, whether a slice comes through the
+    bulk-async ring or (stage_words = 64: too small for any slice) straight from HBM.  (Categorical
+    graphs: the chromatic CSR launches, schedule order.)"""
     monkeypatch.setenv("DWG_LEARN_WARPS", "1")
+    if stage_words:
+        monkeypatch.setenv("DWG_SELL_STAGE_WORDS", stage_words)
     rng = np.random.default_rng(800 + seed)
     raw = random_graph(rng, nvar=2000, nfac=5000, nweight=30, p_cat=[0.0, 0.5][seed % 2], max_arity=3)
     raw.fac_fv[:] = rng.choice([1.0, 0.5, 2.0, -1.0], raw.nfac)
@@ -516,7 +520,10 @@ def test_end_to_end_parallel_schedules(name):
     coupled = name in ("partial_observation", "sparse_domains", "sparse_multinomial2")
     for sched in ([sb.SCHED_CHROMATIC] if coupled else [sb.SCHED_CHROMATIC, sb.SCHED_HOGWILD]):
         ws, ms = [], []
-        for seed in range(1, NSEED + 1):
+        # partial_observation: the reference's own seed-to-seed spread is 9 % of the weight (its
+        # weights grow until the step has decayed away); 120 seeds bring the standard error of the
+        # mean under 1 % so that the 5 % gate tests the kernel, not the seed set
+        for seed in range(1, (120 if name == "partial_observation" else NSEED) + 1):
             w, m = _run_schedule(raw, a, 100 + seed, sched)
             ws.append(w); ms.append(m)
         w = np.mean(ws, axis=0)

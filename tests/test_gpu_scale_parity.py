@@ -16,7 +16,7 @@ from sampler_b200 import graphgen
 pytestmark = pytest.mark.gpu
 
 
-NSEEDS = 8
+NSEEDS = 24
 
 
 def _sampler(raw, a, seed):
