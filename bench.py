@@ -40,11 +40,26 @@ sys.path.insert(0, ROOT)
 
 REF_DW = os.path.join(ROOT, "oracle", "_ref", "dw")
 WORKLOADS = {
-    # name: (generator kwargs, description)
-    "c2": dict(nvar=10_000_000, desc="configs[1]: Boolean 10M vars x (8 unary ISTRUE + 1 IMPLY_NATURAL), "
-               "1k shared weights, 50% evidence, --sample_evidence"),
+    # name: generator, default size, dw-args of the config (SURVEY.md 8(d) "Concrete synthetic inputs")
+    "c2": dict(gen="c2_boolean", nvar=10_000_000,
+               desc="configs[1]: Boolean 10M vars x (8 unary ISTRUE + 1 IMPLY_NATURAL), 1k shared weights, 50% evidence, "
+                    "--sample_evidence",
+               learn=dict(n_epoch=20, alpha=0.01, diminish=0.95, reg_param=0.01), kernel="k_sell_infer_staged<MULTI=1,FV=0>"),
+    "c3": dict(gen="c3_categorical", nvar=5_000_000,
+               desc="configs[2]: categorical 5M vars, cardinality 10, sparse domains, per variable 10 unary + 2 pairwise "
+                    "AND_CATEGORICAL + 1 EQUAL, 1k shared weights, 50% evidence, --sample_evidence",
+               learn=dict(n_epoch=10, alpha=0.01, diminish=1.0, reg_param=0.01), kernel="k_cat_infer_staged"),
 }
-LEARN = dict(n_epoch=20, alpha=0.01, diminish=0.95, reg_param=0.01)  # SURVEY.md 8(d) C2 dw-args
+LEARN = WORKLOADS["c2"]["learn"]
+
+
+def common_config(args, world):
+    """the part of `config` both arms share word for word (the driver compares them)"""
+    wl = WORKLOADS[args.workload]
+    nvar = args.nvar or wl["nvar"]
+    return {"workload": wl["desc"] if nvar == wl["nvar"] else wl["desc"] + " [nvar overridden: %d]" % nvar,
+            "nvar_per_replica": nvar, "replicas": world, "graph_seed": 1234, "sample_evidence": True,
+            "l2_policy": "inputs larger than L2 (the compiled graph streamed per sweep exceeds the 126 MB L2); no flush"}
 
 
 def log(*a):
@@ -114,19 +129,27 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # the reference's CPU path, on a bounded sample of the workload
 # --------------------------------------------------------------------------------------
-def run_reference_cpu(nvar_sample: int, n_infer: int, n_learn: int, tmpdir: str):
-    """oracle/_ref/dw gibbs (the unmodified reference, -Ofast, all host threads) on a C2 graph of
-    nvar_sample variables.  Returns per-epoch vars/sec lists (inference, learning)."""
+def run_reference_cpu(workload: str, nvar: int, n_infer: int, n_learn: int, tmpdir: str):
+    """oracle/_ref/dw gibbs (the unmodified reference, -Ofast, all host threads) on the SAME graph
+    the GPU arm sweeps (same generator, same size, written in the reference's binary format).
+    Returns per-epoch vars/sec lists (inference, learning) as the reference prints them."""
     from sampler_b200 import graphgen, graphio
     if not os.path.exists(REF_DW):
         return None
-    raw = graphgen.c2_boolean(nvar_sample)
+    wl = WORKLOADS[workload]
+    t0 = time.time()
+    raw = getattr(graphgen, wl["gen"])(nvar)
     paths = graphio.write_binary(raw, tmpdir)
+    del raw
+    t_files = time.time() - t0
     threads = os.cpu_count() or 1
+    L = wl["learn"]
     cmd = [REF_DW, "gibbs", "-m", paths["meta"], "-v", paths["variables"], "-f", paths["factors"],
            "-w", paths["weights"], "-o", tmpdir, "-l", str(n_learn), "-i", str(n_infer),
-           "--alpha", str(LEARN["alpha"]), "--diminish", str(LEARN["diminish"]),
-           "--reg_param", str(LEARN["reg_param"]), "--sample_evidence", "-t", str(threads), "-c", "1"]
+           "--alpha", str(L["alpha"]), "--diminish", str(L["diminish"]),
+           "--reg_param", str(L["reg_param"]), "--sample_evidence", "-t", str(threads), "-c", "1"]
+    if os.path.exists(paths.get("domains", "")) and os.path.getsize(paths["domains"]):
+        cmd += ["--domains", paths["domains"]]
     t0 = time.time()
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
     wall = time.time() - t0
@@ -135,9 +158,10 @@ def run_reference_cpu(nvar_sample: int, n_infer: int, n_learn: int, tmpdir: str)
     for k in ("variables", "factors", "weights", "domains"):
         try:
             os.remove(paths[k])
-        except OSError:
+        except (OSError, KeyError):
             pass
-    return dict(infer=inf, learn=lrn, threads=threads, wall=wall, nvar=nvar_sample)
+    log("reference: files %.1fs, dw gibbs %.1fs (%d learning + %d inference epochs)" % (t_files, wall, len(lrn), len(inf)))
+    return dict(infer=inf, learn=lrn, threads=threads, wall=wall, nvar=nvar, tail=out[-400:])
 
 
 def reference_arm(args):
@@ -145,26 +169,27 @@ def reference_arm(args):
     if rank != 0:
         return 0
     wl = WORKLOADS[args.workload]
-    nvar_sample = args.ref_nvar
+    nvar = args.nvar or wl["nvar"]
     tmp = tempfile.mkdtemp(prefix="dwref_")
     try:
-        r = run_reference_cpu(nvar_sample, args.steps + args.warmup, 0, tmp)
+        r = run_reference_cpu(args.workload, nvar, args.steps + args.warmup, 0, tmp)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     if r is None or len(r["infer"]) < args.warmup + 1:
-        args.emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/dw missing or produced no epochs"}))
+        args.emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/dw missing or produced no epochs: %s"
+                              % (r["tail"] if r else "no binary")}))
         return 0
     timed = r["infer"][args.warmup:]
     # whole-run throughput over the timed epochs: total samples / total time
-    secs = [nvar_sample / v for v in timed]
-    value = nvar_sample * len(timed) / sum(secs)
-    sample = "C2 graph scaled to %d variables (same per-variable structure), %d inference sweeps" % (nvar_sample, len(timed))
+    secs = [nvar / v for v in timed]
+    value = nvar * len(timed) / sum(secs)
+    sample = "the whole workload: %d variables, %d inference sweeps after %d warm-up sweeps" % (nvar, len(timed), args.warmup)
     line = {
         "impl": "reference", "metric": "gibbs_variable_samples_per_sec", "value": value, "unit": "variable-samples/s",
         "n_gpus": args.gpus, "steps": len(timed), "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "reference_sample": sample, "binary": "oracle/_ref/dw (unmodified reference, -Ofast)",
-                   "threads": r["threads"], "n_datacopy": 1},
+        "config": common_config(args, 1),
+        "impl_config": {"binary": "oracle/_ref/dw (unmodified reference, -Ofast)", "threads": r["threads"], "n_datacopy": 1},
         "cpu_baseline": {"value": value, "unit": "variable-samples/s", "cores": r["threads"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "variable-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -202,9 +227,10 @@ def ours(args):
     sb.load(build=not os.path.exists(sb.api.lib_path()))
     L = sb.load()
     wl = WORKLOADS[args.workload]
+    LEARN = wl["learn"]
     nvar = args.nvar or wl["nvar"]
     t0 = time.time()
-    raw = graphgen.c2_boolean(nvar)
+    raw = getattr(graphgen, wl["gen"])(nvar)
     t_gen = time.time() - t0
     t0 = time.time()
     graph = sb.Graph.from_raw(raw, sb.SCHED_AUTO)
@@ -229,11 +255,13 @@ def ours(args):
     smp.sync()
     barrier()
     e0, e1 = ev(), ev()
+    l0 = L.dwg_launch_count()
     with torch.cuda.stream(stream):
         e0.record(stream)
         group.learn(LEARN["n_epoch"], step, LEARN["diminish"])
         e1.record(stream)
     smp.sync()
+    learn_launches = (L.dwg_launch_count() - l0) / float(n_learn)  # sweep launches + the averaging epilogue
     learn_ms = e0.elapsed_time(e1) / n_learn
     lt = torch.tensor([learn_ms], device="cuda", dtype=torch.float64)
     if dist is not None:
@@ -274,6 +302,7 @@ def ours(args):
 
     t, ns = smp.tallies()
     assert int(ns[0]) == args.steps
+    # Boolean: share of draws that were 1; categorical: every draw tallies one value (must be exactly 1)
     frac1 = float(t.sum()) / (float(nvar) * args.steps * world) if rank == 0 else 0.0
 
     # ---- e2e through the C ABI from host buffers, every replica at once: create (H2D) + K sweeps +
@@ -307,14 +336,15 @@ def ours(args):
     if not args.no_cpu_baseline:
         tmp = tempfile.mkdtemp(prefix="dwref_")
         try:
-            r = run_reference_cpu(args.ref_nvar, 6, 3, tmp)
+            r = run_reference_cpu(args.workload, args.ref_nvar or nvar, 6, 3, tmp)
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
         if r and len(r["infer"]) >= 3:
             cpu = {"value": float(np.median(r["infer"][1:])), "unit": "variable-samples/s", "cores": r["threads"],
                    "kind": "reference",
-                   "sample": "oracle/_ref/dw (unmodified reference, -Ofast) -t %d -c 1 on the C2 graph scaled to %d variables; "
-                             "median of inference epochs 2..6; learning epochs %s vars/s"
+                   "sample": "oracle/_ref/dw (unmodified reference, -Ofast) -t %d -c 1 on the same graph (%d variables, the "
+                             "files the GPU arm's generator writes): 3 learning + 6 inference epochs, median of inference "
+                             "epochs 2..6; learning epochs %s vars/s"
                              % (r["threads"], r["nvar"], ("%.3g" % np.median(r["learn"][1:])) if len(r["learn"]) > 1 else "n/a")}
         else:
             cpu = {"value": None, "unit": "variable-samples/s", "cores": os.cpu_count(), "kind": "reference",
@@ -323,29 +353,35 @@ def ours(args):
     peak, peak_src = measured_peak()
     bytes_sweep = float(info.bytes_per_sweep_infer)
     achieved = bytes_sweep / (sweep_ms * 1e-3) / 1e9
-    big_launches = max(1, sum(1 for c in range(info.num_colors)))
-    traffic = None
+    # one launch = one colour class: the dominant launch is the largest class
+    _, cstart = graph.schedule()
+    class_sizes = np.diff(cstart.astype(np.int64))
+    launch_share = float(class_sizes.max()) / float(max(1, class_sizes.sum()))
+    traffic = frac_dram = traffic_src = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath) and nvar == wl["nvar"]:
-        try:  # dram bytes of ONE launch of the sweep kernel from the committed `ncu --set full` capture
-            traffic = json.load(open(tpath))["k_sell_infer_staged"]["dram_bytes_per_launch"]
+        try:  # DRAM bytes of the sweep kernel's launches from the committed `ncu --set full` capture of this workload
+            t = json.load(open(tpath))[args.workload]
+            traffic = t["dram_bytes_per_launch"]
+            frac_dram = t["dram_bytes_per_sweep"] / (sweep_ms * 1e-3) / 1e9 / peak
+            traffic_src = t["source"]
         except Exception:
-            traffic = None
+            traffic = frac_dram = None
+    cfg = common_config(args, world)
     line = {
         "metric": "gibbs_variable_samples_per_sec", "value": value, "unit": "variable-samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"] if nvar == wl["nvar"] else wl["desc"] + " [nvar overridden: %d]" % nvar,
-                   "nvar_per_replica": nvar, "schedule": "chromatic" if info.schedule == 2 else "hogwild",
-                   "colors": info.num_colors, "replicas": world,
-                   "l2_policy": "inputs larger than L2 (%.0f MiB streamed per sweep vs 126 MB L2); no flush" % (info.device_bytes / 2**20),
-                   "learn_epochs_before": n_learn + 1, "seed": 1234},
+        "config": cfg,
+        "impl_config": {"schedule": {2: "chromatic", 1: "hogwild", 3: "sequential"}.get(info.schedule), "colors": info.num_colors,
+                        "device_mib_per_replica": info.device_bytes / 2**20, "learn_epochs_before": n_learn + 1, "sampler_seed": 1234},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "k_sell_infer_staged<MULTI=1,FV=0> (one launch per colour class; achieved = bytes of a whole "
-                               "sweep / CUDA-event time of the sweep, i.e. the launch-weighted average)",
+                     "traffic": traffic, "frac_dram": frac_dram, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "kernel": "%s (one launch per colour class; achieved = algorithmic bytes of a whole sweep / CUDA-event "
+                               "time of the sweep, i.e. the launch-weighted average; frac_dram = DRAM bytes of a sweep "
+                               "(ncu) / the same time / peak)" % wl["kernel"],
                      "algorithmic_bytes_per_sweep": bytes_sweep, "bytes_per_variable_sample": bytes_sweep / nvar,
-                     "algorithmic_bytes_per_launch": bytes_sweep / big_launches,
+                     "algorithmic_bytes_per_launch": bytes_sweep * launch_share,
                      "launches_per_sweep": info.num_colors},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "variable-samples/s",
@@ -353,7 +389,8 @@ def ours(args):
                 "what": "dwg_create (upload of the compiled graph from page-locked host memory) + %d sweeps + dwg_get_tallies "
                         "(D2H into host arrays), wall clock: %s" % (args.steps, e2e_parts)},
         "learn": {"value": nvar * world / (learn_ms * 1e-3), "unit": "variable-updates/s", "ms_per_epoch": learn_ms,
-                  "epochs": n_learn, "hbm_gbs": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9},
+                  "epochs": n_learn, "hbm_gbs": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9,
+                  "frac": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9 / peak, "launches_per_epoch": learn_launches},
         "gpu_launches": int(launches), "clocks": clk, "frac_true": frac1,
     }
     args.emit(json.dumps(line))
@@ -383,7 +420,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--nvar", type=int, default=0, help="override variables per replica (debug)")
-    ap.add_argument("--ref-nvar", type=int, default=1_000_000, help="variables of the reference's bounded sample")
+    ap.add_argument("--ref-nvar", type=int, default=0, help="cpu_baseline only: variables of the reference's sample "
+                    "(default: the workload's own size, i.e. the same files)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -144,7 +144,8 @@ void dwg_destroy(dwg_handle *h);
 int dwg_learn_epoch(dwg_handle *h, double stepsize);
 /* GibbsSampler::sample(i_epoch)+wait (src/gibbs_sampler.cc:20-25): one inference sweep. */
 int dwg_infer_epoch(dwg_handle *h);
-/* n sweeps back to back, replayed from a captured CUDA graph when the schedule has >1 launch */
+/* n sweeps back to back (the launches of consecutive colour classes are chained by programmatic
+ * dependent launch; no host synchronisation in between) */
 int dwg_infer_epochs(dwg_handle *h, uint64_t n);
 int dwg_sync(dwg_handle *h);
 void *dwg_stream(dwg_handle *h); /* cudaStream_t the sweeps are launched on */

@@ -1220,10 +1220,11 @@ int dwg_average_weights_multi(dwg_handle *const *hs, void *const *comms, int n, 
       if (rc) return rc;
       for (size_t j = 0; j < nw; ++j) sum[j] += tmp[j];
     }
+    // dwg_get_weights hands out ABI order; the device vector is in internal (hottest first) order:
+    // the sum goes back through dwg_set_weight_sum, which applies the same permutation
     for (int i = 0; i < n; ++i) {
-      CU(cudaSetDevice(hs[i]->device));
-      CU(cudaMemcpyAsync(hs[i]->weights.p, sum.data(), 8 * nw, cudaMemcpyHostToDevice, hs[i]->stream));
-      CU(cudaStreamSynchronize(hs[i]->stream));
+      int rc = dwg_set_weight_sum(hs[i], sum.data());
+      if (rc) return rc;
     }
   }
   for (int i = n - 1; i >= 0; --i) {

@@ -298,6 +298,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
 
   pt.lap("rows");
   // ---- schedule ----
+  const bool auto_schedule = schedule == DWG_SCHED_AUTO;
   if (schedule == DWG_SCHED_AUTO) {
     uint64_t nrec = 0;
     for (uint64_t v = 0; v < nvar; ++v) nrec += inc_end[v] - deg[v];
@@ -315,10 +316,18 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       double n = (double)(raw.fac_ptr[f + 1] - raw.fac_ptr[f]);
       cost += n * n;
     }
-    if (cost > 2e10) {
-      *err = DWG_ERR_UNSUPPORTED;
-      return "chromatic schedule: factor arities too large to colour; use the hogwild schedule";
+    // the conflict lists below hold sum n (n - 1) entries: beyond ~4 G of them (16 GB) colouring is
+    // not worth its memory.  AUTO then sweeps Hogwild like the reference's threads; an explicit
+    // chromatic request is refused.
+    if (cost > 4e9) {
+      if (!auto_schedule) {
+        *err = DWG_ERR_UNSUPPORTED;
+        return "chromatic schedule: factor arities too large to colour; use the hogwild schedule";
+      }
+      schedule = DWG_SCHED_HOGWILD;
     }
+  }
+  if (schedule == DWG_SCHED_CHROMATIC && coupled) {
     // conflict lists (the other variables of every incident factor; repeats are harmless), built
     // in parallel; the two greedy passes below then touch nothing but these and color[]
     std::vector<uint64_t> nb_ptr(nvar + 1, 0);

@@ -230,14 +230,11 @@ int gibbs(const CmdParser &args) {
     }
   }
 
-  // ---- inference, :121-160.  --burn_in (parsed but unused by the reference) discards that many
-  // extra sweeps first; the default 0 is the reference's behaviour. ----
+  // ---- inference, :121-160.  --burn_in is parsed, printed and NOT used, like the reference
+  // (src/cmd_parser.cc:91, no reader): identical arguments give identical schedules. ----
   {
     const uint64_t n_epoch = compute_n_epochs(args.n_inference_epoch);
     Timer t_total, t;
-    if (args.n_inference_epoch > 0)
-      for (uint64_t e = 0; e < args.burn_in; ++e)
-        for (auto *h : R.hs) TRY(dwg_infer_epoch(h));
     for (auto *h : R.hs) TRY(dwg_clear_tallies(h));
     for (uint64_t e = 0; e < n_epoch; ++e) {
       if (progress) {

@@ -338,6 +338,44 @@ def make_scale():
         print(name, "weights", wmean[:4], "+-", np.std(ws, 0)[:4], "mean marginal", np.mean(ms), np.mean(mf))
 
 
+def text2bin_fixtures():
+    """text2bin/: the reference's converter fixtures (test/text2bin/*.txt inputs with their xxd dumps
+    *.bin.txt, test/text2bin.bats:11-27) and, per bundled graph, the TSV inputs of test/<name>/ with
+    their text2bin-args, plus the reference's own bin2text rendering of the binary files committed
+    under graphs/<name>/ -> converter parity both ways."""
+    dst = os.path.join(HERE, "text2bin")
+    os.makedirs(dst, exist_ok=True)
+    for f in sorted(os.listdir(os.path.join(REF_TEST, "text2bin"))):
+        shutil.copy(os.path.join(REF_TEST, "text2bin", f), os.path.join(dst, f))
+    for g in GRAPHS:
+        src, out = os.path.join(REF_TEST, g), os.path.join(dst, g)
+        os.makedirs(out, exist_ok=True)
+        for f in sorted(os.listdir(src)):
+            if f.endswith(".tsv") or f.endswith(".text2bin-args"):
+                shutil.copy(os.path.join(src, f), os.path.join(out, f))
+        # the reference's text2bin output per TSV (count on the last argument's file) and its
+        # bin2text rendering of that output
+        for what, plural in KIND.items():
+            for tsv in sorted(f for f in os.listdir(src) if f.startswith(plural) and f.endswith(".tsv")):
+                stem = tsv[:-4]
+                args = []
+                a = os.path.join(src, stem + ".text2bin-args")
+                if os.path.exists(a):
+                    args = open(a).read().split()
+                binf, cnt = os.path.join(out, stem + ".bin"), os.path.join(out, stem + ".count")
+                subprocess.check_call([ol.REF_DW, "text2bin", what, os.path.join(src, tsv), binf, cnt] + args)
+        # the reference's bin2text rendering of the whole graph as committed under graphs/<name>/
+        gdir, b2t = os.path.join(HERE, "graphs", g), os.path.join(out, "bin2text")
+        os.makedirs(b2t, exist_ok=True)
+        subprocess.check_call([ol.REF_DW, "bin2text", "-m", os.path.join(gdir, "graph.meta"),
+                               "-v", os.path.join(gdir, "graph.variables"), "-f", os.path.join(gdir, "graph.factors"),
+                               "-w", os.path.join(gdir, "graph.weights"), "--domains", os.path.join(gdir, "graph.domains"),
+                               "-o", b2t], stdout=subprocess.DEVNULL)
+        for junk in ("domains.tsv", "graph.meta"):  # dump_domains prints uninitialised memory (src/bin2text.cc:52-69)
+            if os.path.exists(os.path.join(b2t, junk)):
+                os.remove(os.path.join(b2t, junk))
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF_TEST) and ol.have_ref(), "run `make -C oracle` in the build container first"
     what = sys.argv[1:] or ["graphs", "factor", "logadd", "draw", "sampler"]
@@ -353,3 +391,5 @@ if __name__ == "__main__":
         make_graphs()
     if "scale" in what:
         make_scale()
+    if "text2bin" in what:
+        text2bin_fixtures()
