@@ -23,6 +23,7 @@
 #include "../../include/dwg.h"
 #include "dwg_kernels.cuh"
 #include "dwg_sell.cuh"
+#include "dwg_cell.cuh"
 #include "graph_image.h"
 #include "host/parallel.h"
 
@@ -58,9 +59,8 @@ struct dwg_graph {
       if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) pinned.push_back(p);
       else cudaGetLastError();  // not fatal: the copy falls back to pageable memory
     };
-    if (img.sell) {
-      reg(img.blob.data(), img.blob.size() * 4);
-    } else {
+    if (img.sell || img.cell) reg(img.blob.data(), img.blob.size() * 4);
+    if (!img.sell) {
       reg(img.e_wid.data(), img.e_wid.size() * 4);
       reg(img.e_tag.data(), img.e_tag.size());
       reg(img.oth.data(), img.oth.size() * 4);
@@ -79,7 +79,7 @@ struct dwg_graph {
   mutable std::vector<uint32_t> cls_query_end, cls_max_words;  // the latter: longest slice of the class
   const std::vector<uint32_t> &query_end() const {
     std::lock_guard<std::mutex> lk(pin_mu);
-    if (!cls_query_end.empty() || !img.sell) return cls_query_end;
+    if (!cls_query_end.empty() || !(img.sell || img.cell)) return cls_query_end;
     const uint32_t nc = img.ncolor();
     cls_query_end.assign(nc, 0);
     cls_max_words.assign(nc, 0);
@@ -189,6 +189,10 @@ struct dwg_handle {
   // grid cap; 0 stages = not available (DWG_SELL_DIRECT=1, or no room for two stages)
   uint32_t sell_stages = 0, sell_stage_words = 0, sell_staged_warps = 0;
   int sell_blocks_staged = 0;
+  // categorical sliced-ELL inference kernel (dwg_cell.cuh)
+  CellGraph cg{};
+  uint32_t cell_stages = 0, cell_stage_words = 0;
+  int cell_blocks = 0;
   // per colour class: the first slice from which every slice holds evidence / padding only
   // (slices are sorted non-evidence first inside a class, compile.cc)
   std::vector<uint32_t> cls_query_end;
@@ -324,6 +328,43 @@ void sell_learn_launch_t(dwg_handle *h, uint32_t blocks, uint32_t threads, bool 
     else if (m.fv_mode == FV_F32) { CALL(false, FV_F32); }                     \
     else { CALL(false, FV_F64); }                                              \
   }
+constexpr int CELL_THREADS = 256;
+int cell_setup(dwg_handle *h) {
+  const GraphImage &m = *h->img;
+  const uint32_t nwarp = CELL_THREADS / 32, stages = 2;
+  const uint32_t n_tab = (uint32_t)std::min<uint64_t>({m.nweight, (uint64_t)m.n_hot, (uint64_t)SELL_MAX_TAB});
+  const size_t budget = 112 * 1024;  // two CTAs per SM
+  const size_t fixed = sell_staged_ring_off(n_tab, stages, nwarp) + 128 + (size_t)nwarp * m.cell_kmax * 256;
+  if (fixed + (size_t)nwarp * stages * 4 * 128 > budget) return fail(DWG_ERR_UNSUPPORTED, "categorical sweep: cardinality too large for shared memory");
+  uint32_t cap = (uint32_t)((budget - fixed) / (nwarp * stages * 4)) & ~3u;
+  if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) cap = std::min<uint32_t>(cap, std::max(80, atoi(e)) & ~3u);  // tests
+  const uint32_t words = std::max(80u, std::min(cap, (m.sell_max_words + 3u) & ~3u));
+  const size_t smem = cell_smem(n_tab, stages, words, nwarp, m.cell_kmax);
+  const bool allhot = m.nweight <= n_tab;
+  int rc = allhot ? sell_grid(k_cell_infer_staged<true, CELL_THREADS>, smem, h->num_sms, &h->cell_blocks, CELL_THREADS)
+                  : sell_grid(k_cell_infer_staged<false, CELL_THREADS>, smem, h->num_sms, &h->cell_blocks, CELL_THREADS);
+  if (rc) return rc;
+  h->cell_stages = stages;
+  h->cell_stage_words = words;
+  h->cg.sl_off = h->sl_off.p; h->cg.blob = h->blob.p;
+  h->cg.nweight = (uint32_t)m.nweight; h->cg.n_tab = n_tab; h->cg.kmax = m.cell_kmax;
+  return DWG_OK;
+}
+void cell_launch(dwg_handle *h, bool pdl, uint32_t blocks, const CellGraph &cg, const SweepParams &p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(CELL_THREADS);
+  cfg.dynamicSmemBytes = cell_smem(cg.n_tab, h->cell_stages, h->cell_stage_words, CELL_THREADS / 32, cg.kmax);
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  if (h->img->nweight <= cg.n_tab)
+    cudaLaunchKernelEx(&cfg, k_cell_infer_staged<true, CELL_THREADS>, cg, h->ss, p, h->cell_stages, h->cell_stage_words);
+  else
+    cudaLaunchKernelEx(&cfg, k_cell_infer_staged<false, CELL_THREADS>, cg, h->ss, p, h->cell_stages, h->cell_stage_words);
+}
 int sell_setup(dwg_handle *h) {
   const GraphImage &m = *h->img;
   int rc = DWG_OK;
@@ -425,9 +466,9 @@ static size_t image_device_bytes(const GraphImage &m) {
   size_t b = 0;
   b += m.var_flags.size() + m.w_fixed.size();
   b += (size_t)m.assign_bytes * m.nvar_pad * 3;  // evid_val + two chains
-  if (m.sell) {
-    b += 4 * (m.sl_off.size() + m.blob.size());
-  } else {
+  if (m.sell || m.cell) b += 4 * (m.sl_off.size() + m.blob.size());
+  if (m.cell) b += 4 * m.var_row.size();  // (the CSR stream joins when a learning sweep needs it)
+  else if (!m.sell) {
     b += m.e_tag.size() + 4 * (m.var_row.size() + m.row_ptr.size() + m.row_oth.size() + m.e_wid.size() + m.oth.size());
     b += 4 * m.e_fv32.size() + 8 * m.e_fv64.size() + 8 * m.truthiness.size();
   }
@@ -676,7 +717,19 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
   ds.weights = h->weights.p;
   ds.grad_acc = h->grad_acc.p;
   ds.tallies = h->tallies.p;
-  if (!m.sell) {
+  if (m.cell) {
+    // categorical sliced-ELL graph: the inference sweep streams the blob; the CSR stream (learning
+    // sweeps, parity hooks) is uploaded on first use
+    CU(h->sl_off.upload(m.sl_off, s));
+    CU(h->blob.upload(m.blob, s));
+    CU(cudaStreamSynchronize(s));
+    SellState &ss = h->ss;
+    ss.assign_free = h->assign_free8.p; ss.assign_evid = h->assign_evid8.p;
+    ss.weights = h->weights.p; ss.grad_acc = h->grad_acc.p; ss.tallies = h->tallies.p;
+    rc = cell_setup(h.get());
+    if (rc) return rc;
+    h->cls_query_end = g->query_end();
+  } else if (!m.sell) {
     rc = ensure_csr(h.get());
     if (rc) return rc;
   } else {
@@ -819,7 +872,9 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
   SweepParams p = make_params(h, stepsize);
   ++h->sweep_counter;
   const bool use_sell = m.sell && !p.sequential;
-  if (!use_sell) {
+  const bool use_cell = m.cell && !p.sequential && !learn && !getenv("DWG_CELL_OFF");  // categorical inference sweeps
+  if (!use_sell && !use_cell) {
+    h->chain_open = false;
     int rc = ensure_csr(h);
     if (rc) return rc;
   }
@@ -849,7 +904,16 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
       const uint32_t my_units = (units - b + chunks - 1) / chunks;
       p.unit_stride = chunks;
       p.unit_phase = b;
-      if (use_sell) {
+      if (use_cell) {
+        CellGraph cg = h->cg;
+        cg.slice_begin = p.d_begin / 32;
+        cg.slice_end = p.sample_evidence ? p.d_end / 32 : h->cls_query_end[c];  // gibbs_sampler.h:157
+        if (cg.slice_end <= cg.slice_begin) continue;
+        const uint32_t need = (cg.slice_end - cg.slice_begin + CELL_THREADS / 32 - 1) / (CELL_THREADS / 32);
+        const bool pdl = !getenv("DWG_SELL_NO_PDL") && h->chain_open;
+        cell_launch(h, pdl, std::min<uint32_t>(need, (uint32_t)h->cell_blocks), cg, p);
+        h->chain_open = true;
+      } else if (use_sell) {
         SellGraph sg = h->sg;
         sg.slice_begin = p.d_begin / 32;
         sg.slice_end = p.d_end / 32;

@@ -80,6 +80,24 @@ inline constexpr uint32_t sell_unary_record(uint32_t wid, bool fixed, uint32_t c
 inline constexpr uint32_t sell_unary_wid(uint32_t rec) { return (rec & SELL_UN_WID8_MASK) >> 3; }
 constexpr uint64_t SELL_MAX_WEIGHTS = 1ull << 23;
 
+// ---- categorical sliced-ELL blob (graphs whose variables are ALL categorical with cardinality
+// <= CELL_MAX_CARD and whose factors touch at most two variables; parallel schedules) ----------
+// Slice = 32 variables, lane = variable, one contiguous run of words at 8 * sl_off[s]:
+//   header  8 words  CH_*: record columns, others columns, evidence / padding masks, own offset, max cardinality
+//   meta    32 words per lane: cardinality | evidence value << 8
+//   row0    32 words per lane: first tally row of the variable (rows of a variable are consecutive)
+//   records n_rec columns x 32 words, per lane the records of value 0, then of value 1, ... each
+//           row in factor-id order (the reference's order, src/factor_graph.cc:179-195):
+//             wid[21:0] | table[29:22] | consumes-an-others-word << 30 | first-record-of-a-row << 31
+//           table = sign codes (0 -> -1, 1 -> 0, 2 -> +1) at bits 2 * (2 * self_sat + other_sat); a
+//           row without factors holds one CELL_NOP_ROW record, a lane's tail CELL_NOP records
+//   others  n_oc columns x 32 words: (d << 8 | dense equal_to) of the other variable, consumed in order
+constexpr int CH_N_REC = 0, CH_N_OTH = 1, CH_EVID_MASK = 2, CH_PAD_MASK = 3, CH_KMAX = 4, CH_SELF_OFF = 7;
+constexpr uint32_t CELL_MAX_CARD = 32, CELL_MAX_OTH = 32;
+constexpr uint64_t CELL_MAX_WEIGHTS = 1ull << 22, CELL_MAX_VARS = 1ull << 24;
+constexpr uint32_t CELL_WID_MASK = 0x3fffffu, CELL_MULTI_BIT = 1u << 30, CELL_ROW_BIT = 1u << 31;
+constexpr uint32_t CELL_NOP = 0x55u << 22, CELL_NOP_ROW = CELL_NOP | CELL_ROW_BIT;  // every code 1: adds +0.0
+
 // weights with internal id < n_hot are staged in shared memory by the sweep kernels
 #define DWG_HOT_WEIGHTS 4096
 
@@ -99,6 +117,8 @@ struct GraphImage {
   uint64_t nvar_pad = 0;  // variables in schedule order incl. class padding (== nvar unless sell)
   uint64_t ndrow = 0;     // device rows: nrow, or nvar_pad for sell graphs
   bool sell = false;      // Boolean-only + parallel schedule: sliced-ELL arrays below are built
+  bool cell = false;      // categorical-only + parallel schedule: the categorical sliced-ELL blob (CELL_*) is built
+  uint32_t cell_kmax = 0; // largest cardinality (CELL graphs)
 
   // schedule order
   std::vector<uint32_t> perm;         // [nvar]   d -> original vid

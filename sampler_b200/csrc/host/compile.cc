@@ -483,9 +483,9 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   // ... evaluated ONCE per incidence (a random read of the factor each time), kept as
   // form | self position << 2 for the three phases that need it (sort keys, sizing, CSR fill)
   BulkVec<uint8_t> finfo(nedge);
-  int general_seen = 0;
+  int general_seen = 0, wide_seen = 0;
   parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
-    bool any_general = false;
+    bool any_general = false, any_wide = false;
     for (uint64_t v = v0; v < v1; ++v) {
       const bool cat = g->var_dtype[v];
       for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
@@ -493,13 +493,26 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         const int form = edge_form(v, inc[i].fid, inc[i].key, cat, &self_pos);
         finfo[i] = (uint8_t)(form | ((form != (int)FORM_GENERAL ? self_pos : 0) << 2));
         any_general |= form == (int)FORM_GENERAL;
+        any_wide |= form >= 2;
       }
       if (any_general) __atomic_store_n(&general_seen, 1, __ATOMIC_RELAXED);
+      if (any_wide) __atomic_store_n(&wide_seen, 1, __ATOMIC_RELAXED);
     }
   });
   // a general-form record walks the others stream even when its factor has one variable (a Boolean
   // edge with equal_to >= 2, a variable twice in a factor): the stream and its row offsets must exist
   if (general_seen) g->has_multi = true;
+  // graphs of categorical variables only, factors over at most two variables, feature values 1: the
+  // categorical sliced-ELL stream (graph_image.h CELL_*); everything else keeps the CSR kernels
+  {
+    bool all_cat = nvar > 0;
+    for (uint64_t v = 0; v < nvar && all_cat; ++v) all_cat = g->var_dtype[v] && raw.var_card[v] >= 1;
+    g->cell = all_cat && !wide_seen && max_card <= CELL_MAX_CARD && g->fv_mode == FV_ONE &&
+              schedule != DWG_SCHED_SEQUENTIAL && nweight <= CELL_MAX_WEIGHTS && nvar + 64ull * ncolor < CELL_MAX_VARS &&
+              !getenv("DWG_NO_CELL");
+    g->cell_kmax = (uint32_t)max_card;
+  }
+  const bool padded = g->sell || g->cell;  // schedule order with classes padded to whole slices
 
   pt.lap("layout knobs");
   // ---- schedule order: colour-major; SELL graphs additionally sort each class by
@@ -516,14 +529,14 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   g->color_start.assign(ncolor + 1, 0);
   for (uint32_t c = 0; c < ncolor; ++c) {
     uint32_t n = class_count[c];
-    if (g->sell) n = ((class_query[c] + 31u) & ~31u) + ((class_count[c] - class_query[c] + 31u) & ~31u);
+    if (padded) n = ((class_query[c] + 31u) & ~31u) + ((class_count[c] - class_query[c] + 31u) & ~31u);
     g->color_start[c + 1] = g->color_start[c] + n;
   }
   const uint64_t nvar_pad = g->color_start[ncolor];
   g->nvar_pad = nvar_pad;
   g->perm.assign(nvar_pad, 0xffffffffu);
   g->inv.resize(nvar);
-  if (g->sell) {
+  if (padded) {
     // Order inside a class: (is_evidence, id block, then unary / multi / others counts DESCENDING).
     // Evidence last: the evidence tail of a class is one range a query-only sweep never reads.  Id
     // blocks ascending: a LEARNING sweep visits the slices in ascending id block (learn_visit
@@ -599,7 +612,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
 
   pt.lap("schedule order (sort)");
   // ---- emit rows and edge records (CSR) in schedule order ----
-  const uint64_t ndrow = g->sell ? nvar_pad : nrow;  // device rows (pads own an empty row)
+  const uint64_t ndrow = g->sell ? nvar_pad : nrow + (nvar_pad - nvar);  // device rows (pads own an empty row)
   g->ndrow = ndrow;
   g->var_flags.assign(nvar_pad, VF_PAD); g->evid_val.assign(nvar_pad, 0);
   if (g->has_categorical) g->var_row.resize(nvar_pad + 1);
@@ -667,6 +680,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     for (uint64_t d = d0; d < d1; ++d) {
       uint64_t v = g->perm[d];
       if (v == 0xffffffffu) {  // pad: an empty row
+        if (g->has_categorical) g->var_row[d] = (uint32_t)row;
         g->row_ptr[row] = (uint32_t)ei;
         if (g->has_multi) g->row_oth[row] = (uint32_t)oc;
         ++row;
@@ -1007,6 +1021,122 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       }
       h[SH_FLAGS] = (antisym ? SF_ANTISYM : 0u) | (binary ? SF_BINARY : 0u);
     }
+    });
+  }
+  // ---- categorical sliced-ELL blob (graph_image.h CELL_*) ----
+  std::vector<uint32_t> cell_rec, cell_oc;
+  // host mirror of dev_sign (dwg_device.cuh) for one- and two-variable factors, as sign codes
+    auto code1 = [](uint32_t fc, bool self_sat) -> uint32_t {  // arity 1
+      if (self_sat) return 2;
+      switch (fc) {
+        case FC_AND: case FC_OR: case FC_IMPLY_NATURAL: return 0;
+        case FC_EQUAL: return 2;
+        default: return 1;
+      }
+    };
+    auto code2 = [](uint32_t fc, uint32_t nsb, bool head) -> uint32_t {  // arity 2: one body position
+      const bool body_all = nsb == 1;
+      int sgn;
+      switch (fc) {
+        case FC_AND: sgn = (body_all && head) ? 1 : -1; break;
+        case FC_AND_CATEGORICAL: sgn = (body_all && head) ? 1 : 0; break;
+        case FC_OR: sgn = (nsb > 0 || head) ? 1 : -1; break;
+        case FC_EQUAL: sgn = (nsb + (head ? 1u : 0u)) != 1 ? 1 : -1; break;
+        case FC_IMPLY_NATURAL: sgn = body_all ? (head ? 1 : -1) : 0; break;
+        case FC_IMPLY_MLN: sgn = body_all ? (head ? 1 : 0) : 1; break;
+        default: sgn = (head || nsb == 0) ? 1 : 0; break;  // LINEAR / RATIO (log2(1+1) = 1) / LOGICAL
+      }
+      return (uint32_t)(sgn + 1);
+    };
+  if (g->cell) {
+    const uint64_t nslice = nvar_pad / 32;
+    // slice shapes: record columns (an empty row still holds one record), others columns
+    cell_rec.assign(nslice, 0); cell_oc.assign(nslice, 0);
+    std::vector<uint32_t> &s_rec = cell_rec, &s_oc = cell_oc;
+    int too_many_others = 0;
+    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
+      for (uint64_t sidx = a0; sidx < a1; ++sidx) {
+        uint32_t rec = 0, oc = 0;
+        for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
+          if (g->var_flags[d] & VF_PAD) continue;
+          uint32_t r = 0, o = 0;
+          for (uint64_t row = g->var_row[d]; row < g->var_row[d + 1]; ++row) {
+            const uint32_t n = g->row_ptr[row + 1] - g->row_ptr[row];
+            r += n ? n : 1u;
+            if (g->has_multi) o += g->row_oth[row + 1] - g->row_oth[row];
+          }
+          rec = std::max(rec, r); oc = std::max(oc, o);
+        }
+        s_rec[sidx] = rec; s_oc[sidx] = oc;
+        if (oc > CELL_MAX_OTH) __atomic_store_n(&too_many_others, 1, __ATOMIC_RELAXED);
+      }
+    });
+    if (too_many_others) g->cell = false;  // a variable with more than 32 two-variable factors: the CSR kernels sweep this graph
+  }
+  if (g->cell) {
+    const uint64_t nslice = nvar_pad / 32;
+    std::vector<uint32_t> &s_rec = cell_rec, &s_oc = cell_oc;
+    g->sl_off.assign(nslice + 1, 0);
+    uint64_t words = 0;
+    for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
+      g->sl_off[sidx] = (uint32_t)(words / 8);
+      const uint64_t w = SH_WORDS + 32ull * (2 + s_rec[sidx] + s_oc[sidx]);
+      g->sell_max_words = (uint32_t)std::max<uint64_t>(g->sell_max_words, w);
+      words += w;
+      if (words / 8 >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "categorical sliced-ELL stream exceeds 2^32 x 32 B"; }
+    }
+    g->sl_off[nslice] = (uint32_t)(words / 8);
+    g->blob.assign(words, 0);
+    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
+      for (uint64_t sidx = a0; sidx < a1; ++sidx) {
+        uint32_t *h = g->blob.data() + (uint64_t)g->sl_off[sidx] * 8;
+        const uint32_t nrec = s_rec[sidx], noc = s_oc[sidx];
+        const uint64_t o_meta = SH_WORDS, o_row0 = o_meta + 32, o_rec = o_row0 + 32, o_oth = o_rec + 32ull * nrec;
+        h[CH_N_REC] = nrec; h[CH_N_OTH] = noc; h[CH_SELF_OFF] = g->sl_off[sidx];
+        uint32_t kmax = 0;
+        for (uint32_t l = 0; l < 32; ++l) {
+          const uint64_t d = sidx * 32 + l;
+          uint32_t jr = 0, jo = 0;
+          if (g->var_flags[d] & VF_PAD) {
+            h[CH_PAD_MASK] |= 1u << l;
+            h[o_row0 + l] = g->var_row[d];
+          } else {
+            if (g->var_flags[d] & VF_EVID) h[CH_EVID_MASK] |= 1u << l;
+            const uint32_t K = g->var_row[d + 1] - g->var_row[d];
+            kmax = std::max(kmax, K);
+            h[o_meta + l] = K | (g->evid_val[d] << 8);
+            h[o_row0 + l] = g->var_row[d];
+            for (uint64_t row = g->var_row[d]; row < g->var_row[d + 1]; ++row) {
+              bool first = true;
+              uint64_t o = g->has_multi ? g->row_oth[row] : 0;
+              for (uint64_t e = g->row_ptr[row]; e < g->row_ptr[row + 1]; ++e) {
+                const uint8_t tag = g->e_tag[e];
+                const uint32_t fc = tag & TAG_FUNC_MASK, form = tag >> TAG_FORM_SHIFT;
+                uint32_t table = 0;
+                for (uint32_t ss = 0; ss < 2; ++ss)
+                  for (uint32_t os = 0; os < 2; ++os) {
+                    uint32_t c;
+                    if (form == 0) c = code1(fc, ss);
+                    else if (tag & TAG_SELF_HEAD) c = code2(fc, os, ss);
+                    else c = code2(fc, ss, os);
+                    table |= c << (2 * (2 * ss + os));
+                  }
+                uint32_t rec = g->e_wid[e] | (table << 22) | (first ? CELL_ROW_BIT : 0u);
+                if (form == 1) {
+                  rec |= CELL_MULTI_BIT;
+                  h[o_oth + 32ull * jo + l] = (g->oth[2 * o] << 8) | (g->oth[2 * o + 1] & 0xffu);
+                  ++jo; ++o;
+                }
+                h[o_rec + 32ull * jr + l] = rec;
+                ++jr; first = false;
+              }
+              if (first) { h[o_rec + 32ull * jr + l] = CELL_NOP_ROW; ++jr; }  // a value without factors
+            }
+          }
+          for (; jr < nrec; ++jr) h[o_rec + 32ull * jr + l] = CELL_NOP;
+        }
+        h[CH_KMAX] = kmax;
+      }
     });
   }
   pt.lap("sliced-ELL blob");
