@@ -49,8 +49,29 @@ WORKLOADS = {
                desc="configs[2]: categorical 5M vars, cardinality 10, sparse domains, per variable 10 unary + 2 pairwise "
                     "AND_CATEGORICAL + 1 EQUAL, 1k shared weights, 50% evidence, --sample_evidence",
                learn=dict(n_epoch=10, alpha=0.01, diminish=1.0, reg_param=0.01), kernel="k_cat_infer_staged"),
+    # the two graphs too large for any record array: streamed by the library (csrc/host/synth.cc); the
+    # reference's CPU run holds 72 B per edge, so it gets the same generator at 1/10 resp. 1/30 of
+    # the variables ("run the reference on a /10 (C4) / /30 (C5) graph ... and say so")
+    "c4": dict(synth=True, nvar=50_000_000, ref_div=10,
+               desc="configs[3]: logistic-style Boolean 50M vars x 20 unary ISTRUE features (f64 values ~N(0,1)), 1M tied "
+                    "weights (Zipf 1.1), 90% evidence from a planted logistic model, SGD with decay, --sample_evidence",
+               learn=dict(n_epoch=10, alpha=0.001, diminish=0.9, reg_param=0.01), kernel="k_sell_infer_staged<MULTI=0,FV=f64>"),
+    "c5": dict(synth=True, nvar=300_000_000, ref_div=30,
+               desc="configs[4]: README-scale Boolean 300M vars x 10 unary ISTRUE features per replica, 1k shared weights, "
+                    "50% evidence, inference only, --sample_evidence",
+               learn=dict(n_epoch=0, alpha=0.01, diminish=0.95, reg_param=0.01), kernel="k_sell_infer_staged<MULTI=0,FV=0>"),
 }
 LEARN = WORKLOADS["c2"]["learn"]
+
+
+def make_raw(workload, nvar):
+    """the workload's records (numpy): file-backed sizes only"""
+    from sampler_b200 import graphgen
+    wl = WORKLOADS[workload]
+    if wl.get("synth"):
+        spec = dict(graphgen.SYNTH_SPECS[workload], nvar=nvar)
+        return graphgen.synth_unary(seed=1234, **spec)
+    return getattr(graphgen, wl["gen"])(nvar)
 
 
 def common_config(args, world):
@@ -138,7 +159,7 @@ def run_reference_cpu(workload: str, nvar: int, n_infer: int, n_learn: int, tmpd
         return None
     wl = WORKLOADS[workload]
     t0 = time.time()
-    raw = getattr(graphgen, wl["gen"])(nvar)
+    raw = make_raw(workload, nvar)
     paths = graphio.write_binary(raw, tmpdir)
     del raw
     t_files = time.time() - t0
@@ -169,7 +190,8 @@ def reference_arm(args):
     if rank != 0:
         return 0
     wl = WORKLOADS[args.workload]
-    nvar = args.nvar or wl["nvar"]
+    nvar_full = args.nvar or wl["nvar"]
+    nvar = nvar_full // wl.get("ref_div", 1)
     tmp = tempfile.mkdtemp(prefix="dwref_")
     try:
         r = run_reference_cpu(args.workload, nvar, args.steps + args.warmup, 0, tmp)
@@ -184,6 +206,9 @@ def reference_arm(args):
     secs = [nvar / v for v in timed]
     value = nvar * len(timed) / sum(secs)
     sample = "the whole workload: %d variables, %d inference sweeps after %d warm-up sweeps" % (nvar, len(timed), args.warmup)
+    if nvar != nvar_full:
+        sample = ("the workload's generator at 1/%d of the variables (%d; the reference holds 72 B per edge and cannot load "
+                  "the full graph), %d inference sweeps after %d warm-up sweeps" % (wl["ref_div"], nvar, len(timed), args.warmup))
     line = {
         "impl": "reference", "metric": "gibbs_variable_samples_per_sec", "value": value, "unit": "variable-samples/s",
         "n_gpus": args.gpus, "steps": len(timed), "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
@@ -230,12 +255,16 @@ def ours(args):
     LEARN = wl["learn"]
     nvar = args.nvar or wl["nvar"]
     t0 = time.time()
-    raw = getattr(graphgen, wl["gen"])(nvar)
-    t_gen = time.time() - t0
-    t0 = time.time()
-    graph = sb.Graph.from_raw(raw, sb.SCHED_AUTO)
+    if wl.get("synth"):
+        t_gen = 0.0
+        graph = sb.Graph.synthetic_unary(seed=1234, **dict(graphgen.SYNTH_SPECS[args.workload], nvar=nvar))
+    else:
+        raw = make_raw(args.workload, nvar)
+        t_gen = time.time() - t0
+        t0 = time.time()
+        graph = sb.Graph.from_raw(raw, sb.SCHED_AUTO)
+        del raw
     t_compile = time.time() - t0
-    del raw
     info = graph.info
     if rank == 0:
         log("graph: %d vars, %d edge records, %d colours, %.1f MiB/replica; gen %.1fs compile %.1fs"
@@ -251,22 +280,24 @@ def ours(args):
     # ---- learning phase: ceil(l / N) epochs per replica, weights averaged every epoch ----
     n_learn = compute_n_epochs(LEARN["n_epoch"], world)
     step = LEARN["alpha"]
-    smp.learn_epoch(step)  # warm-up epoch (JIT-free, but first touch of everything)
-    smp.sync()
-    barrier()
-    e0, e1 = ev(), ev()
-    l0 = L.dwg_launch_count()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        group.learn(LEARN["n_epoch"], step, LEARN["diminish"])
-        e1.record(stream)
-    smp.sync()
-    learn_launches = (L.dwg_launch_count() - l0) / float(n_learn)  # sweep launches + the averaging epilogue
-    learn_ms = e0.elapsed_time(e1) / n_learn
-    lt = torch.tensor([learn_ms], device="cuda", dtype=torch.float64)
+    learn_ms, learn_launches = None, 0.0
+    if n_learn:
+        smp.learn_epoch(step)  # warm-up epoch (JIT-free, but first touch of everything)
+        smp.sync()
+        barrier()
+        e0, e1 = ev(), ev()
+        l0 = L.dwg_launch_count()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            group.learn(LEARN["n_epoch"], step, LEARN["diminish"])  # every epoch: sweep, allreduce of the weights, average
+            e1.record(stream)
+        smp.sync()
+        learn_launches = (L.dwg_launch_count() - l0) / float(n_learn)  # sweep launches + the averaging epilogue
+        learn_ms = e0.elapsed_time(e1) / n_learn
+    lt = torch.tensor([learn_ms or 0.0], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(lt, op=dist.ReduceOp.MAX)
-    learn_ms = float(lt.item())
+    learn_ms = float(lt.item()) or None
 
     # ---- inference: W warm-up sweeps, K timed ----
     smp.clear_tallies()
@@ -336,16 +367,16 @@ def ours(args):
     if not args.no_cpu_baseline:
         tmp = tempfile.mkdtemp(prefix="dwref_")
         try:
-            r = run_reference_cpu(args.workload, args.ref_nvar or nvar, 6, 3, tmp)
+            r = run_reference_cpu(args.workload, args.ref_nvar or nvar // wl.get("ref_div", 1), 6, 3 if LEARN["n_epoch"] else 0, tmp)
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
         if r and len(r["infer"]) >= 3:
             cpu = {"value": float(np.median(r["infer"][1:])), "unit": "variable-samples/s", "cores": r["threads"],
                    "kind": "reference",
-                   "sample": "oracle/_ref/dw (unmodified reference, -Ofast) -t %d -c 1 on the same graph (%d variables, the "
+                   "sample": "oracle/_ref/dw (unmodified reference, -Ofast) -t %d -c 1 on %s (%d variables, the "
                              "files the GPU arm's generator writes): 3 learning + 6 inference epochs, median of inference "
                              "epochs 2..6; learning epochs %s vars/s"
-                             % (r["threads"], r["nvar"], ("%.3g" % np.median(r["learn"][1:])) if len(r["learn"]) > 1 else "n/a")}
+                             % (r["threads"], "the same graph" if r["nvar"] == nvar else "the same generator at 1/%d of the variables" % wl.get("ref_div", 1), r["nvar"], ("%.3g" % np.median(r["learn"][1:])) if len(r["learn"]) > 1 else "n/a")}
         else:
             cpu = {"value": None, "unit": "variable-samples/s", "cores": os.cpu_count(), "kind": "reference",
                    "sample": "oracle/_ref/dw unavailable on this box"}
@@ -354,9 +385,11 @@ def ours(args):
     bytes_sweep = float(info.bytes_per_sweep_infer)
     achieved = bytes_sweep / (sweep_ms * 1e-3) / 1e9
     # one launch = one colour class: the dominant launch is the largest class
-    _, cstart = graph.schedule()
-    class_sizes = np.diff(cstart.astype(np.int64))
-    launch_share = float(class_sizes.max()) / float(max(1, class_sizes.sum()))
+    launch_share = 1.0
+    if info.num_colors > 1:
+        _, cstart = graph.schedule()
+        class_sizes = np.diff(cstart.astype(np.int64))
+        launch_share = float(class_sizes.max()) / float(max(1, class_sizes.sum()))
     traffic = frac_dram = traffic_src = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath) and nvar == wl["nvar"]:
@@ -388,9 +421,12 @@ def ours(args):
                 "h2d_bytes_per_step": int(info.device_bytes / args.steps), "d2h_bytes_per_step": int(4 * info.num_values / args.steps),
                 "what": "dwg_create (upload of the compiled graph from page-locked host memory) + %d sweeps + dwg_get_tallies "
                         "(D2H into host arrays), wall clock: %s" % (args.steps, e2e_parts)},
-        "learn": {"value": nvar * world / (learn_ms * 1e-3), "unit": "variable-updates/s", "ms_per_epoch": learn_ms,
+        "learn": None if not learn_ms else
+                 {"value": nvar * world / (learn_ms * 1e-3), "unit": "variable-updates/s", "ms_per_epoch": learn_ms,
                   "epochs": n_learn, "hbm_gbs": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9,
-                  "frac": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9 / peak, "launches_per_epoch": learn_launches},
+                  "frac": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9 / peak, "launches_per_epoch": learn_launches,
+                  "what": "one epoch = a learning sweep of every variable + the allreduce of the weight vector (%d B) over "
+                          "the replicas + the averaging epilogue, all inside the timed region" % (8 * info.num_weights)},
         "gpu_launches": int(launches), "clocks": clk, "frac_true": frac1,
     }
     args.emit(json.dumps(line))

@@ -107,6 +107,15 @@ int dwg_graph_from_raw(const dwg_raw_t *raw, int schedule, dwg_graph **out);
 int dwg_graph_from_files(const char *meta, int n_var, const char *const *var_files, int n_dom,
                          const char *const *dom_files, int n_fac, const char *const *fac_files,
                          int n_wgt, const char *const *wgt_files, int schedule, dwg_graph **out);
+/* Benchmark input tooling (no reference counterpart): the compiled image of a synthetic graph of
+ * nvar Boolean variables x `degree` unary ISTRUE factors over nweight tied weights (ids uniform, or
+ * Zipf(zipf) when zipf > 0; feature values 1 or ~N(0,1) when real_features; evidence with
+ * probability p_evid, labelled by a planted logistic model), streamed slice by slice so that graphs
+ * of 10^9 .. 3 x 10^9 factors (BASELINE.json configs[3], configs[4]) never exist as records.  The
+ * same graph, record for record, comes out of sampler_b200/graphgen.py synth_unary.  cdf_out
+ * (optional, nweight doubles): the Zipf table used. */
+int dwg_graph_synthetic_unary(uint64_t nvar, uint32_t degree, uint64_t nweight, double zipf, int real_features,
+                              double p_evid, uint64_t seed, double *cdf_out, dwg_graph **out);
 void dwg_graph_free(dwg_graph *g);
 /* The compiled image is page-locked on the first dwg_create so that every replica's upload is a
  * DMA at the PCIe rate (the reference deep-copies the FactorGraph per NUMA node,

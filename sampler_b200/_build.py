@@ -17,8 +17,8 @@ DW = os.path.join(PKG, "dw")
 
 CU_SOURCES = ["dwg_api.cu"]
 HOST_SOURCES = ["host/compile.cc", "host/loader.cc", "host/cmd_parser.cc", "host/gibbs_app.cc",
-                "host/text2bin.cc"]
-HEADERS = ["dwg_device.cuh", "dwg_kernels.cuh", "dwg_sell.cuh", "graph_image.h", "host/cmd_parser.h",
+                "host/text2bin.cc", "host/synth.cc"]
+HEADERS = ["dwg_device.cuh", "dwg_kernels.cuh", "dwg_sell.cuh", "dwg_cell.cuh", "graph_image.h", "host/parallel.h", "host/cmd_parser.h",
            os.path.join(ROOT, "include", "dwg.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]

@@ -82,6 +82,7 @@ def load(build: bool = False):
     L.dwg_graph_info.argtypes = [vp, C.POINTER(GraphInfo)]
     L.dwg_graph_var_meta.argtypes = [vp, vp, vp, vp, vp]
     L.dwg_debug_schedule.argtypes = [vp, vp, vp]
+    L.dwg_graph_synthetic_unary.argtypes = [u64, C.c_uint32, u64, dbl, i32, dbl, u64, vp, C.POINTER(vp)]
     L.dwg_debug_learn_order.argtypes = [vp, vp, vp]
     L.dwg_debug_image.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(u64), C.POINTER(C.c_uint32)]
     L.dwg_create.argtypes = [vp, C.POINTER(Opts), i32, C.POINTER(vp)]
@@ -145,6 +146,18 @@ class Graph:
         out = C.c_void_p()
         _check(L.dwg_graph_from_raw(C.byref(c), schedule, C.byref(out)))
         return cls(out)
+
+    @classmethod
+    def synthetic_unary(cls, nvar: int, degree: int, nweight: int, zipf: float = 0.0, real_features: bool = False,
+                        p_evid: float = 0.5, seed: int = 1234, want_cdf: bool = False):
+        """the compiled image of graphgen.synth_unary(...) streamed by the library (no records held):
+        BASELINE.json configs[3] / configs[4] at full size"""
+        out = C.c_void_p()
+        cdf = np.zeros(nweight if (want_cdf and zipf > 0) else 0, np.float64)
+        _check(load().dwg_graph_synthetic_unary(nvar, degree, nweight, float(zipf), int(real_features), float(p_evid),
+                                                seed, _ptr(cdf) if len(cdf) else None, C.byref(out)))
+        g = cls(out)
+        return (g, cdf) if want_cdf else g
 
     @classmethod
     def from_files(cls, meta: str, variables: Sequence[str], domains: Sequence[str],

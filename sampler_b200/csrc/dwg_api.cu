@@ -252,31 +252,38 @@ int sell_setup_t(dwg_handle *h) {
   // measured (profiles/r1_v4_ab.txt): with neighbour gathers in the loop 8 warps x <= 128 registers per
   // CTA win (more loads in flight per warp beat more warps), unary-only graphs stream best with 16 x 64
   uint32_t nwarp = MULTI ? 8 : 16;
-  if (const char *e = getenv("DWG_SELL_WARPS")) nwarp = atoi(e) == 16 ? 16 : 8;
+  if (const char *e = getenv("DWG_SELL_WARPS")) nwarp = atoi(e) == 16 ? 16 : atoi(e) == 4 ? 4 : 8;
   const uint32_t n_tab = (uint32_t)std::min<uint64_t>({h->img->nweight, n_hot, SELL_MAX_TAB});
   // the deepest ring (<= SELL_MAX_STAGES, two CTAs per SM) whose stage holds at least 99.5 % of the
   // slices whole (90 % for the two-stage ring); the rare longer slice is staged up to its stage's
-  // end and read from HBM directly
+  // end and read from HBM directly.  Long slices (20 f64-valued features = 7.7 KB) get fewer warps
+  // per CTA (8, then 4) so that two stages still fit.
   const std::vector<uint32_t> &off = h->img->sl_off;
   const size_t nslice = off.empty() ? 0 : off.size() - 1;
   const uint32_t want = (h->img->sell_max_words + 3u) & ~3u;
   uint32_t stages = 0, words = 0;
-  for (uint32_t st = max_stages; st >= 2 && !stages; --st) {
-    const size_t fixed = sell_staged_ring_off(n_tab, st, nwarp);
-    uint32_t cap = (uint32_t)((budget - fixed) / (nwarp * st * 4)) & ~3u;
-    if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) cap = std::min<uint32_t>(cap, std::max(8, atoi(e)) & ~3u);  // tests
-    size_t fit = 0;
-    for (size_t i = 0; i < nslice; ++i) fit += (off[i + 1] - off[i]) * 8u <= cap;
-    if (fit * 1000 >= nslice * 995 || (st == 2 && fit * 10 >= nslice * 9)) { stages = st; words = std::min(cap, want); }
+  for (; !stages; nwarp /= 2) {
+    for (uint32_t st = max_stages; st >= 2 && !stages; --st) {
+      const size_t fixed = sell_staged_ring_off(n_tab, st, nwarp);
+      uint32_t cap = (uint32_t)((budget - fixed) / (nwarp * st * 4)) & ~3u;
+      if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) cap = std::min<uint32_t>(cap, std::max(8, atoi(e)) & ~3u);  // tests
+      size_t fit = 0;
+      // (slices of a streamed synthetic image all have the same length: look at a sample)
+      const size_t stride = nslice > (1u << 22) ? nslice >> 20 : 1;
+      size_t seen = 0;
+      for (size_t i = 0; i < nslice; i += stride, ++seen) fit += (off[i + 1] - off[i]) * 8u <= cap;
+      if (fit * 1000 >= seen * 995 || (st == 2 && fit * 10 >= seen * 9)) { stages = st; words = std::min(cap, want); }
+    }
+    if (stages || nwarp == 4) break;
   }
-  // slices too long for even a two-stage ring (e.g. 20 f64-valued features per variable): the
-  // direct kernel streams them from HBM
+  // slices too long even for four warps x two stages: the direct kernel streams them from HBM
   if (!stages) return DWG_OK;
   const size_t smem = sell_staged_smem(n_tab, stages, words, nwarp);
   const bool allhot = h->img->nweight <= n_tab;
 #define STAGED_GRID(AH, NT) sell_grid(k_sell_infer_staged<MULTI, FV, AH, NT>, smem, h->num_sms, &h->sell_blocks_staged, NT)
   rc = nwarp == 16 ? (allhot ? STAGED_GRID(true, 512) : STAGED_GRID(false, 512))
-                    : (allhot ? STAGED_GRID(true, 256) : STAGED_GRID(false, 256));
+       : nwarp == 8 ? (allhot ? STAGED_GRID(true, 256) : STAGED_GRID(false, 256))
+                    : (allhot ? STAGED_GRID(true, 128) : STAGED_GRID(false, 128));
 #undef STAGED_GRID
   if (rc) return rc;
   h->sell_staged_warps = nwarp;
@@ -304,7 +311,8 @@ void sell_launch_t(dwg_handle *h, bool staged, bool pdl, uint32_t blocks, const 
 #define STAGED_LAUNCH(AH, NT) \
   cudaLaunchKernelEx(&cfg, k_sell_infer_staged<MULTI, FV, AH, NT>, sg, h->ss, p, h->sell_stages, h->sell_stage_words)
     if (h->sell_staged_warps == 16) { if (allhot) STAGED_LAUNCH(true, 512); else STAGED_LAUNCH(false, 512); }
-    else { if (allhot) STAGED_LAUNCH(true, 256); else STAGED_LAUNCH(false, 256); }
+    else if (h->sell_staged_warps == 8) { if (allhot) STAGED_LAUNCH(true, 256); else STAGED_LAUNCH(false, 256); }
+    else { if (allhot) STAGED_LAUNCH(true, 128); else STAGED_LAUNCH(false, 128); }
 #undef STAGED_LAUNCH
   } else k_sell_infer<MULTI, FV><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
 }
@@ -453,6 +461,24 @@ int dwg_graph_from_files(const char *meta, int n_var, const char *const *var_fil
   return DWG_OK;
 }
 
+int dwg_graph_synthetic_unary(uint64_t nvar, uint32_t degree, uint64_t nweight, double zipf, int real_features,
+                              double p_evid, uint64_t seed, double *cdf_out, dwg_graph **out) {
+  if (!out) return fail(DWG_ERR_INVALID, "null argument");
+  try {
+    std::unique_ptr<dwg_graph> g(new dwg_graph);
+    int err = 0;
+    std::vector<double> cdf;
+    const std::string msg = build_synthetic_unary(nvar, degree, nweight, zipf, real_features != 0, p_evid, seed, &g->img,
+                                                  cdf_out ? &cdf : nullptr, &err);
+    if (!msg.empty()) return fail(err, msg);
+    if (cdf_out && !cdf.empty()) std::memcpy(cdf_out, cdf.data(), 8 * cdf.size());
+    *out = g.release();
+  } catch (const std::exception &e) {
+    return fail(DWG_ERR_INVALID, std::string("synthetic graph: ") + e.what());
+  }
+  return DWG_OK;
+}
+
 void dwg_graph_free(dwg_graph *g) { delete g; }
 
 int dwg_graph_set_page_locking(dwg_graph *g, int on) {
@@ -503,8 +529,14 @@ int dwg_graph_var_meta(const dwg_graph *g, uint8_t *dtype, uint8_t *is_evid, uin
   const GraphImage &m = g->img;
   if (dtype) std::memcpy(dtype, m.var_dtype.data(), m.nvar);
   if (is_evid) std::memcpy(is_evid, m.var_is_evid.data(), m.nvar);
-  if (value_base) std::memcpy(value_base, m.value_base.data(), 8 * (m.nvar + 1));
-  if (values) std::memcpy(values, m.values.data(), 8 * m.nrow);
+  if (value_base) {
+    if (m.value_base.empty()) for (uint64_t v = 0; v <= m.nvar; ++v) value_base[v] = v;  // streamed Boolean image: one value per variable
+    else std::memcpy(value_base, m.value_base.data(), 8 * (m.nvar + 1));
+  }
+  if (values) {
+    if (m.values.empty()) std::memset(values, 0, 8 * m.nrow);
+    else std::memcpy(values, m.values.data(), 8 * m.nrow);
+  }
   return DWG_OK;
 }
 
@@ -595,6 +627,8 @@ static int init_state(dwg_handle *h) {
 static int ensure_csr(dwg_handle *h) {
   if (h->csr_ready) return DWG_OK;
   const GraphImage &m = *h->img;
+  if (!m.csr_built)
+    return fail(DWG_ERR_UNSUPPORTED, "a streamed synthetic graph has no CSR stream (parity hooks and the sequential schedule need one)");
   cudaStream_t s = h->stream;
   CU(cudaSetDevice(h->device));
   CU(h->e_tag.upload(m.e_tag, s));

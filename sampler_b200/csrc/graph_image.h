@@ -117,6 +117,7 @@ struct GraphImage {
   uint64_t nvar_pad = 0;  // variables in schedule order incl. class padding (== nvar unless sell)
   uint64_t ndrow = 0;     // device rows: nrow, or nvar_pad for sell graphs
   bool sell = false;      // Boolean-only + parallel schedule: sliced-ELL arrays below are built
+  bool csr_built = true;  // false: a streamed synthetic image (synth.cc) -- no CSR stream, no per-value host tables
   bool cell = false;      // categorical-only + parallel schedule: the categorical sliced-ELL blob (CELL_*) is built
   uint32_t cell_kmax = 0; // largest cardinality (CELL graphs)
 
@@ -218,6 +219,10 @@ RawView view_of(const RawGraph &r);
 
 // compile.cc: returns "" on success, else the error message (code in *err)
 std::string compile_graph(const RawView &raw, int schedule, GraphImage *out, int *err);
+
+// synth.cc: the image of a synthetic unary Boolean graph, streamed (never holds the records)
+std::string build_synthetic_unary(uint64_t nvar, uint32_t degree, uint64_t nweight, double zipf, bool real_features,
+                                  double p_evid, uint64_t seed, GraphImage *out, std::vector<double> *cdf_out, int *err);
 
 // loader.cc: reads the reference's binary files; returns "" or an error message
 struct MetaCounts { uint64_t nweight = 0, nvar = 0, nfac = 0, nedge = 0; };

@@ -133,3 +133,80 @@ def c4_logistic(nvar: int = 50_000_000, degree: int = 20, nweight: int = 1_000_0
 def c5_large(nvar: int = 300_000_000, degree: int = 10, nweight: int = 1000,
              seed: int = DEFAULT_SEED) -> RawGraph:
     return unary_boolean(nvar, degree, nweight, p_evid=0.5, seed=seed)
+
+
+# --------------------------------------------------------------------------------------
+# Counter-based generator (configs[3] / configs[4] at full size).  Every quantity is a pure
+# function of (seed, stream, index) through the splitmix64 finaliser, so the C++ builder
+# (csrc/host/synth.cc, dwg_graph_synthetic_unary) produces the SAME graph record by record
+# without ever holding the records, and this numpy mirror feeds the parity tests and the
+# reference's scaled-down CPU run.  Only +, * and comparisons on doubles (no libm calls) except
+# the logistic label, so both sides agree bit for bit.
+# --------------------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+SYNTH_SQRT3 = 1.7320508075688772
+
+
+def _mix64(x):
+    """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic)"""
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        z = x
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return z ^ (z >> np.uint64(31))
+
+
+def _hash(seed, stream, idx):
+    with np.errstate(over="ignore"):
+        base = _mix64(np.uint64(seed) + np.uint64(stream) * np.uint64(0xD1B54A32D192ED03))
+        return _mix64(base + idx.astype(np.uint64))
+
+
+def _u01(h):
+    return (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def zipf_cdf(nweight, s):
+    ranks = np.arange(1, nweight + 1, dtype=np.float64)
+    cdf = np.cumsum(ranks ** -s)
+    return cdf / cdf[-1]
+
+
+def synth_unary(nvar: int, degree: int, nweight: int, zipf: float = 0.0, real_features: bool = False,
+                p_evid: float = 0.5, seed: int = DEFAULT_SEED, cdf=None) -> RawGraph:
+    """Boolean variables x `degree` unary ISTRUE features, counter-based (see above).
+    C4 = (5e7, 20, 1e6, zipf 1.1, real-valued features, p_evid 0.9); C5 = (3e8, 10, 1000, p_evid 0.5).
+    `cdf`: the Zipf table to use (tests pass the one the C++ builder computed, so that a last-bit
+    difference between two pow() implementations cannot move a weight id)."""
+    nfac = nvar * degree
+    f = np.arange(nfac, dtype=np.uint64)
+    v = np.arange(nvar, dtype=np.uint64)
+    if zipf > 0:
+        cdf = zipf_cdf(nweight, zipf) if cdf is None else cdf
+        wid = np.minimum(np.searchsorted(cdf, _u01(_hash(seed, 3, f)), side="left"), nweight - 1).astype(np.uint64)
+    else:
+        wid = _hash(seed, 3, f) % np.uint64(nweight)
+    if real_features:
+        fv = (((_u01(_hash(seed, 4, f)) + _u01(_hash(seed, 5, f))) + _u01(_hash(seed, 6, f))) + _u01(_hash(seed, 7, f)) - 2.0) * SYNTH_SQRT3
+    else:
+        fv = np.ones(nfac)
+    k = np.arange(nweight, dtype=np.uint64)
+    wstar = 0.5 * ((((_u01(_hash(seed, 8, k)) + _u01(_hash(seed, 9, k))) + _u01(_hash(seed, 10, k))) + _u01(_hash(seed, 11, k)) - 2.0) * SYNTH_SQRT3)
+    term = (wstar[wid.astype(np.int64)] * fv).reshape(nvar, degree)
+    acc = np.zeros(nvar)
+    for j in range(degree):  # sequential sum, like the builder
+        acc = acc + term[:, j]
+    logit = 2.0 * acc
+    label = (_u01(_hash(seed, 2, v)) < 1.0 / (1.0 + np.exp(-logit))).astype(np.uint64)
+    role = (_u01(_hash(seed, 1, v)) < p_evid).astype(np.uint8)
+    return RawGraph(role, np.where(role > 0, label, 0).astype(np.uint64), np.zeros(nvar, np.uint16),
+                    np.full(nvar, 2, np.uint64), *empty_domains(), np.full(nfac, FUNC_ISTRUE, np.int32),
+                    np.arange(nfac + 1, dtype=np.uint64), np.repeat(v, degree), np.ones(nfac, np.uint64), wid, fv,
+                    np.zeros(nweight), np.zeros(nweight, np.uint8)).normalized()
+
+
+SYNTH_SPECS = {
+    "c4": dict(nvar=50_000_000, degree=20, nweight=1_000_000, zipf=1.1, real_features=True, p_evid=0.9),
+    "c5": dict(nvar=300_000_000, degree=10, nweight=1000, zipf=0.0, real_features=False, p_evid=0.5),
+}
