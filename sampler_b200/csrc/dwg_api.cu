@@ -274,9 +274,13 @@ int sell_setup_t(dwg_handle *h) {
       for (size_t i = 0; i < nslice; i += stride, ++seen) fit += (off[i + 1] - off[i]) * 8u <= cap;
       if (fit * 1000 >= seen * 995 || (st == 2 && fit * 10 >= seen * 9)) { stages = st; words = std::min(cap, want); }
     }
-    if (stages || nwarp == 4) break;
+    // measured (profiles/r2_c4_ab.txt, 20 f64 features = 7.7 KB per slice, 20 M variables): four
+    // warps per CTA with a two-stage ring sweep in 2.88 ms, the direct kernel (32 warps per SM, loads
+    // issued a batch ahead) in 1.08 ms -- eight resident warps cannot cover the latency of the
+    // weight gathers.  So the ladder stops at eight warps unless DWG_SELL_WARPS=4 asks for the rest.
+    if (stages || nwarp == 4 || (nwarp == 8 && !getenv("DWG_SELL_WARPS"))) break;
   }
-  // slices too long even for four warps x two stages: the direct kernel streams them from HBM
+  // slices too long for the ring: the direct kernel streams them from HBM
   if (!stages) return DWG_OK;
   const size_t smem = sell_staged_smem(n_tab, stages, words, nwarp);
   const bool allhot = h->img->nweight <= n_tab;
@@ -893,10 +897,17 @@ static int launch_learn_sell(dwg_handle *h, SweepParams &p, double stepsize) {
   // live vector together, sweep a slice each, push their steps together).  Measured on c2_small
   // (scripts/learn_fidelity.py, 32 seeds): mean |dw| 0.0114 against a noise floor of 0.0101; the
   // free-running per-record form (period 0) gives 0.018 at the same width.
-  launch(nslice - tail_slices, nslice, tail_warps, (uint32_t)env_double("DWG_LEARN_TAIL_PERIOD", 1));
+  // (a tail already as wide as the GPU has room left under the cap: it goes into the period)
+  uint32_t tail_period = 1;
+  if (tail_warps >= max_warps && !Hs.empty() && a > 0) {
+    const size_t n = Hs.size(), lo = std::lower_bound(Hs.begin(), Hs.end(), (float)(1.0 / a)) - Hs.begin();
+    const double h_ref = lo < n ? Hs[lo + (size_t)(0.9 * (n - 1 - lo))] : Hs[(size_t)(0.9 * (n - 1))];
+    tail_period = (uint32_t)std::max(1.0, std::min((double)period_wide, std::floor(cap * nslice / (a * h_ref * rho * max_warps))));
+  }
+  launch(nslice - tail_slices, nslice, tail_warps, (uint32_t)env_double("DWG_LEARN_TAIL_PERIOD", tail_period));
   if (getenv("DWG_TIMING"))
-    fprintf(stderr, "[learn] step %.4g: %u slices, head %u on %u warps (period %u), tail %u on %u warps\n", a, nslice,
-            nslice - tail_slices, wide_warps, period_wide, tail_slices, tail_warps);
+    fprintf(stderr, "[learn] step %.4g: %u slices, head %u on %u warps (period %u), tail %u on %u warps (period %u)\n", a, nslice,
+            nslice - tail_slices, wide_warps, period_wide, tail_slices, tail_warps, tail_period);
   return DWG_OK;
 }
 
@@ -919,25 +930,29 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
     CU(cudaGetLastError());
     return DWG_OK;
   }
+  // CSR (categorical) learning: every class is cut into `chunks` CONTIGUOUS parts (ascending
+  // position = ascending id block inside the evidence part) and the sweep runs part 0 of every
+  // class, then part 1 of every class, ...: variables are visited in ascending id block like the
+  // reference's scan (the learned weights depend on it) while every launch stays
+  // inside one colour class.  A batch weight update (k_apply_weights) follows each launch.
+  uint32_t chunks = 1;
+  if (learn && !p.sequential && !use_sell) {
+    chunks = h->opts.learn_chunks > 0 ? (uint32_t)h->opts.learn_chunks
+                                      : std::max(1u, (uint32_t)std::llround(32.0 / (double)std::max(1u, m.ncolor())));
+  }
+  for (uint32_t b = 0; b < chunks; ++b)
   for (uint32_t c = 0; c < m.ncolor(); ++c) {
-    p.d_begin = m.color_start[c];
-    p.d_end = m.color_start[c + 1];
-    const uint32_t n = p.d_end - p.d_begin;
-    if (!n) continue;
-    const uint32_t units = (n + 31) / 32;  // 32-variable units (= slices of the sliced-ELL stream)
-    // CSR (categorical) learning: a sweep of a class runs as `chunks` strided parts with a batch
-    // weight update (k_apply_weights) after each
-    uint32_t chunks = 1;
-    if (learn && !p.sequential) {
-      chunks = h->opts.learn_chunks > 0
-                   ? (uint32_t)h->opts.learn_chunks
-                   : (uint32_t)std::llround(32.0 * (double)n / (double)std::max<uint64_t>(1, m.nvar_pad));
-      chunks = std::max(1u, std::min(chunks, units));
-    }
-    for (uint32_t b = 0; b < chunks; ++b) {
-      const uint32_t my_units = (units - b + chunks - 1) / chunks;
-      p.unit_stride = chunks;
-      p.unit_phase = b;
+    const uint32_t cb = m.color_start[c], ce = m.color_start[c + 1];
+    if (ce <= cb) continue;
+    const uint32_t units = (ce - cb + 31) / 32;  // 32-variable units (= slices of the sliced-ELL streams)
+    const uint32_t u0 = (uint32_t)((uint64_t)units * b / chunks), u1 = (uint32_t)((uint64_t)units * (b + 1) / chunks);
+    if (u1 <= u0) continue;
+    p.d_begin = cb + u0 * 32;
+    p.d_end = std::min(ce, cb + u1 * 32);
+    p.unit_stride = 1;
+    p.unit_phase = 0;
+    const uint32_t my_units = u1 - u0;
+    {
       if (use_cell) {
         CellGraph cg = h->cg;
         cg.slice_begin = p.d_begin / 32;
@@ -953,8 +968,8 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
         sg.slice_end = p.d_end / 32;
         sg.slice_stride = 1;
         if (!p.sample_evidence) sg.slice_end = h->cls_query_end[c];  // gibbs_sampler.h:157: the evidence tail of the class is not read at all
+        if (sg.slice_end <= sg.slice_begin) continue;
         const uint32_t n_sl = sg.slice_end - sg.slice_begin;
-        if (!n_sl) continue;
         const bool staged = h->sell_stages != 0;
         const uint32_t wpb = staged ? h->sell_staged_warps : SELL_THREADS / 32;
         const uint32_t need = (n_sl + wpb - 1) / wpb;

@@ -84,8 +84,11 @@ __device__ __forceinline__ uint32_t cell_draw(const double *buf, uint32_t K, dou
 template <bool ALLHOT>
 __device__ __forceinline__ double cell_signed_weight(uint32_t n_tab, const unsigned char *tab_s, uint32_t plane,
                                                      const double *w, uint32_t code, uint32_t wid) {
-  if (ALLHOT || wid < n_tab) return *reinterpret_cast<const double *>(tab_s + (code * plane + 8u * wid));
-  return sell_term(code, __ldg(w + wid));
+  if (ALLHOT) return *reinterpret_cast<const double *>(tab_s + (code * plane + 8u * wid));
+  const bool hot = wid < n_tab;  // branch-free: one generic load from the table or from L2
+  const double *ptr = hot ? reinterpret_cast<const double *>(tab_s + (code * plane + 8u * wid)) : w + wid;
+  const double v = *ptr;
+  return hot ? v : sell_term(code, v);
 }
 
 // potentials of the lane's K values into buf (lane-strided), records read from `src` (the staged

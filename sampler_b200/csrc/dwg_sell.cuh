@@ -440,8 +440,14 @@ __device__ __forceinline__ double sell_fv_s(const uint32_t *sm, uint32_t fvb, ui
 template <bool ALLHOT>
 __device__ __forceinline__ double sell_signed_weight(const SellGraph &g, const unsigned char *tab_s, uint32_t plane,
                                                      const double *w, uint32_t code, uint32_t wid8) {
-  if (ALLHOT || wid8 < 8u * g.n_tab) return *reinterpret_cast<const double *>(tab_s + (code * plane + wid8));
-  return sell_term(code, __ldg(w + (wid8 >> 3)));
+  if (ALLHOT) return *reinterpret_cast<const double *>(tab_s + (code * plane + wid8));
+  // Branch-free: ONE generic load from either the signed table or the weight vector (L2), so that
+  // the loads of a batch of records issue back to back; a branch per record would serialise a
+  // warp's L2 round trips (nearly every record has some lane beyond the table).
+  const bool hot = wid8 < 8u * g.n_tab;
+  const double *ptr = hot ? reinterpret_cast<const double *>(tab_s + (code * plane + wid8)) : w + (wid8 >> 3);
+  const double v = *ptr;
+  return hot ? v : sell_term(code, v);
 }
 
 // one unary record of a staged slice into pos / neg (same arithmetic and order as sell_unary)
@@ -461,7 +467,7 @@ template <int FV, bool ANTISYM, bool ALLHOT>
 __device__ __forceinline__ void sell_unary_s(const SellGraph &g, const uint32_t *sm, uint32_t b, uint32_t n_un,
                                              const unsigned char *tab_s, uint32_t plane, const double *w,
                                              uint32_t lane, double &pos, double &neg) {
-  constexpr uint32_t U = 4;
+  constexpr uint32_t U = ALLHOT ? 4 : 10;  // beyond the table: more weight loads in flight per batch
   const uint32_t un = b + SH_WORDS + lane, fvb = b + SH_WORDS + 32u * n_un;
   uint32_t j0 = 0;
   for (; j0 + U <= n_un; j0 += U) {
@@ -869,7 +875,7 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
 // stage is read from HBM instead): the blob is static, so the ring runs ahead across the periods.
 constexpr int SELL_LEARN_THREADS = 256;
 constexpr uint32_t SELL_LEARN_STAGES = 2;
-__host__ __device__ inline uint32_t sell_learn_bar_off(uint32_t n_hot) { return (24u * n_hot + 15u) & ~15u; }
+__host__ __device__ inline uint32_t sell_learn_bar_off(uint32_t n_hot) { return (28u * n_hot + 15u) & ~15u; }
 __host__ __device__ inline uint32_t sell_learn_ring_off(uint32_t n_hot) {
   return (sell_learn_bar_off(n_hot) + (SELL_LEARN_THREADS / 32) * SELL_LEARN_STAGES * 8u + 127u) & ~127u;
 }
@@ -885,7 +891,7 @@ k_sell_learn_live(const SellGraph g, const SellState st, const SweepParams p, co
   constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
   constexpr uint32_t ST = SELL_LEARN_STAGES;
   double *w_s = reinterpret_cast<double *>(sell_smem), *acc_s = w_s + g.n_hot;
-  float *as_s = reinterpret_cast<float *>(acc_s + g.n_hot), *lam_s = as_s + g.n_hot;
+  float *as_s = reinterpret_cast<float *>(acc_s + g.n_hot), *lam_s = as_s + g.n_hot, *debt_s = lam_s + g.n_hot;
   const uint32_t *sm = reinterpret_cast<const uint32_t *>(sell_smem);
   __shared__ uint32_t cnt_s;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -906,6 +912,7 @@ k_sell_learn_live(const SellGraph g, const SellState st, const SweepParams p, co
     const double per_update = L.reg_l1 ? L.decay : log1p(L.decay * sc);  // (1 + reg step)^-n = exp(-n log1p(reg step))
     lam_s[i] = (float)((double)__ldg(L.w_N + i) * L.inv_nslice * per_update);
     acc_s[i] = 0.0;
+    debt_s[i] = 0.f;
   }
   // slice index and offsets of this warp's positions, 32 at a time (lane = iteration), one block ahead
   const uint64_t pol = sell_policy_evict_first();
@@ -981,10 +988,16 @@ k_sell_learn_live(const SellGraph g, const SellState st, const SweepParams p, co
     if (lane == 0 && mine) atomicAdd(&cnt_s, mine);
     __syncthreads();
     const uint32_t cnt = cnt_s;
+    // push the period's steps.  The decay of a weight nobody touched in the period is carried as a
+    // debt and paid with the next step of the weight (or once it reaches 1e-3, or at the end of the
+    // launch): a CTA holding a thousand idle weights does not send a thousand atomics per period.
+    const bool last = r1 >= rounds;
     for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) {
       const double a = sell_acc_take<FV>(acc_s, i), x = w_s[i];
-      const double lam = (double)lam_s[i] * (double)cnt;
-      const double dec = L.reg_l1 ? lam * (x < 0 ? 1.0 : 0.0) : x * expm1(-lam);
+      const float debt = debt_s[i] + lam_s[i] * (float)cnt;
+      if (a == 0.0 && debt < 1e-3f && !last) { debt_s[i] = debt; continue; }
+      debt_s[i] = 0.f;
+      const double dec = L.reg_l1 ? (double)debt * (x < 0 ? 1.0 : 0.0) : x * expm1(-(double)debt);
       const double d = dec - (double)as_s[i] * a;
       if (d != 0.0) atomicAdd(L.weights + i, d);
     }
