@@ -302,6 +302,8 @@ def ours(args):
     # ---- inference: W warm-up sweeps, K timed ----
     smp.clear_tallies()
     smp.infer_epochs(args.warmup)
+    if dist is not None:
+        group.reduce_tallies_device()  # warm-up of the collective too (its first call sets up the channels)
     smp.clear_tallies()
     smp.sync()
     torch.cuda.synchronize()
@@ -336,25 +338,46 @@ def ours(args):
     # Boolean: share of draws that were 1; categorical: every draw tallies one value (must be exactly 1)
     frac1 = float(t.sum()) / (float(nvar) * args.steps * world) if rank == 0 else 0.0
 
-    # ---- e2e through the C ABI from host buffers, every replica at once: create (H2D) + K sweeps +
-    # tallies (D2H); whole-job value = all replicas' samples / the slowest replica's wall time ----
+    # ---- e2e through the C ABI from HOST buffers, whole job: the compiled graph goes host -> device
+    # once per node (rank 0: dwg_create from page-locked memory) and reaches the other replicas over
+    # NVLink (defer_upload + broadcast of the graph segments, the analogue of the reference's per-NUMA-
+    # node copies, src/dimmwitted.cc:113-116); K sweeps per replica; tallies reduced onto rank 0 and
+    # read back into a page-locked host array (u32, the device's counter width).  Whole-job value =
+    # all replicas' samples / the slowest rank's wall time. ----
     smp.close()
     torch.cuda.synchronize()
+    t_host = torch.empty(int(info.num_values), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+    n_host = np.empty(int(info.num_variables), np.uint64)
+    n_host[:] = 0  # touch the pages outside the timed region
+    if dist is not None:  # the first broadcast on a communicator sets up its channels: not part of a sweep
+        warm = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+        dist.broadcast(warm, src=0)
+        torch.cuda.synchronize()
     barrier()
     t0 = time.time()
-    s2 = sb.Sampler(graph, device=local, sample_evidence=True, reg_param=LEARN["reg_param"], seed=99, replica=rank)
+    s2 = sb.Sampler(graph, device=local, sample_evidence=True, reg_param=LEARN["reg_param"], seed=99, replica=rank,
+                    defer_upload=(world > 1 and rank != 0))
+    if world > 1:
+        g2 = ReplicaGroup(s2, dist, device=local)
+        g2.broadcast_graph(0)
     t_up = time.time()
     s2.infer_epochs(args.steps)
+    if world > 1:
+        g2.reduce_tallies_device()
     s2.sync()
     t_sw = time.time()
-    t2, n2 = s2.tallies()
+    if rank == 0:
+        s2.tallies(out=(t_host, n_host))
     t_end = time.time()
     e2e_s = t_end - t0
     et = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_value = nvar * world * args.steps / float(et.item())
-    e2e_parts = "upload %.1f ms, sweeps %.1f ms, tallies %.1f ms (rank 0)" % (1e3 * (t_up - t0), 1e3 * (t_sw - t_up), 1e3 * (t_end - t_sw))
+    e2e_parts = "graph to the device(s) %.1f ms, sweeps%s %.1f ms, tallies to the host %.1f ms (rank 0)" % (
+        1e3 * (t_up - t0), " + tally reduction" if world > 1 else "", 1e3 * (t_sw - t_up), 1e3 * (t_end - t_sw))
+    if rank == 0:
+        assert int(t_host.astype(np.uint64).sum()) > 0 and int(n_host[0]) == args.steps
     s2.close()
 
     if rank != 0:
@@ -419,8 +442,9 @@ def ours(args):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "variable-samples/s",
                 "h2d_bytes_per_step": int(info.device_bytes / args.steps), "d2h_bytes_per_step": int(4 * info.num_values / args.steps),
-                "what": "dwg_create (upload of the compiled graph from page-locked host memory) + %d sweeps + dwg_get_tallies "
-                        "(D2H into host arrays), wall clock: %s" % (args.steps, e2e_parts)},
+                "what": "dwg_create (upload of the compiled graph from page-locked host memory, once per node; the other "
+                        "replicas receive it over NVLink) + %d sweeps per replica + tally reduction onto rank 0 + "
+                        "dwg_get_tallies32 (D2H into a page-locked host array), wall clock: %s" % (args.steps, e2e_parts)},
         "learn": None if not learn_ms else
                  {"value": nvar * world / (learn_ms * 1e-3), "unit": "variable-updates/s", "ms_per_epoch": learn_ms,
                   "epochs": n_learn, "hbm_gbs": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9,

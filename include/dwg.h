@@ -68,6 +68,10 @@ typedef struct dwg_opts {
   int learn_chunks;        /* categorical graphs (CSR learning kernels) only: batch weight updates per colour
                               class and learning sweep; 0 = auto (about 32 updates per sweep).  Boolean
                               graphs learn with live weights and ignore it */
+  int defer_upload;        /* dwg_create allocates the replica's device arrays but does not fill the graph
+                              segments: another replica's copy arrives over NVLink (dwg_graph_segments +
+                              a broadcast), then dwg_reset_state.  The reference deep-copies the graph per
+                              NUMA node from replica 0 (src/dimmwitted.cc:113-116) */
 } dwg_opts_t;
 void dwg_opts_default(dwg_opts_t *o);
 
@@ -147,6 +151,14 @@ int dwg_graph_var_meta(const dwg_graph *g, uint8_t *dtype, uint8_t *is_evid, uin
  * (src/gibbs_sampler.cc:5-18, src/inference_result.cc:24-42) -------------------- */
 int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handle **out);
 void dwg_destroy(dwg_handle *h);
+/* The device arrays that hold the replica's copy of the graph (stream, per-variable tables, initial
+ * weights), in a fixed order that depends on the graph only: ptrs[i] / bytes[i] for i < *n (call
+ * with max = 0 to get the count).  What a replica created with defer_upload receives from a
+ * peer (torch.distributed / NCCL broadcast on dwg_stream(), or cudaMemcpyPeer). */
+int dwg_graph_segments(dwg_handle *h, int max, void **ptrs, uint64_t *bytes, int *n);
+/* InferenceResult ctor again (src/inference_result.cc:24-42): both chains to the evidence values,
+ * tallies cleared; the weights stay as they are. */
+int dwg_reset_state(dwg_handle *h);
 
 /* GibbsSampler::sample_sgd(stepsize)+wait (src/gibbs_sampler.cc:27-38): one learning sweep.
  * Asynchronous on the handle's stream. */
@@ -164,6 +176,9 @@ int dwg_clear_tallies(dwg_handle *h);
 /* InferenceResult state accessors (src/inference_result.h:27-43); synchronise first.
  * tallies[num_values], nsamples[num_variables] in original (variable, domain-index) order */
 int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples);
+/* the same with the tallies at the device's own counter width (u32: no widening pass on the host;
+ * a tally cannot exceed the number of sweeps) */
+int dwg_get_tallies32(dwg_handle *h, uint32_t *tallies, uint64_t *nsamples);
 int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsamples); /* aggregate_marginals_from :116-127 */
 int dwg_get_weights(dwg_handle *h, double *out);
 int dwg_set_weights(dwg_handle *h, const double *in);

@@ -27,7 +27,7 @@ class Opts(C.Structure):
     _fields_ = [("sample_evidence", C.c_int), ("learn_non_evidence", C.c_int),
                 ("noise_aware", C.c_int), ("regularization", C.c_int),
                 ("reg_param", C.c_double), ("schedule", C.c_int), ("seed", C.c_uint64),
-                ("replica", C.c_uint32), ("learn_chunks", C.c_int)]
+                ("replica", C.c_uint32), ("learn_chunks", C.c_int), ("defer_upload", C.c_int)]
 
 
 class Raw(C.Structure):
@@ -87,6 +87,8 @@ def load(build: bool = False):
     L.dwg_debug_image.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(u64), C.POINTER(C.c_uint32)]
     L.dwg_create.argtypes = [vp, C.POINTER(Opts), i32, C.POINTER(vp)]
     L.dwg_destroy.argtypes = [vp]
+    L.dwg_graph_segments.argtypes = [vp, i32, vp, vp, C.POINTER(i32)]
+    L.dwg_reset_state.argtypes = [vp]
     L.dwg_learn_epoch.argtypes = [vp, dbl]
     L.dwg_infer_epoch.argtypes = [vp]
     L.dwg_infer_epochs.argtypes = [vp, u64]
@@ -95,6 +97,7 @@ def load(build: bool = False):
     L.dwg_stream.argtypes = [vp]
     L.dwg_clear_tallies.argtypes = [vp]
     L.dwg_get_tallies.argtypes = [vp, vp, vp]
+    L.dwg_get_tallies32.argtypes = [vp, vp, vp]
     L.dwg_add_tallies.argtypes = [vp, vp, vp]
     L.dwg_get_weights.argtypes = [vp, vp]
     L.dwg_set_weights.argtypes = [vp, vp]
@@ -224,11 +227,13 @@ class Sampler:
     src/gibbs_sampler.h:18-57, src/inference_result.h:27-43)."""
 
     def __init__(self, graph: Graph, device: int = 0, sample_evidence=False, learn_non_evidence=False,
-                 noise_aware=False, regularization="l2", reg_param=0.01, seed=0x5eed5eed, replica=0, learn_chunks=0):
+                 noise_aware=False, regularization="l2", reg_param=0.01, seed=0x5eed5eed, replica=0, learn_chunks=0,
+                 defer_upload=False):
         L = load()
         self.graph = graph
         self.opts = Opts(int(sample_evidence), int(learn_non_evidence), int(noise_aware),
-                         1 if regularization == "l1" else 0, float(reg_param), 0, int(seed), int(replica), int(learn_chunks))
+                         1 if regularization == "l1" else 0, float(reg_param), 0, int(seed), int(replica), int(learn_chunks),
+                         int(defer_upload))
         self._h = C.c_void_p()
         _check(L.dwg_create(graph._h, C.byref(self.opts), device, C.byref(self._h)))
         self.device = device
@@ -241,6 +246,18 @@ class Sampler:
         if self._h:
             load().dwg_destroy(self._h)
             self._h = None
+
+    def graph_segments(self):
+        """[(device pointer, bytes)] of the replica's copy of the graph, in a graph-determined order"""
+        n = C.c_int()
+        _check(load().dwg_graph_segments(self._h, 0, None, None, C.byref(n)))
+        ptrs = (C.c_void_p * max(1, n.value))()
+        sizes = (C.c_uint64 * max(1, n.value))()
+        _check(load().dwg_graph_segments(self._h, n.value, ptrs, sizes, C.byref(n)))
+        return [(int(ptrs[i] or 0), int(sizes[i])) for i in range(n.value)]
+
+    def reset_state(self):
+        _check(load().dwg_reset_state(self._h))
 
     def __del__(self):
         try:
@@ -266,10 +283,18 @@ class Sampler:
     def clear_tallies(self):
         _check(load().dwg_clear_tallies(self._h))
 
-    def tallies(self):
-        t = np.zeros(self.nval, np.uint64)
-        n = np.zeros(self.nvar, np.uint64)
-        _check(load().dwg_get_tallies(self._h, _ptr(t), _ptr(n)))
+    def tallies(self, wide: bool = True, out=None):
+        """(tallies[num_values], nsamples[num_variables]); wide=False: u32 tallies (the device's
+        counter width, no widening pass on the host).  out = (t, n): arrays to fill (a page-locked u32
+        t takes the DMA directly)"""
+        if out is not None:
+            t, n = out
+            wide = t.dtype == np.uint64
+            assert t.shape[0] == self.nval and n.shape[0] == self.nvar and n.dtype == np.uint64
+        else:
+            t = np.empty(self.nval, np.uint64 if wide else np.uint32)
+            n = np.empty(self.nvar, np.uint64)
+        _check((load().dwg_get_tallies if wide else load().dwg_get_tallies32)(self._h, _ptr(t), _ptr(n)))
         return t, n
 
     def add_tallies(self, t, n):
@@ -363,6 +388,10 @@ def logadd(a: np.ndarray, b: np.ndarray, device: int = 0) -> np.ndarray:
     out = np.zeros(len(a), np.float64)
     _check(load().dwg_logadd(device, len(a), _ptr(a), _ptr(b), _ptr(out)))
     return out
+
+
+def last_error() -> str:
+    return load().dwg_last_error().decode()
 
 
 def dw_main(argv: Sequence[str]) -> int:

@@ -106,6 +106,14 @@ struct dwg_graph {
 
 
 namespace {
+// dwg_create records every graph array it puts on the device (pointer, bytes) and, for a replica
+// created with defer_upload, skips the copies: a peer replica's arrays arrive later (dwg_graph_segments)
+struct UploadScope {
+  std::vector<std::pair<void *, size_t>> *segments = nullptr;
+  bool defer = false;
+};
+thread_local UploadScope g_upload;
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -121,6 +129,8 @@ struct DevBuf {
     static_assert(sizeof(S) == sizeof(T), "");
     cudaError_t e = alloc(v.size());
     if (e != cudaSuccess || v.empty()) return e;
+    if (g_upload.segments) g_upload.segments->emplace_back((void *)p, v.size() * sizeof(T));
+    if (g_upload.defer) return cudaSuccess;
     return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
   }
   size_t bytes() const { return n * sizeof(T); }
@@ -203,6 +213,7 @@ struct dwg_handle {
   double learn_rho = 1.0;              // coupling: learnable records per learning variable / 10
   uint32_t learn_stage_words = 8;      // capacity of one ring stage of the learning kernel
   size_t device_bytes = 0;
+  std::vector<std::pair<void *, size_t>> segments;  // the graph arrays on the device (dwg_graph_segments)
   // tally download: device row of every (variable, value) in ABI order (uploaded with the graph) and
   // the gathered tallies; the page-locked landing pieces are the process's (g_landing)
   DevBuf<uint32_t> row_of_value, tallies_abi;
@@ -683,8 +694,14 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     if (timing) fprintf(stderr, "[create] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t_prev).count());
     t_prev = n;
   };
-  g->pin();
+  const bool defer = h->opts.defer_upload != 0;
+  if (!defer) g->pin();
   lap("page-lock (first create only)");
+  struct ScopeGuard {
+    ScopeGuard(std::vector<std::pair<void *, size_t>> *seg, bool d) { g_upload.segments = seg; g_upload.defer = d; }
+    ~ScopeGuard() { g_upload = UploadScope(); }
+  } scope_guard(&h->segments, defer);
+  if (defer && (!m.sell && !m.cell)) return fail(DWG_ERR_UNSUPPORTED, "defer_upload: sliced-ELL graphs only");
   CU(h->var_flags.upload(m.var_flags, s));
   if (m.has_categorical) CU(h->var_row.upload(m.var_row, s));
   std::vector<uint8_t> fixed_dev(m.nweight);
@@ -736,7 +753,7 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     h->learn_rho = std::max(1.0, updates / learners / 10.0);
   }
   lap("allocations + copies queued");
-  int rc = init_state(h.get());
+  int rc = defer ? DWG_OK : init_state(h.get());  // (deferred: dwg_reset_state once the graph has arrived)
   if (rc) return rc;
   CU(cudaStreamSynchronize(s));  // the staging vectors go out of scope
   lap("copies done");
@@ -791,6 +808,23 @@ void dwg_destroy(dwg_handle *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   delete h;
+}
+
+int dwg_graph_segments(dwg_handle *h, int max, void **ptrs, uint64_t *bytes, int *n) {
+  if (!h || !n) return fail(DWG_ERR_INVALID, "null argument");
+  *n = (int)h->segments.size();
+  for (int i = 0; i < *n && i < max; ++i) {
+    if (ptrs) ptrs[i] = h->segments[i].first;
+    if (bytes) bytes[i] = h->segments[i].second;
+  }
+  return DWG_OK;
+}
+
+int dwg_reset_state(dwg_handle *h) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  h->chain_open = false;
+  CU(cudaSetDevice(h->device));
+  return init_state(h);
 }
 
 static SweepParams make_params(dwg_handle *h, double stepsize) {
@@ -1051,7 +1085,14 @@ int dwg_clear_tallies(dwg_handle *h) {
   return DWG_OK;
 }
 
+static int get_tallies_impl(dwg_handle *h, uint64_t *tallies, uint32_t *tallies32, uint64_t *nsamples);
 int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
+  return get_tallies_impl(h, tallies, nullptr, nsamples);
+}
+int dwg_get_tallies32(dwg_handle *h, uint32_t *tallies, uint64_t *nsamples) {
+  return get_tallies_impl(h, nullptr, tallies, nsamples);
+}
+static int get_tallies_impl(dwg_handle *h, uint64_t *tallies, uint32_t *tallies32, uint64_t *nsamples) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");
   h->chain_open = false;
   const GraphImage &m = *h->img;
@@ -1063,11 +1104,27 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
     if (timing) fprintf(stderr, "[get_tallies] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t_prev).count());
     t_prev = n;
   };
-  if (tallies && m.nrow) {
+  if ((tallies || tallies32) && m.nrow) {
     // schedule order -> ABI order on the device, then 4 MB pieces through two small page-locked
     // buffers: the DMA of piece c overlaps the widening of piece c - 1 on the host threads (page-locking
     // a buffer for the whole vector would cost more than the transfer)
     constexpr uint64_t PIECE = 1u << 20;  // tallies per piece
+    if (tallies32) {  // a page-locked destination takes the DMA directly
+      cudaPointerAttributes attr{};
+      if (cudaPointerGetAttributes(&attr, tallies32) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+        if (!h->tallies_abi.p) CU(h->tallies_abi.alloc(m.nrow));
+        k_gather_u32<<<(uint32_t)((m.nrow + 255) / 256), 256, 0, h->stream>>>(h->tallies_abi.p, h->tallies.p,
+                                                                             h->row_of_value.p, (uint32_t)m.nrow);
+        ++g_launches;
+        CU(cudaMemcpyAsync(tallies32, h->tallies_abi.p, 4 * m.nrow, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        tallies32 = nullptr;  // done
+      } else {
+        cudaGetLastError();
+      }
+    }
+    if (!tallies && !tallies32) goto tallies_done;
+    {
     std::lock_guard<std::mutex> pool_lock(g_landing.mu);
     uint32_t *landing = g_landing.get(2 * PIECE);
     if (!landing) return fail(DWG_ERR_CUDA, "cannot page-lock the tally landing buffer");
@@ -1084,6 +1141,11 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
     auto widen = [&](uint64_t c) {
       const uint64_t base = c * PIECE, cnt = std::min(PIECE, m.nrow - base);
       const uint32_t *t = landing + (c & 1) * PIECE;
+      if (tallies32) {  // the device's own counter width: a plain copy out of the landing buffer
+        uint32_t *out = tallies32 + base;
+        parallel_for(cnt, [=](uint64_t a, uint64_t b) { std::memcpy(out + a, t + a, 4 * (b - a)); });
+        return;
+      }
       uint64_t *out = tallies + base;
       parallel_for(cnt, [=](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; ++i) out[i] = t[i]; });
     };
@@ -1100,7 +1162,9 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples) {
     CU(cudaEventSynchronize(h->piece_done[(npiece - 1) & 1]));
     widen(npiece - 1);
     lap("widen");
+    }
   }
+tallies_done:
   if (nsamples) {
     // ++agg_nsamples for every sampled variable every sweep (src/gibbs_sampler.h:157,163)
     const uint64_t sweeps = h->infer_sweeps;

@@ -51,6 +51,21 @@ class ReplicaGroup:
             ndrow = getattr(sampler, "ndrow", None) or sampler.nval
             self._t_t = torch.as_tensor(_DevArray(sampler.tallies_device_ptr(), ndrow, "<i4"), device=dev)
 
+    # -- the NUMA copies of the graph (src/dimmwitted.cc:113-116) ---------------------------
+    def broadcast_graph(self, src: int = 0):
+        """NCCL only: replicas created with defer_upload receive replica `src`'s device copy of the
+        graph over NVLink (one host->device upload per node instead of one per GPU), then start
+        from the initial state."""
+        assert self.on_device
+        import torch
+        dev = self._w_t.device
+        with torch.cuda.stream(self._stream):
+            for ptr, nbytes in self.s.graph_segments():
+                t = torch.as_tensor(_DevArray(ptr, nbytes, "|u1"), device=dev)
+                self.dist.broadcast(t, src=src)
+        if self.rank != src:
+            self.s.reset_state()
+
     # -- DimmWitted::update_weights + copy_weights_to ------------------------------------
     def average_weights(self, want_norms: bool = False):
         """Sum the replicas' weights, divide by the replica count; returns (lmax, l2sq) of the

@@ -686,3 +686,94 @@ def test_two_replicas_one_gpu_average_and_aggregate():
     assert L.dwg_reduce_tallies_multi(hs, None, 2) == 0
     t, n = a.tallies()
     assert np.array_equal(t, ta + tb) and (n == 12).all()
+
+
+def test_two_replicas_host_exchange_with_permuted_weight_ids():
+    """the no-NCCL averaging path on a graph with more weights than the shared-memory table: the
+    device holds the weights hottest-first (w_perm), dwg_get_weights / dwg_set_weight_sum speak
+    original ids; averaging two replicas must give the element-wise mean in ORIGINAL order"""
+    import ctypes as C
+    from sampler_b200 import graphgen
+    raw = graphgen.unary_boolean(30_000, 6, 6000, zipf=1.1)  # skewed use counts: w_perm is not the identity
+    g = sb.Graph.from_raw(raw)
+    assert not np.array_equal(g.image("w_perm"), np.arange(raw.nweight))
+    a, b = sb.Sampler(g, replica=0), sb.Sampler(g, replica=1)
+    rng = np.random.default_rng(5)
+    wa, wb = rng.normal(0, 1, raw.nweight), rng.normal(0, 1, raw.nweight)
+    a.set_weights(wa); b.set_weights(wb)
+    hs = (C.c_void_p * 2)(a._h, b._h)
+    assert sb.load().dwg_average_weights_multi(hs, None, 2, None, None) == 0
+    assert np.allclose(a.weights(), 0.5 * (wa + wb), rtol=0, atol=1e-15)
+    assert np.array_equal(a.weights(), b.weights())
+
+
+def _two_gpus():
+    import torch
+    return torch.cuda.device_count() >= 2
+
+
+def test_in_process_replicas_over_nccl(tmp_path):
+    """`dw gibbs -c 2`: one process driving two GPUs (dwg_comm_init_all, dwg_average_weights_multi,
+    dwg_reduce_tallies_multi over NCCL -- src/dimmwitted.cc:97-119,209-243,260-277).  Needs two GPUs."""
+    if not _two_gpus():
+        pytest.skip("needs two GPUs")
+    import ctypes as C
+    from sampler_b200 import graphgen
+    L = sb.load()
+    raw = graphgen.c2_boolean(60_000, nweight=300)
+    g = sb.Graph.from_raw(raw)
+    a, b = sb.Sampler(g, device=0, sample_evidence=True, replica=0), sb.Sampler(g, device=1, sample_evidence=True, replica=1)
+    comms = (C.c_void_p * 2)()
+    devs = (C.c_int * 2)(0, 1)
+    L.dwg_comm_init_all.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    assert L.dwg_comm_init_all(2, devs, comms) == 0, sb.api.last_error()
+    rng = np.random.default_rng(9)
+    wa, wb = rng.normal(0, 1, raw.nweight), rng.normal(0, 1, raw.nweight)
+    a.set_weights(wa); b.set_weights(wb)
+    hs = (C.c_void_p * 2)(a._h, b._h)
+    lmax, l2 = C.c_double(), C.c_double()
+    L.dwg_average_weights_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    assert L.dwg_average_weights_multi(hs, comms, 2, C.byref(lmax), C.byref(l2)) == 0, sb.api.last_error()
+    assert np.allclose(a.weights(), 0.5 * (wa + wb), rtol=0, atol=1e-15) and np.array_equal(a.weights(), b.weights())
+    a.infer_epochs(5); b.infer_epochs(7)
+    ta, _ = a.tallies(); tb, _ = b.tallies()
+    L.dwg_reduce_tallies_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    assert L.dwg_reduce_tallies_multi(hs, comms, 2) == 0, sb.api.last_error()
+    t, n = a.tallies()
+    assert np.array_equal(t, ta + tb) and (n == 12).all()
+    for c in comms:
+        L.dwg_comm_destroy(C.c_void_p(c))
+    a.close(); b.close()
+    # ... and the CLI end to end
+    paths = gio.write_binary(raw, str(tmp_path))
+    out = tmp_path / "out"
+    out.mkdir()
+    argv = ["dw", "gibbs", "-m", paths["meta"], "-v", paths["variables"], "-f", paths["factors"], "-w", paths["weights"],
+            "-o", str(out), "--quiet", "-l", "6", "-i", "20", "--alpha", "0.01", "--sample_evidence", "-c", "2"]
+    assert sb.dw_main(argv) == 0
+    w = gio.read_weights_text(str(out / "inference_result.out.weights.text"))
+    m = gio.read_marginals_text(str(out / "inference_result.out.text"))
+    assert len(w) == 300 and np.isfinite(w).all() and np.abs(w).max() > 0.01
+    assert len(m) == 60_000 and all(0.0 <= p <= 1.0 for p in m.values())
+
+
+def test_deferred_replica_receives_the_graph_from_a_peer():
+    """defer_upload + dwg_graph_segments: a replica whose graph arrays are filled from another
+    replica's (here a device-to-device copy; across GPUs a broadcast over NVLink) sweeps exactly
+    like one that uploaded them itself"""
+    import torch
+    from sampler_b200 import graphgen
+    raw = graphgen.c2_boolean(50_000, nweight=100, planted_weights=True)
+    g = sb.Graph.from_raw(raw)
+    a = sb.Sampler(g, sample_evidence=True, seed=3)
+    b = sb.Sampler(g, sample_evidence=True, seed=3, defer_upload=True)
+    sa, sbb = a.graph_segments(), b.graph_segments()
+    assert len(sa) == len(sbb) > 3 and [n for _, n in sa] == [n for _, n in sbb]
+    from sampler_b200.replicas import _DevArray
+    for (pa, n), (pb, _) in zip(sa, sbb):
+        torch.as_tensor(_DevArray(pb, n, "|u1"), device="cuda").copy_(torch.as_tensor(_DevArray(pa, n, "|u1"), device="cuda"))
+    torch.cuda.synchronize()
+    b.reset_state()
+    a.infer_epochs(5); b.infer_epochs(5)
+    assert np.array_equal(a.assignments(1), b.assignments(1))
+    assert np.array_equal(a.tallies()[0], b.tallies(wide=False)[0].astype(np.uint64))
