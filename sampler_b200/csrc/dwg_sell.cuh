@@ -104,6 +104,14 @@ __device__ __forceinline__ uint32_t sell_chain(const uint8_t *a, uint32_t d) {
   return sell_live(LD) ? (uint32_t)__ldcg(a + d) : (uint32_t)a[d];
 }
 
+// SF_WIDE slices: the 32 lanes hold shares of ONE variable's records; their partial potentials are
+// combined by a butterfly of shuffles (a fixed order: the same sum on every lane, run to run)
+__device__ __forceinline__ double sell_wide_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+
 // sign code (0,1,2) -> the term  sign * t  with t = weight * feature value
 __device__ __forceinline__ double sell_term(uint32_t code, double t) {
   return code == 2u ? t : (code == 0u ? -t : 0.0);
@@ -334,7 +342,9 @@ k_sell_infer(const SellGraph g, const SellState st, const SweepParams p) {
     if (!active) continue;
     const uint32_t d = s * 32u + lane;
     double pos, neg;
-    sell_potentials<MULTI, FV, LD_STREAM>(g, h, w_s, st.weights, lane, d, st.assign_evid, pos, neg);
+    const bool wide = h.flags & SF_WIDE;  // one variable (slot 0), its records dealt to the 32 lanes
+    sell_potentials<MULTI, FV, LD_STREAM>(g, h, w_s, st.weights, lane, wide ? s * 32u : d, st.assign_evid, pos, neg);
+    if (wide) { pos = sell_wide_sum(pos); neg = sell_wide_sum(neg); }
     if (!((active >> lane) & 1u)) continue;
     double r0, r1;
     dev_uniforms(p, d, r0, r1);
@@ -596,7 +606,7 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
       // FactorGraph::potential for proposals 1 and 0 (src/factor_graph.h:127-145)
       double pos = 0.0, neg = 0.0;
       if (SH_WORDS + 32u * ((n_un + n_mu) * (1 + FVW) + h0.z) > stage_words) {
-        sell_unstaged_potentials<MULTI, FV>(g, st, h1.w, n_un, n_mu, flags, lane, d, pos, neg);
+        sell_unstaged_potentials<MULTI, FV>(g, st, h1.w, n_un, n_mu, flags, lane, (flags & SF_WIDE) ? d - lane : d, pos, neg);
       } else {
         const uint32_t mu = b + SH_WORDS + 32u * n_un * (1 + FVW) + lane;
         const uint32_t mufv = b + SH_WORDS + 32u * n_un * (1 + FVW) + 32u * n_mu;
@@ -641,9 +651,11 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
           h.n_un = n_un; h.n_mu = n_mu; h.n_oc = h0.z; h.evid = h0.w; h.pad = h1.x; h.evval = 0;
           h.flags = flags;
           h.un = sm + b + SH_WORDS; h.mu = sm + mu - lane; h.oth = sm + oth - lane;
-          sell_general_multi<FV, LD_SMEM>(gc, h, nullptr, st.weights, lane, d, st.assign_evid, pos, neg);
+          sell_general_multi<FV, LD_SMEM>(gc, h, nullptr, st.weights, lane, (flags & SF_WIDE) ? d - lane : d,
+                                          st.assign_evid, pos, neg);
         }
       }
+      if (flags & SF_WIDE) { pos = sell_wide_sum(pos); neg = sell_wide_sum(neg); }  // warp per variable
       if ((active >> lane) & 1u) {
         const uint32_t prop = sell_draw_boolean(pos, neg, r0);
         st.assign_evid[d] = (uint8_t)prop;
@@ -758,8 +770,15 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
                                                  const SellLearn &L, const SliceHeader &h, const double *w_s,
                                                  double *acc_s, uint32_t lane, uint32_t d) {
   const bool cold = g.nweight > g.n_hot;  // weights outside the shared copy: their decay rides on every visited record
-  const bool pad = (h.pad >> lane) & 1u, evid = (h.evid >> lane) & 1u;
-  const uint32_t ev = (h.evval >> lane) & 1u;  // Variable::assignment_dense
+  // SF_WIDE: the slice is ONE variable (slot 0) whose records are dealt to the 32 lanes -- every lane
+  // takes the variable's flags, uniforms and draws, sums its share of the records and pushes the SGD
+  // steps of its share; lane 0 writes the chains
+  const bool wide = h.flags & SF_WIDE;
+  const uint32_t hl = wide ? 0u : lane;
+  if (wide) d -= lane;
+  const bool writer = !wide || lane == 0;
+  const bool pad = (h.pad >> hl) & 1u, evid = (h.evid >> hl) & 1u;
+  const uint32_t ev = (h.evval >> hl) & 1u;  // Variable::assignment_dense
   double r0, r1;
   dev_uniforms(p, d, r0, r1);
   // Slices of two-variable factors (the common coupled case): the chain values of every other
@@ -805,21 +824,23 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
   } else {
     sell_potentials<MULTI, FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_free, pos, neg, &upos, &uneg);
   }
-  const uint32_t pf = sell_draw_boolean(pos, neg, r0);
-  if (!pad) st.assign_free[d] = (uint8_t)pf;
+  const uint32_t pf = wide ? sell_draw_boolean(sell_wide_sum(pos), sell_wide_sum(neg), r0) : sell_draw_boolean(pos, neg, r0);
+  if (!pad && writer) st.assign_free[d] = (uint8_t)pf;
   // evid chain (sample_evid, gibbs_sampler.h:171-190): clamp hard evidence, else a Gibbs draw
   // (Boolean variables carry no truthiness, so --noise_aware makes evidence variables draw too)
   uint32_t pe = ev;
-  const uint32_t draw_evid = ~h.pad & (p.noise_aware ? 0xffffffffu : ~h.evid);
+  const uint32_t draw_evid = wide ? ((!pad && (p.noise_aware || !evid)) ? 0xffffffffu : 0u)
+                                  : ~h.pad & (p.noise_aware ? 0xffffffffu : ~h.evid);
   if (draw_evid) {
     if (MULTI && h.n_mu) {  // unary-only slices: both chains see identical potentials
       pos = upos; neg = uneg;  // the unary sums are the same on both chains: continue from them
       if (masks) masked_multi(se_mask, pos, neg);
       else sell_multi<FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_evid, nullptr, 0u, pos, neg);
     }
+    if (wide) { pos = sell_wide_sum(pos); neg = sell_wide_sum(neg); }
     if ((draw_evid >> lane) & 1u) pe = sell_draw_boolean(pos, neg, r1);
   }
-  if (!pad) st.assign_evid[d] = (uint8_t)pe;
+  if (!pad && writer) st.assign_evid[d] = (uint8_t)pe;
   // which variables learn (gibbs_sampler.h:144-146); Boolean has_truthiness() is false
   const bool learn = !pad && (p.learn_non_evidence || (!p.noise_aware && evid));
   if (!__any_sync(0xffffffffu, learn)) return;

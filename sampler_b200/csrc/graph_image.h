@@ -70,6 +70,10 @@ constexpr int SH_SELF_OFF = 7;    // sl_off of this slice: a staged copy of the 
 constexpr int SH_WORDS = 8;
 constexpr uint32_t SF_ANTISYM = 1;  // every unary record has sign(1) == -sign(0): neg == -pos
 constexpr uint32_t SF_BINARY = 2;   // every multi record has exactly one other variable
+constexpr uint32_t SF_WIDE = 4;     // ONE variable (lane 0's slot), its records dealt round-robin to the 32 lanes:
+                                    // record i of a section at column i / 32, lane i % 32; the lanes' partial sums
+                                    // are combined by shuffles (warp per variable: hubs)
+constexpr uint64_t SELL_WIDE_MIN = 512;  // incident records from which a variable gets a slice of its own
 constexpr uint32_t SELL_WID_MASK = 0x7fffffu, SELL_FIXED_BIT = 0x800000u;  // multi records
 constexpr uint32_t SELL_BINARY_NOP = 0x55u;                                // tag of a padding binary record
 constexpr uint32_t SELL_UN_WID8_MASK = 0x3fffff8u, SELL_UN_FIXED_BIT = 1u << 2;

@@ -8,6 +8,7 @@
 // sweep schedule (greedy colouring), permutes variables into schedule order and flattens
 // factor -> vifs into per-row edge records (graph_image.h).
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -520,16 +521,26 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   // class to a multiple of 32 ----
   // SELL: a class is its query variables, padded to a multiple of 32, then its evidence variables,
   // padded again: no slice mixes the two (a query-only sweep skips whole slices, and a learning
-  // sweep never meets evidence variables of the first id block behind query variables of the last)
-  std::vector<uint32_t> class_count(ncolor, 0), class_query(ncolor, 0);
-  for (uint64_t v = 0; v < nvar; ++v) {
-    ++class_count[color[v]];
-    if (!g->var_is_evid[v]) ++class_query[color[v]];
-  }
+  // sweep never meets evidence variables of the first id block behind query variables of the last).
+  // A WIDE variable (>= SELL_WIDE_MIN incident records, Boolean sliced-ELL graphs) owns a whole
+  // slice: its records are dealt round-robin to the 32 lanes, which sum their shares and combine
+  // them by shuffles (SF_WIDE, graph_image.h) -- a hub would otherwise be one serial lane and pad
+  // its 31 slice-mates to its length.  Wide variables come first in their part of the class.
+  uint64_t wide_min = SELL_WIDE_MIN;
+  if (const char *e = getenv("DWG_WIDE_MIN")) wide_min = (uint64_t)std::max(1, atoi(e));
+  std::vector<uint8_t> wide(nvar, 0);
+  if (g->sell)
+    parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+      for (uint64_t v = v0; v < v1; ++v) wide[v] = (uint64_t)(inc_end[v] - deg[v]) >= wide_min;
+    });
+  // per class: [0] query wide, [1] query normal, [2] evidence wide, [3] evidence normal
+  std::vector<std::array<uint32_t, 4>> part(ncolor, std::array<uint32_t, 4>{0, 0, 0, 0});
+  for (uint64_t v = 0; v < nvar; ++v) ++part[color[v]][(g->var_is_evid[v] ? 2 : 0) + (wide[v] ? 0 : 1)];
+  auto seg_size = [&](uint32_t c, int ev) { return 32u * part[c][2 * ev] + ((part[c][2 * ev + 1] + 31u) & ~31u); };
   g->color_start.assign(ncolor + 1, 0);
   for (uint32_t c = 0; c < ncolor; ++c) {
-    uint32_t n = class_count[c];
-    if (padded) n = ((class_query[c] + 31u) & ~31u) + ((class_count[c] - class_query[c] + 31u) & ~31u);
+    uint32_t n = part[c][0] + part[c][1] + part[c][2] + part[c][3];
+    if (padded) n = seg_size(c, 0) + seg_size(c, 1);
     g->color_start[c + 1] = g->color_start[c] + n;
   }
   const uint64_t nvar_pad = g->color_start[ncolor];
@@ -563,7 +574,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         n_un = std::min<uint64_t>(n_un, (1u << 16) - 1);
         n_mu = std::min<uint64_t>(n_mu, (1u << 12) - 1);
         ow = std::min<uint64_t>(ow, (1u << 20) - 1);
-        keys[v] = {((uint64_t)color[v] << 32) | ((uint64_t)g->var_is_evid[v] << 31) | (v / id_block),
+        keys[v] = {((uint64_t)color[v] << 34) | ((uint64_t)g->var_is_evid[v] << 33) | ((uint64_t)(wide[v] ? 0 : 1) << 32) | (v / id_block),
                    ((0xffffull - n_un) << 32) | ((0xfffull - n_mu) << 20) | (0xfffffull - ow), (uint32_t)v};
       }
     });
@@ -590,13 +601,17 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     }
     // keys are colour-major: position in the sorted order -> slot of the (padded) class
     std::vector<uint64_t> class_first(ncolor + 1, 0);
-    for (uint32_t c = 0; c < ncolor; ++c) class_first[c + 1] = class_first[c] + class_count[c];
+    for (uint32_t c = 0; c < ncolor; ++c)
+      class_first[c + 1] = class_first[c] + part[c][0] + part[c][1] + part[c][2] + part[c][3];
     parallel_for(nvar, [&](uint64_t i0, uint64_t i1) {
       for (uint64_t i = i0; i < i1; ++i) {
         const uint32_t v = keys[i].v, c = color[v];
-        uint64_t in_class = i - class_first[c];
-        if (in_class >= class_query[c]) in_class += ((class_query[c] + 31u) & ~31u) - class_query[c];  // evidence part
-        const uint32_t d = (uint32_t)(g->color_start[c] + in_class);
+        uint64_t k = i - class_first[c], base = g->color_start[c];
+        const int ev = k >= (uint64_t)part[c][0] + part[c][1];
+        if (ev) { k -= (uint64_t)part[c][0] + part[c][1]; base += seg_size(c, 0); }
+        // inside the part: wide variables (a slice each), then the others packed
+        const uint64_t nw = part[c][2 * ev];
+        const uint32_t d = (uint32_t)(k < nw ? base + 32 * k : base + 32 * nw + (k - nw));
         g->perm[d] = v;
         g->inv[v] = d;
       }
@@ -890,18 +905,42 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     const uint64_t fvw = g->fv_mode == FV_F32 ? 1 : g->fv_mode == FV_F64 ? 2 : 0;  // words per value
     g->sl_off.assign(nslice + 1, 0);
     auto is_unary = [&](uint64_t e) { return (g->e_tag[e] >> TAG_FORM_SHIFT) == 0; };
-    // slice shapes
+    // slice shapes.  A slice whose first slot holds a wide variable is that variable's alone: record
+    // k of a section goes to lane k % 32, column k / 32 (the lanes of a normal slice are variables)
+    auto slice_is_wide = [&](uint64_t sidx) {
+      const uint64_t v = g->perm[sidx * 32];
+      return v != 0xffffffffu && wide[v];
+    };
+    auto others_span = [&](uint64_t e, uint64_t o) -> uint64_t {
+      const uint32_t form = g->e_tag[e] >> TAG_FORM_SHIFT;
+      return form != FORM_GENERAL ? form : 1 + g->oth[o];
+    };
     std::vector<uint32_t> s_un(nslice), s_mu(nslice), s_oc(nslice);
     uint64_t words = 0;
     parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
       for (uint64_t sidx = a0; sidx < a1; ++sidx) {
         uint32_t un = 0, mu = 0, oc = 0;
-        for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
-          uint32_t u = 0;
-          for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) u += is_unary(e);
-          un = std::max(un, u);
-          mu = std::max<uint32_t>(mu, g->row_ptr[d + 1] - g->row_ptr[d] - u);
-          if (g->has_multi) oc = std::max(oc, g->row_oth[d + 1] - g->row_oth[d]);
+        if (slice_is_wide(sidx)) {
+          const uint64_t d = sidx * 32;
+          uint32_t u = 0, m = 0, lane_oc[32] = {0};
+          uint64_t o = g->has_multi ? g->row_oth[d] : 0;
+          for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) {
+            if (is_unary(e)) { ++u; continue; }
+            const uint64_t span = others_span(e, o);
+            lane_oc[m % 32] += (uint32_t)span;
+            o += span;
+            ++m;
+          }
+          un = (u + 31) / 32; mu = (m + 31) / 32;
+          for (uint32_t l = 0; l < 32; ++l) oc = std::max(oc, lane_oc[l]);
+        } else {
+          for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
+            uint32_t u = 0;
+            for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) u += is_unary(e);
+            un = std::max(un, u);
+            mu = std::max<uint32_t>(mu, g->row_ptr[d + 1] - g->row_ptr[d] - u);
+            if (g->has_multi) oc = std::max(oc, g->row_oth[d + 1] - g->row_oth[d]);
+          }
         }
         s_un[sidx] = un; s_mu[sidx] = mu; s_oc[sidx] = oc;
       }
@@ -965,20 +1004,24 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       const uint32_t un = s_un[sidx], mu = s_mu[sidx], oc = s_oc[sidx];
       const uint64_t o_un = SH_WORDS, o_unfv = o_un + 32ull * un, o_mu = o_unfv + 32ull * un * fvw,
                      o_mufv = o_mu + 32ull * mu, o_oth = o_mufv + 32ull * mu * fvw;
+      const bool is_wide = slice_is_wide(sidx);
+      const uint32_t nvars = is_wide ? 1 : 32;  // variables whose rows the slice holds
       // is every multi record of the slice a one-other-variable record?
       bool binary = mu > 0, antisym = true;
-      for (uint64_t d = sidx * 32; d < sidx * 32 + 32 && binary; ++d) {
+      for (uint64_t d = sidx * 32; d < sidx * 32 + nvars && binary; ++d) {
         for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e)
           if (!is_unary(e) && (g->e_tag[e] >> TAG_FORM_SHIFT) != 1) binary = false;
       }
       h[SH_N_UNARY] = un; h[SH_N_MULTI] = mu; h[SH_N_OTH] = oc;
       h[SH_SELF_OFF] = g->sl_off[sidx];
+      uint32_t ju[32] = {0}, jm[32] = {0}, jo[32] = {0};  // per lane: unary / multi columns and others words written
       for (uint32_t l = 0; l < 32; ++l) {
         const uint64_t d = sidx * 32 + l;
         if (g->var_flags[d] & VF_PAD) h[SH_PAD_MASK] |= 1u << l;
         if (g->var_flags[d] & VF_EVID) h[SH_EVID_MASK] |= 1u << l;
         if (g->evid_val[d] == 1) h[SH_EVVAL_MASK] |= 1u << l;
-        uint32_t ju = 0, jm = 0;
+        if (l >= nvars) continue;
+        uint32_t ku = 0, km = 0;  // records of this variable seen so far
         uint64_t o = g->has_multi ? g->row_oth[d] : 0;
         for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) {
           const uint8_t tag = g->e_tag[e];
@@ -986,16 +1029,18 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
           const uint32_t wid = g->e_wid[e];
           const uint32_t base = wid | (raw.w_fixed[g->w_perm[wid]] ? SELL_FIXED_BIT : 0u);
           if (form == 0) {
+            const uint32_t tl = is_wide ? ku % 32 : l;  // target lane
             const uint32_t mm = code_mismatch(fc);
             const uint32_t s1 = (tag & TAG_SELF_EQ1) ? 2 : mm, s0 = (tag & TAG_SELF_EQ1) ? mm : 2;
             if (s1 + s0 != 2) antisym = false;
-            h[o_un + 32ull * ju + l] = sell_unary_record(wid, raw.w_fixed[g->w_perm[wid]], s1, s0);
-            put_fv(h + o_unfv + (32ull * ju + l) * fvw, e);
-            ++ju;
+            h[o_un + 32ull * ju[tl] + tl] = sell_unary_record(wid, raw.w_fixed[g->w_perm[wid]], s1, s0);
+            put_fv(h + o_unfv + (32ull * ju[tl] + tl) * fvw, e);
+            ++ju[tl]; ++ku;
             continue;
           }
+          const uint32_t tl = is_wide ? km % 32 : l;
           uint32_t t = tag;
-          uint64_t span = form != FORM_GENERAL ? form : 1 + g->oth[o];
+          const uint64_t span = others_span(e, o);
           if (binary) {
             // sign table over (this variable's value x, other variable satisfied)
             const uint32_t self_eq = (tag & TAG_SELF_EQ1) ? 1 : 0;
@@ -1007,19 +1052,22 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
                 const int sgn = self_head ? sign2(fc, sat, m) : sign2(fc, m ? 1u : 0u, sat != 0);
                 t |= (uint32_t)(sgn + 1) << (2 * (2 * x + sat));
               }
-            h[o_oth + 32ull * jm + l] = g->oth[o];  // record j owns others column j
+            h[o_oth + 32ull * jm[tl] + tl] = g->oth[o];  // record j owns others column j
           } else {
-            for (uint64_t k = 0; k < span; ++k) h[o_oth + 32ull * (o - g->row_oth[d] + k) + l] = g->oth[o + k];
+            for (uint64_t k = 0; k < span; ++k) h[o_oth + 32ull * (jo[tl] + k) + tl] = g->oth[o + k];
+            jo[tl] += (uint32_t)span;
           }
           o += span;
-          h[o_mu + 32ull * jm + l] = base | (t << 24);
-          put_fv(h + o_mufv + (32ull * jm + l) * fvw, e);
-          ++jm;
+          h[o_mu + 32ull * jm[tl] + tl] = base | (t << 24);
+          put_fv(h + o_mufv + (32ull * jm[tl] + tl) * fvw, e);
+          ++jm[tl]; ++km;
         }
-        for (; ju < un; ++ju) h[o_un + 32ull * ju + l] = SELL_UNARY_NOP;
-        for (; jm < mu; ++jm) h[o_mu + 32ull * jm + l] = binary ? SELL_BINARY_NOP << 24 : 0u;  // form 0
       }
-      h[SH_FLAGS] = (antisym ? SF_ANTISYM : 0u) | (binary ? SF_BINARY : 0u);
+      for (uint32_t l = 0; l < 32; ++l) {
+        for (uint32_t j = ju[l]; j < un; ++j) h[o_un + 32ull * j + l] = SELL_UNARY_NOP;
+        for (uint32_t j = jm[l]; j < mu; ++j) h[o_mu + 32ull * j + l] = binary ? SELL_BINARY_NOP << 24 : 0u;  // form 0
+      }
+      h[SH_FLAGS] = (antisym ? SF_ANTISYM : 0u) | (binary ? SF_BINARY : 0u) | (is_wide ? SF_WIDE : 0u);
     }
     });
   }

@@ -136,6 +136,13 @@ class ImageModel:
         assert not (h["pad"] >> lane) & 1
         assert ((h["evid"] >> lane) & 1) == (1 if self.var_flags[d] & VF_EVID else 0)
         assert ((h["evval"] >> lane) & 1) == int(self.evid_val[d] == 1)
+        if h["flags"] & 4:  # SF_WIDE: one variable (slot 0), its records dealt to the 32 lanes: sum the shares
+            assert lane == 0 and h["pad"] == 0xFFFFFFFE
+            parts = [self._sell_lane_potentials(h, l, d, a, weights) for l in range(32)]
+            return sum(p for p, _ in parts), sum(n for _, n in parts)
+        return self._sell_lane_potentials(h, lane, d, a, weights)
+
+    def _sell_lane_potentials(self, h, lane, d, a, weights):
         pos, neg = 0.0, 0.0
         code = lambda c: float(c - 1)
         antisym = True

@@ -285,3 +285,30 @@ def test_large_chromatic_schedule_is_a_proper_colouring(shape, monkeypatch):
     sizes = np.bincount(color)
     big = sizes[sizes > 0.01 * nvar]
     assert big.max() <= 1.05 * big.min() + 64, sizes
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_wide_slices_hold_the_same_potentials(seed, monkeypatch):
+    """warp-per-variable slices (SF_WIDE: a high-degree variable's records dealt round-robin to the
+    32 lanes): the lanes' shares must add up to the oracle's potentials, for unary, two-variable
+    and general records alike; ordinary variables are untouched"""
+    monkeypatch.setenv("DWG_WIDE_MIN", "12")
+    rng = np.random.default_rng(6000 + seed)
+    raw = random_graph(rng, nvar=120, nfac=700, nweight=15, p_cat=0.0, max_arity=[2, 3, 4][seed])
+    # two hubs: variables 0 and 1 appear in many more factors
+    ev = raw.edge_vid.copy()
+    hub = rng.random(len(ev)) < 0.15
+    ev[hub] = rng.integers(0, 2, hub.sum())
+    raw.edge_vid = ev
+    raw = raw.normalized()
+    g = sb.Graph.from_raw(raw, sb.SCHED_CHROMATIC)
+    m = ImageModel(g)
+    o = ol.Oracle(raw)
+    assert len(m.sl_off) and any(m.slice_header(s)["flags"] & 4 for s in range(len(m.sl_off) - 1))
+    for trial in range(2):
+        a = rng.integers(0, 2, raw.nvar).astype(np.uint64)
+        w = rng.normal(0, 1, raw.nweight)
+        o.assign_evid[:] = a
+        o.weights[:] = w
+        for v in range(raw.nvar):
+            assert np.allclose(m.sell_potentials(v, a, w), (o.potential(v, 1), o.potential(v, 0)), rtol=1e-12, atol=1e-12), v

@@ -777,3 +777,112 @@ def test_deferred_replica_receives_the_graph_from_a_peer():
     a.infer_epochs(5); b.infer_epochs(5)
     assert np.array_equal(a.assignments(1), b.assignments(1))
     assert np.array_equal(a.tallies()[0], b.tallies(wide=False)[0].astype(np.uint64))
+
+
+# ---------------------------------------------------------------- warp per variable (hubs)
+def _hub_graph(rng, nvar, nfac, max_arity, hub_share=0.15, nhub=2):
+    raw = random_graph(rng, nvar=nvar, nfac=nfac, nweight=25, p_cat=0.0, max_arity=max_arity)
+    ev = raw.edge_vid.copy()
+    hub = rng.random(len(ev)) < hub_share
+    ev[hub] = rng.integers(0, nhub, hub.sum())
+    raw.edge_vid = ev
+    return raw.normalized()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_wide_slices_sweep_exactly(seed, monkeypatch):
+    """SF_WIDE slices (a hub's records dealt to the 32 lanes, partial sums combined by shuffles) in
+    the staged and the direct inference kernels and in the learning kernel: chains equal the
+    sequential reference's, on graphs with unary / two-variable / general records"""
+    monkeypatch.setenv("DWG_WIDE_MIN", "16")
+    monkeypatch.setenv("DWG_LEARN_WARPS", "1")
+    if seed % 2:
+        monkeypatch.setenv("DWG_SELL_DIRECT", "1")
+    rng = np.random.default_rng(7100 + seed)
+    raw = _hub_graph(rng, 1500, 6000, [2, 3, 4][seed % 3])
+    raw.fac_fv[:] = rng.choice([1.0, 0.5, 2.0, -1.0], raw.nfac)
+    raw.w_fixed[:] = 1  # (learning sweeps below: chains only)
+    g, s, o = _mk(raw, sb.SCHED_CHROMATIC, sample_evidence=seed % 3 != 0, reg_param=0.0, learn_non_evidence=True)
+    blob, off = g.image("blob"), g.image("sl_off")
+    assert any(blob[int(off[i]) * 8 + 6] & 4 for i in range(len(off) - 1))  # some slice is wide
+    perm, _ = g.schedule()
+    for ep in range(3):
+        r0 = rng.random(o.nvar)
+        s.set_uniforms(r0)
+        s.infer_epoch()
+        o.sweep_infer_seq(perm, r0)
+    assert np.array_equal(s.assignments(1), o.assign_evid)
+    t, n = s.tallies()
+    assert np.array_equal(t, o.tallies) and np.array_equal(n, o.nsamples)
+    order = g.learn_order()
+    for ep in range(2):
+        r0, r1 = rng.random(o.nvar), rng.random(o.nvar)
+        s.set_uniforms(r0, r1)
+        s.learn_epoch(2.0 ** -6)
+        o.sweep_learn_seq(2.0 ** -6, order, r0, r1)
+        _same_state(s, o)
+
+
+def test_wide_slices_gradient_sums(monkeypatch):
+    """the SGD steps of a hub, pushed by 32 lanes each holding a share of its records, add up to the
+    reference's (vanishing dyadic step: w0 - w = step * sum of gradients)"""
+    monkeypatch.setenv("DWG_WIDE_MIN", "16")
+    monkeypatch.setenv("DWG_LEARN_WARPS", "1")
+    rng = np.random.default_rng(7200)
+    raw = _hub_graph(rng, 1200, 5000, 3)
+    raw.fac_fv[:] = rng.choice([1.0, 0.5, 2.0, -1.0], raw.nfac)
+    raw.w_fixed[:] = rng.random(raw.nweight) < 0.2
+    g, s, o = _mk(raw, sb.SCHED_CHROMATIC, reg_param=0.0, learn_non_evidence=True)
+    order = g.learn_order()
+    step = 2.0 ** -30
+    r0, r1 = rng.random(o.nvar), rng.random(o.nvar)
+    w0 = s.weights()
+    s.set_uniforms(r0, r1)
+    s.learn_epoch(step)
+    o.sweep_learn_seq(step, order, r0, r1)
+    _same_state(s, o)
+    got, want = (w0 - s.weights()) / step, (w0 - o.weights) / step
+    assert np.abs(want).max() > 10 and np.allclose(got, want, rtol=1e-4, atol=1e-6)
+
+
+def test_zipf_degree_graph_hubs_cost_per_edge():
+    """a graph whose variable degrees follow a Zipf law (the largest hub has > 10^5 incident
+    factors): the sweep equals the sequential reference's, and costs per edge record at most 1.5 x
+    what a uniform-degree graph of the same size costs (without wide slices the hub would be one
+    serial lane and pad its slice-mates to 10^5 columns)"""
+    import time
+    from sampler_b200 import graphgen
+    rng = np.random.default_rng(7300)
+    nvar, nfac, nweight = 200_000, 2_000_000, 500
+    # unary ISTRUE factors, the variable of a factor drawn from Zipf(1.0) over the variables
+    ranks = np.arange(1, nvar + 1, dtype=np.float64)
+    cdf = np.cumsum(1.0 / ranks); cdf /= cdf[-1]
+    vid = np.searchsorted(cdf, rng.random(nfac)).astype(np.uint64)
+    vid = rng.permutation(nvar).astype(np.uint64)[vid]  # hubs anywhere in the id range
+    vid[:nvar] = np.arange(nvar, dtype=np.uint64)       # every variable has at least one factor
+    raw = gio.RawGraph((rng.random(nvar) < 0.5).astype(np.uint8), rng.integers(0, 2, nvar), np.zeros(nvar, np.uint16),
+                       np.full(nvar, 2, np.uint64), *gio.empty_domains(), np.full(nfac, gio.FUNC_ISTRUE, np.int32),
+                       np.arange(nfac + 1, dtype=np.uint64), vid, np.ones(nfac, np.uint64),
+                       rng.integers(0, nweight, nfac), np.ones(nfac), rng.normal(0, 0.05, nweight),
+                       np.zeros(nweight, np.uint8)).normalized()
+    deg = np.bincount(vid.astype(np.int64), minlength=nvar)
+    assert deg.max() > 100_000
+    g, s, o = _mk(raw, sb.SCHED_AUTO, sample_evidence=True)
+    perm, _ = g.schedule()
+    r0 = rng.random(nvar)
+    s.set_uniforms(r0)
+    s.infer_epoch()
+    o.sweep_infer_seq(perm, r0)
+    assert np.array_equal(s.assignments(1), o.assign_evid)
+    s.set_uniforms(None)
+
+    def ms_per_sweep(smp, n=30):
+        smp.infer_epochs(5); smp.sync()
+        t0 = time.perf_counter(); smp.infer_epochs(n); smp.sync()
+        return 1e3 * (time.perf_counter() - t0) / n
+    t_zipf = ms_per_sweep(s)
+    uni = graphgen.unary_boolean(nvar, nfac // nvar, nweight)
+    su = sb.Sampler(sb.Graph.from_raw(uni), sample_evidence=True)
+    t_uni = ms_per_sweep(su)
+    print("zipf-degree %.3f ms, uniform-degree %.3f ms per sweep of %d edge records" % (t_zipf, t_uni, nfac))
+    assert t_zipf <= 1.5 * t_uni + 0.02, (t_zipf, t_uni)
