@@ -168,6 +168,11 @@ int dwg_infer_epoch(dwg_handle *h);
 /* n sweeps back to back (the launches of consecutive colour classes are chained by programmatic
  * dependent launch; no host synchronisation in between) */
 int dwg_infer_epochs(dwg_handle *h, uint64_t n);
+/* n learning sweeps of ONE replica with stepsize *= decay after each (DimmWitted::learn without the
+ * per-epoch replica averaging, src/dimmwitted.cc:162-207).  Under the sequential schedule (tiny
+ * graphs) dwg_infer_epochs / dwg_learn_epochs run all n epochs in one launch: such graphs are launch
+ * latency and nothing else. */
+int dwg_learn_epochs(dwg_handle *h, uint64_t n, double stepsize, double decay);
 int dwg_sync(dwg_handle *h);
 void *dwg_stream(dwg_handle *h); /* cudaStream_t the sweeps are launched on */
 

@@ -92,6 +92,7 @@ def load(build: bool = False):
     L.dwg_learn_epoch.argtypes = [vp, dbl]
     L.dwg_infer_epoch.argtypes = [vp]
     L.dwg_infer_epochs.argtypes = [vp, u64]
+    L.dwg_learn_epochs.argtypes = [vp, u64, dbl, dbl]
     L.dwg_sync.argtypes = [vp]
     L.dwg_stream.restype = vp
     L.dwg_stream.argtypes = [vp]
@@ -267,6 +268,10 @@ class Sampler:
 
     def learn_epoch(self, stepsize: float):
         _check(load().dwg_learn_epoch(self._h, stepsize))
+
+    def learn_epochs(self, n: int, stepsize: float, decay: float):
+        """n learning sweeps, stepsize *= decay after each (one launch under the sequential schedule)"""
+        _check(load().dwg_learn_epochs(self._h, n, stepsize, decay))
 
     def infer_epoch(self):
         _check(load().dwg_infer_epoch(self._h))

@@ -209,6 +209,8 @@ struct dwg_handle {
   // learning sweeps of sliced-ELL graphs (k_sell_learn_live): visit order, per-weight statistics
   // in internal weight order (device: cls_N / cls_H; host: curvatures sorted for the epoch plan)
   DevBuf<uint32_t> learn_visit;
+  DevBuf<double> part_sums;        // hubs cut into parts (SF_PART): per-slice sums and counters
+  DevBuf<uint32_t> part_done;
   std::vector<float> learn_H_sorted;   // curvature bounds of the learnable weights, ascending
   double learn_rho = 1.0;              // coupling: learnable records per learning variable / 10
   uint32_t learn_stage_words = 8;      // capacity of one ring stage of the learning kernel
@@ -236,17 +238,17 @@ int sell_grid(K kernel, size_t smem, int num_sms, int *blocks, int threads = SEL
   *blocks = per_sm * num_sms;
   return DWG_OK;
 }
-template <bool MULTI, int FV>
+template <bool MULTI, int FV, bool WIDE>
 int sell_setup_t(dwg_handle *h) {
   const size_t n_hot = h->img->n_hot;
-  int rc = sell_grid(k_sell_infer<MULTI, FV>, 8 * n_hot, h->num_sms, &h->sell_blocks_infer);
+  int rc = sell_grid(k_sell_infer<MULTI, FV, WIDE>, 8 * n_hot, h->num_sms, &h->sell_blocks_infer);
   if (rc) return rc;
   {  // learning: a two-stage ring per warp of whatever fits beside the weight tables (longer slices are read from HBM)
     const size_t fixed = sell_learn_ring_off((uint32_t)n_hot), lbudget = 112 * 1024;
     uint32_t cap = fixed + 1024 < lbudget ? (uint32_t)((lbudget - fixed) / ((SELL_LEARN_THREADS / 32) * SELL_LEARN_STAGES * 4)) & ~3u : 8u;
     if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) cap = std::min<uint32_t>(cap, std::max(8, atoi(e)) & ~3u);  // tests
     h->learn_stage_words = std::max(8u, std::min(cap, (h->img->sell_max_words + 3u) & ~3u));
-    rc = sell_grid(k_sell_learn_live<MULTI, FV>, sell_learn_smem((uint32_t)n_hot, h->learn_stage_words), h->num_sms,
+    rc = sell_grid(k_sell_learn_live<MULTI, FV, WIDE>, sell_learn_smem((uint32_t)n_hot, h->learn_stage_words), h->num_sms,
                    &h->sell_blocks_learn, SELL_LEARN_THREADS);
     if (rc) return rc;
   }
@@ -295,7 +297,7 @@ int sell_setup_t(dwg_handle *h) {
   if (!stages) return DWG_OK;
   const size_t smem = sell_staged_smem(n_tab, stages, words, nwarp);
   const bool allhot = h->img->nweight <= n_tab;
-#define STAGED_GRID(AH, NT) sell_grid(k_sell_infer_staged<MULTI, FV, AH, NT>, smem, h->num_sms, &h->sell_blocks_staged, NT)
+#define STAGED_GRID(AH, NT) sell_grid(k_sell_infer_staged<MULTI, FV, AH, NT, WIDE>, smem, h->num_sms, &h->sell_blocks_staged, NT)
   rc = nwarp == 16 ? (allhot ? STAGED_GRID(true, 512) : STAGED_GRID(false, 512))
        : nwarp == 8 ? (allhot ? STAGED_GRID(true, 256) : STAGED_GRID(false, 256))
                     : (allhot ? STAGED_GRID(true, 128) : STAGED_GRID(false, 128));
@@ -307,7 +309,7 @@ int sell_setup_t(dwg_handle *h) {
   h->sell_stage_words = words;
   return DWG_OK;
 }
-template <bool MULTI, int FV>
+template <bool MULTI, int FV, bool WIDE>
 // staged: the bulk-async inference kernel; pdl: programmatic dependent launch behind the previous
 // inference launch
 void sell_launch_t(dwg_handle *h, bool staged, bool pdl, uint32_t blocks, const SellGraph &sg, const SweepParams &p) {
@@ -324,33 +326,36 @@ void sell_launch_t(dwg_handle *h, bool staged, bool pdl, uint32_t blocks, const 
     cfg.numAttrs = pdl ? 1 : 0;  // only behind another launch of this kernel (see launch_sweep)
     const bool allhot = h->img->nweight <= sg.n_tab;
 #define STAGED_LAUNCH(AH, NT) \
-  cudaLaunchKernelEx(&cfg, k_sell_infer_staged<MULTI, FV, AH, NT>, sg, h->ss, p, h->sell_stages, h->sell_stage_words)
+  cudaLaunchKernelEx(&cfg, k_sell_infer_staged<MULTI, FV, AH, NT, WIDE>, sg, h->ss, p, h->sell_stages, h->sell_stage_words)
     if (h->sell_staged_warps == 16) { if (allhot) STAGED_LAUNCH(true, 512); else STAGED_LAUNCH(false, 512); }
     else if (h->sell_staged_warps == 8) { if (allhot) STAGED_LAUNCH(true, 256); else STAGED_LAUNCH(false, 256); }
     else { if (allhot) STAGED_LAUNCH(true, 128); else STAGED_LAUNCH(false, 128); }
 #undef STAGED_LAUNCH
-  } else k_sell_infer<MULTI, FV><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
+  } else k_sell_infer<MULTI, FV, WIDE><<<blocks, SELL_THREADS, 8 * n_hot, h->stream>>>(sg, h->ss, p);
 }
 // live: no shared-memory copy of the weights at all (the narrow tail of a learning sweep: every
 // record reads its weight from L2 and pushes its step there, nothing to refresh or flush)
-template <bool MULTI, int FV>
+template <bool MULTI, int FV, bool WIDE>
 void sell_learn_launch_t(dwg_handle *h, uint32_t blocks, uint32_t threads, bool live, const SweepParams &p,
                          const SellLearn &L) {
   SellGraph sg = h->sg;
   if (live) sg.n_hot = 0;
-  k_sell_learn_live<MULTI, FV><<<blocks, threads, sell_learn_smem(sg.n_hot, h->learn_stage_words), h->stream>>>(
+  k_sell_learn_live<MULTI, FV, WIDE><<<blocks, threads, sell_learn_smem(sg.n_hot, h->learn_stage_words), h->stream>>>(
       sg, h->ss, p, L, h->learn_stage_words);
 }
-#define SELL_SWITCH(CALL)                                                      \
+#define SELL_SWITCH_W(CALL, WD)                                                \
   if (m.has_multi) {                                                           \
-    if (m.fv_mode == FV_ONE) { CALL(true, FV_ONE); }                           \
-    else if (m.fv_mode == FV_F32) { CALL(true, FV_F32); }                      \
-    else { CALL(true, FV_F64); }                                               \
+    if (m.fv_mode == FV_ONE) { CALL(true, FV_ONE, WD); }                       \
+    else if (m.fv_mode == FV_F32) { CALL(true, FV_F32, WD); }                  \
+    else { CALL(true, FV_F64, WD); }                                           \
   } else {                                                                     \
-    if (m.fv_mode == FV_ONE) { CALL(false, FV_ONE); }                          \
-    else if (m.fv_mode == FV_F32) { CALL(false, FV_F32); }                     \
-    else { CALL(false, FV_F64); }                                              \
+    if (m.fv_mode == FV_ONE) { CALL(false, FV_ONE, WD); }                      \
+    else if (m.fv_mode == FV_F32) { CALL(false, FV_F32, WD); }                 \
+    else { CALL(false, FV_F64, WD); }                                          \
   }
+// (graphs with warp-per-variable slices run kernels instantiated with the code for them)
+#define SELL_SWITCH(CALL)                                                      \
+  if (m.has_wide) { SELL_SWITCH_W(CALL, true) } else { SELL_SWITCH_W(CALL, false) }
 constexpr int CELL_THREADS = 256;
 int cell_setup(dwg_handle *h) {
   const GraphImage &m = *h->img;
@@ -391,20 +396,20 @@ void cell_launch(dwg_handle *h, bool pdl, uint32_t blocks, const CellGraph &cg, 
 int sell_setup(dwg_handle *h) {
   const GraphImage &m = *h->img;
   int rc = DWG_OK;
-#define CALL(MU, FV) rc = sell_setup_t<MU, FV>(h)
+#define CALL(MU, FV, WD) rc = sell_setup_t<MU, FV, WD>(h)
   SELL_SWITCH(CALL)
 #undef CALL
   return rc;
 }
 void sell_launch(dwg_handle *h, bool staged, bool pdl, uint32_t blocks, const SellGraph &sg, const SweepParams &p) {
   const GraphImage &m = *h->img;
-#define CALL(MU, FV) sell_launch_t<MU, FV>(h, staged, pdl, blocks, sg, p)
+#define CALL(MU, FV, WD) sell_launch_t<MU, FV, WD>(h, staged, pdl, blocks, sg, p)
   SELL_SWITCH(CALL)
 #undef CALL
 }
 void sell_learn_launch(dwg_handle *h, uint32_t blocks, uint32_t threads, bool live, const SweepParams &p, const SellLearn &L) {
   const GraphImage &m = *h->img;
-#define CALL(MU, FV) sell_learn_launch_t<MU, FV>(h, blocks, threads, live, p, L)
+#define CALL(MU, FV, WD) sell_learn_launch_t<MU, FV, WD>(h, blocks, threads, live, p, L)
   SELL_SWITCH(CALL)
 #undef CALL
 }
@@ -737,6 +742,12 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     CU(h->sl_off.upload(m.sl_off, s));
     CU(h->blob.upload(m.blob, s));
     CU(h->learn_visit.upload(m.learn_visit, s));
+    if (!m.part_slices.empty()) {
+      const size_t nsl = m.sl_off.size() - 1;
+      CU(h->part_sums.alloc(4 * nsl));
+      CU(h->part_done.alloc(nsl));
+      CU(cudaMemsetAsync(h->part_done.p, 0, 4 * nsl, s));
+    }
     // Boolean variables have no truthiness: under --noise_aware only --learn_non_evidence learns
     h->learns = h->opts.learn_non_evidence || !h->opts.noise_aware;
     // the epoch plan of launch_learn_sell: curvature bounds of the learnable weights, sorted, and
@@ -794,6 +805,7 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     SellState &ss = h->ss;
     ss.assign_free = h->assign_free8.p; ss.assign_evid = h->assign_evid8.p;
     ss.weights = h->weights.p; ss.grad_acc = h->grad_acc.p; ss.tallies = h->tallies.p;
+    ss.part_sums = h->part_sums.p; ss.part_done = h->part_done.p;
     rc = sell_setup(h.get());
     if (rc) return rc;
     h->cls_query_end = g->query_end();
@@ -923,6 +935,8 @@ static int launch_learn_sell(dwg_handle *h, SweepParams &p, double stepsize) {
     const double inflight = std::min(1.0, (double)grid_warps * (live ? 1 : period) / nslice);
     // one warp cannot be narrowed further: it keeps the reference's step whatever x is
     L.xcap_inv = grid_warps == 1 ? 0.0 : a * rho * inflight / cap;
+    L.visit = h->learn_visit.p;
+    L.inv_nslice = 1.0 / nslice;
     sell_learn_launch(h, blocks, threads, live, p, L);
     ++g_launches;
   };
@@ -1052,10 +1066,47 @@ int dwg_infer_epoch(dwg_handle *h) {
   return rc;
 }
 
+// n epochs of the sequential schedule in one launch (k_seq_epochs)
+static int launch_seq_epochs(dwg_handle *h, uint64_t n, bool learn, double stepsize, double decay) {
+  const GraphImage &m = *h->img;
+  CU(cudaSetDevice(h->device));
+  h->chain_open = false;
+  int rc = ensure_csr(h);
+  if (rc) return rc;
+  while (n) {
+    const uint32_t chunk = (uint32_t)std::min<uint64_t>(n, 1u << 20);
+    SweepParams p = make_params(h, stepsize);
+    p.d_begin = 0; p.d_end = (uint32_t)m.nvar_pad;
+    if (m.assign_bytes == 1) k_seq_epochs<uint8_t><<<1, 1, 0, h->stream>>>(h->dg, h->ds, p, chunk, learn ? 1 : 0, decay);
+    else k_seq_epochs<uint32_t><<<1, 1, 0, h->stream>>>(h->dg, h->ds, p, chunk, learn ? 1 : 0, decay);
+    ++g_launches;
+    h->sweep_counter += chunk;
+    if (!learn) h->infer_sweeps += chunk;
+    for (uint32_t e = 0; e < chunk && learn; ++e) stepsize *= decay;
+    n -= chunk;
+  }
+  CU(cudaGetLastError());
+  return DWG_OK;
+}
+static bool is_sequential(const dwg_handle *h) { return h->sequential || h->img->schedule == DWG_SCHED_SEQUENTIAL; }
+
 int dwg_infer_epochs(dwg_handle *h, uint64_t n) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  if (is_sequential(h) && n > 1 && !h->explicit_r) return launch_seq_epochs(h, n, false, 0.0, 1.0);
   for (uint64_t i = 0; i < n; ++i) {
     int rc = dwg_infer_epoch(h);
     if (rc) return rc;
+  }
+  return DWG_OK;
+}
+
+int dwg_learn_epochs(dwg_handle *h, uint64_t n, double stepsize, double decay) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  if (is_sequential(h) && n > 1 && !h->explicit_r) return launch_seq_epochs(h, n, true, stepsize, decay);
+  for (uint64_t i = 0; i < n; ++i) {
+    int rc = dwg_learn_epoch(h, stepsize);
+    if (rc) return rc;
+    stepsize *= decay;
   }
   return DWG_OK;
 }

@@ -29,10 +29,33 @@ __device__ __forceinline__ uint32_t dev_draw_sample(const DevGraph &g, uint32_t 
   return dev_draw_categorical<AssignT, LIVE>(g, d, row0, K, a, w, r);
 }
 
+// sample_single_variable (src/gibbs_sampler.h:151-169) for the variable at schedule position d
+template <typename AssignT>
+__device__ __forceinline__ void sweep_infer_var(const DevGraph &g, const DevState &st, const SweepParams &p, uint32_t d) {
+  AssignT *a = static_cast<AssignT *>(st.assign_evid);
+  const uint8_t fl = __ldg(g.var_flags + d);
+  if (fl & VF_PAD) return;
+  if ((fl & VF_EVID) && !p.sample_evidence) return;  // gibbs_sampler.h:157
+  const bool cat = fl & VF_CATEGORICAL;
+  uint32_t row0 = d, K = 1;
+  if (g.var_row) {
+    row0 = __ldg(g.var_row + d);
+    K = __ldg(g.var_row + d + 1) - row0;
+  }
+  double r0, r1;
+  dev_uniforms(p, d, r0, r1);
+  const uint32_t prop = dev_draw_sample<AssignT, false>(g, d, cat, row0, K, a, st.weights, r0);
+  a[d] = (AssignT)prop;  // :160
+  // agg_nsamples is implicit (every sampled variable gains one per sweep, :163);
+  // Boolean: tally only proposal == 1 at the single row; categorical: row of the value (:164-167)
+  // (a RED: nothing waits for the old count)
+  if (cat) atomicAdd(st.tallies + row0 + prop, 1u);
+  else if (prop == 1u) atomicAdd(st.tallies + row0, 1u);
+}
+
 template <typename AssignT>
 __global__ void __launch_bounds__(SWEEP_THREADS)
 k_sweep_infer(const DevGraph g, const DevState st, const SweepParams p) {
-  AssignT *a = static_cast<AssignT *>(st.assign_evid);
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;; tid += nthreads) {
     const uint64_t d64 = sweep_unit_var(p, tid);
@@ -40,25 +63,7 @@ k_sweep_infer(const DevGraph g, const DevState st, const SweepParams p) {
       if (d64 - (tid & 31u) >= p.d_end) break;
       continue;
     }
-    const uint32_t d = (uint32_t)d64;
-    const uint8_t fl = __ldg(g.var_flags + d);
-    if (fl & VF_PAD) continue;
-    if ((fl & VF_EVID) && !p.sample_evidence) continue;  // gibbs_sampler.h:157
-    const bool cat = fl & VF_CATEGORICAL;
-    uint32_t row0 = d, K = 1;
-    if (g.var_row) {
-      row0 = __ldg(g.var_row + d);
-      K = __ldg(g.var_row + d + 1) - row0;
-    }
-    double r0, r1;
-    dev_uniforms(p, d, r0, r1);
-    const uint32_t prop = dev_draw_sample<AssignT, false>(g, d, cat, row0, K, a, st.weights, r0);
-    a[d] = (AssignT)prop;  // :160
-    // agg_nsamples is implicit (every sampled variable gains one per sweep, :163);
-    // Boolean: tally only proposal == 1 at the single row; categorical: row of the value (:164-167)
-    // (a RED: nothing waits for the old count)
-    if (cat) atomicAdd(st.tallies + row0 + prop, 1u);
-    else if (prop == 1u) atomicAdd(st.tallies + row0, 1u);
+    sweep_infer_var<AssignT>(g, st, p, (uint32_t)d64);
   }
 }
 
@@ -114,12 +119,66 @@ __device__ __forceinline__ void dev_sgd_row(const DevGraph &g, const DevState &s
   }
 }
 
+// sample_sgd_single_variable (src/gibbs_sampler.h:127-149) for the variable at schedule position d
 template <typename AssignT>
-__global__ void __launch_bounds__(SWEEP_THREADS)
-k_sweep_learn(const DevGraph g, const DevState st, const SweepParams p) {
+__device__ __forceinline__ void sweep_learn_var(const DevGraph &g, const DevState &st, const SweepParams &p, uint32_t d) {
   AssignT *af = static_cast<AssignT *>(st.assign_free);
   AssignT *ae = static_cast<AssignT *>(st.assign_evid);
   const AssignT *evid_val = static_cast<const AssignT *>(g.evid_val);
+  const uint8_t fl = __ldg(g.var_flags + d);
+  if (fl & VF_PAD) return;
+  const bool cat = fl & VF_CATEGORICAL, evid = fl & VF_EVID, truthy = fl & VF_TRUTHINESS;
+  uint32_t row0 = d, K = 1;
+  if (g.var_row) {
+    row0 = __ldg(g.var_row + d);
+    K = __ldg(g.var_row + d + 1) - row0;
+  }
+  double r0, r1;
+  dev_uniforms(p, d, r0, r1);
+  // the free chain samples EVERY variable, evidence included (gibbs_sampler.h:137-139)
+  const uint32_t pf = dev_draw_sample<AssignT, true>(g, d, cat, row0, K, af, st.weights, r0);
+  af[d] = (AssignT)pf;
+  // sample_evid, gibbs_sampler.h:171-190
+  const uint32_t ev = (uint32_t)evid_val[d];
+  uint32_t pe;
+  if (!p.noise_aware && evid) {
+    pe = ev;
+  } else if (p.noise_aware && truthy) {
+    double sum = 0;
+    pe = 0;
+    const uint32_t card = cat ? K : 2u;
+    for (uint32_t i = 0; i < card; ++i) {
+      sum = __dadd_rn(sum, g.truthiness[row0 + i]);
+      if (sum >= r1) { pe = i; break; }
+    }
+  } else {
+    pe = dev_draw_sample<AssignT, true>(g, d, cat, row0, K, ae, st.weights, r1);
+  }
+  ae[d] = (AssignT)pe;
+  if (!p.learn_non_evidence && ((!p.noise_aware && !evid) || (p.noise_aware && !truthy)))
+    return;  // :144-146
+  // sgd_on_variable, src/factor_graph.cc:262-314
+  if (!cat) {
+    // Boolean: evidence_value is Variable::assignment_dense even for a query variable (:272)
+    dev_sgd_row<AssignT>(g, st, p, d, row0, false, 0u, ev, pf, 1.0);
+  } else {
+    for (uint32_t val = 0; val < K; ++val) {
+      if (!p.noise_aware && val != ev) continue;  // :280
+      double t = 1.0;
+      if (p.noise_aware) {
+        t = g.truthiness ? g.truthiness[row0 + val] : 0.0;
+        if (t <= 0.000001 && t >= -0.000001) continue;  // is_linear_zero :283
+      }
+      dev_sgd_row<AssignT>(g, st, p, d, row0 + val, true, val, val, pf, t);  // :288-292
+      if (val == pf) continue;  // :304
+      dev_sgd_row<AssignT>(g, st, p, d, row0 + pf, true, pf, val, pf, t);  // :306-311
+    }
+  }
+}
+
+template <typename AssignT>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+k_sweep_learn(const DevGraph g, const DevState st, const SweepParams p) {
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;; tid += nthreads) {
     const uint64_t d64 = sweep_unit_var(p, tid);
@@ -127,56 +186,27 @@ k_sweep_learn(const DevGraph g, const DevState st, const SweepParams p) {
       if (d64 - (tid & 31u) >= p.d_end) break;
       continue;
     }
-    const uint32_t d = (uint32_t)d64;
-    const uint8_t fl = __ldg(g.var_flags + d);
-    if (fl & VF_PAD) continue;
-    const bool cat = fl & VF_CATEGORICAL, evid = fl & VF_EVID, truthy = fl & VF_TRUTHINESS;
-    uint32_t row0 = d, K = 1;
-    if (g.var_row) {
-      row0 = __ldg(g.var_row + d);
-      K = __ldg(g.var_row + d + 1) - row0;
+    sweep_learn_var<AssignT>(g, st, p, (uint32_t)d64);
+  }
+}
+
+// The sequential schedule (tiny graphs: one chain walking the variables in id order, the
+// reference's `-t 1 -c 1` semantics bit for bit) for n epochs in ONE launch: such graphs are pure
+// launch latency otherwise (biased_coin: 18 variables x 4000 epochs).  The sweep counter of the
+// Philox stream and the step size advance per epoch exactly as the host loop would advance them
+// (stepsize *= decay, src/dimmwitted.cc:199-204).
+template <typename AssignT>
+__global__ void k_seq_epochs(const DevGraph g, const DevState st, SweepParams p, uint32_t n_epochs, int learn, double decay) {
+  if (blockIdx.x || threadIdx.x) return;
+  uint64_t sweep = ((uint64_t)p.sweep_hi << 32) | p.sweep_lo;
+  for (uint32_t e = 0; e < n_epochs; ++e) {
+    p.sweep_lo = (uint32_t)sweep; p.sweep_hi = (uint32_t)(sweep >> 32);
+    for (uint32_t d = 0; d < g.nvar; ++d) {
+      if (learn) sweep_learn_var<AssignT>(g, st, p, d);
+      else sweep_infer_var<AssignT>(g, st, p, d);
     }
-    double r0, r1;
-    dev_uniforms(p, d, r0, r1);
-    // the free chain samples EVERY variable, evidence included (gibbs_sampler.h:137-139)
-    const uint32_t pf = dev_draw_sample<AssignT, true>(g, d, cat, row0, K, af, st.weights, r0);
-    af[d] = (AssignT)pf;
-    // sample_evid, gibbs_sampler.h:171-190
-    const uint32_t ev = (uint32_t)evid_val[d];
-    uint32_t pe;
-    if (!p.noise_aware && evid) {
-      pe = ev;
-    } else if (p.noise_aware && truthy) {
-      double sum = 0;
-      pe = 0;
-      const uint32_t card = cat ? K : 2u;
-      for (uint32_t i = 0; i < card; ++i) {
-        sum = __dadd_rn(sum, g.truthiness[row0 + i]);
-        if (sum >= r1) { pe = i; break; }
-      }
-    } else {
-      pe = dev_draw_sample<AssignT, true>(g, d, cat, row0, K, ae, st.weights, r1);
-    }
-    ae[d] = (AssignT)pe;
-    if (!p.learn_non_evidence && ((!p.noise_aware && !evid) || (p.noise_aware && !truthy)))
-      continue;  // :144-146
-    // sgd_on_variable, src/factor_graph.cc:262-314
-    if (!cat) {
-      // Boolean: evidence_value is Variable::assignment_dense even for a query variable (:272)
-      dev_sgd_row<AssignT>(g, st, p, d, row0, false, 0u, ev, pf, 1.0);
-    } else {
-      for (uint32_t val = 0; val < K; ++val) {
-        if (!p.noise_aware && val != ev) continue;  // :280
-        double t = 1.0;
-        if (p.noise_aware) {
-          t = g.truthiness ? g.truthiness[row0 + val] : 0.0;
-          if (t <= 0.000001 && t >= -0.000001) continue;  // is_linear_zero :283
-        }
-        dev_sgd_row<AssignT>(g, st, p, d, row0 + val, true, val, val, pf, t);  // :288-292
-        if (val == pf) continue;  // :304
-        dev_sgd_row<AssignT>(g, st, p, d, row0 + pf, true, pf, val, pf, t);  // :306-311
-      }
-    }
+    ++sweep;
+    if (learn) p.stepsize = __dmul_rn(p.stepsize, decay);
   }
 }
 

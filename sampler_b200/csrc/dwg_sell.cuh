@@ -46,6 +46,9 @@ struct SellState {
   const double *weights;  // frozen for the duration of a launch
   double *grad_acc;       // [nweight] sum of gradients of this launch (learning)
   uint32_t *tallies;
+  // hubs cut into parts (SF_PART, graph_image.h), per slice; null when the graph has none
+  double *part_sums;      // [4 * nslice] lane-combined potentials of a part: free pos / neg, evid pos / neg
+  uint32_t *part_done;    // [nslice] at a hub's first slice: parts finished in this sweep
 };
 
 struct SliceHeader {
@@ -110,6 +113,35 @@ __device__ __forceinline__ double sell_wide_sum(double x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
   return x;
+}
+
+// A part of a hub is done: store its (lane-combined) sums and count it; the warp that counts LAST
+// adds the parts' sums in a fixed order (lane q takes parts q, q + 32, ..., then the butterfly) --
+// the same result whichever warp that is.  nv: values per part (2 inference, 4 learning).
+// Returns true on the finishing warp, with v[] = the hub's sums.
+template <int NV>
+__device__ __forceinline__ bool sell_part_finish(const SellState &st, uint32_t s, uint32_t flags, uint32_t lane, double (&v)[NV]) {
+  const uint32_t q = (flags >> 4) & 0x3fffu, n = flags >> 18, sf = s - q;
+  uint32_t old = 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) __stcg(st.part_sums + 4 * (size_t)s + i, v[i]);
+    __threadfence();
+    old = atomicAdd(st.part_done + sf, 1u);
+  }
+  old = __shfl_sync(0xffffffffu, old, 0);
+  if (old != n - 1) return false;
+  __threadfence();
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  for (uint32_t k = lane; k < n; k += 32)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = __dadd_rn(acc[i], __ldcg(st.part_sums + 4 * (size_t)(sf + k) + i));
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = sell_wide_sum(acc[i]);
+  if (lane == 0) st.part_done[sf] = 0;  // ready for the next sweep
+  return true;
 }
 
 // sign code (0,1,2) -> the term  sign * t  with t = weight * feature value
@@ -325,7 +357,36 @@ __device__ __forceinline__ void sell_potentials(const SellGraph &g, const SliceH
   sell_multi<FV, LD>(g, h, w_s, w, lane, self, a, binary ? &c : nullptr, sat, pos, neg);
 }
 
-template <bool MULTI, int FV>
+// The draw of an SF_WIDE slice (inference): combine the lanes' shares, for a part of a hub store
+// them and let the warp that finishes the hub's last part go on, then lane 0 draws for the variable.
+// Only kernels instantiated with WIDE = true contain it: graphs without wide slices run the very
+// code they ran before wide slices existed.
+__device__ __forceinline__ void sell_wide_draw(const SellState &st, const SweepParams &p, uint32_t s, uint32_t flags,
+                                               uint32_t lane, uint32_t active, double pos, double neg) {
+  pos = sell_wide_sum(pos); neg = sell_wide_sum(neg);
+  uint32_t sfirst = s;
+  if (flags & SF_PART) {
+    double v[2] = {pos, neg};
+    if (!sell_part_finish<2>(st, s, flags, lane, v)) return;
+    pos = v[0]; neg = v[1];
+    sfirst = s - ((flags >> 4) & 0x3fffu);
+  }
+  if (lane != 0 || !(active & 1u)) return;
+  const uint32_t d = sfirst * 32u;
+  double r0, r1;
+  dev_uniforms(p, d, r0, r1);
+  const uint32_t prop = sell_draw_boolean(pos, neg, r0);
+  st.assign_evid[d] = (uint8_t)prop;
+  if (prop) atomicAdd(st.tallies + d, 1u);
+}
+// slot of the variable a wide slice belongs to (general records compare positions with it)
+template <bool WIDE>
+__device__ __forceinline__ uint32_t sell_self_slot(uint32_t s, uint32_t flags, uint32_t lane) {
+  if (!WIDE || !(flags & SF_WIDE)) return s * 32u + lane;
+  return (s - ((flags & SF_PART) ? (flags >> 4) & 0x3fffu : 0u)) * 32u;
+}
+
+template <bool MULTI, int FV, bool WIDE>
 __global__ void __launch_bounds__(SELL_THREADS, 2)
 k_sell_infer(const SellGraph g, const SellState st, const SweepParams p) {
   extern __shared__ double w_s[];
@@ -342,9 +403,8 @@ k_sell_infer(const SellGraph g, const SellState st, const SweepParams p) {
     if (!active) continue;
     const uint32_t d = s * 32u + lane;
     double pos, neg;
-    const bool wide = h.flags & SF_WIDE;  // one variable (slot 0), its records dealt to the 32 lanes
-    sell_potentials<MULTI, FV, LD_STREAM>(g, h, w_s, st.weights, lane, wide ? s * 32u : d, st.assign_evid, pos, neg);
-    if (wide) { pos = sell_wide_sum(pos); neg = sell_wide_sum(neg); }
+    sell_potentials<MULTI, FV, LD_STREAM>(g, h, w_s, st.weights, lane, sell_self_slot<WIDE>(s, h.flags, lane), st.assign_evid, pos, neg);
+    if (WIDE && (h.flags & SF_WIDE)) { sell_wide_draw(st, p, s, h.flags, lane, active, pos, neg); continue; }  // warp per variable
     if (!((active >> lane) & 1u)) continue;
     double r0, r1;
     dev_uniforms(p, d, r0, r1);
@@ -497,7 +557,7 @@ __device__ __forceinline__ void sell_unary_s(const SellGraph &g, const uint32_t 
   if (ANTISYM) neg = -pos;
 }
 
-template <bool MULTI, int FV, bool ALLHOT, int NT>
+template <bool MULTI, int FV, bool ALLHOT, int NT, bool WIDE>
 __global__ void __launch_bounds__(NT, 2)
 k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, const uint32_t stages,
                     const uint32_t stage_words) {
@@ -606,7 +666,7 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
       // FactorGraph::potential for proposals 1 and 0 (src/factor_graph.h:127-145)
       double pos = 0.0, neg = 0.0;
       if (SH_WORDS + 32u * ((n_un + n_mu) * (1 + FVW) + h0.z) > stage_words) {
-        sell_unstaged_potentials<MULTI, FV>(g, st, h1.w, n_un, n_mu, flags, lane, (flags & SF_WIDE) ? d - lane : d, pos, neg);
+        sell_unstaged_potentials<MULTI, FV>(g, st, h1.w, n_un, n_mu, flags, lane, sell_self_slot<WIDE>((uint32_t)s64, flags, lane), pos, neg);
       } else {
         const uint32_t mu = b + SH_WORDS + 32u * n_un * (1 + FVW) + lane;
         const uint32_t mufv = b + SH_WORDS + 32u * n_un * (1 + FVW) + 32u * n_mu;
@@ -651,12 +711,13 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
           h.n_un = n_un; h.n_mu = n_mu; h.n_oc = h0.z; h.evid = h0.w; h.pad = h1.x; h.evval = 0;
           h.flags = flags;
           h.un = sm + b + SH_WORDS; h.mu = sm + mu - lane; h.oth = sm + oth - lane;
-          sell_general_multi<FV, LD_SMEM>(gc, h, nullptr, st.weights, lane, (flags & SF_WIDE) ? d - lane : d,
+          sell_general_multi<FV, LD_SMEM>(gc, h, nullptr, st.weights, lane, sell_self_slot<WIDE>((uint32_t)s64, flags, lane),
                                           st.assign_evid, pos, neg);
         }
       }
-      if (flags & SF_WIDE) { pos = sell_wide_sum(pos); neg = sell_wide_sum(neg); }  // warp per variable
-      if ((active >> lane) & 1u) {
+      if (WIDE && (flags & SF_WIDE)) {  // warp per variable (hubs)
+        sell_wide_draw(st, p, (uint32_t)s64, flags, lane, active, pos, neg);
+      } else if ((active >> lane) & 1u) {
         const uint32_t prop = sell_draw_boolean(pos, neg, r0);
         st.assign_evid[d] = (uint8_t)prop;
         if (prop) atomicAdd(st.tallies + d, 1u);  // gibbs_sampler.h:163-167
@@ -762,90 +823,15 @@ __device__ __forceinline__ void sell_apply_weight(uint32_t i, double *w, double 
   w[i] = x - step * S * phi;
 }
 
-// One variable per lane of one slice of a learning sweep (sample_sgd_single_variable,
-// gibbs_sampler.h:127-149): both chains, then the SGD gradients of the lane's records into the
-// launch's accumulators.  LD: where the slice is read from (HBM through L1, or a staged copy).
+// sgd_on_variable (factor_graph.cc:262-277) over the records of slice h held by this lane:
+// evidence_value = assignment_dense (ev), free-chain value pf.
+// grad = sign_free * fv - sign_evid * fv == (code_free - code_evid) * fv exactly.
 template <bool MULTI, int FV, int LD>
-__device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellState &st, const SweepParams &p,
-                                                 const SellLearn &L, const SliceHeader &h, const double *w_s,
-                                                 double *acc_s, uint32_t lane, uint32_t d) {
+__device__ __forceinline__ void sell_sgd_records(const SellGraph &g, const SellState &st, const SellLearn &L,
+                                                 const SliceHeader &h, double *acc_s, uint32_t lane, uint32_t d,
+                                                 uint32_t pf, uint32_t ev, bool learn, bool masks, uint32_t sf_mask,
+                                                 uint32_t se_mask) {
   const bool cold = g.nweight > g.n_hot;  // weights outside the shared copy: their decay rides on every visited record
-  // SF_WIDE: the slice is ONE variable (slot 0) whose records are dealt to the 32 lanes -- every lane
-  // takes the variable's flags, uniforms and draws, sums its share of the records and pushes the SGD
-  // steps of its share; lane 0 writes the chains
-  const bool wide = h.flags & SF_WIDE;
-  const uint32_t hl = wide ? 0u : lane;
-  if (wide) d -= lane;
-  const bool writer = !wide || lane == 0;
-  const bool pad = (h.pad >> hl) & 1u, evid = (h.evid >> hl) & 1u;
-  const uint32_t ev = (h.evval >> hl) & 1u;  // Variable::assignment_dense
-  double r0, r1;
-  dev_uniforms(p, d, r0, r1);
-  // Slices of two-variable factors (the common coupled case): the chain values of every other
-  // variable, both chains, are gathered in ONE batch of independent L2 loads and kept as two bit
-  // masks (bit j: the other variable of record j satisfies its equal_to) -- the free-chain
-  // potentials, the evid-chain potentials and the SGD pass below all read the masks.
-  const bool masks = MULTI && (h.flags & SF_BINARY) && h.n_mu <= 32u;
-  uint32_t sf_mask = 0, se_mask = 0;
-  if (masks) {
-    for (uint32_t j0 = 0; j0 < h.n_mu; j0 += 4) {
-      uint32_t ow[4], af[4], ae[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) ow[u] = j0 + u < h.n_mu ? sell_ld<LD>(h.oth + (size_t)32 * (j0 + u) + lane) : 0u;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { af[u] = sell_chain<LD>(st.assign_free, ow[u] >> 1); ae[u] = sell_chain<LD>(st.assign_evid, ow[u] >> 1); }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (j0 + u < h.n_mu) {
-          sf_mask |= (af[u] == (ow[u] & 1u) ? 1u : 0u) << (j0 + u);
-          se_mask |= (ae[u] == (ow[u] & 1u) ? 1u : 0u) << (j0 + u);
-        }
-    }
-  }
-  // the multi-variable records of a mask slice into (pos, neg) for chain mask m
-  auto masked_multi = [&](uint32_t m, double &ps, double &ng) {
-    for (uint32_t j = 0; j < h.n_mu; ++j) {
-      const uint32_t rec = sell_ld<LD>(h.mu + (size_t)32 * j + lane);
-      const double wt = sell_weight<LD>(g, w_s, st.weights, rec & SELL_WID_MASK);
-      const double t = FV == FV_ONE ? wt : __dmul_rn(wt, sell_fv<FV, LD>(h.mu, h.n_mu, j, lane));
-      const uint32_t tab = (rec >> 24) >> (2u * ((m >> j) & 1u));
-      ps = __dadd_rn(ps, sell_term((tab >> 4) & 3u, t));
-      ng = __dadd_rn(ng, sell_term(tab & 3u, t));
-    }
-  };
-  // free chain: every variable, evidence included (gibbs_sampler.h:137-139)
-  double pos, neg, upos, uneg;
-  if (masks) {
-    pos = 0.0; neg = 0.0;
-    if (h.flags & SF_ANTISYM) sell_unary<FV, LD, true>(g, h, w_s, st.weights, lane, pos, neg);
-    else sell_unary<FV, LD, false>(g, h, w_s, st.weights, lane, pos, neg);
-    upos = pos; uneg = neg;
-    masked_multi(sf_mask, pos, neg);
-  } else {
-    sell_potentials<MULTI, FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_free, pos, neg, &upos, &uneg);
-  }
-  const uint32_t pf = wide ? sell_draw_boolean(sell_wide_sum(pos), sell_wide_sum(neg), r0) : sell_draw_boolean(pos, neg, r0);
-  if (!pad && writer) st.assign_free[d] = (uint8_t)pf;
-  // evid chain (sample_evid, gibbs_sampler.h:171-190): clamp hard evidence, else a Gibbs draw
-  // (Boolean variables carry no truthiness, so --noise_aware makes evidence variables draw too)
-  uint32_t pe = ev;
-  const uint32_t draw_evid = wide ? ((!pad && (p.noise_aware || !evid)) ? 0xffffffffu : 0u)
-                                  : ~h.pad & (p.noise_aware ? 0xffffffffu : ~h.evid);
-  if (draw_evid) {
-    if (MULTI && h.n_mu) {  // unary-only slices: both chains see identical potentials
-      pos = upos; neg = uneg;  // the unary sums are the same on both chains: continue from them
-      if (masks) masked_multi(se_mask, pos, neg);
-      else sell_multi<FV, LD>(g, h, w_s, st.weights, lane, d, st.assign_evid, nullptr, 0u, pos, neg);
-    }
-    if (wide) { pos = sell_wide_sum(pos); neg = sell_wide_sum(neg); }
-    if ((draw_evid >> lane) & 1u) pe = sell_draw_boolean(pos, neg, r1);
-  }
-  if (!pad && writer) st.assign_evid[d] = (uint8_t)pe;
-  // which variables learn (gibbs_sampler.h:144-146); Boolean has_truthiness() is false
-  const bool learn = !pad && (p.learn_non_evidence || (!p.noise_aware && evid));
-  if (!__any_sync(0xffffffffu, learn)) return;
-  // sgd_on_variable (factor_graph.cc:262-277): evidence_value = assignment_dense, free = pf.
-  // grad = sign_free * fv - sign_evid * fv == (code_free - code_evid) * fv exactly.
   if (cold || __any_sync(0xffffffffu, learn && pf != ev)) {  // unary: same value on both chains = zero gradient
     for (uint32_t j = 0; j < h.n_un; ++j) {
       const uint32_t rec = sell_ld<LD>(h.un + (size_t)32 * j + lane);
@@ -889,6 +875,113 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
   }
 }
 
+// One variable per lane of one slice of a learning sweep (sample_sgd_single_variable,
+// gibbs_sampler.h:127-149): both chains, then the SGD gradients of the lane's records into the
+// launch's accumulators.  LD: where the slice is read from (HBM through L1, or a staged copy).
+template <bool MULTI, int FV, int LD, bool WIDE>
+__device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellState &st, const SweepParams &p,
+                                                 const SellLearn &L, const SliceHeader &h, const double *w_s,
+                                                 double *acc_s, uint32_t lane, uint32_t d) {
+  const bool cold = g.nweight > g.n_hot;  // weights outside the shared copy: their decay rides on every visited record
+  // SF_WIDE: the slice is ONE variable (slot 0) whose records are dealt to the 32 lanes -- every lane
+  // takes the variable's flags, uniforms and draws, sums its share of the records and pushes the SGD
+  // steps of its share; lane 0 writes the chains
+  const bool wide = WIDE && (h.flags & SF_WIDE);
+  const uint32_t hl = wide ? 0u : lane;
+  if (wide) d -= lane;
+  const bool writer = !wide || lane == 0;
+  const bool pad = (h.pad >> hl) & 1u, evid = (h.evid >> hl) & 1u;
+  const uint32_t ev = (h.evval >> hl) & 1u;  // Variable::assignment_dense
+  double r0, r1;
+  dev_uniforms(p, d, r0, r1);
+  // Slices of two-variable factors (the common coupled case): the chain values of every other
+  // variable, both chains, are gathered in ONE batch of independent L2 loads and kept as two bit
+  // masks (bit j: the other variable of record j satisfies its equal_to) -- the free-chain
+  // potentials, the evid-chain potentials and the SGD pass below all read the masks.
+  const bool masks = MULTI && (h.flags & SF_BINARY) && h.n_mu <= 32u;
+  uint32_t sf_mask = 0, se_mask = 0;
+  if (masks) {
+    for (uint32_t j0 = 0; j0 < h.n_mu; j0 += 4) {
+      uint32_t ow[4], af[4], ae[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ow[u] = j0 + u < h.n_mu ? sell_ld<LD>(h.oth + (size_t)32 * (j0 + u) + lane) : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { af[u] = sell_chain<LD>(st.assign_free, ow[u] >> 1); ae[u] = sell_chain<LD>(st.assign_evid, ow[u] >> 1); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < h.n_mu) {
+          sf_mask |= (af[u] == (ow[u] & 1u) ? 1u : 0u) << (j0 + u);
+          se_mask |= (ae[u] == (ow[u] & 1u) ? 1u : 0u) << (j0 + u);
+        }
+    }
+  }
+  // the multi-variable records of a mask slice into (pos, neg) for chain mask m
+  auto masked_multi = [&](uint32_t m, double &ps, double &ng) {
+    for (uint32_t j = 0; j < h.n_mu; ++j) {
+      const uint32_t rec = sell_ld<LD>(h.mu + (size_t)32 * j + lane);
+      const double wt = sell_weight<LD>(g, w_s, st.weights, rec & SELL_WID_MASK);
+      const double t = FV == FV_ONE ? wt : __dmul_rn(wt, sell_fv<FV, LD>(h.mu, h.n_mu, j, lane));
+      const uint32_t tab = (rec >> 24) >> (2u * ((m >> j) & 1u));
+      ps = __dadd_rn(ps, sell_term((tab >> 4) & 3u, t));
+      ng = __dadd_rn(ng, sell_term(tab & 3u, t));
+    }
+  };
+  // evid chain (sample_evid, gibbs_sampler.h:171-190): clamp hard evidence, else a Gibbs draw
+  // (Boolean variables carry no truthiness, so --noise_aware makes evidence variables draw too)
+  const uint32_t draw_evid = wide ? ((!pad && (p.noise_aware || !evid)) ? 0xffffffffu : 0u)
+                                  : ~h.pad & (p.noise_aware ? 0xffffffffu : ~h.evid);
+  const bool part = WIDE && (h.flags & SF_PART);  // a part of a hub (graph_image.h): see sell_part_finish
+  const uint32_t sfirst = d / 32u - (part ? (h.flags >> 4) & 0x3fffu : 0u);
+  uint32_t pf, pe = ev;
+  {
+    // free chain: every variable, evidence included (gibbs_sampler.h:137-139)
+    double pos, neg, upos, uneg;
+    if (masks) {
+      pos = 0.0; neg = 0.0;
+      if (h.flags & SF_ANTISYM) sell_unary<FV, LD, true>(g, h, w_s, st.weights, lane, pos, neg);
+      else sell_unary<FV, LD, false>(g, h, w_s, st.weights, lane, pos, neg);
+      upos = pos; uneg = neg;
+      masked_multi(sf_mask, pos, neg);
+    } else {
+      sell_potentials<MULTI, FV, LD>(g, h, w_s, st.weights, lane, part ? sfirst * 32u : d, st.assign_free, pos, neg, &upos, &uneg);
+    }
+    double epos = pos, eneg = neg;  // unary-only slices: both chains see identical potentials
+    if (draw_evid && MULTI && h.n_mu) {
+      epos = upos; eneg = uneg;  // the unary sums are the same on both chains: continue from them
+      if (masks) masked_multi(se_mask, epos, eneg);
+      else sell_multi<FV, LD>(g, h, w_s, st.weights, lane, part ? sfirst * 32u : d, st.assign_evid, nullptr, 0u, epos, eneg);
+    }
+    if (wide) { pos = sell_wide_sum(pos); neg = sell_wide_sum(neg); epos = sell_wide_sum(epos); eneg = sell_wide_sum(eneg); }
+    if (part) {
+      double v[4] = {pos, neg, epos, eneg};
+      if (!sell_part_finish<4>(st, d / 32u, h.flags, lane, v)) return;  // not the hub's last part
+      pos = v[0]; neg = v[1]; epos = v[2]; eneg = v[3];
+      d = sfirst * 32u;
+      dev_uniforms(p, d, r0, r1);
+    }
+    pf = sell_draw_boolean(pos, neg, r0);
+    if (draw_evid && ((draw_evid >> lane) & 1u)) pe = sell_draw_boolean(epos, eneg, r1);
+    if (!pad && writer) {
+      st.assign_free[d] = (uint8_t)pf;
+      st.assign_evid[d] = (uint8_t)pe;
+    }
+  }
+  // which variables learn (gibbs_sampler.h:144-146); Boolean has_truthiness() is false
+  const bool learn = !pad && (p.learn_non_evidence || (!p.noise_aware && evid));
+  if (!__any_sync(0xffffffffu, learn)) return;
+  if (!part) {
+    sell_sgd_records<MULTI, FV, LD>(g, st, L, h, acc_s, lane, d, pf, ev, learn, masks, sf_mask, se_mask);
+    return;
+  }
+  // a hub: this warp finished it and drew for it; it now pushes the SGD steps of ALL its parts, read
+  // from the blob (the other parts were summed by other warps), at the hub's place in the visit order
+  const uint32_t nparts = h.flags >> 18;
+  for (uint32_t q = 0; q < nparts; ++q) {
+    const SliceHeader hq = sell_header<FV>(g, sfirst + q);
+    sell_sgd_records<MULTI, FV, LD_CACHED>(g, st, L, hq, acc_s, lane, d, pf, ev, learn, false, 0u, 0u);
+  }
+}
+
 // One launch of a learning sweep: positions [vbegin, vend) of the visit order, dealt to the warps
 // of the grid round-robin (position vbegin + round * warps + warp: the whole grid moves through the
 // order together, so "later in the order" is "later in time").  Slices come through a per-warp
@@ -904,7 +997,7 @@ __host__ __device__ inline size_t sell_learn_smem(uint32_t n_hot, uint32_t stage
   return sell_learn_ring_off(n_hot) + (size_t)(SELL_LEARN_THREADS / 32) * SELL_LEARN_STAGES * stage_words * 4u;
 }
 
-template <bool MULTI, int FV>
+template <bool MULTI, int FV, bool WIDE>
 __global__ void __launch_bounds__(SELL_LEARN_THREADS, 2)
 k_sell_learn_live(const SellGraph g, const SellState st, const SweepParams p, const SellLearn L,
                   const uint32_t stage_words) {
@@ -993,12 +1086,12 @@ k_sell_learn_live(const SellGraph g, const SellState st, const SweepParams p, co
         h.un = b + SH_WORDS;
         h.mu = h.un + 32u * h.n_un * (1 + FVW);
         h.oth = h.mu + 32u * h.n_mu * (1 + FVW);
-        sell_learn_slice<MULTI, FV, LD_SMEM_LIVE>(g, st, p, L, h, w_s, acc_s, lane, s * 32u + lane);
+        sell_learn_slice<MULTI, FV, LD_SMEM_LIVE, WIDE>(g, st, p, L, h, w_s, acc_s, lane, s * 32u + lane);
       } else {  // longer than a stage: the records come from HBM (the header carries the slice's offset)
         h.un = g.blob + (size_t)h1.w * 8 + SH_WORDS;
         h.mu = h.un + (size_t)32 * h.n_un * (1 + FVW);
         h.oth = h.mu + (size_t)32 * h.n_mu * (1 + FVW);
-        sell_learn_slice<MULTI, FV, LD_CACHED>(g, st, p, L, h, w_s, acc_s, lane, s * 32u + lane);
+        sell_learn_slice<MULTI, FV, LD_CACHED, WIDE>(g, st, p, L, h, w_s, acc_s, lane, s * 32u + lane);
       }
       ++mine;
       __syncwarp();  // every lane is done with this stage before the next copy lands in it

@@ -73,7 +73,16 @@ constexpr uint32_t SF_BINARY = 2;   // every multi record has exactly one other 
 constexpr uint32_t SF_WIDE = 4;     // ONE variable (lane 0's slot), its records dealt round-robin to the 32 lanes:
                                     // record i of a section at column i / 32, lane i % 32; the lanes' partial sums
                                     // are combined by shuffles (warp per variable: hubs)
-constexpr uint64_t SELL_WIDE_MIN = 512;  // incident records from which a variable gets a slice of its own
+constexpr uint64_t SELL_WIDE_MIN = 32;   // incident records from which a variable may get a slice of its own (compile.cc)
+// A hub with more than SELL_PART_RECORDS records is cut into PARTS: consecutive SF_WIDE | SF_PART
+// slices, part p holding an equal share of the unary and of the multi records.  Any warp sweeps
+// any part; a part's lane sums are combined, stored, and the warp that finishes LAST adds the
+// parts' sums in index order and draws (deterministic).  flags: part index << 4 (14 bits), number
+// of parts << 18 (14 bits).  Every part's header repeats the variable's evidence bits at lane 0;
+// the variable itself sits in slot 0 of the first part.
+constexpr uint32_t SF_PART = 8;
+constexpr uint64_t SELL_PART_RECORDS = 2048;
+constexpr uint32_t SELL_MAX_PARTS = 1u << 14;
 constexpr uint32_t SELL_WID_MASK = 0x7fffffu, SELL_FIXED_BIT = 0x800000u;  // multi records
 constexpr uint32_t SELL_BINARY_NOP = 0x55u;                                // tag of a padding binary record
 constexpr uint32_t SELL_UN_WID8_MASK = 0x3fffff8u, SELL_UN_FIXED_BIT = 1u << 2;
@@ -157,6 +166,8 @@ struct GraphImage {
   // interleaved: Hogwild, like the reference's threads), inference sweeps class by class.
   uint32_t id_block = 0;               // variables per id block (compile.cc)
   std::vector<uint32_t> learn_visit;   // [nslice] slice indices in learning order
+  std::vector<uint32_t> part_slices;   // slices that are parts of a hub (SF_PART), ascending
+  bool has_wide = false;               // some slice is SF_WIDE: the kernels with the warp-per-variable code run
 
   // weights: ABI order is the original id; the device uses internal ids, hottest first
   std::vector<double> w_init;      // original order

@@ -526,17 +526,33 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   // slice: its records are dealt round-robin to the 32 lanes, which sum their shares and combine
   // them by shuffles (SF_WIDE, graph_image.h) -- a hub would otherwise be one serial lane and pad
   // its 31 slice-mates to its length.  Wide variables come first in their part of the class.
-  uint64_t wide_min = SELL_WIDE_MIN;
+  // wide from 32 records on (one full column of the 32 lanes), and only when that is well above the
+  // graph's mean: a slice is padded to its longest row, so what hurts is a variable much heavier
+  // than the variables around it, not a graph of uniformly heavy ones
+  uint64_t nrec_total = 0;
+  for (uint64_t v = 0; v < nvar; ++v) nrec_total += inc_end[v] - deg[v];
+  uint64_t wide_min = std::max<uint64_t>(SELL_WIDE_MIN, nvar ? 4 * ((nrec_total + nvar - 1) / nvar) : 0);
   if (const char *e = getenv("DWG_WIDE_MIN")) wide_min = (uint64_t)std::max(1, atoi(e));
   std::vector<uint8_t> wide(nvar, 0);
   if (g->sell)
     parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
       for (uint64_t v = v0; v < v1; ++v) wide[v] = (uint64_t)(inc_end[v] - deg[v]) >= wide_min;
     });
-  // per class: [0] query wide, [1] query normal, [2] evidence wide, [3] evidence normal
+  // slices a wide variable takes: 1, or its number of parts (SELL_PART_RECORDS records each)
+  uint64_t part_records = SELL_PART_RECORDS;
+  if (const char *e = getenv("DWG_PART_RECORDS")) part_records = (uint64_t)std::max(32, atoi(e));
+  auto wide_slices = [&](uint64_t v) -> uint32_t {
+    const uint64_t r = inc_end[v] - deg[v];
+    return (uint32_t)std::min<uint64_t>(SELL_MAX_PARTS - 1, std::max<uint64_t>(1, (r + part_records - 1) / part_records));
+  };
+  // per class: [0] query wide, [1] query normal, [2] evidence wide, [3] evidence normal; wslots: slices of the wide ones
   std::vector<std::array<uint32_t, 4>> part(ncolor, std::array<uint32_t, 4>{0, 0, 0, 0});
-  for (uint64_t v = 0; v < nvar; ++v) ++part[color[v]][(g->var_is_evid[v] ? 2 : 0) + (wide[v] ? 0 : 1)];
-  auto seg_size = [&](uint32_t c, int ev) { return 32u * part[c][2 * ev] + ((part[c][2 * ev + 1] + 31u) & ~31u); };
+  std::vector<std::array<uint32_t, 2>> wslots(ncolor, std::array<uint32_t, 2>{0, 0});
+  for (uint64_t v = 0; v < nvar; ++v) {
+    ++part[color[v]][(g->var_is_evid[v] ? 2 : 0) + (wide[v] ? 0 : 1)];
+    if (wide[v]) wslots[color[v]][g->var_is_evid[v] ? 1 : 0] += wide_slices(v);
+  }
+  auto seg_size = [&](uint32_t c, int ev) { return 32u * wslots[c][ev] + ((part[c][2 * ev + 1] + 31u) & ~31u); };
   g->color_start.assign(ncolor + 1, 0);
   for (uint32_t c = 0; c < ncolor; ++c) {
     uint32_t n = part[c][0] + part[c][1] + part[c][2] + part[c][3];
@@ -609,13 +625,26 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         uint64_t k = i - class_first[c], base = g->color_start[c];
         const int ev = k >= (uint64_t)part[c][0] + part[c][1];
         if (ev) { k -= (uint64_t)part[c][0] + part[c][1]; base += seg_size(c, 0); }
-        // inside the part: wide variables (a slice each), then the others packed
+        // inside the part: wide variables (one slice, or one per part of a hub), then the others packed
         const uint64_t nw = part[c][2 * ev];
-        const uint32_t d = (uint32_t)(k < nw ? base + 32 * k : base + 32 * nw + (k - nw));
+        if (k < nw) continue;  // placed below: their slots depend on the parts of the wide variables before them
+        const uint32_t d = (uint32_t)(base + 32ull * wslots[c][ev] + (k - nw));
         g->perm[d] = v;
         g->inv[v] = d;
       }
     });
+    for (uint32_t c = 0; c < ncolor; ++c)
+      for (int ev = 0; ev < 2; ++ev) {
+        uint64_t i = class_first[c] + (ev ? (uint64_t)part[c][0] + part[c][1] : 0);
+        uint64_t d = g->color_start[c] + (ev ? seg_size(c, 0) : 0);
+        for (uint32_t k = 0; k < part[c][2 * ev]; ++k, ++i) {
+          const uint32_t v = keys[i].v;
+          g->perm[d] = v;
+          g->inv[v] = (uint32_t)d;
+          d += 32ull * wide_slices(v);
+        }
+      }
+
   } else {
     std::vector<uint32_t> fill(g->color_start.begin(), g->color_start.end() - 1);
     for (uint64_t v = 0; v < nvar; ++v) {
@@ -907,9 +936,25 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     auto is_unary = [&](uint64_t e) { return (g->e_tag[e] >> TAG_FORM_SHIFT) == 0; };
     // slice shapes.  A slice whose first slot holds a wide variable is that variable's alone: record
     // k of a section goes to lane k % 32, column k / 32 (the lanes of a normal slice are variables)
-    auto slice_is_wide = [&](uint64_t sidx) {
-      const uint64_t v = g->perm[sidx * 32];
-      return v != 0xffffffffu && wide[v];
+    // slice -> first slice of the wide variable it belongs to (itself for a one-slice wide variable)
+    std::vector<uint32_t> slice_hub(nslice, 0xffffffffu);
+    parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+      for (uint64_t v = v0; v < v1; ++v)
+        if (wide[v]) {
+          const uint32_t s0 = g->inv[v] / 32, n = wide_slices(v);
+          for (uint32_t q = 0; q < n; ++q) slice_hub[s0 + q] = s0;
+        }
+    });
+    for (uint64_t sidx = 0; sidx < nslice; ++sidx)
+      if (slice_hub[sidx] != 0xffffffffu && wide_slices(g->perm[(uint64_t)slice_hub[sidx] * 32]) > 1)
+        g->part_slices.push_back((uint32_t)sidx);
+    auto slice_is_wide = [&](uint64_t sidx) { return slice_hub[sidx] != 0xffffffffu; };
+    for (uint64_t sidx = 0; sidx < nslice && !g->has_wide; ++sidx) g->has_wide = slice_is_wide(sidx);
+    // the share of part q of n: records [q * per, min(total, (q + 1) * per)) of a section
+    auto share = [](uint64_t total, uint32_t q, uint32_t n, uint64_t *lo, uint64_t *hi) {
+      const uint64_t per = (total + n - 1) / n;
+      *lo = std::min(total, per * q);
+      *hi = std::min(total, per * (q + 1));
     };
     auto others_span = [&](uint64_t e, uint64_t o) -> uint64_t {
       const uint32_t form = g->e_tag[e] >> TAG_FORM_SHIFT;
@@ -921,17 +966,24 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
       for (uint64_t sidx = a0; sidx < a1; ++sidx) {
         uint32_t un = 0, mu = 0, oc = 0;
         if (slice_is_wide(sidx)) {
-          const uint64_t d = sidx * 32;
-          uint32_t u = 0, m = 0, lane_oc[32] = {0};
-          uint64_t o = g->has_multi ? g->row_oth[d] : 0;
+          const uint64_t d = (uint64_t)slice_hub[sidx] * 32;
+          const uint32_t q = (uint32_t)(sidx - slice_hub[sidx]), n = wide_slices(g->perm[d]);
+          uint64_t U = 0;
+          for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) U += is_unary(e);
+          const uint64_t M = g->row_ptr[d + 1] - g->row_ptr[d] - U;
+          uint64_t ulo, uhi, mlo, mhi;
+          share(U, q, n, &ulo, &uhi);
+          share(M, q, n, &mlo, &mhi);
+          uint32_t lane_oc[32] = {0};
+          uint64_t m = 0, o = g->has_multi ? g->row_oth[d] : 0;
           for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) {
-            if (is_unary(e)) { ++u; continue; }
+            if (is_unary(e)) continue;
             const uint64_t span = others_span(e, o);
-            lane_oc[m % 32] += (uint32_t)span;
+            if (m >= mlo && m < mhi) lane_oc[(m - mlo) % 32] += (uint32_t)span;
             o += span;
             ++m;
           }
-          un = (u + 31) / 32; mu = (m + 31) / 32;
+          un = (uint32_t)((uhi - ulo + 31) / 32); mu = (uint32_t)((mhi - mlo + 31) / 32);
           for (uint32_t l = 0; l < 32; ++l) oc = std::max(oc, lane_oc[l]);
         } else {
           for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
@@ -961,8 +1013,10 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         for (uint64_t c = c0; c < c1; ++c)
           for (uint64_t sidx = g->color_start[c] / 32; sidx < g->color_start[c + 1] / 32; ++sidx) {
             uint64_t v = 0;
-            for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d)
-              if (g->perm[d] != 0xffffffffu) { v = g->perm[d]; break; }
+            if (slice_hub[sidx] != 0xffffffffu) v = g->perm[(uint64_t)slice_hub[sidx] * 32];  // every part of a hub: the hub
+            else
+              for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d)
+                if (g->perm[d] != 0xffffffffu) { v = g->perm[d]; break; }
             vk[sidx] = ((v / g->id_block) << 40) | (c << 24 & 0xffff000000ull) | (sidx & 0xffffffu);
           }
       });
@@ -1006,22 +1060,34 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
                      o_mufv = o_mu + 32ull * mu, o_oth = o_mufv + 32ull * mu * fvw;
       const bool is_wide = slice_is_wide(sidx);
       const uint32_t nvars = is_wide ? 1 : 32;  // variables whose rows the slice holds
-      // is every multi record of the slice a one-other-variable record?
-      bool binary = mu > 0, antisym = true;
-      for (uint64_t d = sidx * 32; d < sidx * 32 + nvars && binary; ++d) {
+      const uint64_t dbase = is_wide ? (uint64_t)slice_hub[sidx] * 32 : sidx * 32;  // slot of lane 0's variable
+      const uint32_t pq = is_wide ? (uint32_t)(sidx - slice_hub[sidx]) : 0, pn = is_wide ? wide_slices(g->perm[dbase]) : 1;
+      uint64_t ulo = 0, uhi = ~0ull, mlo = 0, mhi = ~0ull;  // this part's share of the variable's records
+      if (pn > 1) {
+        uint64_t U = 0;
+        for (uint64_t e = g->row_ptr[dbase]; e < g->row_ptr[dbase + 1]; ++e) U += is_unary(e);
+        share(U, pq, pn, &ulo, &uhi);
+        share(g->row_ptr[dbase + 1] - g->row_ptr[dbase] - U, pq, pn, &mlo, &mhi);
+      }
+      // is every multi record of the slice a one-other-variable record?  (a hub: of the whole hub,
+      // so that all its parts are read the same way)
+      bool binary = mu > 0 || pn > 1, antisym = true;
+      for (uint64_t d = dbase; d < dbase + nvars && binary; ++d) {
         for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e)
           if (!is_unary(e) && (g->e_tag[e] >> TAG_FORM_SHIFT) != 1) binary = false;
       }
+      if (pn > 1 && mu == 0) binary = false;
       h[SH_N_UNARY] = un; h[SH_N_MULTI] = mu; h[SH_N_OTH] = oc;
       h[SH_SELF_OFF] = g->sl_off[sidx];
       uint32_t ju[32] = {0}, jm[32] = {0}, jo[32] = {0};  // per lane: unary / multi columns and others words written
       for (uint32_t l = 0; l < 32; ++l) {
-        const uint64_t d = sidx * 32 + l;
+        // (every part of a hub carries the hub's bits at lane 0; the other lanes are padding slots)
+        const uint64_t d = l == 0 ? dbase : sidx * 32 + l;
         if (g->var_flags[d] & VF_PAD) h[SH_PAD_MASK] |= 1u << l;
         if (g->var_flags[d] & VF_EVID) h[SH_EVID_MASK] |= 1u << l;
         if (g->evid_val[d] == 1) h[SH_EVVAL_MASK] |= 1u << l;
         if (l >= nvars) continue;
-        uint32_t ku = 0, km = 0;  // records of this variable seen so far
+        uint64_t ku = 0, km = 0;  // records of this variable seen so far
         uint64_t o = g->has_multi ? g->row_oth[d] : 0;
         for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) {
           const uint8_t tag = g->e_tag[e];
@@ -1029,7 +1095,8 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
           const uint32_t wid = g->e_wid[e];
           const uint32_t base = wid | (raw.w_fixed[g->w_perm[wid]] ? SELL_FIXED_BIT : 0u);
           if (form == 0) {
-            const uint32_t tl = is_wide ? ku % 32 : l;  // target lane
+            if (ku < ulo || ku >= uhi) { ++ku; continue; }  // another part's record
+            const uint32_t tl = is_wide ? (uint32_t)((ku - ulo) % 32) : l;  // target lane
             const uint32_t mm = code_mismatch(fc);
             const uint32_t s1 = (tag & TAG_SELF_EQ1) ? 2 : mm, s0 = (tag & TAG_SELF_EQ1) ? mm : 2;
             if (s1 + s0 != 2) antisym = false;
@@ -1038,9 +1105,10 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
             ++ju[tl]; ++ku;
             continue;
           }
-          const uint32_t tl = is_wide ? km % 32 : l;
-          uint32_t t = tag;
           const uint64_t span = others_span(e, o);
+          if (km < mlo || km >= mhi) { ++km; o += span; continue; }  // another part's record
+          const uint32_t tl = is_wide ? (uint32_t)((km - mlo) % 32) : l;
+          uint32_t t = tag;
           if (binary) {
             // sign table over (this variable's value x, other variable satisfied)
             const uint32_t self_eq = (tag & TAG_SELF_EQ1) ? 1 : 0;
@@ -1067,7 +1135,8 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         for (uint32_t j = ju[l]; j < un; ++j) h[o_un + 32ull * j + l] = SELL_UNARY_NOP;
         for (uint32_t j = jm[l]; j < mu; ++j) h[o_mu + 32ull * j + l] = binary ? SELL_BINARY_NOP << 24 : 0u;  // form 0
       }
-      h[SH_FLAGS] = (antisym ? SF_ANTISYM : 0u) | (binary ? SF_BINARY : 0u) | (is_wide ? SF_WIDE : 0u);
+      h[SH_FLAGS] = (antisym ? SF_ANTISYM : 0u) | (binary ? SF_BINARY : 0u) | (is_wide ? SF_WIDE : 0u) |
+                    (pn > 1 ? SF_PART | (pq << 4) | (pn << 18) : 0u);
     }
     });
   }

@@ -185,7 +185,11 @@ int gibbs(const CmdParser &args) {
     const uint64_t n_epoch = compute_n_epochs(args.n_learning_epoch);
     Timer t_total, t;
     double stepsize = args.stepsize;
-    for (uint64_t e = 0; e < n_epoch; ++e) {
+    // one quiet replica: no per-epoch averaging, no per-epoch line -- all epochs in one call (one
+    // launch under the sequential schedule of tiny graphs, which are launch latency and nothing else)
+    const bool batched = !progress && n_samplers == 1;
+    if (batched) TRY(dwg_learn_epochs(R.hs[0], n_epoch, stepsize, args.decay));
+    for (uint64_t e = 0; e < n_epoch && !batched; ++e) {
       if (progress) {
         std::cout << std::setprecision(3) << "LEARNING EPOCH " << e * n_samplers << "~"
                   << ((e + 1) * n_samplers - 1) << "...." << std::flush << std::setprecision(6);
@@ -236,7 +240,10 @@ int gibbs(const CmdParser &args) {
     const uint64_t n_epoch = compute_n_epochs(args.n_inference_epoch);
     Timer t_total, t;
     for (auto *h : R.hs) TRY(dwg_clear_tallies(h));
-    for (uint64_t e = 0; e < n_epoch; ++e) {
+    const bool batched = !progress;
+    if (batched)
+      for (auto *h : R.hs) TRY(dwg_infer_epochs(h, n_epoch));
+    for (uint64_t e = 0; e < n_epoch && !batched; ++e) {
       if (progress) {
         std::cout << std::setprecision(3) << "INFERENCE EPOCH " << e * n_samplers << "~"
                   << ((e + 1) * n_samplers - 1) << "...." << std::flush << std::setprecision(6);

@@ -138,8 +138,16 @@ class ImageModel:
         assert ((h["evval"] >> lane) & 1) == int(self.evid_val[d] == 1)
         if h["flags"] & 4:  # SF_WIDE: one variable (slot 0), its records dealt to the 32 lanes: sum the shares
             assert lane == 0 and h["pad"] == 0xFFFFFFFE
-            parts = [self._sell_lane_potentials(h, l, d, a, weights) for l in range(32)]
-            return sum(p for p, _ in parts), sum(n for _, n in parts)
+            nparts = (h["flags"] >> 18) if h["flags"] & 8 else 1  # SF_PART: a hub cut into consecutive slices
+            assert not (h["flags"] & 8) or ((h["flags"] >> 4) & 0x3FFF) == 0
+            shares = []
+            for q in range(nparts):
+                hq = self.slice_header(s + q)
+                assert hq["flags"] & 4 and hq["pad"] == 0xFFFFFFFE and hq["evid"] == h["evid"] and hq["evval"] == h["evval"]
+                if nparts > 1:
+                    assert hq["flags"] & 8 and ((hq["flags"] >> 4) & 0x3FFF) == q and (hq["flags"] >> 18) == nparts
+                shares += [self._sell_lane_potentials(hq, l, d, a, weights) for l in range(32)]
+            return sum(p for p, _ in shares), sum(n for _, n in shares)
         return self._sell_lane_potentials(h, lane, d, a, weights)
 
     def _sell_lane_potentials(self, h, lane, d, a, weights):

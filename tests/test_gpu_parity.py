@@ -798,6 +798,8 @@ def test_wide_slices_sweep_exactly(seed, monkeypatch):
     monkeypatch.setenv("DWG_LEARN_WARPS", "1")
     if seed % 2:
         monkeypatch.setenv("DWG_SELL_DIRECT", "1")
+    if seed >= 2:
+        monkeypatch.setenv("DWG_PART_RECORDS", "96")  # the hubs (several hundred records) are cut into parts: SF_PART
     rng = np.random.default_rng(7100 + seed)
     raw = _hub_graph(rng, 1500, 6000, [2, 3, 4][seed % 3])
     raw.fac_fv[:] = rng.choice([1.0, 0.5, 2.0, -1.0], raw.nfac)
@@ -805,6 +807,7 @@ def test_wide_slices_sweep_exactly(seed, monkeypatch):
     g, s, o = _mk(raw, sb.SCHED_CHROMATIC, sample_evidence=seed % 3 != 0, reg_param=0.0, learn_non_evidence=True)
     blob, off = g.image("blob"), g.image("sl_off")
     assert any(blob[int(off[i]) * 8 + 6] & 4 for i in range(len(off) - 1))  # some slice is wide
+    assert seed < 2 or any(blob[int(off[i]) * 8 + 6] & 8 for i in range(len(off) - 1))  # ... and some hub is in parts
     perm, _ = g.schedule()
     for ep in range(3):
         r0 = rng.random(o.nvar)
@@ -827,6 +830,7 @@ def test_wide_slices_gradient_sums(monkeypatch):
     """the SGD steps of a hub, pushed by 32 lanes each holding a share of its records, add up to the
     reference's (vanishing dyadic step: w0 - w = step * sum of gradients)"""
     monkeypatch.setenv("DWG_WIDE_MIN", "16")
+    monkeypatch.setenv("DWG_PART_RECORDS", "96")
     monkeypatch.setenv("DWG_LEARN_WARPS", "1")
     rng = np.random.default_rng(7200)
     raw = _hub_graph(rng, 1200, 5000, 3)
@@ -886,3 +890,29 @@ def test_zipf_degree_graph_hubs_cost_per_edge():
     t_uni = ms_per_sweep(su)
     print("zipf-degree %.3f ms, uniform-degree %.3f ms per sweep of %d edge records" % (t_zipf, t_uni, nfac))
     assert t_zipf <= 1.5 * t_uni + 0.02, (t_zipf, t_uni)
+
+
+@pytest.mark.parametrize("name", ["biased_coin", "sparse_domains", "biased_coin_truthiness"])
+def test_multi_epoch_sequential_launch_is_the_epoch_loop(name):
+    """dwg_learn_epochs / dwg_infer_epochs under the sequential schedule run all epochs in one launch
+    (k_seq_epochs): weights, chains and tallies must be bit-identical to launching epoch by epoch"""
+    a = parse_dw_args(dw_args(name))
+    raw = load_golden_graph(name)
+    g = sb.Graph.from_raw(raw)
+    assert g.info.schedule == sb.SCHED_SEQUENTIAL
+    kw = dict(sample_evidence=a["sample_evidence"], noise_aware=a["noise_aware"], reg_param=a["reg_param"], seed=7)
+    s1, s2 = sb.Sampler(g, **kw), sb.Sampler(g, **kw)
+    n = 300
+    step = a["stepsize"]
+    for _ in range(n):
+        s1.learn_epoch(step)
+        step *= a["decay"]
+    s2.learn_epochs(n, a["stepsize"], a["decay"])
+    assert np.array_equal(s1.weights(), s2.weights())
+    s1.clear_tallies(); s2.clear_tallies()
+    for _ in range(n):
+        s1.infer_epoch()
+    s2.infer_epochs(n)
+    assert np.array_equal(s1.assignments(0), s2.assignments(0)) and np.array_equal(s1.assignments(1), s2.assignments(1))
+    t1, n1 = s1.tallies(); t2, n2 = s2.tallies()
+    assert np.array_equal(t1, t2) and np.array_equal(n1, n2)
