@@ -925,7 +925,10 @@ static int launch_learn_sell(dwg_handle *h, SweepParams &p, double stepsize) {
   auto launch = [&](uint32_t vb, uint32_t ve, uint32_t warps, uint32_t period) {
     if (ve <= vb) return;
     const bool live = period == 0;
-    const uint32_t wpc = live ? 1 : SELL_LEARN_THREADS / 32;
+    // warps per CTA: eight on the wide grid; the narrow tail (period 1: a refresh and a flush per
+    // slice) spreads its warps over more SMs, DWG_LEARN_TAIL_WPC per CTA
+    const uint32_t tail_wpc = (uint32_t)std::max(1.0, std::min(8.0, env_double("DWG_LEARN_TAIL_WPC", 8)));
+    const uint32_t wpc = live ? 1 : (vb != 0 || ve != nslice || period == 1) && period == 1 ? tail_wpc : SELL_LEARN_THREADS / 32;
     warps = std::max(1u, std::min(warps, ve - vb));
     uint32_t threads = wpc * 32, blocks = warps / wpc;
     if (warps < wpc) { threads = warps * 32; blocks = 1; }
