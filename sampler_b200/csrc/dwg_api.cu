@@ -203,6 +203,10 @@ struct dwg_handle {
   CellGraph cg{};
   uint32_t cell_stages = 0, cell_stage_words = 0;
   int cell_blocks = 0;
+  // categorical learning kernel (k_cell_learn_live): whole-graph update counts / curvature bounds
+  // per weight, hot weights kept in shared memory (a prefix of the internal order)
+  bool cell_learn = false;
+  DevBuf<float> lv_N, lv_H;
   // per colour class: the first slice from which every slice holds evidence / padding only
   // (slices are sorted non-evidence first inside a class, compile.cc)
   std::vector<uint32_t> cls_query_end;
@@ -393,6 +397,42 @@ void cell_launch(dwg_handle *h, bool pdl, uint32_t blocks, const CellGraph &cg, 
   else
     cudaLaunchKernelEx(&cfg, k_cell_infer_staged<false, CELL_THREADS>, cg, h->ss, p, h->cell_stages, h->cell_stage_words);
 }
+// k_cell_learn_live: the CTA's weight copy (28 B per hot weight), the potentials array and a
+// two-stage ring per warp must fit two CTAs per SM; the hot set is the prefix of the internal
+// (hottest first) order that leaves room for a ring stage holding the longest slice
+int cell_learn_setup(dwg_handle *h) {
+  const GraphImage &m = *h->img;
+  const size_t budget = 112 * 1024, nwarp = SELL_LEARN_THREADS / 32;
+  const size_t bufs = nwarp * (size_t)m.cell_kmax * 256 + 256 + nwarp * SELL_LEARN_STAGES * 8;
+  const uint32_t want = std::max(80u, (m.sell_max_words + 3u) & ~3u);
+  uint32_t words = want;
+  if (const char *e = getenv("DWG_SELL_STAGE_WORDS")) words = std::min<uint32_t>(words, std::max(80, atoi(e)) & ~3u);  // tests
+  const size_t ring = nwarp * SELL_LEARN_STAGES * 4 * (size_t)words;
+  uint32_t n_hot = m.n_hot;
+  if (bufs + ring + 28ull * n_hot > budget) {
+    if (bufs + ring + 28ull * 256 <= budget) n_hot = (uint32_t)((budget - bufs - ring) / 28) & ~15u;
+    else {  // long slices: a shorter stage (the rest of such a slice is read from HBM)
+      n_hot = std::min<uint32_t>(n_hot, 256);
+      if (bufs + 28ull * n_hot + nwarp * SELL_LEARN_STAGES * 4 * 80 > budget) return DWG_OK;  // no room: the CSR kernels learn
+      words = std::max(80u, (uint32_t)((budget - bufs - 28ull * n_hot) / (nwarp * SELL_LEARN_STAGES * 4)) & ~3u);
+    }
+  }
+  h->sg.sl_off = h->sl_off.p; h->sg.blob = h->blob.p;
+  h->sg.nweight = (uint32_t)m.nweight; h->sg.n_hot = n_hot;
+  h->learn_stage_words = words;
+  int rc = sell_grid(k_cell_learn_live, cell_learn_smem(n_hot, words, m.cell_kmax), h->num_sms, &h->sell_blocks_learn,
+                     SELL_LEARN_THREADS);
+  if (rc) return rc;
+  h->cell_learn = true;
+  return DWG_OK;
+}
+void cell_learn_launch(dwg_handle *h, uint32_t blocks, uint32_t threads, bool live, const SweepParams &p, const SellLearn &L) {
+  SellGraph sg = h->sg;
+  if (live) sg.n_hot = 0;
+  CellLearnExtra X{h->w_fixed.p, h->img->cell_kmax, h->opts.learn_non_evidence};
+  k_cell_learn_live<<<blocks, threads, cell_learn_smem(sg.n_hot, h->learn_stage_words, X.kmax), h->stream>>>(
+      sg, h->ss, p, L, X, h->learn_stage_words);
+}
 int sell_setup(dwg_handle *h) {
   const GraphImage &m = *h->img;
   int rc = DWG_OK;
@@ -409,6 +449,7 @@ void sell_launch(dwg_handle *h, bool staged, bool pdl, uint32_t blocks, const Se
 }
 void sell_learn_launch(dwg_handle *h, uint32_t blocks, uint32_t threads, bool live, const SweepParams &p, const SellLearn &L) {
   const GraphImage &m = *h->img;
+  if (m.cell) return cell_learn_launch(h, blocks, threads, live, p, L);
 #define CALL(MU, FV, WD) sell_learn_launch_t<MU, FV, WD>(h, blocks, threads, live, p, L)
   SELL_SWITCH(CALL)
 #undef CALL
@@ -581,7 +622,7 @@ int dwg_debug_learn_order(const dwg_graph *g, uint64_t *perm, uint64_t *n_out) {
   if (!g) return fail(DWG_ERR_INVALID, "null argument");
   const GraphImage &m = g->img;
   uint64_t k = 0;
-  if (m.sell) {
+  if (m.sell || (m.cell && !m.learn_visit.empty() && !getenv("DWG_CELL_OFF"))) {
     for (uint32_t sl : m.learn_visit)
       for (uint64_t d = (uint64_t)sl * 32; d < (uint64_t)sl * 32 + 32; ++d)
         if (m.perm[d] != 0xffffffffu) {
@@ -738,10 +779,28 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     CU(h->cls_Q.upload(all ? m.cls_Q_all : m.cls_Q_evid, s));
     CU(h->cls_H.upload(all ? m.cls_H_all : m.cls_H_evid, s));
   }
-  if (m.sell) {
+  // whole-graph per-weight statistics of a learning sweep (categorical sliced-ELL graphs keep
+  // per-class rows for the CSR kernels: summed here)
+  std::vector<float> lvN, lvH;
+  if (m.cell) {
+    const bool all = h->opts.learn_non_evidence;
+    const std::vector<float> &N = all ? m.cls_N_all : m.cls_N_evid, &H = all ? m.cls_H_all : m.cls_H_evid;
+    lvN.assign(m.nweight, 0.f); lvH.assign(m.nweight, 0.f);
+    const uint64_t rows = m.nweight ? N.size() / m.nweight : 0;
+    for (uint64_t r = 0; r < rows; ++r)
+      for (uint64_t i = 0; i < m.nweight; ++i) { lvN[i] += N[r * m.nweight + i]; lvH[i] += H[r * m.nweight + i]; }
+    if (m.cls_shared)  // one class-averaged row
+      for (uint64_t i = 0; i < m.nweight; ++i) { lvN[i] *= m.ncolor(); lvH[i] *= m.ncolor(); }
+    CU(h->lv_N.upload(lvN, s));
+    CU(h->lv_H.upload(lvH, s));
+    CU(h->learn_visit.upload(m.learn_visit, s));
+  }
+  if (m.sell || m.cell) {
+    if (m.sell) {
     CU(h->sl_off.upload(m.sl_off, s));
     CU(h->blob.upload(m.blob, s));
     CU(h->learn_visit.upload(m.learn_visit, s));
+    }
     if (!m.part_slices.empty()) {
       const size_t nsl = m.sl_off.size() - 1;
       CU(h->part_sums.alloc(4 * nsl));
@@ -753,7 +812,7 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     // the epoch plan of launch_learn_sell: curvature bounds of the learnable weights, sorted, and
     // the coupling factor (SGD steps of one variable move all its weights together)
     const bool all = h->opts.learn_non_evidence;
-    const std::vector<float> &N = all ? m.cls_N_all : m.cls_N_evid, &H = all ? m.cls_H_all : m.cls_H_evid;
+    const std::vector<float> &N = m.cell ? lvN : all ? m.cls_N_all : m.cls_N_evid, &H = m.cell ? lvH : all ? m.cls_H_all : m.cls_H_evid;
     double updates = 0;
     for (uint64_t i = 0; i < m.nweight; ++i) {
       updates += N[i];
@@ -793,6 +852,8 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     ss.assign_free = h->assign_free8.p; ss.assign_evid = h->assign_evid8.p;
     ss.weights = h->weights.p; ss.grad_acc = h->grad_acc.p; ss.tallies = h->tallies.p;
     rc = cell_setup(h.get());
+    if (rc) return rc;
+    rc = cell_learn_setup(h.get());
     if (rc) return rc;
     h->cls_query_end = g->query_end();
   } else if (!m.sell) {
@@ -918,7 +979,7 @@ static int launch_learn_sell(dwg_handle *h, SweepParams &p, double stepsize) {
   L.decay = !h->learns ? 0.0 : p.reg_l1 ? h->opts.reg_param : h->opts.reg_param * a;
   L.inv_nslice = 1.0 / nslice;
   L.reg_l1 = p.reg_l1;
-  L.w_N = h->cls_N.p; L.w_H = h->cls_H.p;
+  L.w_N = m.cell ? h->lv_N.p : h->cls_N.p; L.w_H = m.cell ? h->lv_H.p : h->cls_H.p;
   L.weights = h->weights.p;
   // period 0: the narrow form -- one warp per CTA (an SM to itself while there are SMs), weights
   // read from and pushed to the live vector record by record
@@ -969,12 +1030,15 @@ static int launch_sweep(dwg_handle *h, bool learn, double stepsize) {
   ++h->sweep_counter;
   const bool use_sell = m.sell && !p.sequential;
   const bool use_cell = m.cell && !p.sequential && !learn && !getenv("DWG_CELL_OFF");  // categorical inference sweeps
-  if (!use_sell && !use_cell) {
+  // categorical sliced-ELL graphs learn through k_cell_learn_live (hard evidence; --noise_aware
+  // steps every value by its truthiness: the CSR kernels)
+  const bool cell_learn = m.cell && learn && !p.sequential && h->cell_learn && !p.noise_aware && !getenv("DWG_CELL_OFF");
+  if (!use_sell && !use_cell && !cell_learn) {
     h->chain_open = false;
     int rc = ensure_csr(h);
     if (rc) return rc;
   }
-  if (use_sell && learn) {
+  if ((use_sell && learn) || cell_learn) {
     h->chain_open = false;
     int rc = launch_learn_sell(h, p, stepsize);
     if (rc) return rc;

@@ -227,5 +227,208 @@ k_cell_infer_staged(const CellGraph g, const SellState st, const SweepParams p, 
   }
 }
 
+// ---- learning sweep on the categorical sliced-ELL blob ---------------------------------------
+// sample_sgd_single_variable for categorical variables (src/gibbs_sampler.h:127-149) with
+// sgd_on_variable's categorical branch (src/factor_graph.cc:278-312, hard evidence:
+// --noise_aware graphs keep the CSR kernels): the free chain draws every variable; the evid chain
+// clamps evidence and draws the rest; a learning variable with evidence value e and free value f
+// steps the weights of the factors in row e and, when f != e, in row f:
+//     gradient = sign(free chain, this variable = f) - sign(evid chain, this variable := e)
+// A record of row k has self_sat = (value == k) on either side, so both signs come out of its
+// table.  The schedule is k_sell_learn_live's: live weights, a shared-memory copy
+// refreshed every `period` slices, integer gradient accumulators (feature values are 1), steps of
+// over-shared weights scaled, slices visited in ascending id block.
+struct CellLearnExtra {
+  const uint8_t *w_fixed;  // [nweight] internal order
+  uint32_t kmax;
+  int learn_non_evidence;
+};
+
+__host__ __device__ inline uint32_t cell_learn_buf_off(uint32_t n_hot, uint32_t stage_words) {
+  return (uint32_t)((sell_learn_smem(n_hot, stage_words) + 127u) & ~(size_t)127u);
+}
+__host__ __device__ inline size_t cell_learn_smem(uint32_t n_hot, uint32_t stage_words, uint32_t kmax) {
+  return (size_t)cell_learn_buf_off(n_hot, stage_words) + (size_t)(SELL_LEARN_THREADS / 32) * kmax * 32u * 8u;
+}
+
+// potentials of the lane's values on the chain whose others are summarised in satmask
+__device__ __forceinline__ void cell_potentials_masked(const uint32_t *recs, uint32_t n_rec, uint32_t satmask,
+                                                       const SellGraph &g, const double *w_s, const double *w,
+                                                       double *buf) {
+  double cur = 0.0;
+  uint32_t k = 0xffffffffu, oc = 0;
+  for (uint32_t j = 0; j < n_rec; ++j) {
+    const uint32_t rec = recs[32u * j];
+    if (rec & CELL_ROW_BIT) {
+      if (k != 0xffffffffu) buf[k * 32u] = cur;
+      cur = 0.0;
+      ++k;
+    }
+    const uint32_t multi = (rec >> 30) & 1u, os = multi & (satmask >> oc);
+    oc += multi;
+    const uint32_t code = (rec >> (22u + 2u * (2u + os))) & 3u;
+    const uint32_t wid = rec & CELL_WID_MASK;
+    const double wt = wid < g.n_hot ? w_s[wid] : __ldcg(w + wid);
+    cur = __dadd_rn(cur, sell_term(code, wt));
+  }
+  if (k != 0xffffffffu) buf[k * 32u] = cur;
+}
+
+__global__ void __launch_bounds__(SELL_LEARN_THREADS, 2)
+k_cell_learn_live(const SellGraph g, const SellState st, const SweepParams p, const SellLearn L, const CellLearnExtra X,
+                  const uint32_t stage_words) {
+  extern __shared__ __align__(128) unsigned char sell_smem[];
+  constexpr uint32_t ST = SELL_LEARN_STAGES;
+  double *w_s = reinterpret_cast<double *>(sell_smem), *acc_s = w_s + g.n_hot;
+  float *as_s = reinterpret_cast<float *>(acc_s + g.n_hot), *lam_s = as_s + g.n_hot, *debt_s = lam_s + g.n_hot;
+  const uint32_t *sm = reinterpret_cast<const uint32_t *>(sell_smem);
+  __shared__ uint32_t cnt_s;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t npos = L.vend - L.vbegin, rounds = (npos + warps - 1) / warps;
+  const uint32_t n_my = gw < npos ? (npos - 1 - gw) / warps + 1u : 0u;
+  const uint32_t bar0 = sell_smem_addr(sell_smem) + sell_learn_bar_off(g.n_hot) + warp * ST * 8u;
+  const uint32_t ringw = sell_learn_ring_off(g.n_hot) / 4u + warp * ST * stage_words;
+  const uint32_t ring0 = sell_smem_addr(sell_smem) + ringw * 4u;
+  double *buf = reinterpret_cast<double *>(sell_smem + cell_learn_buf_off(g.n_hot, stage_words)) +
+                (size_t)warp * X.kmax * 32u + lane;
+  if (lane == 0)
+    for (uint32_t i = 0; i < ST; ++i) sell_mbar_init(bar0 + 8u * i, 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) {
+    const bool fixed = __ldg(X.w_fixed + i);
+    const double sc = sell_step_scale(L, i);
+    as_s[i] = fixed ? 0.f : (float)(L.step * sc);
+    const double per_update = L.reg_l1 ? L.decay : log1p(L.decay * sc);
+    lam_s[i] = fixed ? 0.f : (float)((double)__ldg(L.w_N + i) * L.inv_nslice * per_update);
+    acc_s[i] = 0.0;
+    debt_s[i] = 0.f;
+  }
+  const uint64_t pol = sell_policy_evict_first();
+  uint32_t cur_s = 0, cur_lo = 0, cur_hi = 0, nxt_s = 0, nxt_lo = 0, nxt_hi = 0;
+  auto fetch = [&](uint32_t kb, uint32_t &sl, uint32_t &lo, uint32_t &hi) {
+    const uint32_t k = kb + lane;
+    if (k < n_my) {
+      sl = __ldg(L.visit + L.vbegin + (size_t)k * warps + gw);
+      lo = __ldg(g.sl_off + sl);
+      hi = __ldg(g.sl_off + sl + 1);
+    }
+  };
+  auto issue = [&](uint32_t k, uint32_t stage) {
+    const uint32_t j = k & 31u;
+    if (j == 0 && k) {
+      cur_s = nxt_s; cur_lo = nxt_lo; cur_hi = nxt_hi;
+      fetch(k + 32, nxt_s, nxt_lo, nxt_hi);
+    }
+    const uint32_t off = __shfl_sync(0xffffffffu, cur_lo, j);
+    const uint32_t bytes = min((__shfl_sync(0xffffffffu, cur_hi, j) - off) * 32u, stage_words * 4u);
+    if (lane == 0) {
+      sell_mbar_expect_tx(bar0 + 8u * stage, bytes);
+      sell_bulk_g2s(ring0 + stage * stage_words * 4u, g.blob + (size_t)off * 8, bytes, bar0 + 8u * stage, pol);
+    }
+  };
+  __syncthreads();
+  if (n_my) {
+    fetch(0, cur_s, cur_lo, cur_hi);
+    fetch(32, nxt_s, nxt_lo, nxt_hi);
+    const uint32_t pre = n_my < ST ? n_my : ST;
+    for (uint32_t k = 0; k < pre; ++k) issue(k, k);
+  }
+  uint32_t stage = 0, parity = 0, k = 0;
+  uint32_t proc_s = cur_s;
+  for (uint32_t r0 = 0; r0 < rounds; r0 = r0 + L.period < r0 ? rounds : r0 + L.period) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) w_s[i] = __ldcg(L.weights + i);
+    if (threadIdx.x == 0) cnt_s = 0;
+    __syncthreads();
+    uint32_t mine = 0;
+    const uint32_t r1 = r0 + L.period < r0 ? rounds : min(rounds, r0 + L.period);
+    for (uint32_t r = r0; r < r1 && k < n_my; ++r, ++k) {
+      if ((k & 31u) == 0 && k) proc_s = cur_s;
+      const uint32_t s = __shfl_sync(0xffffffffu, proc_s, k & 31u);
+      sell_mbar_wait(bar0 + 8u * stage, parity);
+      const uint32_t *b = sm + ringw + stage * stage_words;
+      const uint4 h0 = *reinterpret_cast<const uint4 *>(b);      // n_rec, n_oc, evid, pad
+      const uint4 h1 = *reinterpret_cast<const uint4 *>(b + 4);  // kmax, -, -, own offset
+      const uint32_t n_rec = h0.x, n_oc = h0.y;
+      // the records: the staged copy, or the blob itself for a slice longer than a stage
+      const bool fits = SH_WORDS + 32u * (2u + n_rec + n_oc) <= stage_words;
+      const uint32_t *src = fits ? b : g.blob + (size_t)h1.w * 8;
+      const uint32_t *recs = src + SH_WORDS + 64u + lane, *oth = recs + 32u * n_rec;
+      const uint32_t meta = b[SH_WORDS + lane], K = meta & 0xffu, ev = (meta >> 8) & 0xffu;
+      const bool pad = (h0.w >> lane) & 1u, evid = (h0.z >> lane) & 1u;
+      const uint32_t d = s * 32u + lane;
+      double u0, u1;
+      dev_uniforms(p, d, u0, u1);
+      // both chains' values of the other variables, one batch of L2 gathers
+      uint32_t fmask = 0, emask = 0;
+      for (uint32_t c0 = 0; c0 < n_oc; c0 += 4) {
+        uint32_t ow[4], af[4], ae[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) ow[u] = c0 + u < n_oc ? oth[32u * (c0 + u)] : 0u;
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) { af[u] = __ldcg(st.assign_free + (ow[u] >> 8)); ae[u] = __ldcg(st.assign_evid + (ow[u] >> 8)); }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u)
+          if (c0 + u < n_oc) {
+            fmask |= (af[u] == (ow[u] & 0xffu) ? 1u : 0u) << (c0 + u);
+            emask |= (ae[u] == (ow[u] & 0xffu) ? 1u : 0u) << (c0 + u);
+          }
+      }
+      // free chain: every variable (gibbs_sampler.h:137-139)
+      cell_potentials_masked(recs, n_rec, fmask, g, w_s, L.weights, buf);
+      const uint32_t pf = pad ? 0u : cell_draw(buf, K, u0);
+      // evid chain (sample_evid, :171-190): hard evidence is clamped, everything else drawn
+      uint32_t pe = ev;
+      if (__any_sync(0xffffffffu, !pad && !evid)) {
+        cell_potentials_masked(recs, n_rec, emask, g, w_s, L.weights, buf);
+        if (!pad && !evid) pe = cell_draw(buf, K, u1);
+      }
+      if (!pad) { st.assign_free[d] = (uint8_t)pf; st.assign_evid[d] = (uint8_t)pe; }
+      // sgd_on_variable, categorical (factor_graph.cc:278-312): rows ev and (if different) pf
+      const bool learn = !pad && (X.learn_non_evidence || evid);
+      if (__any_sync(0xffffffffu, learn)) {
+        uint32_t row = 0xffffffffu, oc = 0;
+        for (uint32_t j = 0; j < n_rec; ++j) {
+          const uint32_t rec = recs[32u * j];
+          row += (rec >> 31) & 1u;  // CELL_ROW_BIT: the first record of the next value
+          const uint32_t multi = (rec >> 30) & 1u;
+          const uint32_t osf = multi & (fmask >> oc), ose = multi & (emask >> oc);
+          oc += multi;
+          if (!learn || (row != ev && row != pf) || (rec & ~CELL_ROW_BIT) == CELL_NOP) continue;
+          const uint32_t tab = rec >> 22, ssf = pf == row, sse = ev == row;
+          const int cf = (int)((tab >> (2u * (2u * ssf + osf))) & 3u), ce = (int)((tab >> (2u * (2u * sse + ose))) & 3u);
+          const uint32_t wid = rec & CELL_WID_MASK;
+          if (wid < g.n_hot) {
+            if (cf != ce) atomicAdd(reinterpret_cast<int *>(acc_s + wid), cf - ce);
+          } else if (!__ldg(X.w_fixed + wid)) {  // beyond the copy: the step and its decay straight into the live vector
+            const double sc = sell_step_scale(L, wid), x = __ldcg(L.weights + wid);
+            const double dec = L.reg_l1 ? L.decay * (x < 0 ? 1.0 : 0.0) : -x * (L.decay * sc) / (1.0 + L.decay * sc);
+            const double dd = dec - L.step * sc * (double)(cf - ce);
+            if (dd != 0.0) atomicAdd(L.weights + wid, dd);
+          }
+        }
+      }
+      ++mine;
+      __syncwarp();
+      if (k + ST < n_my) issue(k + ST, stage);
+      if (++stage == ST) { stage = 0; parity ^= 1u; }
+    }
+    if (lane == 0 && mine) atomicAdd(&cnt_s, mine);
+    __syncthreads();
+    const uint32_t cnt = cnt_s;
+    const bool last = r1 >= rounds;
+    for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) {
+      const double a = sell_acc_take<FV_ONE>(acc_s, i), x = w_s[i];
+      const float debt = debt_s[i] + lam_s[i] * (float)cnt;
+      if (a == 0.0 && debt < 1e-3f && !last) { debt_s[i] = debt; continue; }
+      debt_s[i] = 0.f;
+      const double dec = L.reg_l1 ? (double)debt * (x < 0 ? 1.0 : 0.0) : x * expm1(-(double)debt);
+      const double dlt = dec - (double)as_s[i] * a;
+      if (dlt != 0.0) atomicAdd(L.weights + i, dlt);
+    }
+  }
+}
+
 }  // namespace dwg
 #endif

@@ -1204,6 +1204,23 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     }
     g->sl_off[nslice] = (uint32_t)(words / 8);
     g->blob.assign(words, 0);
+    {  // learning order (k_cell_learn_live): by id block of the slice's first variable, then by class, then by position
+      std::vector<uint64_t> vk(nslice);
+      parallel_for(ncolor, [&](uint64_t c0, uint64_t c1) {
+        for (uint64_t c = c0; c < c1; ++c)
+          for (uint64_t sidx = g->color_start[c] / 32; sidx < g->color_start[c + 1] / 32; ++sidx) {
+            uint64_t v = 0;
+            for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d)
+              if (g->perm[d] != 0xffffffffu) { v = g->perm[d]; break; }
+            vk[sidx] = ((v / g->id_block) << 16) | (c & 0xffffu);
+          }
+      });
+      g->learn_visit.resize(nslice);
+      std::iota(g->learn_visit.begin(), g->learn_visit.end(), 0u);
+      std::stable_sort(g->learn_visit.begin(), g->learn_visit.end(), [&](uint32_t a, uint32_t b) {
+        return vk[a] != vk[b] ? vk[a] < vk[b] : a < b;
+      });
+    }
     parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
       for (uint64_t sidx = a0; sidx < a1; ++sidx) {
         uint32_t *h = g->blob.data() + (uint64_t)g->sl_off[sidx] * 8;

@@ -471,6 +471,53 @@ def test_parallel_learning_gradient_sums_on_coupled_graphs(seed, monkeypatch):
             assert np.allclose(got, want, rtol=1e-4, atol=1e-6), (got, want)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_categorical_sliced_learning_kernel_vs_reference_steps(seed, monkeypatch):
+    """k_cell_learn_live on ONE warp (DWG_LEARN_WARPS=1) walks the visit order slice by slice.  With
+    fixed weights both chains equal the sequential reference run in that order exactly (free-chain
+    draws of every variable, evid-chain clamps / draws); with free weights and a vanishing dyadic
+    step  w0 - w = step * (sum of the reference's categorical SGD gradients: rows of the evidence
+    value and of the free value, src/factor_graph.cc:278-312).  Staged slices and (stage of 80
+    words) slices read from HBM; with and without --learn_non_evidence."""
+    monkeypatch.setenv("DWG_LEARN_WARPS", "1")
+    if seed >= 4:
+        monkeypatch.setenv("DWG_SELL_STAGE_WORDS", "80")
+    rng = np.random.default_rng(2900 + seed)
+    raw = _categorical_graph(rng, 1500, 4000, 24)
+    kw = dict(reg_param=0.0, learn_non_evidence=seed % 2 == 1)
+    raw.w_fixed[:] = 1
+    g, s, o = _mk(raw, sb.SCHED_CHROMATIC, **kw)
+    assert len(g.image("blob")) > 0 and len(g.image("learn_visit")) > 0
+    order = _learn_order(g)
+    assert sorted(order.tolist()) == list(range(raw.nvar))
+    launches = sb.load().dwg_launch_count()
+    for ep in range(3):
+        r0, r1 = rng.random(o.nvar), rng.random(o.nvar)
+        s.set_uniforms(r0, r1)
+        s.learn_epoch(2.0 ** -6)
+        o.sweep_learn_seq(2.0 ** -6, order, r0, r1)
+        _same_state(s, o)
+    assert sb.load().dwg_launch_count() - launches <= 6  # the sliced kernel (at most head + tail per epoch), not the chunked CSR launches
+    s.close()
+    raw.w_fixed[:] = rng.random(raw.nweight) < 0.2
+    g = sb.Graph.from_raw(raw, sb.SCHED_CHROMATIC)
+    s, o = sb.Sampler(g, **kw), ol.Oracle(raw, **kw)
+    order = _learn_order(g)
+    step = 2.0 ** -30
+    for ep in range(2):
+        r0, r1 = rng.random(o.nvar), rng.random(o.nvar)
+        w0 = s.weights()
+        o.weights[:] = w0
+        s.set_uniforms(r0, r1)
+        s.learn_epoch(step)
+        o.sweep_learn_seq(step, order, r0, r1)
+        _same_state(s, o)
+        got, want = (w0 - s.weights()) / step, (w0 - o.weights) / step
+        assert np.abs(want).max() > 10  # gradients were summed
+        assert np.allclose(got, want, rtol=1e-4, atol=1e-6), (got, want)
+        assert np.array_equal(s.weights()[raw.w_fixed != 0], w0[raw.w_fixed != 0])
+
+
 def test_wide_learning_sweep_keeps_chains_and_weights_valid():
     """a full-width Hogwild learning sweep (every SM, classes interleaved in id-block order): chain
     values stay in {0, 1}, evidence stays clamped on the evid chain, fixed weights do not move,
