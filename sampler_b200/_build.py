@@ -12,7 +12,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libdwg.so")
+LIB = os.environ.get("DWG_LIB") or os.path.join(PKG, "libdwg.so")  # DWG_LIB: an experimental build (scripts/ only)
 DW = os.path.join(PKG, "dw")
 
 CU_SOURCES = ["dwg_api.cu"]
@@ -39,7 +39,9 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES + HOST_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = srcs + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     if force or _stale(LIB, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-ldl", "-lpthread"]
+        dev = ["-DDWG_DEV_BUILD"] if os.environ.get("DWG_DEV_BUILD") == "1" else []  # C2-shaped kernels only (see dwg_api.cu)
+        dev += os.environ.get("DWG_NVCC_EXTRA", "").split()
+        cmd = [_nvcc()] + NVCC_FLAGS + dev + ["-shared", "-o", LIB] + srcs + ["-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -269,7 +269,7 @@ int sell_setup_t(dwg_handle *h) {
   // measured (profiles/r1_v4_ab.txt): with neighbour gathers in the loop 8 warps x <= 128 registers per
   // CTA win (more loads in flight per warp beat more warps), unary-only graphs stream best with 16 x 64
   uint32_t nwarp = MULTI ? 8 : 16;
-  if (const char *e = getenv("DWG_SELL_WARPS")) nwarp = atoi(e) == 16 ? 16 : atoi(e) == 4 ? 4 : 8;
+  if (const char *e = getenv("DWG_SELL_WARPS")) nwarp = atoi(e) == 16 ? 16 : atoi(e) == 12 ? 12 : atoi(e) == 4 ? 4 : 8;
   const uint32_t n_tab = (uint32_t)std::min<uint64_t>({h->img->nweight, n_hot, SELL_MAX_TAB});
   // the deepest ring (<= SELL_MAX_STAGES, two CTAs per SM) whose stage holds at least 99.5 % of the
   // slices whole (90 % for the two-stage ring); the rare longer slice is staged up to its stage's
@@ -279,7 +279,7 @@ int sell_setup_t(dwg_handle *h) {
   const size_t nslice = off.empty() ? 0 : off.size() - 1;
   const uint32_t want = (h->img->sell_max_words + 3u) & ~3u;
   uint32_t stages = 0, words = 0;
-  for (; !stages; nwarp /= 2) {
+  for (; !stages; nwarp = nwarp == 12 ? 8 : nwarp / 2) {
     for (uint32_t st = max_stages; st >= 2 && !stages; --st) {
       const size_t fixed = sell_staged_ring_off(n_tab, st, nwarp);
       uint32_t cap = (uint32_t)((budget - fixed) / (nwarp * st * 4)) & ~3u;
@@ -303,6 +303,7 @@ int sell_setup_t(dwg_handle *h) {
   const bool allhot = h->img->nweight <= n_tab;
 #define STAGED_GRID(AH, NT) sell_grid(k_sell_infer_staged<MULTI, FV, AH, NT, WIDE>, smem, h->num_sms, &h->sell_blocks_staged, NT)
   rc = nwarp == 16 ? (allhot ? STAGED_GRID(true, 512) : STAGED_GRID(false, 512))
+       : nwarp == 12 ? (allhot ? STAGED_GRID(true, 384) : STAGED_GRID(false, 384))
        : nwarp == 8 ? (allhot ? STAGED_GRID(true, 256) : STAGED_GRID(false, 256))
                     : (allhot ? STAGED_GRID(true, 128) : STAGED_GRID(false, 128));
 #undef STAGED_GRID
@@ -332,6 +333,7 @@ void sell_launch_t(dwg_handle *h, bool staged, bool pdl, uint32_t blocks, const 
 #define STAGED_LAUNCH(AH, NT) \
   cudaLaunchKernelEx(&cfg, k_sell_infer_staged<MULTI, FV, AH, NT, WIDE>, sg, h->ss, p, h->sell_stages, h->sell_stage_words)
     if (h->sell_staged_warps == 16) { if (allhot) STAGED_LAUNCH(true, 512); else STAGED_LAUNCH(false, 512); }
+    else if (h->sell_staged_warps == 12) { if (allhot) STAGED_LAUNCH(true, 384); else STAGED_LAUNCH(false, 384); }
     else if (h->sell_staged_warps == 8) { if (allhot) STAGED_LAUNCH(true, 256); else STAGED_LAUNCH(false, 256); }
     else { if (allhot) STAGED_LAUNCH(true, 128); else STAGED_LAUNCH(false, 128); }
 #undef STAGED_LAUNCH
@@ -347,6 +349,9 @@ void sell_learn_launch_t(dwg_handle *h, uint32_t blocks, uint32_t threads, bool 
   k_sell_learn_live<MULTI, FV, WIDE><<<blocks, threads, sell_learn_smem(sg.n_hot, h->learn_stage_words), h->stream>>>(
       sg, h->ss, p, L, h->learn_stage_words);
 }
+#ifdef DWG_DEV_BUILD  // development builds (DWG_DEV_BUILD=1 python -m sampler_b200._build): only the C2-shaped kernels, a third of the compile time
+#define SELL_SWITCH(CALL) { (void)m; CALL(true, FV_ONE, false); }
+#else
 #define SELL_SWITCH_W(CALL, WD)                                                \
   if (m.has_multi) {                                                           \
     if (m.fv_mode == FV_ONE) { CALL(true, FV_ONE, WD); }                       \
@@ -360,6 +365,7 @@ void sell_learn_launch_t(dwg_handle *h, uint32_t blocks, uint32_t threads, bool 
 // (graphs with warp-per-variable slices run kernels instantiated with the code for them)
 #define SELL_SWITCH(CALL)                                                      \
   if (m.has_wide) { SELL_SWITCH_W(CALL, true) } else { SELL_SWITCH_W(CALL, false) }
+#endif
 constexpr int CELL_THREADS = 256;
 int cell_setup(dwg_handle *h) {
   const GraphImage &m = *h->img;

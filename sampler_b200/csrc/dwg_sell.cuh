@@ -483,10 +483,13 @@ __host__ __device__ inline uint32_t sell_staged_smem(uint32_t n_tab, uint32_t st
 // the rare slice that is longer than a stage: potentials straight from HBM, as the direct kernel
 // does (out of line, so that it does not cost the staged loop registers).  w_plain: no plain
 // weight table is staged here, every weight comes through L1/L2 (n_hot = 0).
+// (returns (pos, neg) by value: reference parameters would pin the caller's accumulators to local
+// memory for the whole loop -- six STL.64 and two LDL.64 per slice in the round-1 kernel)
 template <bool MULTI, int FV>
-__device__ __noinline__ void sell_unstaged_potentials(const SellGraph &g, const SellState &st, uint32_t off,
-                                                      uint32_t n_un, uint32_t n_mu, uint32_t flags, uint32_t lane,
-                                                      uint32_t d, double &pos, double &neg) {
+__device__ __noinline__ double2 sell_unstaged_potentials(const SellGraph &g, const SellState &st, uint32_t off,
+                                                         uint32_t n_un, uint32_t n_mu, uint32_t flags, uint32_t lane,
+                                                         uint32_t d) {
+  double pos, neg;
   constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
   SellGraph gc = g;
   gc.n_hot = 0;
@@ -497,6 +500,7 @@ __device__ __noinline__ void sell_unstaged_potentials(const SellGraph &g, const 
   h.mu = h.un + (size_t)32 * n_un * (1 + FVW);
   h.oth = h.mu + (size_t)32 * n_mu * (1 + FVW);
   sell_potentials<MULTI, FV, LD_STREAM>(gc, h, nullptr, st.weights, lane, d, st.assign_evid, pos, neg);
+  return make_double2(pos, neg);
 }
 
 template <int FV>
@@ -510,6 +514,9 @@ __device__ __forceinline__ double sell_fv_s(const uint32_t *sm, uint32_t fvb, ui
 template <bool ALLHOT>
 __device__ __forceinline__ double sell_signed_weight(const SellGraph &g, const unsigned char *tab_s, uint32_t plane,
                                                      const double *w, uint32_t code, uint32_t wid8) {
+#ifdef DWG_EXP_NOTAB
+  if (ALLHOT) return __hiloint2double(code * plane, wid8);
+#endif
   if (ALLHOT) return *reinterpret_cast<const double *>(tab_s + (code * plane + wid8));
   // Branch-free: ONE generic load from either the signed table or the weight vector (L2), so that
   // the loads of a batch of records issue back to back; a branch per record would serialise a
@@ -537,9 +544,13 @@ template <int FV, bool ANTISYM, bool ALLHOT>
 __device__ __forceinline__ void sell_unary_s(const SellGraph &g, const uint32_t *sm, uint32_t b, uint32_t n_un,
                                              const unsigned char *tab_s, uint32_t plane, const double *w,
                                              uint32_t lane, double &pos, double &neg) {
-  constexpr uint32_t U = ALLHOT ? 4 : 10;  // beyond the table: more weight loads in flight per batch
+  // batches of 8 (table) / 10 (beyond the table: more weight loads in flight); the batch loop itself
+  // is not unrolled -- the nest of remainder loops ptxas builds otherwise costs more than it saves
+  // (C2: 0.243 -> 0.234 ms per sweep, profiles/r2_c2_ab.txt)
+  constexpr uint32_t U = ALLHOT ? 8 : 10;
   const uint32_t un = b + SH_WORDS + lane, fvb = b + SH_WORDS + 32u * n_un;
   uint32_t j0 = 0;
+#pragma unroll 1
   for (; j0 + U <= n_un; j0 += U) {
     uint32_t rec[U];
     double fv[U];
@@ -563,7 +574,10 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
                     const uint32_t stage_words) {
   extern __shared__ __align__(128) unsigned char sell_smem[];
   constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
-  constexpr uint32_t MC = 2;  // binary records handled together
+#ifndef DWG_EXP_MC
+#define DWG_EXP_MC 2
+#endif
+  constexpr uint32_t MC = DWG_EXP_MC;  // binary records handled together
   // Programmatic dependent launch: the launch of the next colour class may start as soon as SMs
   // free up, run its prologue (weight table, mbarriers, slice offsets, the first bulk copies --
   // all of it data no sweep writes) and park at griddepcontrol.wait below until this class is
@@ -635,7 +649,11 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
 #pragma unroll
       for (uint32_t u = 0; u < MC; ++u) {
         const uint32_t ow = u < h0.y ? sm[oth + 32u * u] : 0u;
+#ifdef DWG_EXP_NOGATHER
+        av[u] = ow >> 9;
+#else
         av[u] = st.assign_evid[ow >> 1];
+#endif
         eq |= (ow & 1u) << u;
       }
     }
@@ -666,7 +684,8 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
       // FactorGraph::potential for proposals 1 and 0 (src/factor_graph.h:127-145)
       double pos = 0.0, neg = 0.0;
       if (SH_WORDS + 32u * ((n_un + n_mu) * (1 + FVW) + h0.z) > stage_words) {
-        sell_unstaged_potentials<MULTI, FV>(g, st, h1.w, n_un, n_mu, flags, lane, sell_self_slot<WIDE>((uint32_t)s64, flags, lane), pos, neg);
+        const double2 pn = sell_unstaged_potentials<MULTI, FV>(g, st, h1.w, n_un, n_mu, flags, lane, sell_self_slot<WIDE>((uint32_t)s64, flags, lane));
+        pos = pn.x; neg = pn.y;
       } else {
         const uint32_t mu = b + SH_WORDS + 32u * n_un * (1 + FVW) + lane;
         const uint32_t mufv = b + SH_WORDS + 32u * n_un * (1 + FVW) + 32u * n_mu;
@@ -683,7 +702,11 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
 #pragma unroll
               for (uint32_t u = 0; u < MC; ++u) ow[u] = j0 + u < n_mu ? sm[oth + 32u * (j0 + u)] : 0u;
 #pragma unroll
+#ifdef DWG_EXP_NOGATHER
+              for (uint32_t u = 0; u < MC; ++u) av[u] = ow[u] >> 9;
+#else
               for (uint32_t u = 0; u < MC; ++u) av[u] = st.assign_evid[ow[u] >> 1];
+#endif
 #pragma unroll
               for (uint32_t u = 0; u < MC; ++u) eq |= (ow[u] & 1u) << u;
             }
@@ -693,8 +716,20 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
               const uint32_t rec = ok ? sm[mu + 32u * (j0 + u)] : (SELL_BINARY_NOP << 24);
               const uint32_t sat = av[u] == ((eq >> u) & 1u) ? 1u : 0u;
               const uint32_t codes = rec >> (24u + 2u * sat), wid8 = (rec & SELL_WID_MASK) << 3;
+#ifdef DWG_EXP_BIN1
+              double t1, t0;
+              if (ALLHOT) {  // one table read (+w plane), the two signs applied in registers
+                const double wv = *reinterpret_cast<const double *>(tab_s + (2u * plane + wid8));
+                t1 = sell_term((codes >> 4) & 3u, wv);
+                t0 = sell_term(codes & 3u, wv);
+              } else {
+                t1 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, (codes >> 4) & 3u, wid8);
+                t0 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, codes & 3u, wid8);
+              }
+#else
               double t1 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, (codes >> 4) & 3u, wid8);
               double t0 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, codes & 3u, wid8);
+#endif
               if (FV != FV_ONE) {
                 const double fv = ok ? sell_fv_s<FV>(sm, mufv, j0 + u, lane) : 0.0;
                 t1 = __dmul_rn(t1, fv);
@@ -718,6 +753,9 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
       if (WIDE && (flags & SF_WIDE)) {  // warp per variable (hubs)
         sell_wide_draw(st, p, (uint32_t)s64, flags, lane, active, pos, neg);
       } else if ((active >> lane) & 1u) {
+#ifdef DWG_EXP_NOPHILOX
+        r0 = __hiloint2double(0x3fe00000u ^ (d & 0xffffu), d);
+#endif
         const uint32_t prop = sell_draw_boolean(pos, neg, r0);
         st.assign_evid[d] = (uint8_t)prop;
         if (prop) atomicAdd(st.tallies + d, 1u);  // gibbs_sampler.h:163-167
