@@ -514,9 +514,6 @@ __device__ __forceinline__ double sell_fv_s(const uint32_t *sm, uint32_t fvb, ui
 template <bool ALLHOT>
 __device__ __forceinline__ double sell_signed_weight(const SellGraph &g, const unsigned char *tab_s, uint32_t plane,
                                                      const double *w, uint32_t code, uint32_t wid8) {
-#ifdef DWG_EXP_NOTAB
-  if (ALLHOT) return __hiloint2double(code * plane, wid8);
-#endif
   if (ALLHOT) return *reinterpret_cast<const double *>(tab_s + (code * plane + wid8));
   // Branch-free: ONE generic load from either the signed table or the weight vector (L2), so that
   // the loads of a batch of records issue back to back; a branch per record would serialise a
@@ -568,16 +565,131 @@ __device__ __forceinline__ void sell_unary_s(const SellGraph &g, const uint32_t 
   if (ANTISYM) neg = -pos;
 }
 
+constexpr uint32_t SELL_MC = 2;  // binary records handled together (4: no faster, profiles/r2_c2_ab.txt)
+
+// wait for the slice in ring stage `b` (word index) and request the chain bytes of the other
+// variables of its first SELL_MC binary records (raw bytes and equal_to bits: compared when the
+// slice is sampled)
+template <bool MULTI, int FV>
+__device__ __forceinline__ void sell_staged_front(const SellState &st, const uint32_t *sm, uint32_t b, uint32_t bar,
+                                                  uint32_t parity, uint32_t stage_words, uint32_t lane,
+                                                  uint32_t (&av)[SELL_MC], uint32_t &eq) {
+  constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
+  sell_mbar_wait(bar, parity);
+  if (!MULTI) return;
+  const uint4 h0 = *reinterpret_cast<const uint4 *>(sm + b);
+  const uint32_t flags = sm[b + SH_FLAGS];
+  eq = 0;
+  if ((flags & SF_BINARY) && SH_WORDS + 32u * ((h0.x + h0.y) * (1 + FVW) + h0.z) <= stage_words) {
+    const uint32_t oth = b + SH_WORDS + 32u * (h0.x + h0.y) * (1 + FVW) + lane;
+#pragma unroll
+    for (uint32_t u = 0; u < SELL_MC; ++u) {
+      const uint32_t ow = u < h0.y ? sm[oth + 32u * u] : 0u;
+      av[u] = st.assign_evid[ow >> 1];  // (other colour classes: constant during the launch)
+      eq |= (ow & 1u) << u;
+    }
+  }
+}
+
+// sample_single_variable (src/gibbs_sampler.h:151-169) for the 32 variables of the slice staged at
+// word `b` of shared memory: potentials of both proposals, the Boolean draw with uniform r0, chain
+// and tally.  av / eq: what sell_staged_front requested for this slice.
+template <bool MULTI, int FV, bool ALLHOT, bool WIDE>
+__device__ __forceinline__ void sell_staged_sample(const SellGraph &g, const SellState &st, const SweepParams &p,
+                                                   const uint32_t *sm, const unsigned char *tab_s, uint32_t plane,
+                                                   uint32_t b, uint32_t stage_words, uint32_t lane, uint32_t s,
+                                                   double r0, uint32_t (&av)[SELL_MC], uint32_t eq) {
+  constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
+  constexpr uint32_t MC = SELL_MC;
+  const uint32_t d = s * 32u + lane;
+  const uint4 h0 = *reinterpret_cast<const uint4 *>(sm + b);      // n_un, n_mu, n_oc, evid
+  const uint4 h1 = *reinterpret_cast<const uint4 *>(sm + b + 4);  // pad, evval, flags, own offset
+  const uint32_t n_un = h0.x, n_mu = h0.y, flags = h1.z;
+  // gibbs_sampler.h:157 -- a slice with nothing to sample is skipped
+  const uint32_t active = ~h1.x & (p.sample_evidence ? 0xffffffffu : ~h0.w);
+  if (!active) return;
+  // FactorGraph::potential for proposals 1 and 0 (src/factor_graph.h:127-145)
+  double pos = 0.0, neg = 0.0;
+  if (SH_WORDS + 32u * ((n_un + n_mu) * (1 + FVW) + h0.z) > stage_words) {
+    const double2 pn = sell_unstaged_potentials<MULTI, FV>(g, st, h1.w, n_un, n_mu, flags, lane, sell_self_slot<WIDE>(s, flags, lane));
+    pos = pn.x; neg = pn.y;
+  } else {
+    const uint32_t mu = b + SH_WORDS + 32u * n_un * (1 + FVW) + lane;
+    const uint32_t mufv = b + SH_WORDS + 32u * n_un * (1 + FVW) + 32u * n_mu;
+    const uint32_t oth = mu + 32u * n_mu * (1 + FVW);
+    if (flags & SF_ANTISYM) sell_unary_s<FV, true, ALLHOT>(g, sm, b, n_un, tab_s, plane, st.weights, lane, pos, neg);
+    else sell_unary_s<FV, false, ALLHOT>(g, sm, b, n_un, tab_s, plane, st.weights, lane, pos, neg);
+    if (MULTI && (flags & SF_BINARY)) {
+      // record j owns others word j; its tag is the factor's sign table code(x, sat) at bits
+      // 2 (2 x + sat): x = 1 feeds pos, x = 0 feeds neg
+      for (uint32_t j0 = 0; j0 < n_mu; j0 += MC) {
+        if (j0) {
+          uint32_t ow[MC];
+          eq = 0;
+#pragma unroll
+          for (uint32_t u = 0; u < MC; ++u) ow[u] = j0 + u < n_mu ? sm[oth + 32u * (j0 + u)] : 0u;
+#pragma unroll
+          for (uint32_t u = 0; u < MC; ++u) av[u] = st.assign_evid[ow[u] >> 1];
+#pragma unroll
+          for (uint32_t u = 0; u < MC; ++u) eq |= (ow[u] & 1u) << u;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < MC; ++u) {
+          const bool ok = j0 + u < n_mu;
+          const uint32_t rec = ok ? sm[mu + 32u * (j0 + u)] : (SELL_BINARY_NOP << 24);
+          const uint32_t sat = av[u] == ((eq >> u) & 1u) ? 1u : 0u;
+          const uint32_t codes = rec >> (24u + 2u * sat), wid8 = (rec & SELL_WID_MASK) << 3;
+          double t1 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, (codes >> 4) & 3u, wid8);
+          double t0 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, codes & 3u, wid8);
+          if (FV != FV_ONE) {
+            const double fv = ok ? sell_fv_s<FV>(sm, mufv, j0 + u, lane) : 0.0;
+            t1 = __dmul_rn(t1, fv);
+            t0 = __dmul_rn(t0, fv);
+          }
+          pos = __dadd_rn(pos, t1);
+          neg = __dadd_rn(neg, t0);
+        }
+      }
+    } else if (MULTI && n_mu) {
+      SellGraph gc = g;
+      gc.n_hot = 0;  // no plain weight table here: the general path reads weights through L1/L2
+      SliceHeader h;
+      h.n_un = n_un; h.n_mu = n_mu; h.n_oc = h0.z; h.evid = h0.w; h.pad = h1.x; h.evval = 0;
+      h.flags = flags;
+      h.un = sm + b + SH_WORDS; h.mu = sm + mu - lane; h.oth = sm + oth - lane;
+      sell_general_multi<FV, LD_SMEM>(gc, h, nullptr, st.weights, lane, sell_self_slot<WIDE>(s, flags, lane), st.assign_evid, pos, neg);
+    }
+  }
+  if (WIDE && (flags & SF_WIDE)) {  // warp per variable (hubs)
+    sell_wide_draw(st, p, s, flags, lane, active, pos, neg);
+  } else if ((active >> lane) & 1u) {
+    const uint32_t prop = sell_draw_boolean(pos, neg, r0);
+    st.assign_evid[d] = (uint8_t)prop;
+    if (prop) atomicAdd(st.tallies + d, 1u);  // gibbs_sampler.h:163-167
+  }
+}
+
+// signed weight table, one mbarrier per (warp, stage)
+__device__ __forceinline__ void sell_staged_prologue(const SellGraph &g, const SellState &st, unsigned char *smem,
+                                                     uint32_t plane, uint32_t bar0, uint32_t stages, uint32_t lane) {
+  if (lane == 0)
+    for (uint32_t i = 0; i < stages; ++i) sell_mbar_init(bar0 + 8u * i, 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  for (uint32_t i = threadIdx.x; i < g.n_tab; i += blockDim.x) {
+    const double w = __ldg(st.weights + i);
+    *reinterpret_cast<double *>(smem + 8u * i) = -w;
+    *reinterpret_cast<double *>(smem + plane + 8u * i) = 0.0;
+    *reinterpret_cast<double *>(smem + 2u * plane + 8u * i) = w;
+  }
+  __syncthreads();
+}
+
 template <bool MULTI, int FV, bool ALLHOT, int NT, bool WIDE>
 __global__ void __launch_bounds__(NT, 2)
 k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, const uint32_t stages,
                     const uint32_t stage_words) {
   extern __shared__ __align__(128) unsigned char sell_smem[];
-  constexpr uint32_t FVW = FV == FV_F32 ? 1 : FV == FV_F64 ? 2 : 0;
-#ifndef DWG_EXP_MC
-#define DWG_EXP_MC 2
-#endif
-  constexpr uint32_t MC = DWG_EXP_MC;  // binary records handled together
+  constexpr uint32_t MC = SELL_MC;
   // Programmatic dependent launch: the launch of the next colour class may start as soon as SMs
   // free up, run its prologue (weight table, mbarriers, slice offsets, the first bulk copies --
   // all of it data no sweep writes) and park at griddepcontrol.wait below until this class is
@@ -590,16 +702,7 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
   const uint32_t bar0 = sell_smem_addr(sell_smem) + sell_staged_bar_off(g.n_tab) + warp * stages * 8u;
   const uint32_t ringw = sell_staged_ring_off(g.n_tab, stages, NT / 32) / 4u + warp * stages * stage_words;  // word index
   const uint32_t ring0 = sell_smem_addr(sell_smem) + ringw * 4u;
-  if (lane == 0)
-    for (uint32_t i = 0; i < stages; ++i) sell_mbar_init(bar0 + 8u * i, 1u);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  for (uint32_t i = threadIdx.x; i < g.n_tab; i += blockDim.x) {
-    const double w = __ldg(st.weights + i);
-    *reinterpret_cast<double *>(sell_smem + 8u * i) = -w;
-    *reinterpret_cast<double *>(sell_smem + plane + 8u * i) = 0.0;
-    *reinterpret_cast<double *>(sell_smem + 2u * plane + 8u * i) = w;
-  }
-  __syncthreads();
+  sell_staged_prologue(g, st, sell_smem, plane, bar0, stages, lane);
 
   // slices of this warp: s(k) = s0 + k * step, k < n_my
   const uint64_t step = (uint64_t)((gridDim.x * blockDim.x) >> 5) * g.slice_stride;
@@ -635,132 +738,21 @@ k_sell_infer_staged(const SellGraph g, const SellState st, const SweepParams p, 
     }
   };
 
-  // wait for the slice in `stage` and request the chain bytes of the other variables of its first MC
-  // binary records (raw bytes and equal_to bits: compared when the slice is sampled)
-  auto front = [&](uint32_t stage, uint32_t parity, uint32_t (&av)[MC], uint32_t &eq) {
-    sell_mbar_wait(bar0 + 8u * stage, parity);
-    if (!MULTI) return;
-    const uint32_t b = ringw + stage * stage_words;
-    const uint4 h0 = *reinterpret_cast<const uint4 *>(sm + b);
-    const uint32_t flags = sm[b + SH_FLAGS];
-    eq = 0;
-    if ((flags & SF_BINARY) && SH_WORDS + 32u * ((h0.x + h0.y) * (1 + FVW) + h0.z) <= stage_words) {
-      const uint32_t oth = b + SH_WORDS + 32u * (h0.x + h0.y) * (1 + FVW) + lane;
-#pragma unroll
-      for (uint32_t u = 0; u < MC; ++u) {
-        const uint32_t ow = u < h0.y ? sm[oth + 32u * u] : 0u;
-#ifdef DWG_EXP_NOGATHER
-        av[u] = ow >> 9;
-#else
-        av[u] = st.assign_evid[ow >> 1];
-#endif
-        eq |= (ow & 1u) << u;
-      }
-    }
-  };
-
   const uint32_t pre = n_my < stages ? n_my : stages;
   for (uint32_t k = 0; k < pre; ++k) issue(k, k);
   uint32_t stage = 0, parity = 0;  // of iteration k
   uint32_t av[MC] = {}, eq = 0, nav[MC] = {}, neq = 0;
   // from here on the kernel reads and writes the chains and tallies: the previous class must be done
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  front(0, 0, av, eq);
+  sell_staged_front<MULTI, FV>(st, sm, ringw, bar0, 0, stage_words, lane, av, eq);
   uint64_t s64 = s0;
   for (uint32_t k = 0; k < n_my; ++k, s64 += step) {
     uint32_t nstage = stage + 1, nparity = parity;
     if (nstage == stages) { nstage = 0; nparity ^= 1u; }
-    const uint32_t d = (uint32_t)s64 * 32u + lane;
     double r0, r1;
-    dev_uniforms(p, d, r0, r1);
-    if (k + 1 < n_my) front(nstage, nparity, nav, neq);
-    const uint32_t b = ringw + stage * stage_words;
-    const uint4 h0 = *reinterpret_cast<const uint4 *>(sm + b);      // n_un, n_mu, n_oc, evid
-    const uint4 h1 = *reinterpret_cast<const uint4 *>(sm + b + 4);  // pad, evval, flags, own offset
-    const uint32_t n_un = h0.x, n_mu = h0.y, flags = h1.z;
-    // gibbs_sampler.h:157 -- a slice with nothing to sample is skipped
-    const uint32_t active = ~h1.x & (p.sample_evidence ? 0xffffffffu : ~h0.w);
-    if (active) {
-      // FactorGraph::potential for proposals 1 and 0 (src/factor_graph.h:127-145)
-      double pos = 0.0, neg = 0.0;
-      if (SH_WORDS + 32u * ((n_un + n_mu) * (1 + FVW) + h0.z) > stage_words) {
-        const double2 pn = sell_unstaged_potentials<MULTI, FV>(g, st, h1.w, n_un, n_mu, flags, lane, sell_self_slot<WIDE>((uint32_t)s64, flags, lane));
-        pos = pn.x; neg = pn.y;
-      } else {
-        const uint32_t mu = b + SH_WORDS + 32u * n_un * (1 + FVW) + lane;
-        const uint32_t mufv = b + SH_WORDS + 32u * n_un * (1 + FVW) + 32u * n_mu;
-        const uint32_t oth = mu + 32u * n_mu * (1 + FVW);
-        if (flags & SF_ANTISYM) sell_unary_s<FV, true, ALLHOT>(g, sm, b, n_un, tab_s, plane, st.weights, lane, pos, neg);
-        else sell_unary_s<FV, false, ALLHOT>(g, sm, b, n_un, tab_s, plane, st.weights, lane, pos, neg);
-        if (MULTI && (flags & SF_BINARY)) {
-          // record j owns others word j; its tag is the factor's sign table code(x, sat) at bits
-          // 2 (2 x + sat): x = 1 feeds pos, x = 0 feeds neg
-          for (uint32_t j0 = 0; j0 < n_mu; j0 += MC) {
-            if (j0) {
-              uint32_t ow[MC];
-              eq = 0;
-#pragma unroll
-              for (uint32_t u = 0; u < MC; ++u) ow[u] = j0 + u < n_mu ? sm[oth + 32u * (j0 + u)] : 0u;
-#pragma unroll
-#ifdef DWG_EXP_NOGATHER
-              for (uint32_t u = 0; u < MC; ++u) av[u] = ow[u] >> 9;
-#else
-              for (uint32_t u = 0; u < MC; ++u) av[u] = st.assign_evid[ow[u] >> 1];
-#endif
-#pragma unroll
-              for (uint32_t u = 0; u < MC; ++u) eq |= (ow[u] & 1u) << u;
-            }
-#pragma unroll
-            for (uint32_t u = 0; u < MC; ++u) {
-              const bool ok = j0 + u < n_mu;
-              const uint32_t rec = ok ? sm[mu + 32u * (j0 + u)] : (SELL_BINARY_NOP << 24);
-              const uint32_t sat = av[u] == ((eq >> u) & 1u) ? 1u : 0u;
-              const uint32_t codes = rec >> (24u + 2u * sat), wid8 = (rec & SELL_WID_MASK) << 3;
-#ifdef DWG_EXP_BIN1
-              double t1, t0;
-              if (ALLHOT) {  // one table read (+w plane), the two signs applied in registers
-                const double wv = *reinterpret_cast<const double *>(tab_s + (2u * plane + wid8));
-                t1 = sell_term((codes >> 4) & 3u, wv);
-                t0 = sell_term(codes & 3u, wv);
-              } else {
-                t1 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, (codes >> 4) & 3u, wid8);
-                t0 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, codes & 3u, wid8);
-              }
-#else
-              double t1 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, (codes >> 4) & 3u, wid8);
-              double t0 = sell_signed_weight<ALLHOT>(g, tab_s, plane, st.weights, codes & 3u, wid8);
-#endif
-              if (FV != FV_ONE) {
-                const double fv = ok ? sell_fv_s<FV>(sm, mufv, j0 + u, lane) : 0.0;
-                t1 = __dmul_rn(t1, fv);
-                t0 = __dmul_rn(t0, fv);
-              }
-              pos = __dadd_rn(pos, t1);
-              neg = __dadd_rn(neg, t0);
-            }
-          }
-        } else if (MULTI && n_mu) {
-          SellGraph gc = g;
-          gc.n_hot = 0;  // no plain weight table here: the general path reads weights through L1/L2
-          SliceHeader h;
-          h.n_un = n_un; h.n_mu = n_mu; h.n_oc = h0.z; h.evid = h0.w; h.pad = h1.x; h.evval = 0;
-          h.flags = flags;
-          h.un = sm + b + SH_WORDS; h.mu = sm + mu - lane; h.oth = sm + oth - lane;
-          sell_general_multi<FV, LD_SMEM>(gc, h, nullptr, st.weights, lane, sell_self_slot<WIDE>((uint32_t)s64, flags, lane),
-                                          st.assign_evid, pos, neg);
-        }
-      }
-      if (WIDE && (flags & SF_WIDE)) {  // warp per variable (hubs)
-        sell_wide_draw(st, p, (uint32_t)s64, flags, lane, active, pos, neg);
-      } else if ((active >> lane) & 1u) {
-#ifdef DWG_EXP_NOPHILOX
-        r0 = __hiloint2double(0x3fe00000u ^ (d & 0xffffu), d);
-#endif
-        const uint32_t prop = sell_draw_boolean(pos, neg, r0);
-        st.assign_evid[d] = (uint8_t)prop;
-        if (prop) atomicAdd(st.tallies + d, 1u);  // gibbs_sampler.h:163-167
-      }
-    }
+    dev_uniforms(p, (uint32_t)s64 * 32u + lane, r0, r1);
+    if (k + 1 < n_my) sell_staged_front<MULTI, FV>(st, sm, ringw + nstage * stage_words, bar0 + 8u * nstage, nparity, stage_words, lane, nav, neq);
+    sell_staged_sample<MULTI, FV, ALLHOT, WIDE>(g, st, p, sm, tab_s, plane, ringw + stage * stage_words, stage_words, lane, (uint32_t)s64, r0, av, eq);
     __syncwarp();  // every lane is done with this stage before the next copy lands in it
     if (k + stages < n_my) issue(k + stages, stage);
     stage = nstage; parity = nparity;
