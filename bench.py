@@ -62,6 +62,8 @@ WORKLOADS = {
                learn=dict(n_epoch=0, alpha=0.01, diminish=0.95, reg_param=0.01), kernel="k_sell_infer_staged<MULTI=0,FV=0>"),
 }
 LEARN = WORKLOADS["c2"]["learn"]
+# the final tally aggregation: all-reduce (NVLS on NVSwitch; default) or reduce onto rank 0 (DWG_BENCH_TALLY_REDUCE=root)
+TO_ALL = os.environ.get("DWG_BENCH_TALLY_REDUCE", "all") != "root"
 
 
 def make_raw(workload, nvar):
@@ -303,7 +305,7 @@ def ours(args):
     smp.clear_tallies()
     smp.infer_epochs(args.warmup)
     if dist is not None:
-        group.reduce_tallies_device()  # warm-up of the collective too (its first call sets up the channels)
+        group.reduce_tallies_device(TO_ALL)  # warm-up of the collective too (its first call sets up the channels)
     smp.clear_tallies()
     smp.sync()
     torch.cuda.synchronize()
@@ -317,7 +319,7 @@ def ours(args):
         smp.infer_epochs(args.steps)
         e1.record(stream)
         if dist is not None:
-            group.reduce_tallies_device()  # sample tallies reduced at the end of inference
+            group.reduce_tallies_device(TO_ALL)  # sample tallies reduced at the end of inference
         e2.record(stream)
     smp.sync()
     torch.cuda.synchronize()
@@ -365,7 +367,7 @@ def ours(args):
         t_up = time.time()
         s2.infer_epochs(args.steps)
         if world > 1:
-            g2.reduce_tallies_device()
+            g2.reduce_tallies_device(TO_ALL)
         s2.sync()
         t_sw = time.time()
         if rank == 0:

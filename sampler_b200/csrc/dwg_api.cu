@@ -235,10 +235,17 @@ struct dwg_handle {
 namespace {
 template <typename K>
 int sell_grid(K kernel, size_t smem, int num_sms, int *blocks, int threads = SELL_THREADS) {
-  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (the 48 KB default covers dynamic + static shared memory: a kernel with a few static words and
+  // exactly 48 KB of dynamic memory needs the opt-in too -- C5's learning ring landed there)
+  if (smem > 40 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-  if (per_sm < 1) return fail(DWG_ERR_CUDA, "sweep kernel does not fit on an SM");
+  if (per_sm < 1) {
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, kernel);
+    return fail(DWG_ERR_CUDA, "sweep kernel does not fit on an SM (" + std::to_string(threads) + " threads x " + std::to_string(fa.numRegs) +
+                                  " registers, " + std::to_string(smem) + " + " + std::to_string(fa.sharedSizeBytes) + " B of shared memory)");
+  }
   *blocks = per_sm * num_sms;
   return DWG_OK;
 }

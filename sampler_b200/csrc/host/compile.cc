@@ -104,6 +104,134 @@ struct PhaseTimer {
   }
 };
 
+// The chromatic schedule: a proper colouring of the conflict graph "two variables share a factor"
+// (greedy in id order), balanced so that every class can fill the GPU.  Returns the colour count;
+// color[v] is written for every variable.  inc / deg / inc_end: the incidences of variable v are
+// inc[deg[v] .. inc_end[v]) (construct_index order).
+template <typename IncVec, typename DegVec, typename EndVec>
+static uint32_t colour_variables(const RawView &raw, uint64_t nvar, const IncVec &inc, const DegVec &deg,
+                                 const EndVec &inc_end, std::vector<uint32_t> &color) {
+  uint32_t ncolor = 1;
+  // conflict lists (the other variables of every incident factor; repeats are harmless), built
+  // in parallel; the two greedy passes below then touch nothing but these and color[]
+  std::vector<uint64_t> nb_ptr(nvar + 1, 0);
+  auto for_neighbours = [&](uint64_t v, auto &&fn) {
+    uint32_t last_f = 0xffffffffu;
+    for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
+      uint32_t f = inc[i].fid;
+      if (f == last_f) continue;
+      last_f = f;
+      const uint64_t a = raw.fac_ptr[f], b = raw.fac_ptr[f + 1];
+      if (b - a < 2) continue;
+      for (uint64_t e = a; e < b; ++e)
+        if (raw.edge_vid[e] != v) fn((uint32_t)raw.edge_vid[e]);
+    }
+  };
+  parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+    for (uint64_t v = v0; v < v1; ++v) {
+      uint64_t n = 0;
+      for_neighbours(v, [&](uint32_t) { ++n; });
+      nb_ptr[v + 1] = n;
+    }
+  });
+  for (uint64_t v = 0; v < nvar; ++v) nb_ptr[v + 1] += nb_ptr[v];
+  BulkVec<uint32_t> nb(nb_ptr[nvar]);
+  parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+    for (uint64_t v = v0; v < v1; ++v) {
+      uint64_t o = nb_ptr[v];
+      for_neighbours(v, [&](uint32_t u) { nb[o++] = u; });
+    }
+  });
+  // Pass 1, first fit, finds how many colours K the graph needs; pass 2 recolours with the
+  // least-loaded admissible colour among those K, so that every class is large enough to
+  // fill the GPU (first fit alone leaves a tail of tiny classes = latency-bound launches).
+  // Pass 1 in parallel wavefronts.  The first-fit colour of v depends only on the colours of its
+  // lower-numbered neighbours, so colouring v once all of those are coloured gives exactly the
+  // sequential result, whatever the interleaving: every round colours the pending variables that
+  // are ready (in id order inside each thread's range), the rest wait for the next round.  Graphs
+  // with long id-ordered dependency chains (v coupled to v+1) make little progress per round:
+  // the remainder is then finished sequentially.
+  {
+    std::fill(color.begin(), color.end(), 0xffffffffu);
+    auto first_fit = [&](uint32_t v, std::vector<uint32_t> &stamp) -> bool {  // false: not ready yet
+      for (uint64_t i = nb_ptr[v]; i < nb_ptr[v + 1]; ++i) {
+        const uint32_t u = nb[i];
+        const uint32_t c = __atomic_load_n(&color[u], __ATOMIC_ACQUIRE);
+        if (c == 0xffffffffu) {
+          if (u < v) return false;
+          continue;
+        }
+        if (c >= stamp.size()) stamp.resize(c + 2, 0);
+        stamp[c] = v + 1;
+      }
+      uint32_t c = 0;
+      while (c < stamp.size() && stamp[c] == v + 1) ++c;
+      __atomic_store_n(&color[v], c, __ATOMIC_RELEASE);
+      return true;
+    };
+    const unsigned T = host_threads();
+    std::vector<uint32_t> pending(nvar);
+    std::iota(pending.begin(), pending.end(), 0u);
+    while (!pending.empty()) {
+      if (T == 1 || pending.size() < (1u << 14)) {
+        std::vector<uint32_t> stamp(ncolor + 2, 0);
+        for (uint32_t v : pending) first_fit(v, stamp);  // in id order every variable is ready
+        break;
+      }
+      std::vector<std::vector<uint32_t>> later(T);
+      parallel_ranges(pending.size(), T, [&](uint64_t i0, uint64_t i1, unsigned t) {
+        std::vector<uint32_t> stamp(64, 0);
+        for (uint64_t i = i0; i < i1; ++i)
+          if (!first_fit(pending[i], stamp)) later[t].push_back(pending[i]);
+      });
+      std::vector<uint32_t> rest;
+      for (auto &l : later) rest.insert(rest.end(), l.begin(), l.end());  // still ascending
+      const bool stalled = rest.size() * 8 > pending.size() * 7;
+      pending.swap(rest);
+      if (stalled && !pending.empty()) {
+        std::vector<uint32_t> stamp(64, 0);
+        for (uint32_t v : pending) first_fit(v, stamp);
+        break;
+      }
+    }
+    uint32_t mx = 0;
+    for (uint64_t v = 0; v < nvar; ++v) mx = std::max(mx, color[v]);
+    ncolor = mx + 1;
+  }
+  // Pass 2 (sequential: the least-loaded choice depends on every earlier one)
+  std::vector<uint32_t> stamp;  // stamp[c] == v+1 : colour c is taken by a neighbour of v
+  std::vector<uint64_t> load;
+  {
+    const uint32_t K = ncolor;
+    std::fill(color.begin(), color.end(), 0xffffffffu);
+    stamp.assign(K + 1, 0);
+    load.assign(K + 1, 0);
+    ncolor = 1;
+    for (uint64_t v = 0; v < nvar; ++v) {
+      // the colours of the neighbours are random reads: ask for those of variable v + 16 now
+      if (v + 16 < nvar)
+        for (uint64_t i = nb_ptr[v + 16]; i < nb_ptr[v + 17]; ++i) __builtin_prefetch(&color[nb[i]]);
+      for (uint64_t i = nb_ptr[v]; i < nb_ptr[v + 1]; ++i) {
+        uint32_t c = color[nb[i]];
+        if (c == 0xffffffffu) continue;
+        stamp[c] = (uint32_t)v + 1;
+      }
+      uint32_t c = 0xffffffffu;
+      for (uint32_t k = 0; k < K; ++k)
+        if (stamp[k] != (uint32_t)v + 1 && (c == 0xffffffffu || load[k] < load[c])) c = k;
+      if (c == 0xffffffffu) {  // every planned colour is taken around v: open a new one
+        c = K;
+        while (c < stamp.size() && stamp[c] == (uint32_t)v + 1) ++c;
+      }
+      if (c + 1 >= stamp.size()) { stamp.resize(c + 2, 0); load.resize(c + 2, 0); }
+      color[v] = c;
+      ++load[c];
+      ncolor = std::max(ncolor, c + 1);
+    }
+  }
+  return ncolor;
+}
+
 std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *err) {
   *err = DWG_ERR_INVALID;
   *g = GraphImage();
@@ -329,123 +457,7 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
     }
   }
   if (schedule == DWG_SCHED_CHROMATIC && coupled) {
-    // conflict lists (the other variables of every incident factor; repeats are harmless), built
-    // in parallel; the two greedy passes below then touch nothing but these and color[]
-    std::vector<uint64_t> nb_ptr(nvar + 1, 0);
-    auto for_neighbours = [&](uint64_t v, auto &&fn) {
-      uint32_t last_f = 0xffffffffu;
-      for (uint32_t i = deg[v]; i < inc_end[v]; ++i) {
-        uint32_t f = inc[i].fid;
-        if (f == last_f) continue;
-        last_f = f;
-        const uint64_t a = raw.fac_ptr[f], b = raw.fac_ptr[f + 1];
-        if (b - a < 2) continue;
-        for (uint64_t e = a; e < b; ++e)
-          if (raw.edge_vid[e] != v) fn((uint32_t)raw.edge_vid[e]);
-      }
-    };
-    parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
-      for (uint64_t v = v0; v < v1; ++v) {
-        uint64_t n = 0;
-        for_neighbours(v, [&](uint32_t) { ++n; });
-        nb_ptr[v + 1] = n;
-      }
-    });
-    for (uint64_t v = 0; v < nvar; ++v) nb_ptr[v + 1] += nb_ptr[v];
-    BulkVec<uint32_t> nb(nb_ptr[nvar]);
-    parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
-      for (uint64_t v = v0; v < v1; ++v) {
-        uint64_t o = nb_ptr[v];
-        for_neighbours(v, [&](uint32_t u) { nb[o++] = u; });
-      }
-    });
-    // Pass 1, first fit, finds how many colours K the graph needs; pass 2 recolours with the
-    // least-loaded admissible colour among those K, so that every class is large enough to
-    // fill the GPU (first fit alone leaves a tail of tiny classes = latency-bound launches).
-    // Pass 1 in parallel wavefronts.  The first-fit colour of v depends only on the colours of its
-    // lower-numbered neighbours, so colouring v once all of those are coloured gives exactly the
-    // sequential result, whatever the interleaving: every round colours the pending variables that
-    // are ready (in id order inside each thread's range), the rest wait for the next round.  Graphs
-    // with long id-ordered dependency chains (v coupled to v+1) make little progress per round:
-    // the remainder is then finished sequentially.
-    {
-      std::fill(color.begin(), color.end(), 0xffffffffu);
-      auto first_fit = [&](uint32_t v, std::vector<uint32_t> &stamp) -> bool {  // false: not ready yet
-        for (uint64_t i = nb_ptr[v]; i < nb_ptr[v + 1]; ++i) {
-          const uint32_t u = nb[i];
-          const uint32_t c = __atomic_load_n(&color[u], __ATOMIC_ACQUIRE);
-          if (c == 0xffffffffu) {
-            if (u < v) return false;
-            continue;
-          }
-          if (c >= stamp.size()) stamp.resize(c + 2, 0);
-          stamp[c] = v + 1;
-        }
-        uint32_t c = 0;
-        while (c < stamp.size() && stamp[c] == v + 1) ++c;
-        __atomic_store_n(&color[v], c, __ATOMIC_RELEASE);
-        return true;
-      };
-      const unsigned T = host_threads();
-      std::vector<uint32_t> pending(nvar);
-      std::iota(pending.begin(), pending.end(), 0u);
-      while (!pending.empty()) {
-        if (T == 1 || pending.size() < (1u << 14)) {
-          std::vector<uint32_t> stamp(ncolor + 2, 0);
-          for (uint32_t v : pending) first_fit(v, stamp);  // in id order every variable is ready
-          break;
-        }
-        std::vector<std::vector<uint32_t>> later(T);
-        parallel_ranges(pending.size(), T, [&](uint64_t i0, uint64_t i1, unsigned t) {
-          std::vector<uint32_t> stamp(64, 0);
-          for (uint64_t i = i0; i < i1; ++i)
-            if (!first_fit(pending[i], stamp)) later[t].push_back(pending[i]);
-        });
-        std::vector<uint32_t> rest;
-        for (auto &l : later) rest.insert(rest.end(), l.begin(), l.end());  // still ascending
-        const bool stalled = rest.size() * 8 > pending.size() * 7;
-        pending.swap(rest);
-        if (stalled && !pending.empty()) {
-          std::vector<uint32_t> stamp(64, 0);
-          for (uint32_t v : pending) first_fit(v, stamp);
-          break;
-        }
-      }
-      uint32_t mx = 0;
-      for (uint64_t v = 0; v < nvar; ++v) mx = std::max(mx, color[v]);
-      ncolor = mx + 1;
-    }
-    // Pass 2 (sequential: the least-loaded choice depends on every earlier one)
-    std::vector<uint32_t> stamp;  // stamp[c] == v+1 : colour c is taken by a neighbour of v
-    std::vector<uint64_t> load;
-    {
-      const uint32_t K = ncolor;
-      std::fill(color.begin(), color.end(), 0xffffffffu);
-      stamp.assign(K + 1, 0);
-      load.assign(K + 1, 0);
-      ncolor = 1;
-      for (uint64_t v = 0; v < nvar; ++v) {
-        // the colours of the neighbours are random reads: ask for those of variable v + 16 now
-        if (v + 16 < nvar)
-          for (uint64_t i = nb_ptr[v + 16]; i < nb_ptr[v + 17]; ++i) __builtin_prefetch(&color[nb[i]]);
-        for (uint64_t i = nb_ptr[v]; i < nb_ptr[v + 1]; ++i) {
-          uint32_t c = color[nb[i]];
-          if (c == 0xffffffffu) continue;
-          stamp[c] = (uint32_t)v + 1;
-        }
-        uint32_t c = 0xffffffffu;
-        for (uint32_t k = 0; k < K; ++k)
-          if (stamp[k] != (uint32_t)v + 1 && (c == 0xffffffffu || load[k] < load[c])) c = k;
-        if (c == 0xffffffffu) {  // every planned colour is taken around v: open a new one
-          c = K;
-          while (c < stamp.size() && stamp[c] == (uint32_t)v + 1) ++c;
-        }
-        if (c + 1 >= stamp.size()) { stamp.resize(c + 2, 0); load.resize(c + 2, 0); }
-        color[v] = c;
-        ++load[c];
-        ncolor = std::max(ncolor, c + 1);
-      }
-    }
+    ncolor = colour_variables(raw, nvar, inc, deg, inc_end, color);
   } else if (schedule == DWG_SCHED_CHROMATIC) {
     // nothing couples two variables: one class, i.e. the hogwild launch, and it is exact
   }

@@ -173,6 +173,7 @@ int gibbs(const CmdParser &args) {
       R.comms.clear();
     }
   }
+  lap("replicas up (CUDA context, upload)");
   void *const *comms = R.comms.empty() ? nullptr : R.comms.data();
   auto compute_n_epochs = [&](uint64_t n) {  // :280-282
     return (uint64_t)std::ceil((double)n / n_samplers);
@@ -212,7 +213,7 @@ int gibbs(const CmdParser &args) {
     }
     for (auto *h : R.hs) TRY(dwg_sync(h));
     std::cout << "TOTAL LEARNING TIME: " << t_total.elapsed() << " sec." << std::endl;
-    lap("replicas up + learning");
+    lap("learning");
   }
 
   // ---- dump_weights, :245-258 (written even with -l 0) ----

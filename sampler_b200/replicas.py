@@ -105,13 +105,19 @@ class ReplicaGroup:
         return n_epoch
 
     # -- aggregate_marginals_from ------------------------------------------------------------
-    def reduce_tallies_device(self):
-        """NCCL only: sum the u32 tally arrays onto rank 0 on the replica's stream (the timed
-        exchange of bench.py).  The per-variable sample counts are implicit (sweeps run)."""
+    def reduce_tallies_device(self, to_all: bool = True):
+        """NCCL only: sum the u32 tally arrays over the replicas on the replica's stream (the timed
+        exchange of bench.py); rank 0 reads the result.  to_all: an all-reduce instead of a reduce
+        onto rank 0 -- on NVSwitch the sum is formed in the switch (NVLS) and 40 MB take about half
+        the time of the tree reduce (profiles/r2_bench_c2_8gpu.json); every rank then holds the
+        aggregate, which only rank 0 reports.  The per-variable sample counts are implicit."""
         assert self.on_device
         import torch
         with torch.cuda.stream(self._stream):
-            self.dist.reduce(self._t_t, dst=0)
+            if to_all:
+                self.dist.all_reduce(self._t_t)
+            else:
+                self.dist.reduce(self._t_t, dst=0)
 
     def aggregate(self):
         """(tallies[num_values], nsamples[num_variables]) summed over replicas; valid on rank 0."""

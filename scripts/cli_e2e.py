@@ -16,10 +16,48 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def bundled():
+    """configs[0] (C1): whole-process wall time of `dw gibbs` on the reference's bundled graphs with
+    their own dw-args -- ours (one GPU, the multi-epoch sequential launches) beside the unmodified
+    reference binary oracle/_ref/dw on the host cores (-t 1, the schedule ours reproduces bit for bit,
+    and its default thread count).  Median of 5 runs each; prints one JSON line per graph."""
+    from sampler_b200 import _build
+    gdir = os.path.join(ROOT, "tests", "golden", "graphs")
+    ref = os.path.join(ROOT, "oracle", "_ref", "dw")
+    for name in sorted(os.listdir(gdir)):
+        g = os.path.join(gdir, name)
+        dwargs = open(os.path.join(g, "dw-args")).read().split()
+        files = ["-m", g + "/graph.meta", "-v", g + "/graph.variables", "-f", g + "/graph.factors", "-w", g + "/graph.weights"]
+        if os.path.getsize(g + "/graph.domains"):
+            files += ["--domains", g + "/graph.domains"]
+        row = {"graph": name, "dw_args": " ".join(dwargs)}
+        for label, exe, extra in (("ours_gpu", _build.DW, ["-c", "1"]), ("reference_t1", ref, ["-t", "1", "-c", "1"]), ("reference_default", ref, [])):
+            if not os.path.exists(exe):
+                row[label + "_s"] = None
+                continue
+            times = []
+            for _ in range(5):
+                d = tempfile.mkdtemp(prefix="dwc1_")
+                try:
+                    t0 = time.time()
+                    r = subprocess.run([exe, "gibbs"] + files + ["-o", d, "-q"] + dwargs + extra, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+                    times.append(time.time() - t0)
+                    if r.returncode:
+                        row[label + "_error"] = r.stderr[-300:]
+                finally:
+                    shutil.rmtree(d, ignore_errors=True)
+            row[label + "_s"] = sorted(times)[len(times) // 2]
+        print(json.dumps(row), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nvar", type=int, default=10_000_000)
+    ap.add_argument("--bundled", action="store_true", help="C1: the reference's bundled graphs, ours vs oracle/_ref/dw")
     args = ap.parse_args()
+    if args.bundled:
+        return bundled()
     from sampler_b200 import _build, graphgen, graphio
     raw = graphgen.c2_boolean(args.nvar)
     d = tempfile.mkdtemp(prefix="dwcli_")
