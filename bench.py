@@ -62,8 +62,8 @@ WORKLOADS = {
                learn=dict(n_epoch=0, alpha=0.01, diminish=0.95, reg_param=0.01), kernel="k_sell_infer_staged<MULTI=0,FV=0>"),
 }
 LEARN = WORKLOADS["c2"]["learn"]
-# the final tally aggregation: all-reduce (NVLS on NVSwitch; default) or reduce onto rank 0 (DWG_BENCH_TALLY_REDUCE=root)
-TO_ALL = os.environ.get("DWG_BENCH_TALLY_REDUCE", "all") != "root"
+# the final tally aggregation: reduce onto rank 0 (default; the faster one on 8 B200s) or all-reduce (DWG_BENCH_TALLY_REDUCE=all)
+TO_ALL = os.environ.get("DWG_BENCH_TALLY_REDUCE", "root") == "all"
 
 
 def make_raw(workload, nvar):
@@ -356,8 +356,8 @@ def ours(args):
         dist.broadcast(warm, src=0)
         torch.cuda.synchronize()
     reps = []
-    for rep in range(3):  # three whole repetitions, the median is reported (an allocation of 0.6 GB right
-        barrier()         # after a free occasionally costs the driver tens of ms)
+    for rep in range(5):  # five whole repetitions, the median is reported (the first maps the device memory
+        barrier()         # of the replica; later ones find it in the library's pool)
         t0 = time.time()
         s2 = sb.Sampler(graph, device=local, sample_evidence=True, reg_param=LEARN["reg_param"], seed=99 + rep, replica=rank,
                         defer_upload=(world > 1 and rank != 0))
@@ -382,10 +382,10 @@ def ours(args):
         s2.close()
         torch.cuda.synchronize()
     reps.sort()
-    e2e_s, p_up, p_sw, p_dn = reps[1]
+    e2e_s, p_up, p_sw, p_dn = reps[len(reps) // 2]
     e2e_value = nvar * world * args.steps / e2e_s
-    e2e_parts = "median of 3 repetitions (%s ms): graph to the device(s) %.1f ms, sweeps%s %.1f ms, tallies to the host %.1f ms (rank 0)" % (
-        ", ".join("%.1f" % (1e3 * r[0]) for r in reps), 1e3 * p_up, " + tally reduction" if world > 1 else "", 1e3 * p_sw, 1e3 * p_dn)
+    e2e_parts = "median of %d repetitions (%s ms): graph to the device(s) %.1f ms, sweeps%s %.1f ms, tallies to the host %.1f ms (rank 0)" % (
+        len(reps), ", ".join("%.1f" % (1e3 * r[0]) for r in reps), 1e3 * p_up, " + tally reduction" if world > 1 else "", 1e3 * p_sw, 1e3 * p_dn)
 
     if rank != 0:
         if dist is not None:

@@ -114,15 +114,62 @@ struct UploadScope {
 };
 thread_local UploadScope g_upload;
 
+// Device memory comes from the device's default stream-ordered pool with an unlimited release
+// threshold: what a destroyed handle frees stays mapped in the process, so the next dwg_create (a
+// replica per inference request, the repetitions of a benchmark) does not pay the driver for mapping
+// 0.6 GB again -- that cost was 20 to 130 ms at random, more than the 12 ms upload it precedes.
+// Allocation and release are ordered on the legacy default stream and completed before returning
+// (the handles work on their own non-blocking streams); DWG_NO_POOL=1 restores cudaMalloc.
+static bool dev_pool_on(int dev) {
+  static std::mutex mu;
+  static std::vector<int> state;  // per device: 0 unknown, 1 pool, 2 plain
+  std::lock_guard<std::mutex> lock(mu);
+  if ((int)state.size() <= dev) state.resize(dev + 1, 0);
+  if (!state[dev]) {
+    int ok = 0;
+    cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev);
+    const char *e = getenv("DWG_NO_POOL");
+    cudaMemPool_t pool = nullptr;
+    if (ok && !(e && *e == '1') && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      ok = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+    } else ok = 0;
+    cudaGetLastError();
+    state[dev] = ok ? 1 : 2;
+  }
+  return state[dev] == 1;
+}
+static cudaError_t dev_alloc(void **p, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!dev_pool_on(dev)) return cudaMalloc(p, bytes);
+  cudaError_t e = cudaMallocAsync(p, bytes, (cudaStream_t)0);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize((cudaStream_t)0);
+}
+static void dev_free(void *p) {
+  cudaPointerAttributes a{};
+  int dev = 0;
+  if (cudaPointerGetAttributes(&a, p) == cudaSuccess) dev = a.device;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != dev) cudaSetDevice(dev);
+  if (dev_pool_on(dev)) {
+    cudaFreeAsync(p, (cudaStream_t)0);
+    cudaStreamSynchronize((cudaStream_t)0);
+  } else cudaFree(p);
+  if (cur != dev) cudaSetDevice(cur);
+}
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { if (p) dev_free(p); }
   cudaError_t alloc(size_t count) {
     n = count;
     // 16 B of slack so tile-granular (16 B) bulk copies may overrun the logical end
-    return cudaMalloc((void **)&p, count * sizeof(T) + 16);
+    return dev_alloc((void **)&p, count * sizeof(T) + 16);
   }
   template <typename S>
   cudaError_t upload(const std::vector<S> &v, cudaStream_t s) {

@@ -105,12 +105,12 @@ class ReplicaGroup:
         return n_epoch
 
     # -- aggregate_marginals_from ------------------------------------------------------------
-    def reduce_tallies_device(self, to_all: bool = True):
-        """NCCL only: sum the u32 tally arrays over the replicas on the replica's stream (the timed
-        exchange of bench.py); rank 0 reads the result.  to_all: an all-reduce instead of a reduce
-        onto rank 0 -- on NVSwitch the sum is formed in the switch (NVLS) and 40 MB take about half
-        the time of the tree reduce (profiles/r2_bench_c2_8gpu.json); every rank then holds the
-        aggregate, which only rank 0 reports.  The per-variable sample counts are implicit."""
+    def reduce_tallies_device(self, to_all: bool = False):
+        """NCCL only: sum the u32 tally arrays onto rank 0 on the replica's stream (the timed
+        exchange of bench.py).  The per-variable sample counts are implicit (sweeps run).
+        to_all: an all-reduce instead (every rank ends with the aggregate) -- measured on 8 B200s
+        with 40 MB of tallies it is the slower of the two (0.81 ms against 0.27 ms for the reduce,
+        profiles/r2b_bench_c2_8gpu*.json), so the reduce onto the root stays the default."""
         assert self.on_device
         import torch
         with torch.cuda.stream(self._stream):
