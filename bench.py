@@ -305,7 +305,7 @@ def ours(args):
     smp.clear_tallies()
     smp.infer_epochs(args.warmup)
     if dist is not None:
-        group.reduce_tallies_device(TO_ALL)  # warm-up of the collective too (its first call sets up the channels)
+        group.reduce_tallies_device(TO_ALL, max_count=args.warmup * world)  # warm-up of the collective too (its first call sets up the channels)
     smp.clear_tallies()
     smp.sync()
     torch.cuda.synchronize()
@@ -319,7 +319,7 @@ def ours(args):
         smp.infer_epochs(args.steps)
         e1.record(stream)
         if dist is not None:
-            group.reduce_tallies_device(TO_ALL)  # sample tallies reduced at the end of inference
+            group.reduce_tallies_device(TO_ALL, max_count=args.steps * world)  # sample tallies reduced at the end of inference (narrow counters)
         e2.record(stream)
     smp.sync()
     torch.cuda.synchronize()
@@ -367,7 +367,7 @@ def ours(args):
         t_up = time.time()
         s2.infer_epochs(args.steps)
         if world > 1:
-            g2.reduce_tallies_device(TO_ALL)
+            g2.reduce_tallies_device(TO_ALL, max_count=args.steps * world)
         s2.sync()
         t_sw = time.time()
         if rank == 0:

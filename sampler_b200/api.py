@@ -109,6 +109,8 @@ def load(build: bool = False):
     L.dwg_weights_device_ptr.argtypes = [vp]
     L.dwg_tallies_device_ptr.restype = vp
     L.dwg_tallies_device_ptr.argtypes = [vp]
+    L.dwg_tallies_pack.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
+    L.dwg_tallies_unpack.argtypes = [vp, i32]
     L.dwg_finish_weight_average.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.dwg_average_weights_nccl.argtypes = [vp, vp, i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.dwg_eval_potentials.argtypes = [vp, u64, vp, vp, i32, vp]
@@ -337,6 +339,15 @@ class Sampler:
 
     def tallies_device_ptr(self) -> int:
         return load().dwg_tallies_device_ptr(self._h) or 0
+
+    def tallies_pack(self, fields: int):
+        """(device pointer, words): the tallies as `fields` narrow counters per u32 word (dwg.h)"""
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(load().dwg_tallies_pack(self._h, int(fields), C.byref(p), C.byref(n)))
+        return p.value or 0, int(n.value)
+
+    def tallies_unpack(self, fields: int):
+        _check(load().dwg_tallies_unpack(self._h, int(fields)))
 
     def finish_weight_average(self, n_replicas: int, want_norms=True):
         a, b = C.c_double(), C.c_double()

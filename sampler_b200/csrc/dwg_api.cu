@@ -165,7 +165,15 @@ template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
-  ~DevBuf() { if (p) dev_free(p); }
+  ~DevBuf() { reset(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  void reset() {
+    if (p) dev_free(p);
+    p = nullptr;
+    n = 0;
+  }
   cudaError_t alloc(size_t count) {
     n = count;
     // 16 B of slack so tile-granular (16 B) bulk copies may overrun the logical end
@@ -269,7 +277,7 @@ struct dwg_handle {
   std::vector<std::pair<void *, size_t>> segments;  // the graph arrays on the device (dwg_graph_segments)
   // tally download: device row of every (variable, value) in ABI order (uploaded with the graph) and
   // the gathered tallies; the page-locked landing pieces are the process's (g_landing)
-  DevBuf<uint32_t> row_of_value, tallies_abi;
+  DevBuf<uint32_t> row_of_value, tallies_abi, tallies_packed;
   cudaEvent_t piece_done[2] = {nullptr, nullptr};
   ~dwg_handle() {
     for (cudaEvent_t e : piece_done)
@@ -1252,6 +1260,47 @@ void *dwg_stream(dwg_handle *h) {
 }
 void *dwg_weights_device_ptr(dwg_handle *h) { return h ? (void *)h->weights.p : nullptr; }
 void *dwg_tallies_device_ptr(dwg_handle *h) { return h ? (void *)h->tallies.p : nullptr; }
+
+int dwg_tallies_pack(dwg_handle *h, int fields, void **words, uint64_t *nwords) {
+  if (!h || !words || !nwords) return fail(DWG_ERR_INVALID, "null argument");
+  if (fields != 1 && fields != 2 && fields != 4) return fail(DWG_ERR_INVALID, "fields must be 1, 2 or 4");
+  h->chain_open = false;
+  CU(cudaSetDevice(h->device));
+  const uint64_t n = h->img->ndrow, nw = (n + fields - 1) / fields;
+  if (h->tallies_packed.n < nw) {
+    h->tallies_packed.reset();
+    CU(h->tallies_packed.alloc(nw));
+  }
+  const uint32_t blocks = (uint32_t)((nw + 255) / 256);
+  if (nw) {
+    if (fields == 4) k_pack_tallies<4><<<blocks, 256, 0, h->stream>>>(h->tallies_packed.p, h->tallies.p, (uint32_t)n);
+    else if (fields == 2) k_pack_tallies<2><<<blocks, 256, 0, h->stream>>>(h->tallies_packed.p, h->tallies.p, (uint32_t)n);
+    else k_pack_tallies<1><<<blocks, 256, 0, h->stream>>>(h->tallies_packed.p, h->tallies.p, (uint32_t)n);
+    ++g_launches;
+  }
+  CU(cudaGetLastError());
+  *words = h->tallies_packed.p;
+  *nwords = nw;
+  return DWG_OK;
+}
+
+int dwg_tallies_unpack(dwg_handle *h, int fields) {
+  if (!h) return fail(DWG_ERR_INVALID, "null handle");
+  if (fields != 1 && fields != 2 && fields != 4) return fail(DWG_ERR_INVALID, "fields must be 1, 2 or 4");
+  const uint64_t n = h->img->ndrow, nw = (n + fields - 1) / fields;
+  if (h->tallies_packed.n < nw || !h->tallies_packed.p) return fail(DWG_ERR_INVALID, "dwg_tallies_unpack without dwg_tallies_pack");
+  h->chain_open = false;
+  CU(cudaSetDevice(h->device));
+  const uint32_t blocks = (uint32_t)((nw + 255) / 256);
+  if (nw) {
+    if (fields == 4) k_unpack_tallies<4><<<blocks, 256, 0, h->stream>>>(h->tallies.p, h->tallies_packed.p, (uint32_t)n);
+    else if (fields == 2) k_unpack_tallies<2><<<blocks, 256, 0, h->stream>>>(h->tallies.p, h->tallies_packed.p, (uint32_t)n);
+    else k_unpack_tallies<1><<<blocks, 256, 0, h->stream>>>(h->tallies.p, h->tallies_packed.p, (uint32_t)n);
+    ++g_launches;
+  }
+  CU(cudaGetLastError());
+  return DWG_OK;
+}
 
 int dwg_clear_tallies(dwg_handle *h) {
   if (!h) return fail(DWG_ERR_INVALID, "null handle");

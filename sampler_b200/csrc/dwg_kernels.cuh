@@ -299,6 +299,31 @@ __global__ void k_gather_u32(uint32_t *dst, const uint32_t *src, const uint32_t 
   if (i < n) dst[i] = src[__ldg(idx + i)];
 }
 
+// narrow counters for the cross-replica exchange: FIELDS tallies of 32 / FIELDS bits per word
+template <int FIELDS>
+__global__ void k_pack_tallies(uint32_t *words, const uint32_t *t, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((uint64_t)i * FIELDS >= n) return;
+  uint32_t w = 0;
+#pragma unroll
+  for (int f = 0; f < FIELDS; ++f) {
+    const uint32_t k = i * FIELDS + f;
+    if (k < n) w |= t[k] << (f * (32 / FIELDS));
+  }
+  words[i] = w;
+}
+template <int FIELDS>
+__global__ void k_unpack_tallies(uint32_t *t, const uint32_t *words, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((uint64_t)i * FIELDS >= n) return;
+  const uint32_t w = words[i];
+#pragma unroll
+  for (int f = 0; f < FIELDS; ++f) {
+    const uint32_t k = i * FIELDS + f;
+    if (k < n) t[k] = FIELDS == 1 ? w : (w >> (f * (32 / FIELDS))) & ((1u << (32 / FIELDS)) - 1u);
+  }
+}
+
 // tallies (schedule order, u32) += host-provided counts (aggregate_marginals_from)
 __global__ void k_add_u32(uint32_t *dst, const uint32_t *src, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

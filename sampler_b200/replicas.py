@@ -105,7 +105,7 @@ class ReplicaGroup:
         return n_epoch
 
     # -- aggregate_marginals_from ------------------------------------------------------------
-    def reduce_tallies_device(self, to_all: bool = False):
+    def reduce_tallies_device(self, to_all: bool = False, max_count: Optional[int] = None):
         """NCCL only: sum the u32 tally arrays onto rank 0 on the replica's stream (the timed
         exchange of bench.py).  The per-variable sample counts are implicit (sweeps run).
         to_all: an all-reduce instead (every rank ends with the aggregate) -- measured on 8 B200s
@@ -113,11 +113,20 @@ class ReplicaGroup:
         profiles/r2b_bench_c2_8gpu*.json), so the reduce onto the root stays the default."""
         assert self.on_device
         import torch
+        # max_count: an upper bound of every AGGREGATED tally (sweeps summed over the replicas).  Counters
+        # that fit 8 / 16 bits travel four / two to a word (dwg_tallies_pack): a quarter / half of the bytes
+        fields = 1 if max_count is None else 4 if max_count < (1 << 8) else 2 if max_count < (1 << 16) else 1
         with torch.cuda.stream(self._stream):
+            t = self._t_t
+            if fields > 1:
+                ptr, nwords = self.s.tallies_pack(fields)
+                t = torch.as_tensor(_DevArray(ptr, nwords, "<i4"), device=self._t_t.device)
             if to_all:
-                self.dist.all_reduce(self._t_t)
+                self.dist.all_reduce(t)
             else:
-                self.dist.reduce(self._t_t, dst=0)
+                self.dist.reduce(t, dst=0)
+            if fields > 1 and (to_all or self.rank == 0):
+                self.s.tallies_unpack(fields)
 
     def aggregate(self):
         """(tallies[num_values], nsamples[num_variables]) summed over replicas; valid on rank 0."""

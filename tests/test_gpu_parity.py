@@ -735,6 +735,39 @@ def test_two_replicas_one_gpu_average_and_aggregate():
     assert np.array_equal(t, ta + tb) and (n == 12).all()
 
 
+@pytest.mark.parametrize("shape", ["boolean", "categorical"])
+def test_narrow_counter_tally_exchange(shape):
+    """dwg_tallies_pack / dwg_tallies_unpack: the cross-replica sum of the tallies taken on words of
+    four 8-bit (two 16-bit) counters equals the sum of the u32 tallies as long as every aggregated
+    count fits its field -- two replicas on one device, the packed words added by torch"""
+    import torch
+    from sampler_b200 import graphgen
+    from sampler_b200.replicas import _DevArray
+    rng = np.random.default_rng(5)
+    raw = graphgen.c2_boolean(40_003, nweight=50) if shape == "boolean" else graphgen.c3_categorical(20_001, nweight=50)
+    g = sb.Graph.from_raw(raw)
+    dev = torch.device("cuda", 0)
+    for fields, sweeps in ((4, (100, 27)), (2, (300, 41)), (1, (3, 2))):
+        a = sb.Sampler(g, sample_evidence=True, seed=1, replica=0)
+        b = sb.Sampler(g, sample_evidence=True, seed=1, replica=1)
+        w = rng.normal(0, 1, raw.nweight)
+        a.set_weights(w); b.set_weights(w)
+        a.infer_epochs(sweeps[0]); b.infer_epochs(sweeps[1])
+        ta, _ = a.tallies(); tb, _ = b.tallies()
+        assert ta.max() > (255 if fields == 2 else 0)  # the 16-bit case really needs more than 8 bits
+        pa, na = a.tallies_pack(fields); pb, nb = b.tallies_pack(fields)
+        assert na == nb == -(-g.info.num_device_rows // fields)
+        a.sync(); b.sync()
+        wa = torch.as_tensor(_DevArray(pa, na, "<i4"), device=dev)
+        wb = torch.as_tensor(_DevArray(pb, nb, "<i4"), device=dev)
+        wa += wb  # what the reduce over the replicas does
+        torch.cuda.synchronize()
+        a.tallies_unpack(fields)
+        t, _ = a.tallies()
+        assert np.array_equal(t, ta + tb)
+        a.close(); b.close()
+
+
 def test_two_replicas_host_exchange_with_permuted_weight_ids():
     """the no-NCCL averaging path on a graph with more weights than the shared-memory table: the
     device holds the weights hottest-first (w_perm), dwg_get_weights / dwg_set_weight_sum speak
