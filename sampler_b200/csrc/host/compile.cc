@@ -228,6 +228,63 @@ static uint32_t colour_variables(const RawView &raw, uint64_t nvar, const IncVec
       ++load[c];
       ncolor = std::max(ncolor, c + 1);
     }
+    // Pass 3: the balancing pass strands a few variables whose neighbours hold all K planned colours in
+    // an overflow class of their own (C2: 448 of 10 M) -- a whole launch boundary per sweep for a class
+    // that cannot fill one SM.  Each is brought back by moving the neighbours that hold one planned
+    // colour c to another colour free around THEM (a one-step Kempe move); v then takes c.
+    if (ncolor > K) {
+      uint32_t tick = (uint32_t)nvar + 1;  // stamps beyond the per-variable ones of pass 2
+      std::vector<uint32_t> mark(stamp.size(), 0);
+      auto next_tick = [&]() {
+        if (++tick == 0) { std::fill(mark.begin(), mark.end(), 0u); tick = 1; }
+        return tick;
+      };
+      // a planned colour != avoid that no neighbour of u holds (the least loaded one), or none
+      auto free_colour = [&](uint32_t u, uint32_t avoid) -> uint32_t {
+        const uint32_t t = next_tick();
+        for (uint64_t i = nb_ptr[u]; i < nb_ptr[u + 1]; ++i) mark[color[nb[i]]] = t;
+        uint32_t best = 0xffffffffu;
+        for (uint32_t k = 0; k < K; ++k)
+          if (k != avoid && mark[k] != t && (best == 0xffffffffu || load[k] < load[best])) best = k;
+        return best;
+      };
+      std::vector<std::pair<uint32_t, uint32_t>> moves;
+      for (uint64_t v = 0; v < nvar; ++v) {
+        if (color[v] < K) continue;
+        for (uint32_t c = 0; c < K; ++c) {
+          moves.clear();
+          bool ok = true;
+          for (uint64_t i = nb_ptr[v]; i < nb_ptr[v + 1] && ok; ++i) {
+            const uint32_t u = nb[i];
+            if (color[u] != c) continue;
+            bool seen = false;  // (a neighbour listed twice: two shared factors)
+            for (auto &m : moves) seen |= m.first == u;
+            if (seen) continue;
+            const uint32_t c2 = free_colour(u, c);
+            if (c2 == 0xffffffffu) ok = false;
+            else moves.emplace_back(u, c2);
+          }
+          if (!ok) continue;
+          // the holders of c around v are pairwise non-adjacent (they shared a colour): their moves do not interact
+          for (auto &m : moves) { --load[c]; ++load[m.second]; color[m.first] = m.second; }
+          --load[color[v]];
+          color[v] = c;
+          ++load[c];
+          break;
+        }
+      }
+      // close the gaps empty overflow colours leave
+      std::vector<uint32_t> remap(load.size(), 0xffffffffu);
+      uint32_t used = 0;
+      for (uint32_t k = 0; k < load.size(); ++k)
+        if (load[k] || k < K) remap[k] = used++;
+      bool changed = false;
+      for (uint32_t k = 0; k < load.size(); ++k) changed |= remap[k] != 0xffffffffu && remap[k] != k;
+      if (changed) parallel_for(nvar, [&](uint64_t v0, uint64_t v1) { for (uint64_t v = v0; v < v1; ++v) color[v] = remap[color[v]]; });
+      ncolor = 1;
+      for (uint32_t k = 0; k < load.size(); ++k)
+        if (load[k]) ncolor = std::max(ncolor, remap[k] + 1);
+    }
   }
   return ncolor;
 }
