@@ -504,6 +504,10 @@ void cell_learn_launch(dwg_handle *h, uint32_t blocks, uint32_t threads, bool li
 int sell_setup(dwg_handle *h) {
   const GraphImage &m = *h->img;
   int rc = DWG_OK;
+#ifdef DWG_DEV_BUILD
+  if (!(m.has_multi && m.fv_mode == FV_ONE && !m.has_wide))
+    return fail(DWG_ERR_UNSUPPORTED, "development build (DWG_DEV_BUILD): only coupled Boolean graphs with unit feature values");
+#endif
 #define CALL(MU, FV, WD) rc = sell_setup_t<MU, FV, WD>(h)
   SELL_SWITCH(CALL)
 #undef CALL

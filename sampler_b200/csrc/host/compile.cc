@@ -289,6 +289,479 @@ static uint32_t colour_variables(const RawView &raw, uint64_t nvar, const IncVec
   return ncolor;
 }
 
+// Per-weight statistics of a learning sweep, from the CSR rows of a compiled image (the curvature-
+// aware batch update of the CSR kernels and the epoch plan of the live-weight kernels read them).
+static void class_statistics(const RawView &raw, GraphImage *g, uint64_t nvar_pad, uint32_t ncolor, uint64_t nweight,
+                             uint64_t ow) {
+  // ---- per colour class, per weight: how many SGD updates one learning launch makes (N) and
+  // their summed curvature bound (Q), for the semi-implicit batch update (dwg_kernels.cuh).
+  // q = (fv * sign range)^2 / 4 >= Var(f | rest): the conditional is a Bernoulli. ----
+  {
+    uint64_t cells = (uint64_t)ncolor * nweight;
+    g->cls_shared = g->sell || cells > (64ull << 20);  // sell: whole-graph sums; too many cells: one class-averaged row
+    uint64_t rows_n = g->cls_shared ? 1 : ncolor;
+    g->cls_N_evid.assign(rows_n * nweight, 0.f); g->cls_Q_evid.assign(rows_n * nweight, 0.f);
+    g->cls_N_all.assign(rows_n * nweight, 0.f); g->cls_Q_all.assign(rows_n * nweight, 0.f);
+    g->cls_H_evid.assign(rows_n * nweight, 0.f); g->cls_H_all.assign(rows_n * nweight, 0.f);
+    auto srange = [](uint32_t fc, uint64_t n) -> double {
+      switch (fc) {
+        case FC_AND: case FC_OR: case FC_EQUAL: case FC_IMPLY_NATURAL: return 2.0;
+        case FC_LINEAR: return n > 1 ? (double)(n - 1) : 1.0;
+        case FC_RATIO: return n > 1 ? std::log2((double)n) : 1.0;
+        default: return 1.0;
+      }
+    };
+    // delta(e) = |fv| * (sign range) of record e.  One SGD step of variable v moves weight k
+    // by a gradient whose covariance over the draw is p(1-p) * delta delta^T <= 1/4 delta delta^T;
+    // diag(|delta_k| * sum_j |delta_j|) dominates delta delta^T, so
+    //   q(e) = 1/4 * delta(e) * sum_{e' learnable in the row} delta(e')
+    // summed over a launch bounds the curvature of ALL weights moving together (the features
+    // of one variable are perfectly correlated: a per-weight diagonal alone would overshoot).
+    auto walk_row = [&](uint64_t r, auto &&fn) {
+      uint64_t oc = g->has_multi ? g->row_oth[r] : 0;
+      for (uint64_t e = g->row_ptr[r]; e < g->row_ptr[r + 1]; ++e) {
+        uint8_t tag = g->e_tag[e];
+        uint32_t form = tag >> TAG_FORM_SHIFT;
+        uint64_t n = form != FORM_GENERAL ? form + 1 : g->oth[oc * ow];
+        oc += form != FORM_GENERAL ? form : 1 + n;
+        uint32_t w = g->e_wid[e];
+        if (raw.w_fixed[g->w_perm[w]]) continue;
+        double fv = g->fv_mode == FV_F32 ? g->e_fv32[e] : g->fv_mode == FV_F64 ? g->e_fv64[e] : 1.0;
+        fn(w, std::fabs(fv) * srange(tag & TAG_FUNC_MASK, n));
+      }
+    };
+    if (g->sell) {
+      // Sliced-ELL graphs learn in ONE visit order over all classes (learn_visit below): whole-graph
+      // sums, one row.  Accumulated as 2^-20 fixed point with integer atomics: the result does not
+      // depend on the thread count or the interleaving.
+      g->cls_shared = true;
+      std::vector<uint64_t> acc(6 * nweight, 0);
+      auto fx = [](double x) { return (uint64_t)std::llround(x * 1048576.0); };
+      parallel_for(nvar_pad, [&](uint64_t d0, uint64_t d1) {
+        for (uint64_t d = d0; d < d1; ++d) {
+          uint64_t v = g->perm[d];
+          if (v == 0xffffffffu) continue;
+          const bool ev = g->var_is_evid[v];
+          double rowsum = 0;
+          walk_row(d, [&](uint32_t, double delta) { rowsum += delta; });
+          walk_row(d, [&](uint32_t w, double delta) {
+            const uint64_t q = fx(0.25 * delta * rowsum), hd = fx(0.25 * delta * delta);
+            __atomic_fetch_add(&acc[0 * nweight + w], 1ull << 20, __ATOMIC_RELAXED);
+            __atomic_fetch_add(&acc[1 * nweight + w], q, __ATOMIC_RELAXED);
+            __atomic_fetch_add(&acc[2 * nweight + w], hd, __ATOMIC_RELAXED);
+            if (ev) {
+              __atomic_fetch_add(&acc[3 * nweight + w], 1ull << 20, __ATOMIC_RELAXED);
+              __atomic_fetch_add(&acc[4 * nweight + w], q, __ATOMIC_RELAXED);
+              __atomic_fetch_add(&acc[5 * nweight + w], hd, __ATOMIC_RELAXED);
+            }
+          });
+        }
+      });
+      for (uint64_t w = 0; w < nweight; ++w) {
+        g->cls_N_all[w] = (float)((double)acc[0 * nweight + w] / 1048576.0);
+        g->cls_Q_all[w] = (float)((double)acc[1 * nweight + w] / 1048576.0);
+        g->cls_H_all[w] = (float)((double)acc[2 * nweight + w] / 1048576.0);
+        g->cls_N_evid[w] = (float)((double)acc[3 * nweight + w] / 1048576.0);
+        g->cls_Q_evid[w] = (float)((double)acc[4 * nweight + w] / 1048576.0);
+        g->cls_H_evid[w] = (float)((double)acc[5 * nweight + w] / 1048576.0);
+      }
+    } else {
+    // every class owns its row of the tables: classes in parallel (the float sums of a row keep
+    // their sequential order); a shared row is filled by one thread
+    parallel_ranges(ncolor, g->cls_shared ? 1u : std::min<unsigned>(ncolor, host_threads()),
+                    [&](uint64_t c0, uint64_t c1, unsigned) {
+    for (uint64_t c = c0; c < c1; ++c) {
+      uint64_t base = g->cls_shared ? 0 : (uint64_t)c * nweight;
+      for (uint64_t d = g->color_start[c]; d < g->color_start[c + 1]; ++d) {
+        uint64_t v = g->perm[d];
+        if (v == 0xffffffffu) continue;
+        bool cat = g->var_dtype[v], ev = g->var_is_evid[v];
+        uint64_t r0 = g->has_categorical ? g->var_row[d] : d;
+        uint64_t r = cat ? r0 + std::min<uint64_t>(g->evid_val[d], raw.var_card[v] ? raw.var_card[v] - 1 : 0) : r0;
+        if (cat && raw.var_card[v] == 0) continue;
+        double rowsum = 0;
+        walk_row(r, [&](uint32_t, double delta) { rowsum += delta; });
+        const float one = cat ? 2.f : 1.f;  // a categorical step also visits the row of the free value
+        walk_row(r, [&](uint32_t w, double delta) {
+          float q = (float)(0.25 * delta * rowsum) * one, hd = (float)(0.25 * delta * delta) * one;
+          g->cls_N_all[base + w] += one; g->cls_Q_all[base + w] += q; g->cls_H_all[base + w] += hd;
+          if (ev) { g->cls_N_evid[base + w] += one; g->cls_Q_evid[base + w] += q; g->cls_H_evid[base + w] += hd; }
+        });
+      }
+    }
+    }, 1);
+    if (g->cls_shared && !g->sell)
+      for (uint64_t w = 0; w < nweight; ++w) {
+        g->cls_N_evid[w] /= ncolor; g->cls_Q_evid[w] /= ncolor; g->cls_H_evid[w] /= ncolor;
+        g->cls_N_all[w] /= ncolor; g->cls_Q_all[w] /= ncolor; g->cls_H_all[w] /= ncolor;
+      }
+    }
+  }
+
+}
+
+// ---- sliced-ELL blob of a Boolean graph (graph_image.h) from the CSR rows of a compiled image.
+// wide[v]: variable v owns its slice(s) (warp per variable); wide_slices(v): how many. ----
+template <typename WideSlices>
+static std::string build_sell_blob(const RawView &raw, GraphImage *g, uint64_t nvar, uint64_t nvar_pad, uint32_t ncolor,
+                                   const std::vector<uint8_t> &wide, WideSlices &&wide_slices, int *err) {
+  // ---- sliced-ELL blob (graph_image.h): per 32-variable slice one contiguous run of words:
+  // header, unary records (+ feature values), multi records (+ feature values), others.
+  // A warp streams its slice with coalesced 128 B requests, every record exactly once. ----
+  if (g->sell) {
+    const uint64_t nslice = nvar_pad / 32;
+    const uint64_t fvw = g->fv_mode == FV_F32 ? 1 : g->fv_mode == FV_F64 ? 2 : 0;  // words per value
+    g->sl_off.assign(nslice + 1, 0);
+    auto is_unary = [&](uint64_t e) { return (g->e_tag[e] >> TAG_FORM_SHIFT) == 0; };
+    // slice shapes.  A slice whose first slot holds a wide variable is that variable's alone: record
+    // k of a section goes to lane k % 32, column k / 32 (the lanes of a normal slice are variables)
+    // slice -> first slice of the wide variable it belongs to (itself for a one-slice wide variable)
+    std::vector<uint32_t> slice_hub(nslice, 0xffffffffu);
+    parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
+      for (uint64_t v = v0; v < v1; ++v)
+        if (wide[v]) {
+          const uint32_t s0 = g->inv[v] / 32, n = wide_slices(v);
+          for (uint32_t q = 0; q < n; ++q) slice_hub[s0 + q] = s0;
+        }
+    });
+    for (uint64_t sidx = 0; sidx < nslice; ++sidx)
+      if (slice_hub[sidx] != 0xffffffffu && wide_slices(g->perm[(uint64_t)slice_hub[sidx] * 32]) > 1)
+        g->part_slices.push_back((uint32_t)sidx);
+    auto slice_is_wide = [&](uint64_t sidx) { return slice_hub[sidx] != 0xffffffffu; };
+    for (uint64_t sidx = 0; sidx < nslice && !g->has_wide; ++sidx) g->has_wide = slice_is_wide(sidx);
+    // the share of part q of n: records [q * per, min(total, (q + 1) * per)) of a section
+    auto share = [](uint64_t total, uint32_t q, uint32_t n, uint64_t *lo, uint64_t *hi) {
+      const uint64_t per = (total + n - 1) / n;
+      *lo = std::min(total, per * q);
+      *hi = std::min(total, per * (q + 1));
+    };
+    auto others_span = [&](uint64_t e, uint64_t o) -> uint64_t {
+      const uint32_t form = g->e_tag[e] >> TAG_FORM_SHIFT;
+      return form != FORM_GENERAL ? form : 1 + g->oth[o];
+    };
+    std::vector<uint32_t> s_un(nslice), s_mu(nslice), s_oc(nslice);
+    uint64_t words = 0;
+    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
+      for (uint64_t sidx = a0; sidx < a1; ++sidx) {
+        uint32_t un = 0, mu = 0, oc = 0;
+        if (slice_is_wide(sidx)) {
+          const uint64_t d = (uint64_t)slice_hub[sidx] * 32;
+          const uint32_t q = (uint32_t)(sidx - slice_hub[sidx]), n = wide_slices(g->perm[d]);
+          uint64_t U = 0;
+          for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) U += is_unary(e);
+          const uint64_t M = g->row_ptr[d + 1] - g->row_ptr[d] - U;
+          uint64_t ulo, uhi, mlo, mhi;
+          share(U, q, n, &ulo, &uhi);
+          share(M, q, n, &mlo, &mhi);
+          uint32_t lane_oc[32] = {0};
+          uint64_t m = 0, o = g->has_multi ? g->row_oth[d] : 0;
+          for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) {
+            if (is_unary(e)) continue;
+            const uint64_t span = others_span(e, o);
+            if (m >= mlo && m < mhi) lane_oc[(m - mlo) % 32] += (uint32_t)span;
+            o += span;
+            ++m;
+          }
+          un = (uint32_t)((uhi - ulo + 31) / 32); mu = (uint32_t)((mhi - mlo + 31) / 32);
+          for (uint32_t l = 0; l < 32; ++l) oc = std::max(oc, lane_oc[l]);
+        } else {
+          for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
+            uint32_t u = 0;
+            for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) u += is_unary(e);
+            un = std::max(un, u);
+            mu = std::max<uint32_t>(mu, g->row_ptr[d + 1] - g->row_ptr[d] - u);
+            if (g->has_multi) oc = std::max(oc, g->row_oth[d + 1] - g->row_oth[d]);
+          }
+        }
+        s_un[sidx] = un; s_mu[sidx] = mu; s_oc[sidx] = oc;
+      }
+    });
+    for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
+      const uint32_t un = s_un[sidx], mu = s_mu[sidx], oc = s_oc[sidx];
+      g->sl_off[sidx] = (uint32_t)(words / 8);
+      uint64_t w = SH_WORDS + 32ull * ((uint64_t)(un + mu) * (1 + fvw) + oc);
+      g->sell_max_words = (uint32_t)std::max<uint64_t>(g->sell_max_words, std::min<uint64_t>(w, U32_LIMIT));
+      words += w;
+      if (words / 8 >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "sliced-ELL stream exceeds 2^32 x 32 B"; }
+    }
+    g->sl_off[nslice] = (uint32_t)(words / 8);
+    g->blob.assign(words, 0);
+    {  // learning order: by id block of the slice's first variable, then by class, then by position
+      std::vector<uint64_t> vk(nslice);
+      parallel_for(ncolor, [&](uint64_t c0, uint64_t c1) {
+        for (uint64_t c = c0; c < c1; ++c)
+          for (uint64_t sidx = g->color_start[c] / 32; sidx < g->color_start[c + 1] / 32; ++sidx) {
+            uint64_t v = 0;
+            if (slice_hub[sidx] != 0xffffffffu) v = g->perm[(uint64_t)slice_hub[sidx] * 32];  // every part of a hub: the hub
+            else
+              for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d)
+                if (g->perm[d] != 0xffffffffu) { v = g->perm[d]; break; }
+            vk[sidx] = ((v / g->id_block) << 40) | (c << 24 & 0xffff000000ull) | (sidx & 0xffffffu);
+          }
+      });
+      // (the low fields only break ties; the slice index is recovered from a parallel array)
+      g->learn_visit.resize(nslice);
+      std::iota(g->learn_visit.begin(), g->learn_visit.end(), 0u);
+      std::stable_sort(g->learn_visit.begin(), g->learn_visit.end(), [&](uint32_t a, uint32_t b) {
+        const uint64_t ka = vk[a] >> 24, kb = vk[b] >> 24;
+        return ka != kb ? ka < kb : a < b;
+      });
+    }
+    // sign tables (host mirror of dev_sign, dwg_device.cuh): codes 0 -> -1, 1 -> 0, 2 -> +1
+    auto sign2 = [](uint32_t fc, uint32_t nsb, bool head) -> int {  // arity 2
+      const bool body_all = nsb == 1;
+      switch (fc) {
+        case FC_AND: return (body_all && head) ? 1 : -1;
+        case FC_AND_CATEGORICAL: return (body_all && head) ? 1 : 0;
+        case FC_OR: return (nsb > 0 || head) ? 1 : -1;
+        case FC_EQUAL: return (nsb + (head ? 1u : 0u)) != 1 ? 1 : -1;
+        case FC_IMPLY_NATURAL: return body_all ? (head ? 1 : -1) : 0;
+        case FC_IMPLY_MLN: return body_all ? (head ? 1 : 0) : 1;
+        default: return (head || nsb == 0) ? 1 : 0;  // LINEAR / RATIO (log2(1+1) = 1) / LOGICAL
+      }
+    };
+    auto code_mismatch = [](uint32_t fc) -> uint32_t {  // arity 1, variable does not satisfy
+      switch (fc) {
+        case FC_AND: case FC_OR: case FC_IMPLY_NATURAL: return 0;  // -1
+        case FC_EQUAL: return 2;                                   // +1
+        default: return 1;                                         //  0
+      }
+    };
+    auto put_fv = [&](uint32_t *slot, uint64_t e) {
+      if (g->fv_mode == FV_F32) std::memcpy(slot, &g->e_fv32[e], 4);
+      else if (g->fv_mode == FV_F64) std::memcpy(slot, &g->e_fv64[e], 8);
+    };
+    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
+    for (uint64_t sidx = a0; sidx < a1; ++sidx) {
+      uint32_t *h = g->blob.data() + (uint64_t)g->sl_off[sidx] * 8;
+      const uint32_t un = s_un[sidx], mu = s_mu[sidx], oc = s_oc[sidx];
+      const uint64_t o_un = SH_WORDS, o_unfv = o_un + 32ull * un, o_mu = o_unfv + 32ull * un * fvw,
+                     o_mufv = o_mu + 32ull * mu, o_oth = o_mufv + 32ull * mu * fvw;
+      const bool is_wide = slice_is_wide(sidx);
+      const uint32_t nvars = is_wide ? 1 : 32;  // variables whose rows the slice holds
+      const uint64_t dbase = is_wide ? (uint64_t)slice_hub[sidx] * 32 : sidx * 32;  // slot of lane 0's variable
+      const uint32_t pq = is_wide ? (uint32_t)(sidx - slice_hub[sidx]) : 0, pn = is_wide ? wide_slices(g->perm[dbase]) : 1;
+      uint64_t ulo = 0, uhi = ~0ull, mlo = 0, mhi = ~0ull;  // this part's share of the variable's records
+      if (pn > 1) {
+        uint64_t U = 0;
+        for (uint64_t e = g->row_ptr[dbase]; e < g->row_ptr[dbase + 1]; ++e) U += is_unary(e);
+        share(U, pq, pn, &ulo, &uhi);
+        share(g->row_ptr[dbase + 1] - g->row_ptr[dbase] - U, pq, pn, &mlo, &mhi);
+      }
+      // is every multi record of the slice a one-other-variable record?  (a hub: of the whole hub,
+      // so that all its parts are read the same way)
+      bool binary = mu > 0 || pn > 1, antisym = true;
+      for (uint64_t d = dbase; d < dbase + nvars && binary; ++d) {
+        for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e)
+          if (!is_unary(e) && (g->e_tag[e] >> TAG_FORM_SHIFT) != 1) binary = false;
+      }
+      if (pn > 1 && mu == 0) binary = false;
+      h[SH_N_UNARY] = un; h[SH_N_MULTI] = mu; h[SH_N_OTH] = oc;
+      h[SH_SELF_OFF] = g->sl_off[sidx];
+      uint32_t ju[32] = {0}, jm[32] = {0}, jo[32] = {0};  // per lane: unary / multi columns and others words written
+      for (uint32_t l = 0; l < 32; ++l) {
+        // (every part of a hub carries the hub's bits at lane 0; the other lanes are padding slots)
+        const uint64_t d = l == 0 ? dbase : sidx * 32 + l;
+        if (g->var_flags[d] & VF_PAD) h[SH_PAD_MASK] |= 1u << l;
+        if (g->var_flags[d] & VF_EVID) h[SH_EVID_MASK] |= 1u << l;
+        if (g->evid_val[d] == 1) h[SH_EVVAL_MASK] |= 1u << l;
+        if (l >= nvars) continue;
+        uint64_t ku = 0, km = 0;  // records of this variable seen so far
+        uint64_t o = g->has_multi ? g->row_oth[d] : 0;
+        for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) {
+          const uint8_t tag = g->e_tag[e];
+          const uint32_t fc = tag & TAG_FUNC_MASK, form = tag >> TAG_FORM_SHIFT;
+          const uint32_t wid = g->e_wid[e];
+          const uint32_t base = wid | (raw.w_fixed[g->w_perm[wid]] ? SELL_FIXED_BIT : 0u);
+          if (form == 0) {
+            if (ku < ulo || ku >= uhi) { ++ku; continue; }  // another part's record
+            const uint32_t tl = is_wide ? (uint32_t)((ku - ulo) % 32) : l;  // target lane
+            const uint32_t mm = code_mismatch(fc);
+            const uint32_t s1 = (tag & TAG_SELF_EQ1) ? 2 : mm, s0 = (tag & TAG_SELF_EQ1) ? mm : 2;
+            if (s1 + s0 != 2) antisym = false;
+            h[o_un + 32ull * ju[tl] + tl] = sell_unary_record(wid, raw.w_fixed[g->w_perm[wid]], s1, s0);
+            put_fv(h + o_unfv + (32ull * ju[tl] + tl) * fvw, e);
+            ++ju[tl]; ++ku;
+            continue;
+          }
+          const uint64_t span = others_span(e, o);
+          if (km < mlo || km >= mhi) { ++km; o += span; continue; }  // another part's record
+          const uint32_t tl = is_wide ? (uint32_t)((km - mlo) % 32) : l;
+          uint32_t t = tag;
+          if (binary) {
+            // sign table over (this variable's value x, other variable satisfied)
+            const uint32_t self_eq = (tag & TAG_SELF_EQ1) ? 1 : 0;
+            const bool self_head = tag & TAG_SELF_HEAD;
+            t = 0;
+            for (uint32_t x = 0; x < 2; ++x)
+              for (uint32_t sat = 0; sat < 2; ++sat) {
+                const bool m = x == self_eq;
+                const int sgn = self_head ? sign2(fc, sat, m) : sign2(fc, m ? 1u : 0u, sat != 0);
+                t |= (uint32_t)(sgn + 1) << (2 * (2 * x + sat));
+              }
+            h[o_oth + 32ull * jm[tl] + tl] = g->oth[o];  // record j owns others column j
+          } else {
+            for (uint64_t k = 0; k < span; ++k) h[o_oth + 32ull * (jo[tl] + k) + tl] = g->oth[o + k];
+            jo[tl] += (uint32_t)span;
+          }
+          o += span;
+          h[o_mu + 32ull * jm[tl] + tl] = base | (t << 24);
+          put_fv(h + o_mufv + (32ull * jm[tl] + tl) * fvw, e);
+          ++jm[tl]; ++km;
+        }
+      }
+      for (uint32_t l = 0; l < 32; ++l) {
+        for (uint32_t j = ju[l]; j < un; ++j) h[o_un + 32ull * j + l] = SELL_UNARY_NOP;
+        for (uint32_t j = jm[l]; j < mu; ++j) h[o_mu + 32ull * j + l] = binary ? SELL_BINARY_NOP << 24 : 0u;  // form 0
+      }
+      h[SH_FLAGS] = (antisym ? SF_ANTISYM : 0u) | (binary ? SF_BINARY : 0u) | (is_wide ? SF_WIDE : 0u) |
+                    (pn > 1 ? SF_PART | (pq << 4) | (pn << 18) : 0u);
+    }
+    });
+  }
+  return "";
+}
+
+// ---- categorical sliced-ELL blob (graph_image.h CELL_*) from the CSR rows of a compiled image:
+// slice shapes, offsets, learning order, and per slice header | meta | first tally row | record
+// columns (rows in value order, a row's records in factor-id order) | others columns.  Clears
+// g->cell when some variable has more two-variable factors than a lane's mask holds. ----
+static std::string build_cell_blob(GraphImage *g, uint64_t nvar_pad, uint32_t ncolor, int *err) {
+  std::vector<uint32_t> cell_rec, cell_oc;
+  // host mirror of dev_sign (dwg_device.cuh) for one- and two-variable factors, as sign codes
+    auto code1 = [](uint32_t fc, bool self_sat) -> uint32_t {  // arity 1
+      if (self_sat) return 2;
+      switch (fc) {
+        case FC_AND: case FC_OR: case FC_IMPLY_NATURAL: return 0;
+        case FC_EQUAL: return 2;
+        default: return 1;
+      }
+    };
+    auto code2 = [](uint32_t fc, uint32_t nsb, bool head) -> uint32_t {  // arity 2: one body position
+      const bool body_all = nsb == 1;
+      int sgn;
+      switch (fc) {
+        case FC_AND: sgn = (body_all && head) ? 1 : -1; break;
+        case FC_AND_CATEGORICAL: sgn = (body_all && head) ? 1 : 0; break;
+        case FC_OR: sgn = (nsb > 0 || head) ? 1 : -1; break;
+        case FC_EQUAL: sgn = (nsb + (head ? 1u : 0u)) != 1 ? 1 : -1; break;
+        case FC_IMPLY_NATURAL: sgn = body_all ? (head ? 1 : -1) : 0; break;
+        case FC_IMPLY_MLN: sgn = body_all ? (head ? 1 : 0) : 1; break;
+        default: sgn = (head || nsb == 0) ? 1 : 0; break;  // LINEAR / RATIO (log2(1+1) = 1) / LOGICAL
+      }
+      return (uint32_t)(sgn + 1);
+    };
+  if (g->cell) {
+    const uint64_t nslice = nvar_pad / 32;
+    // slice shapes: record columns (an empty row still holds one record), others columns
+    cell_rec.assign(nslice, 0); cell_oc.assign(nslice, 0);
+    std::vector<uint32_t> &s_rec = cell_rec, &s_oc = cell_oc;
+    int too_many_others = 0;
+    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
+      for (uint64_t sidx = a0; sidx < a1; ++sidx) {
+        uint32_t rec = 0, oc = 0;
+        for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
+          if (g->var_flags[d] & VF_PAD) continue;
+          uint32_t r = 0, o = 0;
+          for (uint64_t row = g->var_row[d]; row < g->var_row[d + 1]; ++row) {
+            const uint32_t n = g->row_ptr[row + 1] - g->row_ptr[row];
+            r += n ? n : 1u;
+            if (g->has_multi) o += g->row_oth[row + 1] - g->row_oth[row];
+          }
+          rec = std::max(rec, r); oc = std::max(oc, o);
+        }
+        s_rec[sidx] = rec; s_oc[sidx] = oc;
+        if (oc > CELL_MAX_OTH) __atomic_store_n(&too_many_others, 1, __ATOMIC_RELAXED);
+      }
+    });
+    if (too_many_others) g->cell = false;  // a variable with more than 32 two-variable factors: the CSR kernels sweep this graph
+  }
+  if (g->cell) {
+    const uint64_t nslice = nvar_pad / 32;
+    std::vector<uint32_t> &s_rec = cell_rec, &s_oc = cell_oc;
+    g->sl_off.assign(nslice + 1, 0);
+    uint64_t words = 0;
+    for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
+      g->sl_off[sidx] = (uint32_t)(words / 8);
+      const uint64_t w = SH_WORDS + 32ull * (2 + s_rec[sidx] + s_oc[sidx]);
+      g->sell_max_words = (uint32_t)std::max<uint64_t>(g->sell_max_words, w);
+      words += w;
+      if (words / 8 >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "categorical sliced-ELL stream exceeds 2^32 x 32 B"; }
+    }
+    g->sl_off[nslice] = (uint32_t)(words / 8);
+    g->blob.assign(words, 0);
+    {  // learning order (k_cell_learn_live): by id block of the slice's first variable, then by class, then by position
+      std::vector<uint64_t> vk(nslice);
+      parallel_for(ncolor, [&](uint64_t c0, uint64_t c1) {
+        for (uint64_t c = c0; c < c1; ++c)
+          for (uint64_t sidx = g->color_start[c] / 32; sidx < g->color_start[c + 1] / 32; ++sidx) {
+            uint64_t v = 0;
+            for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d)
+              if (g->perm[d] != 0xffffffffu) { v = g->perm[d]; break; }
+            vk[sidx] = ((v / g->id_block) << 16) | (c & 0xffffu);
+          }
+      });
+      g->learn_visit.resize(nslice);
+      std::iota(g->learn_visit.begin(), g->learn_visit.end(), 0u);
+      std::stable_sort(g->learn_visit.begin(), g->learn_visit.end(), [&](uint32_t a, uint32_t b) {
+        return vk[a] != vk[b] ? vk[a] < vk[b] : a < b;
+      });
+    }
+    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
+      for (uint64_t sidx = a0; sidx < a1; ++sidx) {
+        uint32_t *h = g->blob.data() + (uint64_t)g->sl_off[sidx] * 8;
+        const uint32_t nrec = s_rec[sidx], noc = s_oc[sidx];
+        const uint64_t o_meta = SH_WORDS, o_row0 = o_meta + 32, o_rec = o_row0 + 32, o_oth = o_rec + 32ull * nrec;
+        h[CH_N_REC] = nrec; h[CH_N_OTH] = noc; h[CH_SELF_OFF] = g->sl_off[sidx];
+        uint32_t kmax = 0;
+        for (uint32_t l = 0; l < 32; ++l) {
+          const uint64_t d = sidx * 32 + l;
+          uint32_t jr = 0, jo = 0;
+          if (g->var_flags[d] & VF_PAD) {
+            h[CH_PAD_MASK] |= 1u << l;
+            h[o_row0 + l] = g->var_row[d];
+          } else {
+            if (g->var_flags[d] & VF_EVID) h[CH_EVID_MASK] |= 1u << l;
+            const uint32_t K = g->var_row[d + 1] - g->var_row[d];
+            kmax = std::max(kmax, K);
+            h[o_meta + l] = K | (g->evid_val[d] << 8);
+            h[o_row0 + l] = g->var_row[d];
+            for (uint64_t row = g->var_row[d]; row < g->var_row[d + 1]; ++row) {
+              bool first = true;
+              uint64_t o = g->has_multi ? g->row_oth[row] : 0;
+              for (uint64_t e = g->row_ptr[row]; e < g->row_ptr[row + 1]; ++e) {
+                const uint8_t tag = g->e_tag[e];
+                const uint32_t fc = tag & TAG_FUNC_MASK, form = tag >> TAG_FORM_SHIFT;
+                uint32_t table = 0;
+                for (uint32_t ss = 0; ss < 2; ++ss)
+                  for (uint32_t os = 0; os < 2; ++os) {
+                    uint32_t c;
+                    if (form == 0) c = code1(fc, ss);
+                    else if (tag & TAG_SELF_HEAD) c = code2(fc, os, ss);
+                    else c = code2(fc, ss, os);
+                    table |= c << (2 * (2 * ss + os));
+                  }
+                uint32_t rec = g->e_wid[e] | (table << 22) | (first ? CELL_ROW_BIT : 0u);
+                if (form == 1) {
+                  rec |= CELL_MULTI_BIT;
+                  h[o_oth + 32ull * jo + l] = (g->oth[2 * o] << 8) | (g->oth[2 * o + 1] & 0xffu);
+                  ++jo; ++o;
+                }
+                h[o_rec + 32ull * jr + l] = rec;
+                ++jr; first = false;
+              }
+              if (first) { h[o_rec + 32ull * jr + l] = CELL_NOP_ROW; ++jr; }  // a value without factors
+            }
+          }
+          for (; jr < nrec; ++jr) h[o_rec + 32ull * jr + l] = CELL_NOP;
+        }
+        h[CH_KMAX] = kmax;
+      }
+    });
+  }
+  return "";
+}
+
 std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *err) {
   *err = DWG_ERR_INVALID;
   *g = GraphImage();
@@ -889,458 +1362,15 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
   }
 
   pt.lap("weight ids");
-  // ---- per colour class, per weight: how many SGD updates one learning launch makes (N) and
-  // their summed curvature bound (Q), for the semi-implicit batch update (dwg_kernels.cuh).
-  // q = (fv * sign range)^2 / 4 >= Var(f | rest): the conditional is a Bernoulli. ----
-  {
-    uint64_t cells = (uint64_t)ncolor * nweight;
-    g->cls_shared = g->sell || cells > (64ull << 20);  // sell: whole-graph sums; too many cells: one class-averaged row
-    uint64_t rows_n = g->cls_shared ? 1 : ncolor;
-    g->cls_N_evid.assign(rows_n * nweight, 0.f); g->cls_Q_evid.assign(rows_n * nweight, 0.f);
-    g->cls_N_all.assign(rows_n * nweight, 0.f); g->cls_Q_all.assign(rows_n * nweight, 0.f);
-    g->cls_H_evid.assign(rows_n * nweight, 0.f); g->cls_H_all.assign(rows_n * nweight, 0.f);
-    auto srange = [](uint32_t fc, uint64_t n) -> double {
-      switch (fc) {
-        case FC_AND: case FC_OR: case FC_EQUAL: case FC_IMPLY_NATURAL: return 2.0;
-        case FC_LINEAR: return n > 1 ? (double)(n - 1) : 1.0;
-        case FC_RATIO: return n > 1 ? std::log2((double)n) : 1.0;
-        default: return 1.0;
-      }
-    };
-    // delta(e) = |fv| * (sign range) of record e.  One SGD step of variable v moves weight k
-    // by a gradient whose covariance over the draw is p(1-p) * delta delta^T <= 1/4 delta delta^T;
-    // diag(|delta_k| * sum_j |delta_j|) dominates delta delta^T, so
-    //   q(e) = 1/4 * delta(e) * sum_{e' learnable in the row} delta(e')
-    // summed over a launch bounds the curvature of ALL weights moving together (the features
-    // of one variable are perfectly correlated: a per-weight diagonal alone would overshoot).
-    auto walk_row = [&](uint64_t r, auto &&fn) {
-      uint64_t oc = g->has_multi ? g->row_oth[r] : 0;
-      for (uint64_t e = g->row_ptr[r]; e < g->row_ptr[r + 1]; ++e) {
-        uint8_t tag = g->e_tag[e];
-        uint32_t form = tag >> TAG_FORM_SHIFT;
-        uint64_t n = form != FORM_GENERAL ? form + 1 : g->oth[oc * ow];
-        oc += form != FORM_GENERAL ? form : 1 + n;
-        uint32_t w = g->e_wid[e];
-        if (raw.w_fixed[g->w_perm[w]]) continue;
-        double fv = g->fv_mode == FV_F32 ? g->e_fv32[e] : g->fv_mode == FV_F64 ? g->e_fv64[e] : 1.0;
-        fn(w, std::fabs(fv) * srange(tag & TAG_FUNC_MASK, n));
-      }
-    };
-    if (g->sell) {
-      // Sliced-ELL graphs learn in ONE visit order over all classes (learn_visit below): whole-graph
-      // sums, one row.  Accumulated as 2^-20 fixed point with integer atomics: the result does not
-      // depend on the thread count or the interleaving.
-      g->cls_shared = true;
-      std::vector<uint64_t> acc(6 * nweight, 0);
-      auto fx = [](double x) { return (uint64_t)std::llround(x * 1048576.0); };
-      parallel_for(nvar_pad, [&](uint64_t d0, uint64_t d1) {
-        for (uint64_t d = d0; d < d1; ++d) {
-          uint64_t v = g->perm[d];
-          if (v == 0xffffffffu) continue;
-          const bool ev = g->var_is_evid[v];
-          double rowsum = 0;
-          walk_row(d, [&](uint32_t, double delta) { rowsum += delta; });
-          walk_row(d, [&](uint32_t w, double delta) {
-            const uint64_t q = fx(0.25 * delta * rowsum), hd = fx(0.25 * delta * delta);
-            __atomic_fetch_add(&acc[0 * nweight + w], 1ull << 20, __ATOMIC_RELAXED);
-            __atomic_fetch_add(&acc[1 * nweight + w], q, __ATOMIC_RELAXED);
-            __atomic_fetch_add(&acc[2 * nweight + w], hd, __ATOMIC_RELAXED);
-            if (ev) {
-              __atomic_fetch_add(&acc[3 * nweight + w], 1ull << 20, __ATOMIC_RELAXED);
-              __atomic_fetch_add(&acc[4 * nweight + w], q, __ATOMIC_RELAXED);
-              __atomic_fetch_add(&acc[5 * nweight + w], hd, __ATOMIC_RELAXED);
-            }
-          });
-        }
-      });
-      for (uint64_t w = 0; w < nweight; ++w) {
-        g->cls_N_all[w] = (float)((double)acc[0 * nweight + w] / 1048576.0);
-        g->cls_Q_all[w] = (float)((double)acc[1 * nweight + w] / 1048576.0);
-        g->cls_H_all[w] = (float)((double)acc[2 * nweight + w] / 1048576.0);
-        g->cls_N_evid[w] = (float)((double)acc[3 * nweight + w] / 1048576.0);
-        g->cls_Q_evid[w] = (float)((double)acc[4 * nweight + w] / 1048576.0);
-        g->cls_H_evid[w] = (float)((double)acc[5 * nweight + w] / 1048576.0);
-      }
-    } else {
-    // every class owns its row of the tables: classes in parallel (the float sums of a row keep
-    // their sequential order); a shared row is filled by one thread
-    parallel_ranges(ncolor, g->cls_shared ? 1u : std::min<unsigned>(ncolor, host_threads()),
-                    [&](uint64_t c0, uint64_t c1, unsigned) {
-    for (uint64_t c = c0; c < c1; ++c) {
-      uint64_t base = g->cls_shared ? 0 : (uint64_t)c * nweight;
-      for (uint64_t d = g->color_start[c]; d < g->color_start[c + 1]; ++d) {
-        uint64_t v = g->perm[d];
-        if (v == 0xffffffffu) continue;
-        bool cat = g->var_dtype[v], ev = g->var_is_evid[v];
-        uint64_t r0 = g->has_categorical ? g->var_row[d] : d;
-        uint64_t r = cat ? r0 + std::min<uint64_t>(g->evid_val[d], raw.var_card[v] ? raw.var_card[v] - 1 : 0) : r0;
-        if (cat && raw.var_card[v] == 0) continue;
-        double rowsum = 0;
-        walk_row(r, [&](uint32_t, double delta) { rowsum += delta; });
-        const float one = cat ? 2.f : 1.f;  // a categorical step also visits the row of the free value
-        walk_row(r, [&](uint32_t w, double delta) {
-          float q = (float)(0.25 * delta * rowsum) * one, hd = (float)(0.25 * delta * delta) * one;
-          g->cls_N_all[base + w] += one; g->cls_Q_all[base + w] += q; g->cls_H_all[base + w] += hd;
-          if (ev) { g->cls_N_evid[base + w] += one; g->cls_Q_evid[base + w] += q; g->cls_H_evid[base + w] += hd; }
-        });
-      }
-    }
-    }, 1);
-    if (g->cls_shared && !g->sell)
-      for (uint64_t w = 0; w < nweight; ++w) {
-        g->cls_N_evid[w] /= ncolor; g->cls_Q_evid[w] /= ncolor; g->cls_H_evid[w] /= ncolor;
-        g->cls_N_all[w] /= ncolor; g->cls_Q_all[w] /= ncolor; g->cls_H_all[w] /= ncolor;
-      }
-    }
-  }
-
+  class_statistics(raw, g, nvar_pad, ncolor, nweight, ow);
   pt.lap("class statistics");
-  // ---- sliced-ELL blob (graph_image.h): per 32-variable slice one contiguous run of words:
-  // header, unary records (+ feature values), multi records (+ feature values), others.
-  // A warp streams its slice with coalesced 128 B requests, every record exactly once. ----
-  if (g->sell) {
-    const uint64_t nslice = nvar_pad / 32;
-    const uint64_t fvw = g->fv_mode == FV_F32 ? 1 : g->fv_mode == FV_F64 ? 2 : 0;  // words per value
-    g->sl_off.assign(nslice + 1, 0);
-    auto is_unary = [&](uint64_t e) { return (g->e_tag[e] >> TAG_FORM_SHIFT) == 0; };
-    // slice shapes.  A slice whose first slot holds a wide variable is that variable's alone: record
-    // k of a section goes to lane k % 32, column k / 32 (the lanes of a normal slice are variables)
-    // slice -> first slice of the wide variable it belongs to (itself for a one-slice wide variable)
-    std::vector<uint32_t> slice_hub(nslice, 0xffffffffu);
-    parallel_for(nvar, [&](uint64_t v0, uint64_t v1) {
-      for (uint64_t v = v0; v < v1; ++v)
-        if (wide[v]) {
-          const uint32_t s0 = g->inv[v] / 32, n = wide_slices(v);
-          for (uint32_t q = 0; q < n; ++q) slice_hub[s0 + q] = s0;
-        }
-    });
-    for (uint64_t sidx = 0; sidx < nslice; ++sidx)
-      if (slice_hub[sidx] != 0xffffffffu && wide_slices(g->perm[(uint64_t)slice_hub[sidx] * 32]) > 1)
-        g->part_slices.push_back((uint32_t)sidx);
-    auto slice_is_wide = [&](uint64_t sidx) { return slice_hub[sidx] != 0xffffffffu; };
-    for (uint64_t sidx = 0; sidx < nslice && !g->has_wide; ++sidx) g->has_wide = slice_is_wide(sidx);
-    // the share of part q of n: records [q * per, min(total, (q + 1) * per)) of a section
-    auto share = [](uint64_t total, uint32_t q, uint32_t n, uint64_t *lo, uint64_t *hi) {
-      const uint64_t per = (total + n - 1) / n;
-      *lo = std::min(total, per * q);
-      *hi = std::min(total, per * (q + 1));
-    };
-    auto others_span = [&](uint64_t e, uint64_t o) -> uint64_t {
-      const uint32_t form = g->e_tag[e] >> TAG_FORM_SHIFT;
-      return form != FORM_GENERAL ? form : 1 + g->oth[o];
-    };
-    std::vector<uint32_t> s_un(nslice), s_mu(nslice), s_oc(nslice);
-    uint64_t words = 0;
-    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
-      for (uint64_t sidx = a0; sidx < a1; ++sidx) {
-        uint32_t un = 0, mu = 0, oc = 0;
-        if (slice_is_wide(sidx)) {
-          const uint64_t d = (uint64_t)slice_hub[sidx] * 32;
-          const uint32_t q = (uint32_t)(sidx - slice_hub[sidx]), n = wide_slices(g->perm[d]);
-          uint64_t U = 0;
-          for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) U += is_unary(e);
-          const uint64_t M = g->row_ptr[d + 1] - g->row_ptr[d] - U;
-          uint64_t ulo, uhi, mlo, mhi;
-          share(U, q, n, &ulo, &uhi);
-          share(M, q, n, &mlo, &mhi);
-          uint32_t lane_oc[32] = {0};
-          uint64_t m = 0, o = g->has_multi ? g->row_oth[d] : 0;
-          for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) {
-            if (is_unary(e)) continue;
-            const uint64_t span = others_span(e, o);
-            if (m >= mlo && m < mhi) lane_oc[(m - mlo) % 32] += (uint32_t)span;
-            o += span;
-            ++m;
-          }
-          un = (uint32_t)((uhi - ulo + 31) / 32); mu = (uint32_t)((mhi - mlo + 31) / 32);
-          for (uint32_t l = 0; l < 32; ++l) oc = std::max(oc, lane_oc[l]);
-        } else {
-          for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
-            uint32_t u = 0;
-            for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) u += is_unary(e);
-            un = std::max(un, u);
-            mu = std::max<uint32_t>(mu, g->row_ptr[d + 1] - g->row_ptr[d] - u);
-            if (g->has_multi) oc = std::max(oc, g->row_oth[d + 1] - g->row_oth[d]);
-          }
-        }
-        s_un[sidx] = un; s_mu[sidx] = mu; s_oc[sidx] = oc;
-      }
-    });
-    for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
-      const uint32_t un = s_un[sidx], mu = s_mu[sidx], oc = s_oc[sidx];
-      g->sl_off[sidx] = (uint32_t)(words / 8);
-      uint64_t w = SH_WORDS + 32ull * ((uint64_t)(un + mu) * (1 + fvw) + oc);
-      g->sell_max_words = (uint32_t)std::max<uint64_t>(g->sell_max_words, std::min<uint64_t>(w, U32_LIMIT));
-      words += w;
-      if (words / 8 >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "sliced-ELL stream exceeds 2^32 x 32 B"; }
-    }
-    g->sl_off[nslice] = (uint32_t)(words / 8);
-    g->blob.assign(words, 0);
-    {  // learning order: by id block of the slice's first variable, then by class, then by position
-      std::vector<uint64_t> vk(nslice);
-      parallel_for(ncolor, [&](uint64_t c0, uint64_t c1) {
-        for (uint64_t c = c0; c < c1; ++c)
-          for (uint64_t sidx = g->color_start[c] / 32; sidx < g->color_start[c + 1] / 32; ++sidx) {
-            uint64_t v = 0;
-            if (slice_hub[sidx] != 0xffffffffu) v = g->perm[(uint64_t)slice_hub[sidx] * 32];  // every part of a hub: the hub
-            else
-              for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d)
-                if (g->perm[d] != 0xffffffffu) { v = g->perm[d]; break; }
-            vk[sidx] = ((v / g->id_block) << 40) | (c << 24 & 0xffff000000ull) | (sidx & 0xffffffu);
-          }
-      });
-      // (the low fields only break ties; the slice index is recovered from a parallel array)
-      g->learn_visit.resize(nslice);
-      std::iota(g->learn_visit.begin(), g->learn_visit.end(), 0u);
-      std::stable_sort(g->learn_visit.begin(), g->learn_visit.end(), [&](uint32_t a, uint32_t b) {
-        const uint64_t ka = vk[a] >> 24, kb = vk[b] >> 24;
-        return ka != kb ? ka < kb : a < b;
-      });
-    }
-    // sign tables (host mirror of dev_sign, dwg_device.cuh): codes 0 -> -1, 1 -> 0, 2 -> +1
-    auto sign2 = [](uint32_t fc, uint32_t nsb, bool head) -> int {  // arity 2
-      const bool body_all = nsb == 1;
-      switch (fc) {
-        case FC_AND: return (body_all && head) ? 1 : -1;
-        case FC_AND_CATEGORICAL: return (body_all && head) ? 1 : 0;
-        case FC_OR: return (nsb > 0 || head) ? 1 : -1;
-        case FC_EQUAL: return (nsb + (head ? 1u : 0u)) != 1 ? 1 : -1;
-        case FC_IMPLY_NATURAL: return body_all ? (head ? 1 : -1) : 0;
-        case FC_IMPLY_MLN: return body_all ? (head ? 1 : 0) : 1;
-        default: return (head || nsb == 0) ? 1 : 0;  // LINEAR / RATIO (log2(1+1) = 1) / LOGICAL
-      }
-    };
-    auto code_mismatch = [](uint32_t fc) -> uint32_t {  // arity 1, variable does not satisfy
-      switch (fc) {
-        case FC_AND: case FC_OR: case FC_IMPLY_NATURAL: return 0;  // -1
-        case FC_EQUAL: return 2;                                   // +1
-        default: return 1;                                         //  0
-      }
-    };
-    auto put_fv = [&](uint32_t *slot, uint64_t e) {
-      if (g->fv_mode == FV_F32) std::memcpy(slot, &g->e_fv32[e], 4);
-      else if (g->fv_mode == FV_F64) std::memcpy(slot, &g->e_fv64[e], 8);
-    };
-    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
-    for (uint64_t sidx = a0; sidx < a1; ++sidx) {
-      uint32_t *h = g->blob.data() + (uint64_t)g->sl_off[sidx] * 8;
-      const uint32_t un = s_un[sidx], mu = s_mu[sidx], oc = s_oc[sidx];
-      const uint64_t o_un = SH_WORDS, o_unfv = o_un + 32ull * un, o_mu = o_unfv + 32ull * un * fvw,
-                     o_mufv = o_mu + 32ull * mu, o_oth = o_mufv + 32ull * mu * fvw;
-      const bool is_wide = slice_is_wide(sidx);
-      const uint32_t nvars = is_wide ? 1 : 32;  // variables whose rows the slice holds
-      const uint64_t dbase = is_wide ? (uint64_t)slice_hub[sidx] * 32 : sidx * 32;  // slot of lane 0's variable
-      const uint32_t pq = is_wide ? (uint32_t)(sidx - slice_hub[sidx]) : 0, pn = is_wide ? wide_slices(g->perm[dbase]) : 1;
-      uint64_t ulo = 0, uhi = ~0ull, mlo = 0, mhi = ~0ull;  // this part's share of the variable's records
-      if (pn > 1) {
-        uint64_t U = 0;
-        for (uint64_t e = g->row_ptr[dbase]; e < g->row_ptr[dbase + 1]; ++e) U += is_unary(e);
-        share(U, pq, pn, &ulo, &uhi);
-        share(g->row_ptr[dbase + 1] - g->row_ptr[dbase] - U, pq, pn, &mlo, &mhi);
-      }
-      // is every multi record of the slice a one-other-variable record?  (a hub: of the whole hub,
-      // so that all its parts are read the same way)
-      bool binary = mu > 0 || pn > 1, antisym = true;
-      for (uint64_t d = dbase; d < dbase + nvars && binary; ++d) {
-        for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e)
-          if (!is_unary(e) && (g->e_tag[e] >> TAG_FORM_SHIFT) != 1) binary = false;
-      }
-      if (pn > 1 && mu == 0) binary = false;
-      h[SH_N_UNARY] = un; h[SH_N_MULTI] = mu; h[SH_N_OTH] = oc;
-      h[SH_SELF_OFF] = g->sl_off[sidx];
-      uint32_t ju[32] = {0}, jm[32] = {0}, jo[32] = {0};  // per lane: unary / multi columns and others words written
-      for (uint32_t l = 0; l < 32; ++l) {
-        // (every part of a hub carries the hub's bits at lane 0; the other lanes are padding slots)
-        const uint64_t d = l == 0 ? dbase : sidx * 32 + l;
-        if (g->var_flags[d] & VF_PAD) h[SH_PAD_MASK] |= 1u << l;
-        if (g->var_flags[d] & VF_EVID) h[SH_EVID_MASK] |= 1u << l;
-        if (g->evid_val[d] == 1) h[SH_EVVAL_MASK] |= 1u << l;
-        if (l >= nvars) continue;
-        uint64_t ku = 0, km = 0;  // records of this variable seen so far
-        uint64_t o = g->has_multi ? g->row_oth[d] : 0;
-        for (uint64_t e = g->row_ptr[d]; e < g->row_ptr[d + 1]; ++e) {
-          const uint8_t tag = g->e_tag[e];
-          const uint32_t fc = tag & TAG_FUNC_MASK, form = tag >> TAG_FORM_SHIFT;
-          const uint32_t wid = g->e_wid[e];
-          const uint32_t base = wid | (raw.w_fixed[g->w_perm[wid]] ? SELL_FIXED_BIT : 0u);
-          if (form == 0) {
-            if (ku < ulo || ku >= uhi) { ++ku; continue; }  // another part's record
-            const uint32_t tl = is_wide ? (uint32_t)((ku - ulo) % 32) : l;  // target lane
-            const uint32_t mm = code_mismatch(fc);
-            const uint32_t s1 = (tag & TAG_SELF_EQ1) ? 2 : mm, s0 = (tag & TAG_SELF_EQ1) ? mm : 2;
-            if (s1 + s0 != 2) antisym = false;
-            h[o_un + 32ull * ju[tl] + tl] = sell_unary_record(wid, raw.w_fixed[g->w_perm[wid]], s1, s0);
-            put_fv(h + o_unfv + (32ull * ju[tl] + tl) * fvw, e);
-            ++ju[tl]; ++ku;
-            continue;
-          }
-          const uint64_t span = others_span(e, o);
-          if (km < mlo || km >= mhi) { ++km; o += span; continue; }  // another part's record
-          const uint32_t tl = is_wide ? (uint32_t)((km - mlo) % 32) : l;
-          uint32_t t = tag;
-          if (binary) {
-            // sign table over (this variable's value x, other variable satisfied)
-            const uint32_t self_eq = (tag & TAG_SELF_EQ1) ? 1 : 0;
-            const bool self_head = tag & TAG_SELF_HEAD;
-            t = 0;
-            for (uint32_t x = 0; x < 2; ++x)
-              for (uint32_t sat = 0; sat < 2; ++sat) {
-                const bool m = x == self_eq;
-                const int sgn = self_head ? sign2(fc, sat, m) : sign2(fc, m ? 1u : 0u, sat != 0);
-                t |= (uint32_t)(sgn + 1) << (2 * (2 * x + sat));
-              }
-            h[o_oth + 32ull * jm[tl] + tl] = g->oth[o];  // record j owns others column j
-          } else {
-            for (uint64_t k = 0; k < span; ++k) h[o_oth + 32ull * (jo[tl] + k) + tl] = g->oth[o + k];
-            jo[tl] += (uint32_t)span;
-          }
-          o += span;
-          h[o_mu + 32ull * jm[tl] + tl] = base | (t << 24);
-          put_fv(h + o_mufv + (32ull * jm[tl] + tl) * fvw, e);
-          ++jm[tl]; ++km;
-        }
-      }
-      for (uint32_t l = 0; l < 32; ++l) {
-        for (uint32_t j = ju[l]; j < un; ++j) h[o_un + 32ull * j + l] = SELL_UNARY_NOP;
-        for (uint32_t j = jm[l]; j < mu; ++j) h[o_mu + 32ull * j + l] = binary ? SELL_BINARY_NOP << 24 : 0u;  // form 0
-      }
-      h[SH_FLAGS] = (antisym ? SF_ANTISYM : 0u) | (binary ? SF_BINARY : 0u) | (is_wide ? SF_WIDE : 0u) |
-                    (pn > 1 ? SF_PART | (pq << 4) | (pn << 18) : 0u);
-    }
-    });
+  {
+    std::string e = build_sell_blob(raw, g, nvar, nvar_pad, ncolor, wide, wide_slices, err);
+    if (!e.empty()) return e;
   }
-  // ---- categorical sliced-ELL blob (graph_image.h CELL_*) ----
-  std::vector<uint32_t> cell_rec, cell_oc;
-  // host mirror of dev_sign (dwg_device.cuh) for one- and two-variable factors, as sign codes
-    auto code1 = [](uint32_t fc, bool self_sat) -> uint32_t {  // arity 1
-      if (self_sat) return 2;
-      switch (fc) {
-        case FC_AND: case FC_OR: case FC_IMPLY_NATURAL: return 0;
-        case FC_EQUAL: return 2;
-        default: return 1;
-      }
-    };
-    auto code2 = [](uint32_t fc, uint32_t nsb, bool head) -> uint32_t {  // arity 2: one body position
-      const bool body_all = nsb == 1;
-      int sgn;
-      switch (fc) {
-        case FC_AND: sgn = (body_all && head) ? 1 : -1; break;
-        case FC_AND_CATEGORICAL: sgn = (body_all && head) ? 1 : 0; break;
-        case FC_OR: sgn = (nsb > 0 || head) ? 1 : -1; break;
-        case FC_EQUAL: sgn = (nsb + (head ? 1u : 0u)) != 1 ? 1 : -1; break;
-        case FC_IMPLY_NATURAL: sgn = body_all ? (head ? 1 : -1) : 0; break;
-        case FC_IMPLY_MLN: sgn = body_all ? (head ? 1 : 0) : 1; break;
-        default: sgn = (head || nsb == 0) ? 1 : 0; break;  // LINEAR / RATIO (log2(1+1) = 1) / LOGICAL
-      }
-      return (uint32_t)(sgn + 1);
-    };
-  if (g->cell) {
-    const uint64_t nslice = nvar_pad / 32;
-    // slice shapes: record columns (an empty row still holds one record), others columns
-    cell_rec.assign(nslice, 0); cell_oc.assign(nslice, 0);
-    std::vector<uint32_t> &s_rec = cell_rec, &s_oc = cell_oc;
-    int too_many_others = 0;
-    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
-      for (uint64_t sidx = a0; sidx < a1; ++sidx) {
-        uint32_t rec = 0, oc = 0;
-        for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d) {
-          if (g->var_flags[d] & VF_PAD) continue;
-          uint32_t r = 0, o = 0;
-          for (uint64_t row = g->var_row[d]; row < g->var_row[d + 1]; ++row) {
-            const uint32_t n = g->row_ptr[row + 1] - g->row_ptr[row];
-            r += n ? n : 1u;
-            if (g->has_multi) o += g->row_oth[row + 1] - g->row_oth[row];
-          }
-          rec = std::max(rec, r); oc = std::max(oc, o);
-        }
-        s_rec[sidx] = rec; s_oc[sidx] = oc;
-        if (oc > CELL_MAX_OTH) __atomic_store_n(&too_many_others, 1, __ATOMIC_RELAXED);
-      }
-    });
-    if (too_many_others) g->cell = false;  // a variable with more than 32 two-variable factors: the CSR kernels sweep this graph
-  }
-  if (g->cell) {
-    const uint64_t nslice = nvar_pad / 32;
-    std::vector<uint32_t> &s_rec = cell_rec, &s_oc = cell_oc;
-    g->sl_off.assign(nslice + 1, 0);
-    uint64_t words = 0;
-    for (uint64_t sidx = 0; sidx < nslice; ++sidx) {
-      g->sl_off[sidx] = (uint32_t)(words / 8);
-      const uint64_t w = SH_WORDS + 32ull * (2 + s_rec[sidx] + s_oc[sidx]);
-      g->sell_max_words = (uint32_t)std::max<uint64_t>(g->sell_max_words, w);
-      words += w;
-      if (words / 8 >= U32_LIMIT) { *err = DWG_ERR_UNSUPPORTED; return "categorical sliced-ELL stream exceeds 2^32 x 32 B"; }
-    }
-    g->sl_off[nslice] = (uint32_t)(words / 8);
-    g->blob.assign(words, 0);
-    {  // learning order (k_cell_learn_live): by id block of the slice's first variable, then by class, then by position
-      std::vector<uint64_t> vk(nslice);
-      parallel_for(ncolor, [&](uint64_t c0, uint64_t c1) {
-        for (uint64_t c = c0; c < c1; ++c)
-          for (uint64_t sidx = g->color_start[c] / 32; sidx < g->color_start[c + 1] / 32; ++sidx) {
-            uint64_t v = 0;
-            for (uint64_t d = sidx * 32; d < sidx * 32 + 32; ++d)
-              if (g->perm[d] != 0xffffffffu) { v = g->perm[d]; break; }
-            vk[sidx] = ((v / g->id_block) << 16) | (c & 0xffffu);
-          }
-      });
-      g->learn_visit.resize(nslice);
-      std::iota(g->learn_visit.begin(), g->learn_visit.end(), 0u);
-      std::stable_sort(g->learn_visit.begin(), g->learn_visit.end(), [&](uint32_t a, uint32_t b) {
-        return vk[a] != vk[b] ? vk[a] < vk[b] : a < b;
-      });
-    }
-    parallel_for(nslice, [&](uint64_t a0, uint64_t a1) {
-      for (uint64_t sidx = a0; sidx < a1; ++sidx) {
-        uint32_t *h = g->blob.data() + (uint64_t)g->sl_off[sidx] * 8;
-        const uint32_t nrec = s_rec[sidx], noc = s_oc[sidx];
-        const uint64_t o_meta = SH_WORDS, o_row0 = o_meta + 32, o_rec = o_row0 + 32, o_oth = o_rec + 32ull * nrec;
-        h[CH_N_REC] = nrec; h[CH_N_OTH] = noc; h[CH_SELF_OFF] = g->sl_off[sidx];
-        uint32_t kmax = 0;
-        for (uint32_t l = 0; l < 32; ++l) {
-          const uint64_t d = sidx * 32 + l;
-          uint32_t jr = 0, jo = 0;
-          if (g->var_flags[d] & VF_PAD) {
-            h[CH_PAD_MASK] |= 1u << l;
-            h[o_row0 + l] = g->var_row[d];
-          } else {
-            if (g->var_flags[d] & VF_EVID) h[CH_EVID_MASK] |= 1u << l;
-            const uint32_t K = g->var_row[d + 1] - g->var_row[d];
-            kmax = std::max(kmax, K);
-            h[o_meta + l] = K | (g->evid_val[d] << 8);
-            h[o_row0 + l] = g->var_row[d];
-            for (uint64_t row = g->var_row[d]; row < g->var_row[d + 1]; ++row) {
-              bool first = true;
-              uint64_t o = g->has_multi ? g->row_oth[row] : 0;
-              for (uint64_t e = g->row_ptr[row]; e < g->row_ptr[row + 1]; ++e) {
-                const uint8_t tag = g->e_tag[e];
-                const uint32_t fc = tag & TAG_FUNC_MASK, form = tag >> TAG_FORM_SHIFT;
-                uint32_t table = 0;
-                for (uint32_t ss = 0; ss < 2; ++ss)
-                  for (uint32_t os = 0; os < 2; ++os) {
-                    uint32_t c;
-                    if (form == 0) c = code1(fc, ss);
-                    else if (tag & TAG_SELF_HEAD) c = code2(fc, os, ss);
-                    else c = code2(fc, ss, os);
-                    table |= c << (2 * (2 * ss + os));
-                  }
-                uint32_t rec = g->e_wid[e] | (table << 22) | (first ? CELL_ROW_BIT : 0u);
-                if (form == 1) {
-                  rec |= CELL_MULTI_BIT;
-                  h[o_oth + 32ull * jo + l] = (g->oth[2 * o] << 8) | (g->oth[2 * o + 1] & 0xffu);
-                  ++jo; ++o;
-                }
-                h[o_rec + 32ull * jr + l] = rec;
-                ++jr; first = false;
-              }
-              if (first) { h[o_rec + 32ull * jr + l] = CELL_NOP_ROW; ++jr; }  // a value without factors
-            }
-          }
-          for (; jr < nrec; ++jr) h[o_rec + 32ull * jr + l] = CELL_NOP;
-        }
-        h[CH_KMAX] = kmax;
-      }
-    });
+  {
+    std::string e = build_cell_blob(g, nvar_pad, ncolor, err);
+    if (!e.empty()) return e;
   }
   pt.lap("sliced-ELL blob");
   *err = DWG_OK;
