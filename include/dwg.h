@@ -151,6 +151,10 @@ int dwg_graph_var_meta(const dwg_graph *g, uint8_t *dtype, uint8_t *is_evid, uin
  * (src/gibbs_sampler.cc:5-18, src/inference_result.cc:24-42) -------------------- */
 int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handle **out);
 void dwg_destroy(dwg_handle *h);
+/* Device memory of destroyed replicas stays in the device's stream-ordered pool for the next
+ * dwg_create (no equivalent in the reference: its replicas live as long as the process).  This
+ * returns what the pool holds unused to the driver. */
+int dwg_release_cached_memory(int device);
 /* The device arrays that hold the replica's copy of the graph (stream, per-variable tables, initial
  * weights), in a fixed order that depends on the graph only: ptrs[i] / bytes[i] for i < *n (call
  * with max = 0 to get the count).  What a replica created with defer_upload receives from a

@@ -6,4 +6,4 @@ that ABI (api.py), the build recipe (_build.py) and input tooling (graphio.py, g
 """
 from . import graphio  # noqa: F401
 from .api import (DwgError, Graph, Sampler, SCHED_AUTO, SCHED_CHROMATIC, SCHED_HOGWILD, SCHED_SEQUENTIAL,  # noqa: F401
-                  draw, dw_main, load, logadd)
+                  draw, dw_main, load, logadd, release_cached_memory)

@@ -87,6 +87,7 @@ def load(build: bool = False):
     L.dwg_debug_image.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(u64), C.POINTER(C.c_uint32)]
     L.dwg_create.argtypes = [vp, C.POINTER(Opts), i32, C.POINTER(vp)]
     L.dwg_destroy.argtypes = [vp]
+    L.dwg_release_cached_memory.argtypes = [i32]
     L.dwg_graph_segments.argtypes = [vp, i32, vp, vp, C.POINTER(i32)]
     L.dwg_reset_state.argtypes = [vp]
     L.dwg_learn_epoch.argtypes = [vp, dbl]
@@ -388,6 +389,11 @@ class Sampler:
                 for j in range(int(base[v + 1]) - b):
                     out[(v, int(values[b + j]))] = float(t[b + j]) / float(n[v])
         return out
+
+
+def release_cached_memory(device: int = 0) -> None:
+    """return the device memory destroyed samplers left in the library's pool to the driver"""
+    _check(load().dwg_release_cached_memory(int(device)))
 
 
 def draw(pots: np.ndarray, card: np.ndarray, r: np.ndarray, device: int = 0) -> np.ndarray:

@@ -948,6 +948,16 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
   return DWG_OK;
 }
 
+int dwg_release_cached_memory(int device) {
+  CU(cudaSetDevice(device));
+  if (!dev_pool_on(device)) return DWG_OK;
+  cudaMemPool_t pool = nullptr;
+  CU(cudaDeviceGetDefaultMemPool(&pool, device));
+  CU(cudaStreamSynchronize((cudaStream_t)0));
+  CU(cudaMemPoolTrimTo(pool, 0));
+  return DWG_OK;
+}
+
 void dwg_destroy(dwg_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);

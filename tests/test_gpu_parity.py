@@ -735,6 +735,29 @@ def test_two_replicas_one_gpu_average_and_aggregate():
     assert np.array_equal(t, ta + tb) and (n == 12).all()
 
 
+def test_memory_pool_keeps_and_releases_device_memory():
+    """device memory of a destroyed replica stays in the library's pool (the next dwg_create does
+    not map it again) until dwg_release_cached_memory hands it back to the driver"""
+    import torch
+    from sampler_b200 import graphgen
+    raw = graphgen.c2_boolean(400_000, nweight=50)
+    g = sb.Graph.from_raw(raw)
+    sb.release_cached_memory(0)
+    free0 = torch.cuda.mem_get_info(0)[0]
+    s = sb.Sampler(g, sample_evidence=True)
+    s.infer_epochs(2)
+    used = free0 - torch.cuda.mem_get_info(0)[0]
+    assert used >= g.info.device_bytes // 2
+    s.close()
+    kept = free0 - torch.cuda.mem_get_info(0)[0]
+    assert kept >= g.info.device_bytes // 2  # still held by the pool
+    s = sb.Sampler(g, sample_evidence=True)  # ... and reused: no growth
+    assert free0 - torch.cuda.mem_get_info(0)[0] <= used + (32 << 20)
+    s.close()
+    sb.release_cached_memory(0)
+    assert free0 - torch.cuda.mem_get_info(0)[0] <= (64 << 20)
+
+
 @pytest.mark.parametrize("shape", ["boolean", "categorical"])
 def test_narrow_counter_tally_exchange(shape):
     """dwg_tallies_pack / dwg_tallies_unpack: the cross-replica sum of the tallies taken on words of
