@@ -96,9 +96,10 @@ __device__ __forceinline__ double cell_signed_weight(uint32_t n_tab, const unsig
 template <bool ALLHOT>
 __device__ __forceinline__ void cell_potentials(const uint32_t *src, uint32_t n_rec, uint32_t n_oc, uint32_t lane,
                                                 const uint8_t *a, uint32_t n_tab, const unsigned char *tab_s,
-                                                uint32_t plane, const double *w, double *buf) {
+                                                uint32_t plane, const double *w, double *buf, uint32_t kmax) {
   const uint32_t *recs = src + SH_WORDS + 64u + lane, *oth = recs + 32u * n_rec;
-  // 1. other variables' chain values: independent L2 gathers, four at a time
+  // 1. other variables' chain values: independent L2 gathers, four at a time.  (Requesting them a
+  //    slice ahead, as the Boolean kernel does, costs 10 registers and measured 4.7 % SLOWER on C3.)
   uint32_t satmask = 0;
   for (uint32_t c0 = 0; c0 < n_oc; c0 += 4) {
     uint32_t ow[4], av[4];
@@ -110,29 +111,30 @@ __device__ __forceinline__ void cell_potentials(const uint32_t *src, uint32_t n_
     for (uint32_t u = 0; u < 4; ++u)
       if (c0 + u < n_oc) satmask |= (av[u] == (ow[u] & 0xffu) ? 1u : 0u) << (c0 + u);
   }
-  // 2. the record column: rows in value order, a row's records in factor-id order
+  // 2. the record column: rows in value order, a row's records in factor-id order.  Branch-free: the
+  //    running sum of the current row is stored after EVERY record (lane-strided, conflict-free), the
+  //    last store of a row is its potential; a flagged record opens the next row with a fresh sum.
+  //    (A branch per record on the row flag diverges in every warp: lanes change rows at different j.)
   double cur = 0.0;
   uint32_t k = 0xffffffffu, oc = 0;
+#pragma unroll 4
   for (uint32_t j = 0; j < n_rec; ++j) {
     const uint32_t rec = recs[32u * j];
-    if (rec & CELL_ROW_BIT) {
-      if (k != 0xffffffffu) buf[k * 32u] = cur;
-      cur = 0.0;
-      ++k;
-    }
+    const bool first = rec & CELL_ROW_BIT;  // (the first record of a lane always carries it: k becomes 0)
+    k += first ? 1u : 0u;
     const uint32_t multi = (rec >> 30) & 1u, os = multi & (satmask >> oc);
     oc += multi;
     const uint32_t code = (rec >> (22u + 2u * (2u + os))) & 3u;  // this variable takes the row's value: self_sat = 1
-    cur = __dadd_rn(cur, cell_signed_weight<ALLHOT>(n_tab, tab_s, plane, w, code, rec & CELL_WID_MASK));
+    cur = __dadd_rn(first ? 0.0 : cur, cell_signed_weight<ALLHOT>(n_tab, tab_s, plane, w, code, rec & CELL_WID_MASK));
+    buf[min(k, kmax - 1u) * 32u] = cur;  // (a padding lane has no flagged record: k stays -1, its stores land in the last row)
   }
-  if (k != 0xffffffffu) buf[k * 32u] = cur;
 }
 
 template <bool ALLHOT>
 __device__ __noinline__ void cell_unstaged_potentials(const CellGraph &g, uint32_t off, uint32_t n_rec, uint32_t n_oc,
                                                       uint32_t lane, const uint8_t *a, const unsigned char *tab_s,
                                                       uint32_t plane, const double *w, double *buf) {
-  cell_potentials<ALLHOT>(g.blob + (size_t)off * 8, n_rec, n_oc, lane, a, g.n_tab, tab_s, plane, w, buf);
+  cell_potentials<ALLHOT>(g.blob + (size_t)off * 8, n_rec, n_oc, lane, a, g.n_tab, tab_s, plane, w, buf, g.kmax);
 }
 
 template <bool ALLHOT, int NT>
@@ -214,7 +216,7 @@ k_cell_infer_staged(const CellGraph g, const SellState st, const SweepParams p, 
       if (SH_WORDS + 32u * (2u + n_rec + n_oc) > stage_words)
         cell_unstaged_potentials<ALLHOT>(g, h1.w, n_rec, n_oc, lane, st.assign_evid, tab_s, plane, st.weights, buf);
       else
-        cell_potentials<ALLHOT>(sm + b, n_rec, n_oc, lane, st.assign_evid, g.n_tab, tab_s, plane, st.weights, buf);
+        cell_potentials<ALLHOT>(sm + b, n_rec, n_oc, lane, st.assign_evid, g.n_tab, tab_s, plane, st.weights, buf, g.kmax);
       if ((active >> lane) & 1u) {
         const uint32_t prop = cell_draw(buf, meta & 0xffu, r0);
         st.assign_evid[d] = (uint8_t)prop;              // gibbs_sampler.h:160
@@ -254,24 +256,23 @@ __host__ __device__ inline size_t cell_learn_smem(uint32_t n_hot, uint32_t stage
 // potentials of the lane's values on the chain whose others are summarised in satmask
 __device__ __forceinline__ void cell_potentials_masked(const uint32_t *recs, uint32_t n_rec, uint32_t satmask,
                                                        const SellGraph &g, const double *w_s, const double *w,
-                                                       double *buf) {
+                                                       double *buf, uint32_t kmax) {
+  // (branch-free like cell_potentials: the running row sum is stored after every record)
   double cur = 0.0;
   uint32_t k = 0xffffffffu, oc = 0;
+#pragma unroll 4
   for (uint32_t j = 0; j < n_rec; ++j) {
     const uint32_t rec = recs[32u * j];
-    if (rec & CELL_ROW_BIT) {
-      if (k != 0xffffffffu) buf[k * 32u] = cur;
-      cur = 0.0;
-      ++k;
-    }
+    const bool first = rec & CELL_ROW_BIT;
+    k += first ? 1u : 0u;
     const uint32_t multi = (rec >> 30) & 1u, os = multi & (satmask >> oc);
     oc += multi;
     const uint32_t code = (rec >> (22u + 2u * (2u + os))) & 3u;
     const uint32_t wid = rec & CELL_WID_MASK;
     const double wt = wid < g.n_hot ? w_s[wid] : __ldcg(w + wid);
-    cur = __dadd_rn(cur, sell_term(code, wt));
+    cur = __dadd_rn(first ? 0.0 : cur, sell_term(code, wt));
+    buf[min(k, kmax - 1u) * 32u] = cur;
   }
-  if (k != 0xffffffffu) buf[k * 32u] = cur;
 }
 
 __global__ void __launch_bounds__(SELL_LEARN_THREADS, 2)
@@ -376,12 +377,12 @@ k_cell_learn_live(const SellGraph g, const SellState st, const SweepParams p, co
           }
       }
       // free chain: every variable (gibbs_sampler.h:137-139)
-      cell_potentials_masked(recs, n_rec, fmask, g, w_s, L.weights, buf);
+      cell_potentials_masked(recs, n_rec, fmask, g, w_s, L.weights, buf, X.kmax);
       const uint32_t pf = pad ? 0u : cell_draw(buf, K, u0);
       // evid chain (sample_evid, :171-190): hard evidence is clamped, everything else drawn
       uint32_t pe = ev;
       if (__any_sync(0xffffffffu, !pad && !evid)) {
-        cell_potentials_masked(recs, n_rec, emask, g, w_s, L.weights, buf);
+        cell_potentials_masked(recs, n_rec, emask, g, w_s, L.weights, buf, X.kmax);
         if (!pad && !evid) pe = cell_draw(buf, K, u1);
       }
       if (!pad) { st.assign_free[d] = (uint8_t)pf; st.assign_evid[d] = (uint8_t)pe; }
