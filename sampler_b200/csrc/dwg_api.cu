@@ -1085,6 +1085,13 @@ static int launch_learn_sell(dwg_handle *h, SweepParams &p, double stepsize) {
     L.inv_nslice = 1.0 / nslice;
     sell_learn_launch(h, blocks, threads, live, p, L);
     ++g_launches;
+    // the decay of the weights outside the CTAs' shared copies for this launch's share of the sweep
+    const uint32_t n_hot = live ? 0u : h->sg.n_hot;
+    if (m.nweight > n_hot && L.decay != 0.0) {
+      const uint32_t ncold = (uint32_t)m.nweight - n_hot;
+      k_cold_decay<<<(ncold + 255) / 256, 256, 0, h->stream>>>(L, h->w_fixed.p, n_hot, (uint32_t)m.nweight, (double)(ve - vb) / nslice);
+      ++g_launches;
+    }
   };
   launch(0, nslice - tail_slices, wide_warps, period_wide);
   // tail: the CTA's weight copy is refreshed before every slice (period 1: eight warps read the

@@ -402,11 +402,8 @@ k_cell_learn_live(const SellGraph g, const SellState st, const SweepParams p, co
           const uint32_t wid = rec & CELL_WID_MASK;
           if (wid < g.n_hot) {
             if (cf != ce) atomicAdd(reinterpret_cast<int *>(acc_s + wid), cf - ce);
-          } else if (!__ldg(X.w_fixed + wid)) {  // beyond the copy: the step and its decay straight into the live vector
-            const double sc = sell_step_scale(L, wid), x = __ldcg(L.weights + wid);
-            const double dec = L.reg_l1 ? L.decay * (x < 0 ? 1.0 : 0.0) : -x * (L.decay * sc) / (1.0 + L.decay * sc);
-            const double dd = dec - L.step * sc * (double)(cf - ce);
-            if (dd != 0.0) atomicAdd(L.weights + wid, dd);
+          } else if (cf != ce && !__ldg(X.w_fixed + wid)) {  // beyond the copy: the step straight into the live vector (decay: k_cold_decay)
+            atomicAdd(L.weights + wid, -L.step * sell_step_scale(L, wid) * (double)(cf - ce));
           }
         }
       }

@@ -799,7 +799,11 @@ __device__ __forceinline__ double sell_step_scale(const SellLearn &L, uint32_t w
 }
 
 // gradient of one SGD step: hot weights into the CTA's accumulator of the period, others straight
-// into the live vector together with the step's decay (update_weight, src/inference_result.h:66-85).
+// into the live vector (update_weight, src/inference_result.h:66-85).  The DECAY of the weights
+// outside the shared copy is applied per launch by k_cold_decay from their static update counts --
+// like the hot weights' decay (lumped per period) it does not ride on the records: a record whose
+// gradient is zero (the free draw agrees with the evidence) costs no atomic.  C4 (1 M weights, 23 %
+// of the record visits outside the copy) went from 24.3 to the figure in DESIGN.md 4 with it.
 // Graphs whose feature values are all 1 have integer gradients (differences of sign codes): their
 // accumulators are int32 (a native shared-memory atomic instead of a compare-and-swap loop).
 template <int FV>
@@ -812,10 +816,20 @@ __device__ __forceinline__ void sell_grad(const SellGraph &g, const SellLearn &L
     else atomicAdd(acc_s + wid, grad);
     return;
   }
-  const double sc = sell_step_scale(L, wid), x = __ldcg(L.weights + wid);
-  const double dec = L.reg_l1 ? L.decay * (x < 0 ? 1.0 : 0.0) : -x * (L.decay * sc) / (1.0 + L.decay * sc);
-  const double d = dec - L.step * sc * grad;
-  if (d != 0.0) atomicAdd(L.weights + wid, d);
+  if (grad == 0.0) return;
+  atomicAdd(L.weights + wid, -L.step * sell_step_scale(L, wid) * grad);
+}
+
+// decay of the weights outside the shared-memory copy for one learning launch that visited `share`
+// of the sweep: weight k took N_k * share SGD steps, each  w <- w / (1 + reg step)  resp.
+// w += reg (w < 0)  (src/inference_result.h:72-80)
+__global__ void k_cold_decay(const SellLearn L, const uint8_t *fixed, uint32_t n_hot, uint32_t nweight, double share) {
+  const uint32_t i = n_hot + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nweight || fixed[i]) return;
+  const double n = (double)L.w_N[i] * share;
+  if (n == 0.0) return;
+  const double x = L.weights[i];
+  L.weights[i] = L.reg_l1 ? x + n * L.decay * (x < 0 ? 1.0 : 0.0) : x * exp(-n * log1p(L.decay * sell_step_scale(L, i)));
 }
 template <int FV>
 __device__ __forceinline__ double sell_acc_take(double *acc_s, uint32_t i) {  // read and clear
@@ -861,15 +875,14 @@ __device__ __forceinline__ void sell_sgd_records(const SellGraph &g, const SellS
                                                  const SliceHeader &h, double *acc_s, uint32_t lane, uint32_t d,
                                                  uint32_t pf, uint32_t ev, bool learn, bool masks, uint32_t sf_mask,
                                                  uint32_t se_mask) {
-  const bool cold = g.nweight > g.n_hot;  // weights outside the shared copy: their decay rides on every visited record
-  if (cold || __any_sync(0xffffffffu, learn && pf != ev)) {  // unary: same value on both chains = zero gradient
+  if (__any_sync(0xffffffffu, learn && pf != ev)) {  // unary: same value on both chains = zero gradient
     for (uint32_t j = 0; j < h.n_un; ++j) {
       const uint32_t rec = sell_ld<LD>(h.un + (size_t)32 * j + lane);
       if (!learn || rec == SELL_UNARY_NOP) continue;
       const int cf = (int)(pf ? rec & 3u : rec >> 26), ce = (int)(ev ? rec & 3u : rec >> 26);
-      if (cf == ce && !cold) continue;
+      if (cf == ce) continue;
       sell_grad<FV>(g, L, acc_s, sell_unary_wid(rec), rec & SELL_UN_FIXED_BIT,
-                cf == ce ? 0.0 : __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.un, h.n_un, j, lane)));
+                __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.un, h.n_un, j, lane)));
     }
   }
   if (!MULTI || !h.n_mu) return;
@@ -883,9 +896,9 @@ __device__ __forceinline__ void sell_sgd_records(const SellGraph &g, const SellS
       if (masks) { sf = (sf_mask >> j) & 1u; se = (se_mask >> j) & 1u; }
       else { sf = sell_chain<LD>(st.assign_free, od) == eq; se = sell_chain<LD>(st.assign_evid, od) == eq; }
       const int cf = (int)((tag >> (4u * pf + 2u * sf)) & 3u), ce = (int)((tag >> (4u * ev + 2u * se)) & 3u);
-      if ((cf == ce && !cold) || tag == SELL_BINARY_NOP) continue;
+      if (cf == ce || tag == SELL_BINARY_NOP) continue;
       sell_grad<FV>(g, L, acc_s, rec & SELL_WID_MASK, rec & SELL_FIXED_BIT,
-                cf == ce ? 0.0 : __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.mu, h.n_mu, j, lane)));
+                __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.mu, h.n_mu, j, lane)));
     }
   } else {
     uint32_t oc = 0;
@@ -912,7 +925,6 @@ template <bool MULTI, int FV, int LD, bool WIDE>
 __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellState &st, const SweepParams &p,
                                                  const SellLearn &L, const SliceHeader &h, const double *w_s,
                                                  double *acc_s, uint32_t lane, uint32_t d) {
-  const bool cold = g.nweight > g.n_hot;  // weights outside the shared copy: their decay rides on every visited record
   // SF_WIDE: the slice is ONE variable (slot 0) whose records are dealt to the 32 lanes -- every lane
   // takes the variable's flags, uniforms and draws, sums its share of the records and pushes the SGD
   // steps of its share; lane 0 writes the chains

@@ -1359,6 +1359,8 @@ std::string compile_graph(const RawView &raw, int schedule, GraphImage *g, int *
         for (uint64_t e = e0; e < e1; ++e) g->e_wid[e] = g->w_inv[g->e_wid[e]];
       });
     g->n_hot = (uint32_t)std::min<uint64_t>(nweight, DWG_HOT_WEIGHTS);
+    if (const char *e = getenv("DWG_HOT_WEIGHTS"))  // tests: a small shared-memory copy, most weights read from / pushed to L2
+      g->n_hot = (uint32_t)std::min<uint64_t>(g->n_hot, (uint64_t)std::max(16, atoi(e)));
   }
 
   pt.lap("weight ids");

@@ -436,6 +436,48 @@ def test_learning_decay_follows_the_update_counts():
     assert np.allclose(s.weights(), want, rtol=1e-3), (s.weights()[:4], want[:4])
 
 
+@pytest.mark.parametrize("reg", ["l2", "l1"])
+def test_learning_decay_of_weights_outside_the_shared_copy(reg):
+    """graphs with more weights than a CTA's shared-memory copy holds (> 4096): the decay of the
+    others is applied per launch from their static update counts (k_cold_decay), the gradient steps
+    by atomics on the live vector.  Zero gradients (free draws forced to the evidence): every weight
+    must end at  w0 * (1 + reg * step)^(-N_k)  (l1, sic: w0 + N_k * reg for negative weights);
+    opposite draws on a second graph: w0 - step * (sum of gradients) on top of the decay."""
+    rng = np.random.default_rng(13)
+    nvar, nw, deg = 60000, 6000, 5
+    func = np.full(nvar * deg, gio.FUNC_ISTRUE, np.int32)
+    ptr = np.arange(nvar * deg + 1, dtype=np.uint64)
+    evid = np.repeat(np.arange(nvar, dtype=np.uint64), deg)
+    label = rng.integers(0, 2, nvar)
+    wid = rng.integers(0, nw, nvar * deg)  # ~50 uses each: the copy holds the 4096 most used, the rest are read from L2
+    w0 = np.where(rng.random(nw) < 0.5, -0.5, 0.5)
+    raw = gio.RawGraph(np.ones(nvar, np.uint8), label, np.zeros(nvar, np.uint16), np.full(nvar, 2, np.uint64),
+                       *gio.empty_domains(), func, ptr, evid, np.ones(nvar * deg, np.uint64), wid,
+                       np.ones(nvar * deg), w0, np.zeros(nw, np.uint8)).normalized()
+    g = sb.Graph.from_raw(raw, sb.SCHED_AUTO)
+    regp, step = (0.5, 2.0 ** -10) if reg == "l2" else (2.0 ** -16, 2.0 ** -10)
+    n_k = np.bincount(wid, minlength=nw).astype(np.float64)
+    assert (n_k > 0).sum() > 4096 + 500 and n_k.max() < 120  # weights outside the copy are in use; steps are not scaled
+    # 1. zero gradients
+    s = sb.Sampler(g, reg_param=regp, regularization=reg)
+    s.set_uniforms(np.where(label == 1, 0.0, 1.0 - 1e-9), np.zeros(nvar))  # r = 0 draws 1, r -> 1 draws 0
+    s.learn_epoch(step)
+    assert np.array_equal(s.assignments(0), label.astype(np.uint64))
+    want = w0 * (1.0 + regp * step) ** (-n_k) if reg == "l2" else w0 + n_k * regp * (w0 < 0)
+    assert np.abs(want - w0).max() > (1e-3 if reg == "l2" else 1e-4)  # the decay is visible
+    assert np.allclose(s.weights(), want, rtol=1e-3, atol=1e-7), np.abs(s.weights() - want).max()
+    s.close()
+    # 2. every free draw opposite to the evidence: gradient of an ISTRUE record = sign(free) - sign(evid) = -+2
+    s = sb.Sampler(g, reg_param=0.0, regularization=reg)
+    s.set_uniforms(np.where(label == 1, 1.0 - 1e-9, 0.0), np.zeros(nvar))
+    step = 2.0 ** -20
+    s.learn_epoch(step)
+    assert np.array_equal(s.assignments(0), (1 - label).astype(np.uint64))
+    grad = np.bincount(wid, weights=np.repeat(np.where(label == 1, -2.0, 2.0), deg), minlength=nw)
+    assert np.allclose(s.weights(), w0 - step * grad, rtol=0, atol=1e-12)
+    assert np.abs(step * grad).max() > 10 * step  # gradients were summed
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_parallel_learning_gradient_sums_on_coupled_graphs(seed, monkeypatch):
     """The gradient a learning sweep accumulates per weight (sliced-ELL sign codes and 2x2 sign

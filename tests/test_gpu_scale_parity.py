@@ -72,10 +72,15 @@ def test_inference_under_fixed_weights_vs_reference(name):
     assert np.quantile(d, 0.999) <= 0.08, np.quantile(d, 0.999)
 
 
-@pytest.mark.parametrize("name", GRAPHS)
-def test_mid_size_graph_vs_reference(name):
+@pytest.mark.parametrize("name", GRAPHS + ["c4_small/256"])
+def test_mid_size_graph_vs_reference(name, monkeypatch):
     """learn + infer end to end with the graph's dw-args, NSEEDS sampler seeds against the mean of
-    the reference's 16"""
+    the reference's 16.  "c4_small/256": the same graph with a 256-entry shared-memory weight copy, so
+    that most of its 2000 weights take the path of weights outside the copy (read from L2, steps by
+    global atomics, decay per launch from the update counts) -- what C4's million weights do"""
+    if "/" in name:
+        name, hot = name.split("/")
+        monkeypatch.setenv("DWG_HOT_WEIGHTS", hot)
     z, raw, a = _load(name)
     ws, ms = [], []
     for seed in range(1, NSEEDS + 1):
