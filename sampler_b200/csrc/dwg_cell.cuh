@@ -339,7 +339,7 @@ k_cell_learn_live(const SellGraph g, const SellState st, const SweepParams p, co
   uint32_t proc_s = cur_s;
   for (uint32_t r0 = 0; r0 < rounds; r0 = r0 + L.period < r0 ? rounds : r0 + L.period) {
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) w_s[i] = __ldcg(L.weights + i);
+    sell_refresh_weights(w_s, L.weights, g.n_hot);
     if (threadIdx.x == 0) cnt_s = 0;
     __syncthreads();
     uint32_t mine = 0;

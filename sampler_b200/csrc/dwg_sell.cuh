@@ -876,13 +876,25 @@ __device__ __forceinline__ void sell_sgd_records(const SellGraph &g, const SellS
                                                  uint32_t pf, uint32_t ev, bool learn, bool masks, uint32_t sf_mask,
                                                  uint32_t se_mask) {
   if (__any_sync(0xffffffffu, learn && pf != ev)) {  // unary: same value on both chains = zero gradient
-    for (uint32_t j = 0; j < h.n_un; ++j) {
-      const uint32_t rec = sell_ld<LD>(h.un + (size_t)32 * j + lane);
-      if (!learn || rec == SELL_UNARY_NOP) continue;
-      const int cf = (int)(pf ? rec & 3u : rec >> 26), ce = (int)(ev ? rec & 3u : rec >> 26);
-      if (cf == ce) continue;
-      sell_grad<FV>(g, L, acc_s, sell_unary_wid(rec), rec & SELL_UN_FIXED_BIT,
-                __dmul_rn((double)(cf - ce), sell_fv<FV, LD>(h.un, h.n_un, j, lane)));
+    // records (and feature values) in batches: a slice longer than a ring stage is read from L2 / HBM
+    // here, and one record per trip exposed a full round trip per record (C4: a quarter of the stalls)
+    constexpr uint32_t U = FV == FV_F64 ? 4 : 8;
+    for (uint32_t j0 = 0; j0 < h.n_un; j0 += U) {
+      uint32_t rec[U];
+      double fv[U];
+#pragma unroll
+      for (uint32_t u = 0; u < U; ++u) {
+        const bool ok = j0 + u < h.n_un;
+        rec[u] = ok ? sell_ld<LD>(h.un + (size_t)32 * (j0 + u) + lane) : SELL_UNARY_NOP;
+        fv[u] = (FV != FV_ONE && ok) ? sell_fv<FV, LD>(h.un, h.n_un, j0 + u, lane) : 1.0;
+      }
+#pragma unroll
+      for (uint32_t u = 0; u < U; ++u) {
+        if (!learn || rec[u] == SELL_UNARY_NOP) continue;
+        const int cf = (int)(pf ? rec[u] & 3u : rec[u] >> 26), ce = (int)(ev ? rec[u] & 3u : rec[u] >> 26);
+        if (cf == ce) continue;
+        sell_grad<FV>(g, L, acc_s, sell_unary_wid(rec[u]), rec[u] & SELL_UN_FIXED_BIT, __dmul_rn((double)(cf - ce), fv[u]));
+      }
     }
   }
   if (!MULTI || !h.n_mu) return;
@@ -1024,6 +1036,18 @@ __device__ __forceinline__ void sell_learn_slice(const SellGraph &g, const SellS
   }
 }
 
+// the CTA's copy of the hot weights from the live vector (L2), four loads in flight per thread
+__device__ __forceinline__ void sell_refresh_weights(double *w_s, const double *w, uint32_t n_hot) {
+  for (uint32_t i0 = threadIdx.x; i0 < n_hot; i0 += 4u * blockDim.x) {
+    double v[4];
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u) v[u] = i0 + u * blockDim.x < n_hot ? __ldcg(w + i0 + u * blockDim.x) : 0.0;
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u)
+      if (i0 + u * blockDim.x < n_hot) w_s[i0 + u * blockDim.x] = v[u];
+  }
+}
+
 // One launch of a learning sweep: positions [vbegin, vend) of the visit order, dealt to the warps
 // of the grid round-robin (position vbegin + round * warps + warp: the whole grid moves through the
 // order together, so "later in the order" is "later in time").  Slices come through a per-warp
@@ -1107,7 +1131,7 @@ k_sell_learn_live(const SellGraph g, const SellState st, const SweepParams p, co
   uint32_t proc_s = cur_s;  // slice indices of the block being processed
   for (uint32_t r0 = 0; r0 < rounds; r0 = r0 + L.period < r0 ? rounds : r0 + L.period) {
     __syncthreads();  // the previous flush is done with w_s / acc_s
-    for (uint32_t i = threadIdx.x; i < g.n_hot; i += blockDim.x) w_s[i] = __ldcg(L.weights + i);
+    sell_refresh_weights(w_s, L.weights, g.n_hot);
     if (threadIdx.x == 0) cnt_s = 0;
     __syncthreads();
     uint32_t mine = 0;
