@@ -177,7 +177,8 @@ __device__ __forceinline__ uint32_t sell_draw_boolean(double pos, double neg, do
 template <int FV, int LD, bool ANTISYM>
 __device__ __forceinline__ void sell_unary(const SellGraph &g, const SliceHeader &h, const double *w_s,
                                            const double *w, uint32_t lane, double &pos, double &neg) {
-  constexpr int U = FV == FV_F64 ? 4 : 8;
+  // (a learning sweep reading a long slice from L2 / HBM -- LD_CACHED, 128-register kernel -- keeps more loads in flight)
+  constexpr int U = FV == FV_F64 ? (LD == LD_CACHED ? 10 : 4) : 8;
   for (uint32_t j0 = 0; j0 < h.n_un; j0 += U) {
     uint32_t rec[U];
     double fv[U];
