@@ -1352,6 +1352,20 @@ static int get_tallies_impl(dwg_handle *h, uint64_t *tallies, uint32_t *tallies3
     if (timing) fprintf(stderr, "[get_tallies] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t_prev).count());
     t_prev = n;
   };
+  // ++agg_nsamples for every sampled variable every sweep (src/gibbs_sampler.h:157,163): implicit on the
+  // device, written out here by the host threads
+  auto fill_nsamples = [&]() {
+    if (!nsamples) return;
+    const uint64_t sweeps = h->infer_sweeps;
+    const bool all = h->opts.sample_evidence;
+    const uint8_t *ev = m.var_is_evid.data();
+    const uint64_t *extra = h->extra_nsamples.empty() ? nullptr : h->extra_nsamples.data();
+    uint64_t *out = nsamples;
+    parallel_for(m.nvar, [=](uint64_t a, uint64_t b) {
+      for (uint64_t v = a; v < b; ++v) out[v] = ((!ev[v] || all) ? sweeps : 0) + (extra ? extra[v] : 0);
+    });
+    nsamples = nullptr;  // done
+  };
   if ((tallies || tallies32) && m.nrow) {
     // schedule order -> ABI order on the device, then 4 MB pieces through two small page-locked
     // buffers: the DMA of piece c overlaps the widening of piece c - 1 on the host threads (page-locking
@@ -1365,6 +1379,7 @@ static int get_tallies_impl(dwg_handle *h, uint64_t *tallies, uint32_t *tallies3
                                                                              h->row_of_value.p, (uint32_t)m.nrow);
         ++g_launches;
         CU(cudaMemcpyAsync(tallies32, h->tallies_abi.p, 4 * m.nrow, cudaMemcpyDeviceToHost, h->stream));
+        fill_nsamples();  // while the DMA runs
         CU(cudaStreamSynchronize(h->stream));
         tallies32 = nullptr;  // done
       } else {
@@ -1414,14 +1429,7 @@ static int get_tallies_impl(dwg_handle *h, uint64_t *tallies, uint32_t *tallies3
   }
 tallies_done:
   if (nsamples) {
-    // ++agg_nsamples for every sampled variable every sweep (src/gibbs_sampler.h:157,163)
-    const uint64_t sweeps = h->infer_sweeps;
-    const bool all = h->opts.sample_evidence;
-    const uint8_t *ev = m.var_is_evid.data();
-    const uint64_t *extra = h->extra_nsamples.empty() ? nullptr : h->extra_nsamples.data();
-    parallel_for(m.nvar, [=](uint64_t a, uint64_t b) {
-      for (uint64_t v = a; v < b; ++v) nsamples[v] = ((!ev[v] || all) ? sweeps : 0) + (extra ? extra[v] : 0);
-    });
+    fill_nsamples();
     lap("nsamples");
   }
   return DWG_OK;
