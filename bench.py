@@ -349,8 +349,8 @@ def ours(args):
     smp.close()
     torch.cuda.synchronize()
     t_host = torch.empty(int(info.num_values), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
-    n_host = np.empty(int(info.num_variables), np.uint64)
-    n_host[:] = 0  # touch the pages outside the timed region
+    # (page-locked as well: the per-variable sample counts then arrive by DMA instead of being written by the host's threads)
+    n_host = torch.zeros(int(info.num_variables), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
     if dist is not None:  # the first broadcast on a communicator sets up its channels: not part of a sweep
         warm = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
         dist.broadcast(warm, src=0)
@@ -448,10 +448,10 @@ def ours(args):
                      "launches_per_sweep": info.num_colors},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "variable-samples/s",
-                "h2d_bytes_per_step": int(info.device_bytes / args.steps), "d2h_bytes_per_step": int(4 * info.num_values / args.steps),
+                "h2d_bytes_per_step": int(info.device_bytes / args.steps), "d2h_bytes_per_step": int((4 * info.num_values + 8 * info.num_variables) / args.steps),
                 "what": "dwg_create (upload of the compiled graph from page-locked host memory, once per node; the other "
                         "replicas receive it over NVLink) + %d sweeps per replica + tally reduction onto rank 0 + "
-                        "dwg_get_tallies32 (D2H into a page-locked host array), wall clock: %s" % (args.steps, e2e_parts)},
+                        "dwg_get_tallies32 (u32 tallies and u64 sample counts, D2H into page-locked host arrays), wall clock: %s" % (args.steps, e2e_parts)},
         "learn": None if not learn_ms else
                  {"value": nvar * world / (learn_ms * 1e-3), "unit": "variable-updates/s", "ms_per_epoch": learn_ms,
                   "epochs": n_learn, "hbm_gbs": float(info.bytes_per_sweep_learn) / (learn_ms * 1e-3) / 1e9,

@@ -186,7 +186,10 @@ int dwg_clear_tallies(dwg_handle *h);
  * tallies[num_values], nsamples[num_variables] in original (variable, domain-index) order */
 int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples);
 /* the same with the tallies at the device's own counter width (u32: no widening pass on the host;
- * a tally cannot exceed the number of sweeps) */
+ * a tally cannot exceed the number of sweeps).  Page-locked destinations (cudaHostAlloc /
+ * cudaHostRegister memory) are filled by DMA straight from the device -- the tallies of
+ * dwg_get_tallies32 and the sample counts of both getters; pageable ones by the host's threads.
+ * Either pointer may be NULL. */
 int dwg_get_tallies32(dwg_handle *h, uint32_t *tallies, uint64_t *nsamples);
 int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsamples); /* aggregate_marginals_from :116-127 */
 int dwg_get_weights(dwg_handle *h, double *out);

@@ -324,6 +324,15 @@ __global__ void k_unpack_tallies(uint32_t *t, const uint32_t *words, uint32_t n)
   }
 }
 
+// agg_nsamples of every variable in ABI order (src/gibbs_sampler.h:157,163: one count per sweep for
+// every sampled variable): `sweeps`, or 0 for evidence when evidence is not sampled (evid = nullptr:
+// every variable is sampled).  Written on the device so that a page-locked destination receives it
+// by DMA: the copy engine fills host memory faster than the host's threads do.
+__global__ void k_fill_nsamples(unsigned long long *out, const uint8_t *evid, unsigned long long sweeps, uint64_t n) {
+  for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < n; v += (uint64_t)gridDim.x * blockDim.x)
+    out[v] = (evid && __ldg(evid + v)) ? 0ull : sweeps;
+}
+
 // tallies (schedule order, u32) += host-provided counts (aggregate_marginals_from)
 __global__ void k_add_u32(uint32_t *dst, const uint32_t *src, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

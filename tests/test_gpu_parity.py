@@ -924,6 +924,42 @@ def test_deferred_replica_receives_the_graph_from_a_peer():
     assert np.array_equal(a.tallies()[0], b.tallies(wide=False)[0].astype(np.uint64))
 
 
+def test_page_locked_destinations_receive_the_same_tallies_and_sample_counts():
+    """dwg_get_tallies / dwg_get_tallies32 into page-locked arrays: tallies by direct DMA, the
+    per-variable sample counts (src/gibbs_sampler.h:157,163) made on the device and copied out,
+    equal to what pageable destinations get from the host threads -- with evidence sampled or not,
+    Boolean and categorical, and right after dwg_create (the tally row map is still in flight)"""
+    import torch
+    from sampler_b200 import graphgen
+    rng = np.random.default_rng(5)
+    for raw in (graphgen.c2_boolean(30_000, nweight=100, planted_weights=True), graphgen.c3_categorical(4_000, nweight=60),
+                random_graph(rng, nvar=500, nfac=1500, nweight=20, max_arity=3)):
+        g = sb.Graph.from_raw(raw, sb.SCHED_CHROMATIC)
+        nval, nvar = int(g.info.num_values), int(g.info.num_variables)
+        t_pin = torch.zeros(nval, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+        n_pin = torch.zeros(nvar, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+        for se in (False, True):
+            s = sb.Sampler(g, sample_evidence=se, seed=11)
+            n_pin[:] = 77
+            s.tallies(out=(t_pin, n_pin))  # nothing sampled yet
+            assert not t_pin.any() and not n_pin.any()
+            s.infer_epochs(3)
+            t0, n0 = s.tallies()
+            t_pin[:] = 9; n_pin[:] = 9
+            s.tallies(out=(t_pin, n_pin))
+            assert np.array_equal(t0, t_pin.astype(np.uint64)) and np.array_equal(n0, n_pin)
+            assert n0.max() == 3 and (se or (n0 == 0).sum() == int(np.count_nonzero(raw.var_role)))
+            t1 = np.empty(nval, np.uint64)
+            n_pin[:] = 9
+            s.tallies(out=(t1, n_pin))  # pageable u64 tallies, page-locked counts
+            assert np.array_equal(t0, t1) and np.array_equal(n0, n_pin)
+            s.add_tallies(t0, n0)       # counts from another replica: the host path adds them
+            t2, n2 = s.tallies()
+            s.tallies(out=(t_pin, n_pin))
+            assert np.array_equal(n2, 2 * n0) and np.array_equal(n2, n_pin) and np.array_equal(t2, t_pin.astype(np.uint64))
+            s.close()
+
+
 # ---------------------------------------------------------------- warp per variable (hubs)
 def _hub_graph(rng, nvar, nfac, max_arity, hub_share=0.15, nhub=2):
     raw = random_graph(rng, nvar=nvar, nfac=nfac, nweight=25, p_cat=0.0, max_arity=max_arity)
