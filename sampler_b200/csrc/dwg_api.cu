@@ -1404,17 +1404,20 @@ static int get_tallies_impl(dwg_handle *h, uint64_t *tallies, uint32_t *tallies3
     nsamples = nullptr;  // done
   };
   // A page-locked destination gets the counts by DMA from the device (the copy engine writes host
-  // memory at the link rate, 52 GB/s measured; sixteen host threads manage 23 GB/s on the same box)
+  // memory at the link rate, 52 GB/s measured; sixteen host threads manage 23 GB/s on the same box).
+  // The counts depend on the NUMBER of sweeps queued, not on their results: kernel and copy go to the
+  // `late` stream and run under sweeps that are still in flight on the handle's stream.
   bool nsamples_dma = false;
   if (nsamples && m.nvar && h->extra_nsamples.empty()) {
     cudaPointerAttributes attr{};
     if (cudaPointerGetAttributes(&attr, nsamples) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+      if (!h->late) CU(cudaStreamCreateWithFlags(&h->late, cudaStreamNonBlocking));
       if (!h->nsamples_dev.p) CU(h->nsamples_dev.alloc(m.nvar));
-      if (!h->opts.sample_evidence && !h->evid_abi.p) CU(h->evid_abi.upload(m.var_is_evid, h->stream));
-      k_fill_nsamples<<<(uint32_t)std::min<uint64_t>((m.nvar + 255) / 256, 8192), 256, 0, h->stream>>>(
+      if (!h->opts.sample_evidence && !h->evid_abi.p) CU(h->evid_abi.upload(m.var_is_evid, h->late));
+      k_fill_nsamples<<<(uint32_t)std::min<uint64_t>((m.nvar + 255) / 256, 8192), 256, 0, h->late>>>(
           h->nsamples_dev.p, h->opts.sample_evidence ? nullptr : h->evid_abi.p, h->infer_sweeps, m.nvar);
       ++g_launches;
-      CU(cudaMemcpyAsync(nsamples, h->nsamples_dev.p, 8 * m.nvar, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(nsamples, h->nsamples_dev.p, 8 * m.nvar, cudaMemcpyDeviceToHost, h->late));
       nsamples = nullptr;  // queued; awaited below
       nsamples_dma = true;
     } else {
@@ -1485,7 +1488,7 @@ static int get_tallies_impl(dwg_handle *h, uint64_t *tallies, uint32_t *tallies3
   }
 tallies_done:
   if (nsamples_dma) {
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->late));
     lap("nsamples (DMA)");
   }
   if (nsamples) {

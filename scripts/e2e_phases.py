@@ -1,6 +1,8 @@
 """Phase times of the host-buffer path (dwg_create -> sweeps -> dwg_get_tallies32) on the C2 graph, with
 the library's own lap timers (DWG_TIMING=1 on stderr) and three destinations for the per-variable
-sample counts: a pageable array (what bench.py's e2e leg passes), none, a page-locked array.
+sample counts: a pageable array, none, a page-locked array (what bench.py's e2e leg passes) -- the
+last also without a synchronisation between the sweeps and the getter (the counts then travel while
+the sweeps run).
     python scripts/e2e_phases.py [nvar] [sweeps]
 """
 import os
@@ -27,12 +29,13 @@ def main():
     n_page = np.zeros(int(info.num_variables), np.uint64)
     n_pin = torch.zeros(int(info.num_variables), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
     for rep in range(4):
-        for mode in ("pageable", "none", "page-locked"):
+        for mode in ("pageable", "none", "page-locked", "page-locked, sweeps in flight"):
             t0 = time.time()
             s = sb.Sampler(g, sample_evidence=True, seed=rep)
             t1 = time.time()
             s.infer_epochs(sweeps)
-            s.sync()
+            if "in flight" not in mode:
+                s.sync()
             t2 = time.time()
             if mode == "none":
                 rc = load().dwg_get_tallies32(s._h, _ptr(t_host), None)
@@ -40,7 +43,7 @@ def main():
             else:
                 s.tallies(out=(t_host, n_page if mode == "pageable" else n_pin))
             t3 = time.time()
-            print("rep %d nsamples -> %-11s create %.2f ms, sweeps %.2f ms, tallies %.2f ms" % (
+            print("rep %d nsamples -> %-30s create %.2f ms, sweeps %.2f ms, tallies %.2f ms" % (
                 rep, mode, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)), file=sys.stderr, flush=True)
             s.close()
 
