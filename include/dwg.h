@@ -191,7 +191,9 @@ int dwg_get_tallies(dwg_handle *h, uint64_t *tallies, uint64_t *nsamples);
  * dwg_get_tallies32 and the sample counts of both getters; pageable ones by the host's threads.
  * Either pointer may be NULL. */
 int dwg_get_tallies32(dwg_handle *h, uint32_t *tallies, uint64_t *nsamples);
-int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsamples); /* aggregate_marginals_from :116-127 */
+/* aggregate_marginals_from :116-127.  The device counts in 32 bits: an aggregate of more than
+ * 2^32 - 1 samples of one variable is refused (DWG_ERR_UNSUPPORTED), never wrapped */
+int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsamples);
 int dwg_get_weights(dwg_handle *h, double *out);
 int dwg_set_weights(dwg_handle *h, const double *in);
 int dwg_get_assignments(dwg_handle *h, int evid_chain, uint64_t *out); /* dense values */

@@ -1503,8 +1503,17 @@ int dwg_add_tallies(dwg_handle *h, const uint64_t *tallies, const uint64_t *nsam
   h->chain_open = false;
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
+  // the device's counters are 32 bits wide: a tally is bounded by its variable's sample count, so the
+  // counts decide whether the aggregate still fits (refused rather than wrapped)
+  uint64_t most = 0;
+  for (uint64_t v = 0; v < m.nvar; ++v) most = std::max(most, nsamples[v] + (h->extra_nsamples.empty() ? 0 : h->extra_nsamples[v]));
+  if (most + h->infer_sweeps > 0xffffffffull)
+    return fail(DWG_ERR_UNSUPPORTED, "dwg_add_tallies: more than 2^32 - 1 samples of one variable (the tally counters are 32 bits wide)");
   std::vector<uint32_t> t(m.ndrow, 0);
-  for (uint64_t i = 0; i < m.nrow; ++i) t[m.row_of_value[i]] = (uint32_t)tallies[i];
+  for (uint64_t i = 0; i < m.nrow; ++i) {
+    if (tallies[i] > 0xffffffffull) return fail(DWG_ERR_INVALID, "dwg_add_tallies: a tally exceeds its variable's sample count");
+    t[m.row_of_value[i]] = (uint32_t)tallies[i];
+  }
   DevBuf<uint32_t> tmp;
   CU(tmp.upload(t, h->stream));
   if (m.ndrow) {

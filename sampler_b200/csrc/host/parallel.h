@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <exception>
 #include <thread>
 #include <vector>
 
@@ -31,10 +32,19 @@ void parallel_ranges(uint64_t n, unsigned parts, F f, uint64_t min_parallel = 40
     for (unsigned p = 0; p < parts; ++p) f(n * p / parts, n * (p + 1) / parts, p);
     return;
   }
+  // an exception in a worker (std::bad_alloc on a graph too large for the host) is carried back to
+  // the caller, whose C-ABI entry point turns it into an error code; left in the thread it would
+  // be std::terminate
   std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err(parts);
   th.reserve(parts);
-  for (unsigned p = 0; p < parts; ++p) th.emplace_back([=] { f(n * p / parts, n * (p + 1) / parts, p); });
+  for (unsigned p = 0; p < parts; ++p)
+    th.emplace_back([=, &err] {
+      try { f(n * p / parts, n * (p + 1) / parts, p); } catch (...) { err[p] = std::current_exception(); }
+    });
   for (auto &t : th) t.join();
+  for (auto &e : err)
+    if (e) std::rethrow_exception(e);
 }
 
 template <typename F>

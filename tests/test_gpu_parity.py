@@ -957,6 +957,11 @@ def test_page_locked_destinations_receive_the_same_tallies_and_sample_counts():
             t2, n2 = s.tallies()
             s.tallies(out=(t_pin, n_pin))
             assert np.array_equal(n2, 2 * n0) and np.array_equal(n2, n_pin) and np.array_equal(t2, t_pin.astype(np.uint64))
+            big = n0.copy()
+            big[0] = 1 << 32  # the device counts in 32 bits: refused, not wrapped, and nothing is added
+            with pytest.raises(sb.api.DwgError):
+                s.add_tallies(t0, big)
+            assert np.array_equal(s.tallies()[1], n2)
             s.close()
 
 
