@@ -286,10 +286,12 @@ struct dwg_handle {
   cudaEvent_t piece_done[2] = {nullptr, nullptr};
   // row_of_value is read by the tally getters only: its host -> device copy is queued on `late`
   // once the graph's other copies have landed (so that it does not share the link with them) and
-  // rides under the first sweeps; the getters and dwg_graph_segments wait for late_done
+  // rides under the first sweeps; the getters wait for late_done
   cudaStream_t late = nullptr;
   cudaEvent_t late_done = nullptr;
+  bool row_map_ready = false;
   ~dwg_handle() {
+    if (stream) cudaStreamSynchronize(stream);  // (a failed dwg_create may leave copies in flight)
     for (cudaEvent_t e : piece_done)
       if (e) cudaEventDestroy(e);
     if (late_done) cudaEventDestroy(late_done);
@@ -850,15 +852,11 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     CU(h->assign_evid32.alloc(m.nvar_pad));
   }
   CU(h->tallies.alloc(m.ndrow));
-  // dwg_get_tallies: schedule order -> ABI order on the device.  Allocated (and listed among the
-  // segments) here, copied behind everything else on the `late` stream (below)
-  {
-    const bool d = g_upload.defer;
-    g_upload.defer = true;
-    cudaError_t e = h->row_of_value.upload(m.row_of_value, s);
-    g_upload.defer = d;
-    CU(e);
-  }
+  // dwg_get_tallies: schedule order -> ABI order on the device.  Allocated here, copied behind
+  // everything else on the `late` stream (below).  It is not one of the segments a peer receives:
+  // only the replica that hands tallies to the host reads it, and a deferred replica that does
+  // uploads its own copy on first use (get_tallies_impl).
+  CU(h->row_of_value.alloc(m.row_of_value.size()));
   CU(h->w_fixed.upload(fixed_dev, s));
   CU(h->weights.upload(w_dev, s));
   CU(h->prev_weights.upload(w_dev, s));
@@ -917,8 +915,8 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
   lap("allocations + copies queued");
   int rc = defer ? DWG_OK : init_state(h.get());  // (deferred: dwg_reset_state once the graph has arrived)
   if (rc) return rc;
-  CU(cudaStreamSynchronize(s));  // the staging vectors go out of scope
-  lap("copies done");
+  // (no synchronisation yet: the kernel setup below is host work -- occupancy queries, function
+  // attributes, the epoch plan -- and runs while the copies are on the link)
   h->device_bytes = image_device_bytes(m);
 
   DevGraph &dg = h->dg;
@@ -939,7 +937,6 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     // sweeps, parity hooks) is uploaded on first use
     CU(h->sl_off.upload(m.sl_off, s));
     CU(h->blob.upload(m.blob, s));
-    CU(cudaStreamSynchronize(s));
     SellState &ss = h->ss;
     ss.assign_free = h->assign_free8.p; ss.assign_evid = h->assign_evid8.p;
     ss.weights = h->weights.p; ss.grad_acc = h->grad_acc.p; ss.tallies = h->tallies.p;
@@ -963,14 +960,17 @@ int dwg_create(const dwg_graph *g, const dwg_opts_t *opts, int device, dwg_handl
     if (rc) return rc;
     h->cls_query_end = g->query_end();
   }
+  lap("kernel setup");
+  CU(cudaStreamSynchronize(s));  // the staging vectors go out of scope
+  lap("copies done");
   if (!defer && !m.row_of_value.empty()) {
     // (stream s has drained: this copy has the link to itself and overlaps whatever the caller does next)
     CU(cudaStreamCreateWithFlags(&h->late, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->late_done, cudaEventDisableTiming));
     CU(cudaMemcpyAsync(h->row_of_value.p, m.row_of_value.data(), 4 * m.row_of_value.size(), cudaMemcpyHostToDevice, h->late));
     CU(cudaEventRecord(h->late_done, h->late));
+    h->row_map_ready = true;
   }
-  lap("kernel setup");
   *out = h.release();
   return DWG_OK;
 }
@@ -994,7 +994,6 @@ void dwg_destroy(dwg_handle *h) {
 
 int dwg_graph_segments(dwg_handle *h, int max, void **ptrs, uint64_t *bytes, int *n) {
   if (!h || !n) return fail(DWG_ERR_INVALID, "null argument");
-  if (h->late) CU(cudaStreamSynchronize(h->late));  // every segment is whole before a peer copies it
   *n = (int)h->segments.size();
   for (int i = 0; i < *n && i < max; ++i) {
     if (ptrs) ptrs[i] = h->segments[i].first;
@@ -1374,6 +1373,10 @@ static int get_tallies_impl(dwg_handle *h, uint64_t *tallies, uint32_t *tallies3
   const GraphImage &m = *h->img;
   CU(cudaSetDevice(h->device));
   if (h->late_done) CU(cudaStreamWaitEvent(h->stream, h->late_done, 0));  // row_of_value has arrived
+  if (!h->row_map_ready && !m.row_of_value.empty()) {  // a deferred replica asked for tallies
+    CU(cudaMemcpyAsync(h->row_of_value.p, m.row_of_value.data(), 4 * m.row_of_value.size(), cudaMemcpyHostToDevice, h->stream));
+    h->row_map_ready = true;
+  }
   const bool timing = getenv("DWG_TIMING") != nullptr;
   auto t_prev = std::chrono::steady_clock::now();
   auto lap = [&](const char *what) {
