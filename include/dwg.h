@@ -158,7 +158,9 @@ int dwg_release_cached_memory(int device);
 /* The device arrays that hold the replica's copy of the graph (stream, per-variable tables, initial
  * weights), in a fixed order that depends on the graph only: ptrs[i] / bytes[i] for i < *n (call
  * with max = 0 to get the count).  What a replica created with defer_upload receives from a
- * peer (torch.distributed / NCCL broadcast on dwg_stream(), or cudaMemcpyPeer). */
+ * peer (torch.distributed / NCCL broadcast on dwg_stream(), or cudaMemcpyPeer).  The map that
+ * orders tallies for the host is not among them: a deferred replica that is asked for tallies
+ * uploads its own. */
 int dwg_graph_segments(dwg_handle *h, int max, void **ptrs, uint64_t *bytes, int *n);
 /* InferenceResult ctor again (src/inference_result.cc:24-42): both chains to the evidence values,
  * tallies cleared; the weights stay as they are. */
