@@ -358,6 +358,7 @@ def ours(args):
     reps = []
     for rep in range(5):  # five whole repetitions, the median is reported (the first maps the device memory
         barrier()         # of the replica; later ones find it in the library's pool)
+        n_host[0] = n_host[-1] = 0  # (the check below must see this repetition's counts)
         t0 = time.time()
         s2 = sb.Sampler(graph, device=local, sample_evidence=True, reg_param=LEARN["reg_param"], seed=99 + rep, replica=rank,
                         defer_upload=(world > 1 and rank != 0))
@@ -378,7 +379,7 @@ def ours(args):
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         reps.append((float(et.item()), t_up - t0, t_sw - t_up, t_end - t_sw))
         if rank == 0:
-            assert int(t_host.astype(np.uint64).sum()) > 0 and int(n_host[0]) == args.steps
+            assert int(t_host.astype(np.uint64).sum()) > 0 and int(n_host[0]) == args.steps and int(n_host[-1]) == args.steps
         s2.close()
         torch.cuda.synchronize()
     reps.sort()
