@@ -113,7 +113,7 @@ class ClockSampler:
             return
         try:
             self.proc = subprocess.Popen([exe, "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -128,25 +128,35 @@ class ClockSampler:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
+        for _ in range(60):  # (nvidia-smi takes a few hundred ms to print its first line)
+            if self.lines:
+                break
+            time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        mx, parsed = None, []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for ts, line in self.lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                clk, mxc = float(f[1]), float(f[2])
+                clk, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            mx = mxc
-            if t0 - 0.05 <= ts <= t1 + 0.15:
-                sm.append(clk)
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:  # region shorter than the sampling period: take whatever we saw
-            sm = [float(l.split(",")[1]) for _, l in self.lines if len(l.split(",")) >= 9][-3:] or [0.0]
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+            parsed.append((ts, clk, [n for n, val in zip(names, f[5:9]) if val.lower().startswith("active")]))
+        if not parsed:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": ["nvidia-smi printed no sample"], "samples": 0}
+        used = [p for p in parsed if t0 - 0.05 <= p[0] <= t1 + 0.15]
+        out = {}
+        if not used:
+            # region shorter than the sampling period: the samples nearest to it (the sampler has been running
+            # since before the learning epochs and the warm-up sweeps, i.e. under the same kind of load)
+            mid = 0.5 * (t0 + t1)
+            used = sorted(parsed, key=lambda p: abs(p[0] - mid))[:3]
+            out["note"] = "no sample inside the %.1f ms timed region: the %d nearest ones" % (1e3 * (t1 - t0), len(used))
+        out.update({"sm_mhz": float(np.median([p[1] for p in used])), "sm_max_mhz": mx,
+                    "reasons": sorted({r for p in used for r in p[2]}), "samples": len(used)})
+        return out
 
 
 # --------------------------------------------------------------------------------------
@@ -271,6 +281,7 @@ def ours(args):
     if rank == 0:
         log("graph: %d vars, %d edge records, %d colours, %.1f MiB/replica; gen %.1fs compile %.1fs"
             % (info.num_variables, info.num_index_entries, info.num_colors, info.device_bytes / 2**20, t_gen, t_compile))
+    clocks = ClockSampler(local) if rank == 0 else None  # (started here: running well before the timed region)
     smp = sb.Sampler(graph, device=local, sample_evidence=True, reg_param=LEARN["reg_param"], seed=1234, replica=rank)
     stream = torch.cuda.ExternalStream(smp.stream(), device=torch.device("cuda", local))
     # one replica per rank: DimmWitted's learn / inference schedule over torch.distributed (NCCL)
@@ -310,7 +321,6 @@ def ours(args):
     smp.sync()
     torch.cuda.synchronize()
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
     launches0 = L.dwg_launch_count()
     e0, e1, e2 = ev(), ev(), ev()
     t_wall0 = time.time()
